@@ -1,0 +1,123 @@
+// Shared declarations of the nkb200 CUDA library (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdio>
+#include <string>
+
+#include "nkb200.h"
+
+namespace nkb {
+
+void set_error(const std::string &msg);
+extern std::atomic<uint64_t> g_launches;
+
+inline void count_launch(uint64_t n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define NKB_CUDA(call)                                                                        \
+    do {                                                                                      \
+        cudaError_t err__ = (call);                                                           \
+        if (err__ != cudaSuccess) {                                                           \
+            ::nkb::set_error(std::string(#call) + ": " + cudaGetErrorString(err__) + " at " + \
+                             __FILE__ + ":" + std::to_string(__LINE__));                      \
+            return 1;                                                                         \
+        }                                                                                     \
+    } while (0)
+
+#define NKB_REQUIRE(cond, msg)                   \
+    do {                                         \
+        if (!(cond)) {                           \
+            ::nkb::set_error(std::string(msg));  \
+            return 2;                            \
+        }                                        \
+    } while (0)
+
+// ARS(2,2,2) IMEX Runge-Kutta constants (Ascher, Ruuth, Spiteri 1997)
+constexpr double kGamma = 0.29289321881345247559915563789515;   // 1 - 1/sqrt(2)
+constexpr double kDelta = -0.70710678118654752440084436210485;  // 1 - 1/(2 gamma)
+
+// device-side description of one tracer module (time-invariant tables live in HBM)
+struct ModelDev {
+    int nz, ny, T, kind, n_classes, column_model;
+    int class_of[NKB_MAX_TRACERS];
+    double t0, t1;
+    const double *depth_edges;  // [nz+1]
+    const double *depth_mid;    // [nz]
+    const double *dz_r;         // [nz]
+    const double *dz_mid;       // [nz-1]
+    const double *dz_mid_r;     // [nz-1]
+    const double *wvel;         // [nz+1][ny] (boundary rows zeroed)
+    const double *estencil;     // [3][nz][ny] or nullptr
+    const double *bld_max;      // [ny]
+    double surf_diag[NKB_MAX_CLASSES], surf_aff[NKB_MAX_CLASSES], decay[NKB_MAX_CLASSES],
+        sink_vel[NKB_MAX_CLASSES];
+    int n_flux_pts;
+    double flux_t[8], flux_v[8];
+    double src_const[NKB_MAX_TRACERS];
+    double sink_thres;
+    int n_frc;
+    const double *frc_time;  // [n_frc]
+    const double *frc_data;  // [n_frc][nz][ny]
+    const double *light;     // [nz][ny]
+    double po4_halfsat, max_uptake_rate, sigma, dop_remin_rate, pop_remin_rate;
+    int po4_s_restoring_opt;
+};
+
+// arguments of one fused stage launch (K1+K2)
+struct StageArgs {
+    const double *u[2];   // stage inputs [T][nz][ny][ldb]
+    double *out;          // [T][nz][ny][ldb]
+    const double *sub;    // optional: out = x - sub (final F = x(T) - x(0)), else nullptr
+    double a[2];          // rhs = sum_i a[i]*u[i] + he[i]*E(u[i])
+    double he[2];
+    const double *est;    // [3][nz][ny] or nullptr
+    const double *tri;    // [ncls][3][nz][ny] (m, ib, g) of this stage (raw sub,diag,sup for tend)
+    const double *aff;    // [ncls][ny]  hg*affine surface source
+    const double *src[2]; // [nz][ny] forcing at the explicit time of input i (FORCED_FILE)
+    const double *light;  // [nz][ny]
+    int nz, ny, B, ldb, T;
+    int class_of[NKB_MAX_TRACERS];
+    double src_const[NKB_MAX_TRACERS];
+    double sink_thres_r;  // 1/sink_thres or 0
+    double halfsat, umax, sigma, rdop, rpop;
+};
+
+int launch_stage_tables(const ModelDev &m, int n_stages, const double *d_t, const double *d_hg, int mode,
+                        double *tri, double *aff, cudaStream_t st);
+int launch_mixing_coeff(const ModelDev &m, double time, double *out, cudaStream_t st);
+int launch_forcing_tables(const ModelDev &m, int n_times, const double *d_t, double *src, cudaStream_t st);
+int launch_gather_member(const double *src, double *dst, size_t n, size_t ldb, int b, cudaStream_t st);
+int launch_pack(const double *src, double *dst, int n, int B, int ldb, cudaStream_t st);
+int launch_unpack(const double *src, double *dst, int n, int B, int ldb, cudaStream_t st);
+int launch_stage(int kind, int nin, const StageArgs &a, cudaStream_t st);
+int launch_tend(int kind, const StageArgs &a, cudaStream_t st);
+
+}  // namespace nkb
+
+// the opaque handle of the C ABI
+struct nkb_model {
+    nkb::ModelDev dev;
+    void *arena = nullptr;      // one allocation holding all time-invariant tables
+    // schedule
+    int n_steps = 0;
+    double *h_t_start = nullptr, *h_h = nullptr;  // host copies
+    // per-stage tables, stage s = 2*step + {0,1}
+    double *tri = nullptr;      // [n_stages][n_classes][3][nz][ny]  (m, ib, g)
+    double *aff = nullptr;      // [n_stages][n_classes][ny]  h*gamma*(affine surface source) per column
+    double *src = nullptr;      // [n_stages][nz][ny] forcing at the explicit stage times (or nullptr)
+    // scratch for tend()/mixing_coeff()
+    double *tri_raw = nullptr;  // [n_classes][3][nz][ny]
+    double *aff_raw = nullptr;  // [n_classes][ny]
+    double *src_raw = nullptr;  // [nz][ny]
+    // host-buffer path
+    double *d_stage_major = nullptr, *d_stage_x = nullptr, *d_stage_f = nullptr, *d_stage_work = nullptr;
+    size_t stage_cap = 0;
+    cudaGraphExec_t graph = nullptr;
+    const double *graph_x0 = nullptr;
+    double *graph_f = nullptr, *graph_work = nullptr;
+    int graph_B = 0, graph_ldb = 0;
+    cudaStream_t own_stream = nullptr;
+};

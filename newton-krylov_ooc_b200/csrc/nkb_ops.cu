@@ -1,0 +1,190 @@
+// K5 / K6 — Krylov vector kernels on member-fastest batches.
+//   pack/unpack : layout conversion member-major <-> member-fastest (tiled transpose)
+//   wdot        : region-weighted dot products / means (TracerModuleStateBase.dot_prod/mean,
+//                 tracer_module_state_base.py:371-388, with the CSR region-mean matrix of
+//                 model_config.py:292-315); deterministic two-pass reduction, warp shuffles
+//                 across the cell lanes of a warp
+//   axpby       : y = alpha[r][b]*x + beta[r][b]*y with per-(region, member) scalars
+//                 (tracer_module_state_base.py:255-369, broadcast_region_vals :502-515)
+//   fd_sigma    : sigma = 1e-4*norm, 1 where 0 (model_state_base.py:509-511)
+#include "nkb_common.cuh"
+
+namespace nkb {
+
+// ---- transpose ------------------------------------------------------------------------
+// src [rows][src_ld] -> dst [cols][dst_ld] for the rows x cols logical matrix
+__global__ void transpose_kernel(const double *__restrict__ src, double *__restrict__ dst, int rows, int cols,
+                                 size_t src_ld, size_t dst_ld) {
+    __shared__ double tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int r = r0 + i, c = c0 + threadIdx.x;
+        if (r < rows && c < cols) tile[i][threadIdx.x] = src[(size_t)r * src_ld + c];
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) dst[(size_t)c * dst_ld + r] = tile[threadIdx.x][i];
+    }
+}
+
+static int launch_transpose(const double *src, double *dst, int rows, int cols, size_t src_ld, size_t dst_ld,
+                            cudaStream_t st) {
+    dim3 block(32, 8), grid((cols + 31) / 32, (rows + 31) / 32);
+    transpose_kernel<<<grid, block, 0, st>>>(src, dst, rows, cols, src_ld, dst_ld);
+    count_launch();
+    NKB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// member-major [B][n] -> member-fastest [n][ldb]
+int launch_pack(const double *src, double *dst, int n, int B, int ldb, cudaStream_t st) {
+    return launch_transpose(src, dst, B, n, (size_t)n, (size_t)ldb, st);
+}
+// member-fastest [n][ldb] -> member-major [B][n]
+int launch_unpack(const double *src, double *dst, int n, int B, int ldb, cudaStream_t st) {
+    return launch_transpose(src, dst, n, B, (size_t)ldb, (size_t)n, st);
+}
+
+// ---- weighted dot -----------------------------------------------------------------------
+// block (BX member lanes, BY cell lanes), BX*BY == 256, BX power of two <= 32.
+// grid (member blocks, regions, chunks).  partial[chunk][r][b].
+__global__ void __launch_bounds__(256)
+wdot_partial_kernel(const int *__restrict__ indptr, const int *__restrict__ indices,
+                    const double *__restrict__ wdata, int T, size_t ncell, const double *__restrict__ a,
+                    const double *__restrict__ bb, int B, size_t ldb, int R, double *__restrict__ partial) {
+    __shared__ double red[256];
+    const int bx = blockDim.x, by = blockDim.y;
+    const int b = blockIdx.x * bx + threadIdx.x;
+    const int r = blockIdx.y;
+    const int lo = indptr[r], hi = indptr[r + 1];
+    const int nchunk = gridDim.z;
+    const int per = (hi - lo + nchunk - 1) / nchunk;
+    const int c_lo = lo + blockIdx.z * per;
+    const int c_hi = min(hi, c_lo + per);
+    double acc = 0.0;
+    if (b < B) {
+        for (int i = c_lo + threadIdx.y; i < c_hi; i += by) {
+            const size_t cell = indices[i];
+            const double w = wdata[i];
+            double s = 0.0;
+            for (int t = 0; t < T; ++t) {
+                const size_t off = ((size_t)t * ncell + cell) * ldb + b;
+                const double av = a[off];
+                s += bb ? av * bb[off] : av;
+            }
+            acc = fma(w, s, acc);
+        }
+    }
+    // reduce over the cell lanes: first inside each warp (lanes that share a member are
+    // bx apart), then across warps through shared memory
+    for (int off = 16; off >= bx; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
+    const int tid = threadIdx.y * bx + threadIdx.x;
+    red[tid] = acc;
+    __syncthreads();
+    if (tid < bx) {
+        double s = 0.0;
+        for (int wrp = 0; wrp < 256 / 32; ++wrp) s += red[wrp * 32 + tid];
+        if (b < B) partial[((size_t)blockIdx.z * R + r) * B + b] = s;
+    }
+}
+
+__global__ void wdot_final_kernel(const double *__restrict__ partial, int nchunk, size_t n, double *__restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s = 0.0;
+    for (int c = 0; c < nchunk; ++c) s += partial[(size_t)c * n + i];
+    out[i] = s;
+}
+
+// ---- axpby ---------------------------------------------------------------------------------
+__global__ void axpby_kernel(const int *__restrict__ region, int R, int T, size_t ncell,
+                             const double *__restrict__ alpha, const double *__restrict__ x,
+                             const double *__restrict__ beta, double *__restrict__ y, double fill_alpha,
+                             double fill_beta, int B, size_t ldb) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t cell = (size_t)blockIdx.y * blockDim.y + threadIdx.y;
+    if (b >= B || cell >= ncell) return;
+    const int r = region ? region[cell] : 1;
+    double al = fill_alpha, be = fill_beta;
+    if (r > 0) {
+        if (alpha) al = alpha[(size_t)(r - 1) * B + b];
+        if (beta) be = beta[(size_t)(r - 1) * B + b];
+    }
+    for (int t = 0; t < T; ++t) {
+        const size_t off = ((size_t)t * ncell + cell) * ldb + b;
+        double v = 0.0;
+        if (x) v = al * x[off];
+        if (be != 0.0) v = fma(be, y[off], v);
+        y[off] = v;
+    }
+}
+
+__global__ void fd_sigma_kernel(const double *__restrict__ nrm, double *__restrict__ sigma, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double s = 1.0e-4 * nrm[i];
+    sigma[i] = (s == 0.0) ? 1.0 : s;
+}
+
+}  // namespace nkb
+
+extern "C" {
+
+int nkb_pack_members(const double *d_src_major, double *d_dst_fast, int n, int B, int ldb, void *stream) {
+    NKB_REQUIRE(d_src_major && d_dst_fast && n > 0 && B > 0 && ldb >= B, "nkb_pack_members: bad argument");
+    return nkb::launch_pack(d_src_major, d_dst_fast, n, B, ldb, (cudaStream_t)stream);
+}
+
+int nkb_unpack_members(const double *d_src_fast, double *d_dst_major, int n, int B, int ldb, void *stream) {
+    NKB_REQUIRE(d_src_fast && d_dst_major && n > 0 && B > 0 && ldb >= B, "nkb_unpack_members: bad argument");
+    return nkb::launch_unpack(d_src_fast, d_dst_major, n, B, ldb, (cudaStream_t)stream);
+}
+
+int nkb_wdot_chunks(int ncell_max) {
+    int c = (ncell_max + 4095) / 4096;
+    return c < 1 ? 1 : (c > 64 ? 64 : c);
+}
+
+int nkb_wdot(const int32_t *d_indptr, const int32_t *d_indices, const double *d_wdata, int R, int T, int ncell,
+             const double *d_a, const double *d_b, int B, int ldb, double *d_partial, int n_chunks,
+             double *d_out, void *stream) {
+    NKB_REQUIRE(d_indptr && d_indices && d_wdata && d_a && d_out && d_partial, "nkb_wdot: null argument");
+    NKB_REQUIRE(R >= 1 && T >= 1 && ncell >= 1 && B >= 1 && ldb >= B && n_chunks >= 1, "nkb_wdot: bad size");
+    cudaStream_t st = (cudaStream_t)stream;
+    int bx = 1;
+    while (bx < B && bx < 32) bx <<= 1;
+    dim3 block(bx, 256 / bx), grid((B + bx - 1) / bx, R, n_chunks);
+    nkb::wdot_partial_kernel<<<grid, block, 0, st>>>(d_indptr, d_indices, d_wdata, T, (size_t)ncell, d_a, d_b, B,
+                                                     (size_t)ldb, R, d_partial);
+    nkb::count_launch();
+    const size_t n = (size_t)R * B;
+    nkb::wdot_final_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_partial, n_chunks, n, d_out);
+    nkb::count_launch();
+    NKB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int nkb_axpby(const int32_t *d_region, int R, int T, int ncell, const double *d_alpha, const double *d_x,
+              const double *d_beta, double *d_y, double fill_alpha, double fill_beta, int B, int ldb,
+              void *stream) {
+    NKB_REQUIRE(d_y && T >= 1 && ncell >= 1 && B >= 1 && ldb >= B, "nkb_axpby: bad argument");
+    int bx = 1;
+    while (bx < B && bx < 32) bx <<= 1;
+    dim3 block(bx, 256 / bx), grid((B + bx - 1) / bx, (ncell + block.y - 1) / block.y);
+    nkb::axpby_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(d_region, R, T, (size_t)ncell, d_alpha, d_x, d_beta,
+                                                               d_y, fill_alpha, fill_beta, B, (size_t)ldb);
+    nkb::count_launch();
+    NKB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int nkb_fd_sigma(const double *d_norm, double *d_sigma, int n, void *stream) {
+    NKB_REQUIRE(d_norm && d_sigma && n >= 1, "nkb_fd_sigma: bad argument");
+    nkb::fd_sigma_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_norm, d_sigma, n);
+    nkb::count_launch();
+    NKB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,195 @@
+// K3 — member-independent coefficient generation on the device.
+//
+// For every implicit stage time of the fixed schedule: boundary-layer depth, conservative
+// remap of the log-mixing ramp onto the interior depth edges, Peclet limiter, assembly of
+// the vertical (tridiagonal) operator per tracer class and its LU (Thomas) factors.
+// Replaces, per reference RHS/Jacobian evaluation:
+//   py_driver_2d/vert_mix.py:43-101 (mixing_coeff, bldepth), spatial_axis.py:136-187
+//   (remap_linear_interpolant), vert_mix.py:140-188 + advection.py:111-179 (vertical part of
+//   comp_jacobian), test_problem/vert_mix.py:27-57, and SciPy Radau's sparse LU.
+// One thread per (stage, column); writes are coalesced over ypos.
+
+#include "nkb_common.cuh"
+
+namespace nkb {
+
+__device__ __forceinline__ double interp_clamped2(double x, double x0, double x1, double y0, double y1) {
+    // np.interp with two points: constant outside, slope*(x-x0)+y0 inside
+    if (x <= x0) return y0;
+    if (x >= x1) return y1;
+    return (y1 - y0) / (x1 - x0) * (x - x0) + y0;
+}
+
+// average over [a, b] of the clamped linear ramp (x0,y0)-(x1,y1)  == remap_linear_interpolant
+// for a two-point interpolant (spatial_axis.py:136-187): exact integral by trapezoids
+__device__ __forceinline__ double ramp_layer_mean(double a, double b, double x0, double x1, double y0,
+                                                  double y1) {
+    const double fa = interp_clamped2(a, x0, x1, y0, y1);
+    const double fb = interp_clamped2(b, x0, x1, y0, y1);
+    const bool x0_in = (x0 >= a) && (x0 < b);
+    const bool x1_in = (x1 >= a) && (x1 < b);
+    if (!x0_in && !x1_in) return 0.5 * (fa + fb);
+    double acc;
+    if (x0_in && x1_in) {
+        acc = (x0 - a) * (0.5 * (fa + y0)) + (x1 - x0) * (0.5 * (y0 + y1)) + (b - x1) * (0.5 * (y1 + fb));
+    } else if (x0_in) {
+        acc = (x0 - a) * (0.5 * (fa + y0)) + (b - x0) * (0.5 * (y0 + fb));
+    } else {
+        acc = (x1 - a) * (0.5 * (fa + y1)) + (b - x1) * (0.5 * (y1 + fb));
+    }
+    return acc / (b - a);
+}
+
+__device__ __forceinline__ double interp_pw(double x, const double *xp, const double *fp, int n) {
+    if (x <= xp[0]) return fp[0];
+    if (x >= xp[n - 1]) return fp[n - 1];
+    int i = 0;
+    while (i < n - 2 && x >= xp[i + 1]) ++i;
+    return (fp[i + 1] - fp[i]) / (xp[i + 1] - xp[i]) * (x - xp[i]) + fp[i];
+}
+
+// boundary layer depth: vert_mix.py:89-101 (column_model 0), test_problem/vert_mix.py:50-57 (1)
+__device__ __forceinline__ double bldepth(const ModelDev &m, double time, int j) {
+    if (m.column_model == 0) {
+        const double T = 365.0 * 86400.0;
+        const double tv[4] = {T * 0.25, T * 0.35, T * 0.65, T * 0.75};
+        const double fv[4] = {0.0, 1.0, 1.0, 0.0};
+        const double frac = interp_pw(time, tv, fv, 4);
+        return 35.0 + (m.bld_max[j] - 35.0) * frac;
+    }
+    const double year_per_sec = 1.0 / (86400.0 * 365.0);
+    const double frac = 0.5 + 0.5 * cos((2.0 * 3.141592653589793) * (year_per_sec * time - 0.25));
+    return 50.0 + (150.0 - 50.0) * frac;
+}
+
+// mixing coefficient / dz_mid at interior edge ke (1..nz-1)
+__device__ __forceinline__ double mixing_coeff_edge(const ModelDev &m, double bld, int ke, int j) {
+    const int i = ke - 1;
+    if (m.column_model == 0) {
+        const double lg = ramp_layer_mean(m.depth_mid[i], m.depth_mid[i + 1], bld - 20.0, bld + 20.0,
+                                          2.302585092994046 /* ln 10 */, -7.600902459542082 /* ln 5e-4 */);
+        double kap = exp(lg);
+        const double pe = 0.5 * m.dz_mid[i] * fabs(m.wvel[ke * m.ny + j]) / kap;
+        kap *= (pe > 1.0 ? pe : 1.0);
+        return kap * m.dz_mid_r[i];
+    }
+    const double lg = interp_clamped2(m.depth_edges[ke], bld - 20.0, bld + 20.0, 0.0, -5.0);
+    return pow(10.0, lg) * m.dz_mid_r[i];
+}
+
+__device__ __forceinline__ double surf_flux(const ModelDev &m, double time) {
+    if (m.n_flux_pts <= 0) return 0.0;
+    return interp_pw(time, m.flux_t, m.flux_v, m.n_flux_pts);
+}
+
+// mode 0: raw (sub, diag, sup, aff);  mode 1: factored (m, ib, g, hg*aff) of I - hg*L
+// stage times/hg: t_stage[s], hg_stage[s]
+__global__ void stage_tables_kernel(ModelDev m, int n_stages, const double *__restrict__ t_stage,
+                                    const double *__restrict__ hg_stage, int mode,
+                                    double *__restrict__ tri, double *__restrict__ aff) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = blockIdx.y;
+    if (j >= m.ny || s >= n_stages) return;
+    const int nz = m.nz, ny = m.ny, nc = m.n_classes;
+    const double time = t_stage[s];
+    const double hg = hg_stage[s];
+    const double bld = bldepth(m, time, j);
+    const size_t plane = (size_t)nz * ny;
+
+    double mc_up = 0.0;                       // mixing coeff at edge k (above cell k)
+    double prev_ib[NKB_MAX_CLASSES], prev_c[NKB_MAX_CLASSES];
+    for (int k = 0; k < nz; ++k) {
+        const double mc_dn = (k < nz - 1) ? mixing_coeff_edge(m, bld, k + 1, j) : 0.0;
+        const double w_up = (k > 0 && m.wvel) ? m.wvel[k * ny + j] : 0.0;
+        const double w_dn = (k < nz - 1 && m.wvel) ? m.wvel[(k + 1) * ny + j] : 0.0;
+        const double dzr = m.dz_r[k];
+        for (int c = 0; c < nc; ++c) {
+            double sub = (k > 0) ? dzr * (-0.5 * w_up + mc_up) : 0.0;
+            double sup = (k < nz - 1) ? dzr * (0.5 * w_dn + mc_dn) : 0.0;
+            double diag = dzr * (0.5 * w_dn - 0.5 * w_up - mc_dn - mc_up);
+            if (k == 0) diag += m.surf_diag[c];
+            diag += m.decay[c];
+            const double sv = m.sink_vel[c];
+            if (sv != 0.0) {
+                if (k > 0) sub += sv * dzr;
+                if (k < nz - 1) diag -= sv * dzr;
+            }
+            double *base = tri + (((size_t)s * nc + c) * 3) * plane + (size_t)k * ny + j;
+            if (mode == 0) {
+                base[0] = sub;
+                base[plane] = diag;
+                base[2 * plane] = sup;
+            } else {
+                const double a = -hg * sub, b = 1.0 - hg * diag, cc = -hg * sup;
+                double mk = 0.0, beta = b;
+                if (k > 0) {
+                    mk = a * prev_ib[c];
+                    beta = b - mk * prev_c[c];
+                }
+                const double ib = 1.0 / beta;
+                base[0] = mk;
+                base[plane] = ib;
+                base[2 * plane] = (k < nz - 1) ? cc * ib : 0.0;
+                prev_ib[c] = ib;
+                prev_c[c] = cc;
+            }
+        }
+        mc_up = mc_dn;
+    }
+    const double flux = surf_flux(m, time) * m.dz_r[0];
+    for (int c = 0; c < nc; ++c) {
+        const double a = m.surf_aff[c] + flux;
+        aff[((size_t)s * nc + c) * ny + j] = (mode == 0) ? a : hg * a;
+    }
+}
+
+__global__ void mixing_coeff_kernel(ModelDev m, double time, double *__restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m.ny) return;
+    const double bld = bldepth(m, time, j);
+    for (int ke = 1; ke < m.nz; ++ke) out[(size_t)(ke - 1) * m.ny + j] = mixing_coeff_edge(m, bld, ke, j);
+}
+
+// forcing record interpolated to the explicit stage times (utils.py:533-535: interp1d,
+// linear, fill_value="extrapolate")
+__global__ void forcing_tables_kernel(ModelDev m, int n_times, const double *__restrict__ t_eval,
+                                      double *__restrict__ src) {
+    const size_t plane = (size_t)m.nz * m.ny;
+    const size_t cell = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = blockIdx.y;
+    if (cell >= plane || s >= n_times) return;
+    const double t = t_eval[s];
+    int i = 0;
+    while (i < m.n_frc - 2 && t >= m.frc_time[i + 1]) ++i;
+    const double lo = m.frc_data[(size_t)i * plane + cell];
+    const double hi = m.frc_data[(size_t)(i + 1) * plane + cell];
+    const double slope = (hi - lo) / (m.frc_time[i + 1] - m.frc_time[i]);
+    src[(size_t)s * plane + cell] = slope * (t - m.frc_time[i]) + lo;
+}
+
+int launch_stage_tables(const ModelDev &m, int n_stages, const double *d_t, const double *d_hg, int mode,
+                        double *tri, double *aff, cudaStream_t st) {
+    dim3 block(64), grid((m.ny + 63) / 64, n_stages);
+    stage_tables_kernel<<<grid, block, 0, st>>>(m, n_stages, d_t, d_hg, mode, tri, aff);
+    count_launch();
+    NKB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_mixing_coeff(const ModelDev &m, double time, double *out, cudaStream_t st) {
+    mixing_coeff_kernel<<<(m.ny + 63) / 64, 64, 0, st>>>(m, time, out);
+    count_launch();
+    NKB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_forcing_tables(const ModelDev &m, int n_times, const double *d_t, double *src, cudaStream_t st) {
+    const size_t plane = (size_t)m.nz * m.ny;
+    dim3 block(128), grid((unsigned)((plane + 127) / 128), n_times);
+    forcing_tables_kernel<<<grid, block, 0, st>>>(m, n_times, d_t, src);
+    count_launch();
+    NKB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace nkb

@@ -1,0 +1,221 @@
+"""TEST INFRASTRUCTURE: generate tests/golden/*.npz from the REFERENCE itself.
+
+Runs only in the build container (needs /root/reference).  It imports the reference's own
+numerical modules through oracle/ref_harness.py (stubbed netCDF4/xarray/pint), evaluates them
+on seeded inputs, and copies the values of the committed baselines
+(/root/reference/baselines/ci_*) that the hot path is compared against.  The fixtures are
+small (values only, float64/int32) and are committed together with this script.
+
+    python -m oracle.gen_golden            # from the repo root
+"""
+
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_harness as rh  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+YEAR = 365.0 * 86400.0
+
+
+def baselines():
+    """values of the committed CI baselines that involve the hot path"""
+    base = os.path.join(rh.REF_ROOT, "baselines")
+    out = {}
+    want = {
+        "ci_short": ["depth_axis", "fcn_00", "init_iterate", "init_iterate_00"],
+        "ci_long_iage": ["basis_00", "increment_00", "iterate_01", "krylov_res_00", "perturb_fcn_w_raw_00",
+                         "precond_00", "precond_fcn_00", "w_00", "w_raw_00"],
+        "ci_py_driver_2d_iage": ["fcn_0000", "grid_vars", "init_iterate", "init_iterate_0000"],
+        "ci_py_driver_2d_iage_column_regions": ["basis_00", "fcn_0000", "grid_vars", "increment_00", "init_iterate",
+                                                "init_iterate_0000", "iterate_01", "krylov_res_00",
+                                                "perturb_fcn_w_raw_00", "precond_fcn_00"],
+    }
+    for cfg, files in want.items():
+        for f in files:
+            for var, vals in rh.read_nc(os.path.join(base, cfg, f + ".nc")).items():
+                out[f"{cfg}/{f}/{var}"] = vals
+    # a few hist variables (process fields, pinned at rtol 1e-3/atol 1e-6 by the CI script)
+    hist = rh.read_nc(os.path.join(base, "ci_py_driver_2d_iage", "hist_0000.nc"))
+    for var in ["time", "stream", "vvel", "wvel", "horiz_mixing_coeff", "bldepth", "vert_mixing_coeff", "iage",
+                "iage_slow_rest"]:
+        out[f"ci_py_driver_2d_iage/hist_0000/{var}"] = hist[var]
+    hist = rh.read_nc(os.path.join(base, "ci_short", "hist_00.nc"))
+    for var in ["time", "bldepth", "mixing_coeff", "iage"]:
+        out[f"ci_short/hist_00/{var}"] = hist[var]
+    np.savez_compressed(os.path.join(OUT, "baselines.npz"), **out)
+    print("baselines.npz:", len(out), "arrays")
+
+
+def remap_cases():
+    """SpatialAxis.remap_linear_interpolant of the reference on seeded inputs + the known
+    answers of the reference's unit tests (tests/test_spatial_axis.py:138-198)"""
+    rng = np.random.default_rng(100)
+    out = {}
+    ax5 = rh.make_axis("depth", edge_end=50.0, nlevs=5, delta_ratio_max=1.0)
+    out["known/edges"] = ax5.edges
+    known = [
+        ([-15.0, -5.0], [1.0, 2.0], [2.0] * 5),
+        ([-15.0, 25.0], [0.0, 8.0], [4.0, 6.0, 7.75, 8.0, 8.0]),
+        ([5.0, 25.0], [0.0, 8.0], [0.5, 4.0, 7.5, 8.0, 8.0]),
+        ([22.5, 27.5], [0.0, 8.0], [0.0, 0.0, 4.0, 8.0, 8.0]),
+        ([42.5, 47.5], [0.0, 8.0], [0.0, 0.0, 0.0, 0.0, 4.0]),
+        ([45.0, 55.0], [0.0, 8.0], [0.0, 0.0, 0.0, 0.0, 1.0]),
+    ]
+    for i, (x, y, e) in enumerate(known):
+        assert (ax5.remap_linear_interpolant(np.array(x), np.array(y)) == np.array(e)).all()
+        out[f"known/{i}/x"], out[f"known/{i}/y"], out[f"known/{i}/expected"] = map(np.array, (x, y, e))
+    out["known/count"] = np.array(len(known))
+    ax = rh.make_axis("depth", nlevs=30)
+    out["rand/edges"] = ax.edges
+    n_case = 60
+    for i in range(n_case):
+        n = int(rng.integers(1, 6))
+        x = np.sort(rng.uniform(-150.0, 1050.0, n))
+        y = rng.normal(size=n)
+        out[f"rand/{i}/x"], out[f"rand/{i}/y"] = x, y
+        out[f"rand/{i}/res"] = ax.remap_linear_interpolant(x, y)
+    out["rand/count"] = np.array(n_case)
+    np.savez_compressed(os.path.join(OUT, "remap.npz"), **out)
+    print("remap.npz:", len(out), "arrays")
+
+
+def synthetic_forcing(nz, ny, seed):
+    """small synthetic forcing record standing in for input/py_driver_2d/po4_sms.nc"""
+    rng = np.random.default_rng(seed)
+    nt = 13
+    times = np.linspace(0.0, YEAR, nt)
+    data = 3.0e-8 * rng.normal(size=(nt, nz, ny))
+    return times, data
+
+
+def write_forcing_nc(fname, times, data, depth_mid, ypos_mid):
+    from scipy.io import netcdf_file
+
+    with netcdf_file(fname, "w", version=2) as f:
+        f.createDimension("time", len(times))
+        f.createDimension("depth", len(depth_mid))
+        f.createDimension("ypos", len(ypos_mid))
+        for name, vals in (("time", times), ("depth", depth_mid), ("ypos", ypos_mid)):
+            v = f.createVariable(name, "f8", (name,))
+            v[:] = vals
+        v = f.createVariable("po4_sms", "f8", ("time", "depth", "ypos"))
+        v[:] = data
+
+
+def py_driver_2d_cases():
+    """reference process fields + comp_tend / comp_jacobian / apply_precond_jacobian of the three
+    py_driver_2d tracer modules on seeded states"""
+    rng = np.random.default_rng(200)
+    out = {}
+    for tag, (nz, ny, ratio, vvel, kh) in {
+        "g14x11": (14, 11, 19.0, 0.1, 1000.0),
+        "g20x3cr": (20, 3, 19.0, 0.0, 0.0),
+        "g30x30": (30, 30, 19.0, 0.1, 1000.0),
+    }.items():
+        depth, ypos, procs = rh.make_py_driver_2d(nz, ny, ratio, vvel, kh)
+        from nk_ooc.py_driver_2d.advection import Advection
+
+        out[f"{tag}/params"] = np.array([nz, ny, ratio, vvel, kh])
+        out[f"{tag}/depth_edges"], out[f"{tag}/ypos_edges"] = depth.edges, ypos.edges
+        out[f"{tag}/stream"], out[f"{tag}/vvel"], out[f"{tag}/wvel"] = Advection.stream, Advection.vvel, Advection.wvel
+        out[f"{tag}/hmix"] = procs["horiz_mix"]._mixing_coeff
+        times = YEAR * np.array([0.0, 0.1, 0.26, 0.3, 0.349, 0.5, 0.66, 0.7, 0.99])
+        out[f"{tag}/times"] = times
+        out[f"{tag}/bldepth"] = np.stack([procs["vert_mix"].bldepth(t) for t in times])
+        out[f"{tag}/mixing_coeff"] = np.stack([procs["vert_mix"].mixing_coeff(t).copy() for t in times])
+        if tag == "g30x30":
+            continue
+        # tracer modules
+        iage = rh.make_2d_iage(depth, ypos)
+        x = rng.normal(size=(2, nz, ny))
+        out[f"{tag}/iage/x"] = x
+        out[f"{tag}/iage/tend"] = np.stack([iage.comp_tend(t, x.reshape(-1), procs).reshape(x.shape) for t in times[:4]])
+        out[f"{tag}/iage/jac_dense_t3"] = iage.comp_jacobian(times[3], x.reshape(-1), procs).toarray()
+
+        class _Res:  # receives apply_precond_jacobian's result
+            def set_tracer_vals_all(self, vals, reseat_vals=False):
+                self.vals = vals
+
+        iage.get_tracer_vals_all = lambda x=x: x
+        res = _Res()
+        iage.apply_precond_jacobian((0.0, YEAR), res, procs)
+        out[f"{tag}/iage/precond"] = res.vals
+
+        phos = rh.make_2d_phosphorus(depth, ypos)
+        x = np.abs(rng.normal(size=(3, nz, ny))) * np.array([2.0, 0.05, 0.01])[:, None, None]
+        out[f"{tag}/phosphorus/x"] = x
+        out[f"{tag}/phosphorus/tend"] = np.stack(
+            [phos.comp_tend(t, x.reshape(-1), procs).reshape(x.shape) for t in times[:4]]
+        )
+
+        ft, fd = synthetic_forcing(nz, ny, 300)
+        fname = f"/tmp/golden_forcing_{tag}.nc"
+        write_forcing_nc(fname, ft, fd, depth.mid, ypos.mid)
+        modelinfo = {
+            "forced_surf_restore_opt": "const", "forced_surf_restore_const": "1.0",
+            "forced_surf_restore_rate_10m": "1.0 / 3600.0", "forced_sms_opt": "file",
+            "forced_sms_fname": fname, "forced_sms_varname": "po4_sms", "forced_sms_scalef": "-1.0 / 3.0",
+            "forced_sink_thres": "0.05",
+        }
+        forced = rh.make_2d_forced(depth, ypos, modelinfo)
+        x = np.abs(rng.normal(size=(1, nz, ny))) * 0.06
+        out[f"{tag}/forced/frc_time"], out[f"{tag}/forced/frc_data"] = ft, fd
+        out[f"{tag}/forced/x"] = x
+        tt = YEAR * np.array([0.0, 0.1234, 0.5, 0.987])
+        out[f"{tag}/forced/times"] = tt
+        out[f"{tag}/forced/tend"] = np.stack([forced.comp_tend(t, x.reshape(-1), procs).reshape(x.shape) for t in tt])
+    np.savez_compressed(os.path.join(OUT, "py_driver_2d.npz"), **out)
+    print("py_driver_2d.npz:", len(out), "arrays")
+
+
+def test_problem_cases():
+    """reference test_problem vert_mix + tracer-module tendencies + tridiagonal preconditioners"""
+    rng = np.random.default_rng(400)
+    out = {}
+    nz = 20
+    depth, vert_mix = rh.make_test_problem(nz)
+    out["depth_edges"] = depth.edges
+    times = YEAR * np.array([0.0, 0.05, 0.15, 0.3, 0.5, 0.65, 0.9])
+    out["times"] = times
+    out["bldepth"] = np.array([vert_mix.bldepth(t) for t in times])
+    out["mixing_coeff"] = np.stack([vert_mix.mixing_coeff(t).copy() for t in times])
+    for kind, name in (("iage", "iage"), ("dye_decay", "dye_decay_010"), ("phosphorus", "phosphorus")):
+        tm = rh.make_tp_module(kind, depth, name)
+        x = np.abs(rng.normal(size=(tm.tracer_cnt, nz)))
+        out[f"{name}/x"] = x
+        out[f"{name}/tend"] = np.stack([tm.comp_tend(t, x.reshape(-1), vert_mix).reshape(x.shape) for t in times])
+        if kind != "phosphorus":
+            mca = np.abs(rng.normal(size=nz - 1)) * 1.0e-3
+
+            class _Res:
+                def set_tracer_vals_all(self, vals, reseat_vals=False):
+                    self.vals = vals
+
+            tm.get_tracer_vals_all = lambda x=x: x
+            res = _Res()
+            tm.apply_precond_jacobian((0.0, YEAR), res, mca)
+            out[f"{name}/mca"] = mca
+            out[f"{name}/precond"] = res.vals
+    np.savez_compressed(os.path.join(OUT, "test_problem.npz"), **out)
+    print("test_problem.npz:", len(out), "arrays")
+
+
+def main():
+    if not rh.available():
+        raise SystemExit("reference tree not found: golden vectors can only be generated in the build container")
+    os.makedirs(OUT, exist_ok=True)
+    rh.install_stubs()
+    baselines()
+    remap_cases()
+    py_driver_2d_cases()
+    test_problem_cases()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,134 @@
+"""GPU parity tests of the fused stage kernel / coefficient tables against the oracle.
+
+All calls go through the C ABI (ctypes).  Tolerances: the CUDA path and the numpy
+restatement of the SAME scheme (oracle/imex_oracle.py) agree to rounding error
+(rtol 1e-11); the tendency agrees with the reference's comp_tend restatement
+(oracle/nk_oracle.py) to rtol 1e-12 of the field maximum.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+def _grid(nz, ny, ratio=19.0, vvel=0.1, kh=1000.0):
+    from oracle import nk_oracle as o
+    from nk_ooc_b200.py_driver_2d.modules import Transport2D
+    from nk_ooc_b200.spatial_axis import SpatialAxis
+
+    ze = o.stretched_edges(nz, 0.0, 4000.0, ratio)
+    ye = o.stretched_edges(ny, 0.0, 50.0e5, 1.0)
+    g = o.Grid2D(ze, ye, vvel, kh)
+    tr = Transport2D(SpatialAxis("depth", ze), SpatialAxis("ypos", ye), vvel, kh)
+    return g, tr
+
+
+def _to_dev(x):  # [T, nz, ny, B] host -> padded member-fastest device tensor
+    from nk_ooc_b200.engine import padded_members
+
+    B = x.shape[-1]
+    ldb = padded_members(B)
+    out = torch.zeros(x.shape[:-1] + (ldb,), dtype=torch.float64, device="cuda")
+    out[..., :B] = torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    return out
+
+
+def _forcing(g, rng):
+    nt = 13
+    times = np.linspace(0.0, 365.0 * 86400.0, nt)
+    data = -1.0e-8 * np.abs(rng.normal(size=(nt, g.nz, g.ny)))
+    return times, data
+
+
+@pytest.mark.parametrize("nz,ny", [(12, 9), (30, 30)])
+def test_mixing_coeff_matches_oracle(nz, ny):
+    from nk_ooc_b200.py_driver_2d.modules import iage_model
+
+    g, tr = _grid(nz, ny)
+    m = iage_model(tr)
+    for frac in [0.0, 0.26, 0.3, 0.349, 0.5, 0.7, 0.99]:
+        t = frac * 365.0 * 86400.0
+        got = m.mixing_coeff(t).cpu().numpy()
+        want = g.vert_mixing_coeff(t)
+        np.testing.assert_allclose(got, want, rtol=1e-12, atol=0.0)
+
+
+@pytest.mark.parametrize("kind", ["iage", "phosphorus", "forced"])
+@pytest.mark.parametrize("B", [1, 3, 40])
+def test_tend_matches_reference_comp_tend(kind, B):
+    from oracle import nk_oracle as o
+    from nk_ooc_b200.py_driver_2d import modules
+
+    rng = np.random.default_rng(5)
+    g, tr = _grid(14, 11)
+    if kind == "iage":
+        om, m = o.Iage2D(g), modules.iage_model(tr)
+    elif kind == "phosphorus":
+        om, m = o.Phosphorus2D(g), modules.phosphorus_model(tr)
+    else:
+        times, data = _forcing(g, rng)
+        om = o.Forced2D(g, restore_rate_10m=1.0 / 3600.0, restore_const=1.0, sms_opt="file", sms_times=times,
+                        sms_data=data, sink_thres=0.05)
+        m = modules.forced_model(tr, "const", 1.0, 1.0 / 3600.0, "file", sms_times=times, sms_data=data,
+                                 sink_thres=0.05)
+    x = np.abs(rng.normal(size=(om.tracer_cnt, g.nz, g.ny, B))) * 0.08
+    for t in [0.0, 0.31 * 365 * 86400.0, 0.8 * 365 * 86400.0]:
+        got = m.tend(t, _to_dev(x), B).cpu().numpy()[..., :B]
+        want = np.stack([om.comp_tend(t, x[..., b].reshape(-1)).reshape(x.shape[:-1]) for b in range(B)], axis=-1)
+        scale = np.abs(want).max()
+        np.testing.assert_allclose(got, want, rtol=0.0, atol=1e-12 * scale)
+
+
+@pytest.mark.parametrize("kind", ["iage", "phosphorus", "forced"])
+@pytest.mark.parametrize("B", [1, 5, 70])
+def test_model_year_matches_scheme_oracle(kind, B):
+    """same ARS(2,2,2) schedule in numpy and in CUDA: agreement to rounding"""
+    from oracle import imex_oracle as im
+    from oracle import nk_oracle as o
+    from nk_ooc_b200.py_driver_2d import modules
+
+    rng = np.random.default_rng(11)
+    g, tr = _grid(10, 7)
+    nsteps = 24
+    if kind == "iage":
+        mod, m = im.Module2D("iage", g), modules.iage_model(tr)
+    elif kind == "phosphorus":
+        mod, m = im.Module2D("phosphorus", g, phos=o.Phosphorus2D(g)), modules.phosphorus_model(tr)
+    else:
+        times, data = _forcing(g, rng)
+        f = o.Forced2D(g, restore_rate_10m=1.0 / 3600.0, restore_const=1.0, sms_opt="file", sms_times=times,
+                       sms_data=data, sink_thres=0.05)
+        mod = im.Module2D("forced", g, forced=f)
+        m = modules.forced_model(tr, "const", 1.0, 1.0 / 3600.0, "file", sms_times=times, sms_data=data,
+                                 sink_thres=0.05)
+    x = np.abs(rng.normal(size=(mod.T, g.nz, g.ny, B))) * 0.5
+    m.set_uniform_schedule(nsteps)
+    got = m.eval(_to_dev(x), B).cpu().numpy()[..., :B]
+    want = im.model_year_2d(mod, x, nsteps)
+    np.testing.assert_allclose(got, want, rtol=0.0, atol=1e-9 * np.abs(want).max())
+
+
+def test_hist_snapshots_and_host_path():
+    from oracle import imex_oracle as im
+    from nk_ooc_b200.py_driver_2d import modules
+
+    rng = np.random.default_rng(3)
+    g, tr = _grid(10, 7)
+    m = modules.iage_model(tr)
+    m.set_uniform_schedule(12)
+    B = 6
+    x = rng.normal(size=(2, g.nz, g.ny, B))
+    snaps = []
+    want = im.model_year_2d(im.Module2D("iage", g), x, 12, snapshots=snaps)
+    f, hist = m.eval(_to_dev(x), B, hist_steps=[0, 4, 8, 12])
+    hist = hist.cpu().numpy()
+    np.testing.assert_allclose(hist[0], x[..., 0], rtol=0, atol=0)
+    np.testing.assert_allclose(hist[1], snaps[3][1][..., 0], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(hist[2], snaps[7][1][..., 0], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(hist[3], x[..., 0] + want[..., 0], rtol=0, atol=1e-12)
+    # host-buffer entry point (member-major layout)
+    xm = np.ascontiguousarray(np.moveaxis(x, -1, 0))
+    fh = m.eval_host(xm).numpy()
+    np.testing.assert_allclose(np.moveaxis(fh, 0, -1), want, rtol=0, atol=1e-11 * np.abs(want).max())
