@@ -69,7 +69,12 @@ int nkb_model_create(nkb_model **out, const nkb_model_desc *d) {
     }
     const size_t o_w = push(w.data(), w.size());
     size_t o_est = 0, o_bld = 0, o_ft = 0, o_fd = 0, o_light = 0;
-    if (d->h_estencil) o_est = push(d->h_estencil, 3 * plane);
+    if (d->h_estencil) {  // [3][nz][ny] -> packed [nz][ny][4] {eL, eC, eR, 0}
+        std::vector<double> e4(4 * plane, 0.0);
+        for (size_t c = 0; c < plane; ++c)
+            for (int q = 0; q < 3; ++q) e4[4 * c + q] = d->h_estencil[(size_t)q * plane + c];
+        o_est = push(e4.data(), e4.size());
+    }
     if (d->h_bld_max) o_bld = push(d->h_bld_max, ny);
     if (d->n_frc > 0) {
         o_ft = push(d->h_frc_time, d->n_frc);
@@ -111,9 +116,9 @@ int nkb_model_create(nkb_model **out, const nkb_model_desc *d) {
     v.dop_remin_rate = d->dop_remin_rate; v.pop_remin_rate = d->pop_remin_rate;
     v.po4_s_restoring_opt = d->po4_s_restoring_opt;
 
-    NKB_CUDA(cudaMalloc(&m->tri_raw, (size_t)v.n_classes * 3 * plane * sizeof(double)));
+    NKB_CUDA(cudaMalloc(&m->tri_raw, (size_t)v.n_classes * 4 * plane * sizeof(double)));
     NKB_CUDA(cudaMalloc(&m->aff_raw, (size_t)v.n_classes * ny * sizeof(double)));
-    NKB_CUDA(cudaMalloc(&m->src_raw, plane * sizeof(double)));
+    NKB_CUDA(cudaMalloc(&m->src_raw, 2 * plane * sizeof(double)));
     NKB_CUDA(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
     *out = m;
     return 0;
@@ -160,13 +165,13 @@ int nkb_model_set_schedule(nkb_model *m, int n_steps, const double *h_t_start, c
     NKB_CUDA(cudaMalloc(&d_hg, n_stages * sizeof(double)));
     NKB_CUDA(cudaMemcpy(d_t, t_imp.data(), n_stages * sizeof(double), cudaMemcpyHostToDevice));
     NKB_CUDA(cudaMemcpy(d_hg, hg.data(), n_stages * sizeof(double), cudaMemcpyHostToDevice));
-    NKB_CUDA(cudaMalloc(&m->tri, (size_t)n_stages * v.n_classes * 3 * plane * sizeof(double)));
+    NKB_CUDA(cudaMalloc(&m->tri, (size_t)n_stages * v.n_classes * 4 * plane * sizeof(double)));
     NKB_CUDA(cudaMalloc(&m->aff, (size_t)n_stages * v.n_classes * v.ny * sizeof(double)));
     const int chunk = 32768;
     for (int s0 = 0; s0 < n_stages; s0 += chunk) {
         const int ns = (n_stages - s0 < chunk) ? n_stages - s0 : chunk;
         if (nkb::launch_stage_tables(v, ns, d_t + s0, d_hg + s0, 1,
-                                     m->tri + (size_t)s0 * v.n_classes * 3 * plane,
+                                     m->tri + (size_t)s0 * v.n_classes * 4 * plane,
                                      m->aff + (size_t)s0 * v.n_classes * v.ny, 0))
             return 1;
     }
@@ -175,7 +180,7 @@ int nkb_model_set_schedule(nkb_model *m, int n_steps, const double *h_t_start, c
         NKB_CUDA(cudaMalloc(&m->src, (size_t)n_stages * plane * sizeof(double)));
         for (int s0 = 0; s0 < n_stages; s0 += chunk) {
             const int ns = (n_stages - s0 < chunk) ? n_stages - s0 : chunk;
-            if (nkb::launch_forcing_tables(v, ns, d_t + s0, m->src + (size_t)s0 * plane, 0)) return 1;
+            if (nkb::launch_forcing_tables(v, ns, d_t + s0, m->src + (size_t)s0 * plane, 0)) return 1;  // [step][cell][2]
         }
     }
     NKB_CUDA(cudaDeviceSynchronize());
@@ -205,13 +210,13 @@ int nkb_model_tend(nkb_model *m, double time, const double *d_x, double *d_tend,
     const ModelDev &v = m->dev;
     double *d_t = nullptr;
     NKB_CUDA(cudaMalloc(&d_t, 2 * sizeof(double)));
-    const double th[2] = {time, 0.0};
+    const double th[2] = {time, time};
     NKB_CUDA(cudaMemcpyAsync(d_t, th, 2 * sizeof(double), cudaMemcpyHostToDevice, st));
     if (nkb::launch_stage_tables(v, 1, d_t, d_t + 1, 0, m->tri_raw, m->aff_raw, st)) return 1;
-    if (v.kind == NKB_MOD_FORCED_FILE && nkb::launch_forcing_tables(v, 1, d_t, m->src_raw, st)) return 1;
+    if (v.kind == NKB_MOD_FORCED_FILE && nkb::launch_forcing_tables(v, 2, d_t, m->src_raw, st)) return 1;
     StageArgs a;
     fill_args(m, a, B, ldb);
-    a.u[0] = d_x; a.out = d_tend; a.tri = m->tri_raw; a.aff = m->aff_raw; a.src[0] = m->src_raw;
+    a.u[0] = d_x; a.out = d_tend; a.tri = m->tri_raw; a.aff = m->aff_raw; a.src2 = m->src_raw;
     const int rc = nkb::launch_tend(v.kind, a, st);
     NKB_CUDA(cudaStreamSynchronize(st));
     cudaFree(d_t);
@@ -235,7 +240,7 @@ int nkb_model_eval(nkb_model *m, const double *d_x0, double *d_f, double *d_work
     const size_t nstate = (size_t)v.T * plane * ldb;
     double *w_u1 = d_work, *w_alt = d_work + nstate;
     const int S = m->n_steps;
-    const size_t tri_stride = (size_t)v.n_classes * 3 * plane, aff_stride = (size_t)v.n_classes * v.ny;
+    const size_t tri_stride = (size_t)v.n_classes * 4 * plane, aff_stride = (size_t)v.n_classes * v.ny;
     const double a1 = (1.0 - nkb::kGamma) / nkb::kGamma, a0 = 1.0 - a1;
 
     StageArgs a;
@@ -262,8 +267,7 @@ int nkb_model_eval(nkb_model *m, const double *d_x0, double *d_f, double *d_work
         a.a[0] = 1.0; a.he[0] = nkb::kGamma * h; a.a[1] = 0.0; a.he[1] = 0.0;
         a.tri = m->tri + (size_t)(2 * n) * tri_stride;
         a.aff = m->aff + (size_t)(2 * n) * aff_stride;
-        a.src[0] = m->src ? m->src + (size_t)(2 * n) * plane : nullptr;
-        a.src[1] = nullptr;
+        a.src2 = m->src ? m->src + (size_t)(2 * n) * plane : nullptr;
         if (nkb::launch_stage(v.kind, 1, a, st)) return 1;
         // stage 2: (I - h*gamma*L(t_n + h)) u2 = a0 u_n + a1 u1 + h(delta-1+gamma) E_n + h(1-delta) E(u1)
         a.u[0] = un; a.u[1] = w_u1; a.out = dest; a.sub = last ? d_x0 : nullptr;
@@ -271,8 +275,6 @@ int nkb_model_eval(nkb_model *m, const double *d_x0, double *d_f, double *d_work
         a.he[0] = h * (nkb::kDelta - 1.0 + nkb::kGamma); a.he[1] = h * (1.0 - nkb::kDelta);
         a.tri = m->tri + (size_t)(2 * n + 1) * tri_stride;
         a.aff = m->aff + (size_t)(2 * n + 1) * aff_stride;
-        a.src[0] = m->src ? m->src + (size_t)(2 * n) * plane : nullptr;
-        a.src[1] = m->src ? m->src + (size_t)(2 * n + 1) * plane : nullptr;
         if (nkb::launch_stage(v.kind, 2, a, st)) return 1;
         un = dest;
         if (n_hist > 0 && !last && emit_hist(n + 1, dest)) return 1;

@@ -50,7 +50,7 @@ struct ModelDev {
     const double *dz_mid;       // [nz-1]
     const double *dz_mid_r;     // [nz-1]
     const double *wvel;         // [nz+1][ny] (boundary rows zeroed)
-    const double *estencil;     // [3][nz][ny] or nullptr
+    const double *estencil;     // [nz][ny][4] {eL, eC, eR, 0} or nullptr
     const double *bld_max;      // [ny]
     double surf_diag[NKB_MAX_CLASSES], surf_aff[NKB_MAX_CLASSES], decay[NKB_MAX_CLASSES],
         sink_vel[NKB_MAX_CLASSES];
@@ -73,12 +73,13 @@ struct StageArgs {
     const double *sub;    // optional: out = x - sub (final F = x(T) - x(0)), else nullptr
     double a[2];          // rhs = sum_i a[i]*u[i] + he[i]*E(u[i])
     double he[2];
-    const double *est;    // [3][nz][ny] or nullptr
-    const double *tri;    // [ncls][3][nz][ny] (m, ib, g) of this stage (raw sub,diag,sup for tend)
+    const double *est;    // [nz][ny][4] {eL, eC, eR, 0} or nullptr
+    const double *tri;    // [ncls][nz][ny][4] {ib, g, m, 0} of this stage ({sub, diag, sup, 0} raw, for tend)
     const double *aff;    // [ncls][ny]  hg*affine surface source
-    const double *src[2]; // [nz][ny] forcing at the explicit time of input i (FORCED_FILE)
+    const double *src2;   // [nz][ny][2] forcing at the explicit times of inputs 0 and 1 (FORCED_FILE)
     const double *light;  // [nz][ny]
     int nz, ny, B, ldb, T;
+    int ksm;              // levels [0, ksm) keep the forward-sweep intermediates in shared memory
     int class_of[NKB_MAX_TRACERS];
     double src_const[NKB_MAX_TRACERS];
     double sink_thres_r;  // 1/sink_thres or 0
@@ -105,13 +106,13 @@ struct nkb_model {
     int n_steps = 0;
     double *h_t_start = nullptr, *h_h = nullptr;  // host copies
     // per-stage tables, stage s = 2*step + {0,1}
-    double *tri = nullptr;      // [n_stages][n_classes][3][nz][ny]  (m, ib, g)
+    double *tri = nullptr;      // [n_stages][n_classes][nz][ny][4]  {ib, g, m, 0}
     double *aff = nullptr;      // [n_stages][n_classes][ny]  h*gamma*(affine surface source) per column
-    double *src = nullptr;      // [n_stages][nz][ny] forcing at the explicit stage times (or nullptr)
+    double *src = nullptr;      // [n_steps][nz][ny][2] forcing at the two explicit stage times (or nullptr)
     // scratch for tend()/mixing_coeff()
-    double *tri_raw = nullptr;  // [n_classes][3][nz][ny]
+    double *tri_raw = nullptr;  // [n_classes][nz][ny][4]
     double *aff_raw = nullptr;  // [n_classes][ny]
-    double *src_raw = nullptr;  // [nz][ny]
+    double *src_raw = nullptr;  // [nz][ny][2]
     // host-buffer path
     double *d_stage_major = nullptr, *d_stage_x = nullptr, *d_stage_f = nullptr, *d_stage_work = nullptr;
     size_t stage_cap = 0;

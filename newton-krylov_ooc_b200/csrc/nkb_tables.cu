@@ -114,11 +114,12 @@ __global__ void stage_tables_kernel(ModelDev m, int n_stages, const double *__re
                 if (k > 0) sub += sv * dzr;
                 if (k < nz - 1) diag -= sv * dzr;
             }
-            double *base = tri + (((size_t)s * nc + c) * 3) * plane + (size_t)k * ny + j;
+            double *base = tri + ((((size_t)s * nc + c) * plane) + (size_t)k * ny + j) * 4;
+            base[3] = 0.0;
             if (mode == 0) {
                 base[0] = sub;
-                base[plane] = diag;
-                base[2 * plane] = sup;
+                base[1] = diag;
+                base[2] = sup;
             } else {
                 const double a = -hg * sub, b = 1.0 - hg * diag, cc = -hg * sup;
                 double mk = 0.0, beta = b;
@@ -127,9 +128,9 @@ __global__ void stage_tables_kernel(ModelDev m, int n_stages, const double *__re
                     beta = b - mk * prev_c[c];
                 }
                 const double ib = 1.0 / beta;
-                base[0] = mk;
-                base[plane] = ib;
-                base[2 * plane] = (k < nz - 1) ? cc * ib : 0.0;
+                base[0] = ib;
+                base[1] = (k < nz - 1) ? cc * ib : 0.0;
+                base[2] = mk;
                 prev_ib[c] = ib;
                 prev_c[c] = cc;
             }
@@ -151,7 +152,7 @@ __global__ void mixing_coeff_kernel(ModelDev m, double time, double *__restrict_
 }
 
 // forcing record interpolated to the explicit stage times (utils.py:533-535: interp1d,
-// linear, fill_value="extrapolate")
+// linear, fill_value="extrapolate").  t_eval holds 2 times per step; output [step][cell][2].
 __global__ void forcing_tables_kernel(ModelDev m, int n_times, const double *__restrict__ t_eval,
                                       double *__restrict__ src) {
     const size_t plane = (size_t)m.nz * m.ny;
@@ -164,7 +165,7 @@ __global__ void forcing_tables_kernel(ModelDev m, int n_times, const double *__r
     const double lo = m.frc_data[(size_t)i * plane + cell];
     const double hi = m.frc_data[(size_t)(i + 1) * plane + cell];
     const double slope = (hi - lo) / (m.frc_time[i + 1] - m.frc_time[i]);
-    src[(size_t)s * plane + cell] = slope * (t - m.frc_time[i]) + lo;
+    src[((size_t)(s >> 1) * plane + cell) * 2 + (s & 1)] = slope * (t - m.frc_time[i]) + lo;
 }
 
 int launch_stage_tables(const ModelDev &m, int n_stages, const double *d_t, const double *d_hg, int mode,

@@ -86,6 +86,30 @@ class Axis:
         return res
 
 
+    def remap_ramp(self, x0, x1, y0, y1):
+        """remap_linear_interpolant([x0, x1], [y0, y1]) vectorised over layers: the only form
+        the hot path uses (vert_mix.py:61-70).  Same trapezoids as the generic routine."""
+        e = self.edges
+        f = np.interp(e, [x0, x1], [y0, y1])
+        a, b, fa, fb = e[:-1], e[1:], f[:-1], f[1:]
+        res = 0.5 * (fa + fb)
+        in0 = (x0 >= a) & (x0 < b)
+        in1 = (x1 >= a) & (x1 < b)
+        both = in0 & in1
+        only0 = in0 & ~in1
+        only1 = in1 & ~in0
+        if both.any():
+            acc = (x0 - a) * (0.5 * (fa + y0)) + (x1 - x0) * (0.5 * (y0 + y1)) + (b - x1) * (0.5 * (y1 + fb))
+            res = np.where(both, acc * self.delta_r, res)
+        if only0.any():
+            acc = (x0 - a) * (0.5 * (fa + y0)) + (b - x0) * (0.5 * (y0 + fb))
+            res = np.where(only0, acc * self.delta_r, res)
+        if only1.any():
+            acc = (x1 - a) * (0.5 * (fa + y1)) + (b - x1) * (0.5 * (y1 + fb))
+            res = np.where(only1, acc * self.delta_r, res)
+        return res
+
+
 # --------------------------------------------------------------------------------------
 # py_driver_2d transport  (nk_ooc/py_driver_2d/{advection,horiz_mix,vert_mix}.py)
 # --------------------------------------------------------------------------------------
@@ -146,18 +170,27 @@ class Grid2D:
         return bld_min + (bld_max - bld_min) * frac
 
     def vert_mixing_coeff(self, time):
-        """kappa/dz_mid at interior depth edges, [nz-1, ny]  (vert_mix.py:43-87)"""
+        """kappa/dz_mid at interior depth edges, [nz-1, ny]  (vert_mix.py:43-87).
+        Like the reference, the last result is cached by time (vert_mix.py:50-54) and columns
+        with equal bldepth share one remap (vert_mix.py:60-72)."""
+        if time == getattr(self, "_mc_time", None):
+            return self._mc_vals
         bld = self.bldepth(time)
         log_sh, log_dp = np.log(1.0e1), np.log(5.0e-4)
         out = np.empty((self.nz - 1, self.ny))
+        cache_val, cache_j = None, 0
         for j in range(self.ny):
-            out[:, j] = self.depth_edges_axis.remap_linear_interpolant(
-                [bld[j] - 20.0, bld[j] + 20.0], [log_sh, log_dp]
-            )
+            if bld[j] != cache_val:
+                out[:, j] = self.depth_edges_axis.remap_ramp(bld[j] - 20.0, bld[j] + 20.0, log_sh, log_dp)
+                cache_val, cache_j = bld[j], j
+            else:
+                out[:, j] = out[:, cache_j]
         out = np.exp(out)
         pe = 0.5 * self.depth.delta_mid[:, None] * np.abs(self.wvel[1:-1, :]) / out
         out = out * np.where(pe > 1.0, pe, 1.0)
-        return out * self.depth.delta_mid_r[:, None]
+        self._mc_time = time
+        self._mc_vals = out * self.depth.delta_mid_r[:, None]
+        return self._mc_vals
 
     def transport_tend(self, time, c):
         """advection + horizontal mixing + vertical mixing for c[T, nz, ny]

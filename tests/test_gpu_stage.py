@@ -91,7 +91,9 @@ def test_model_year_matches_scheme_oracle(kind, B):
 
     rng = np.random.default_rng(11)
     g, tr = _grid(10, 7)
-    nsteps = 24
+    # phosphorus: the explicit uptake term (1/(3 days)) needs h well below 3 days, otherwise the
+    # scheme is unstable and rounding differences are amplified
+    nsteps = 240 if kind == "phosphorus" else 24
     if kind == "iage":
         mod, m = im.Module2D("iage", g), modules.iage_model(tr)
     elif kind == "phosphorus":
