@@ -79,6 +79,7 @@ struct StageArgs {
     const double *src2;   // [nz][ny][2] forcing at the explicit times of inputs 0 and 1 (FORCED_FILE)
     const double *light;  // [nz][ny]
     int nz, ny, B, ldb, T;
+    int hints;            // bit0: evict_first on streamed data, bit1: evict_last on intermediates
     int ksm;              // levels [0, ksm) keep the forward-sweep intermediates in shared memory
     int class_of[NKB_MAX_TRACERS];
     double src_const[NKB_MAX_TRACERS];

@@ -42,6 +42,36 @@ struct Vec<2> {
     __device__ __forceinline__ static Vec splat(double s) { return {make_double2(s, s)}; }
 };
 
+// L2 eviction-priority policies (createpolicy + .L2::cache_hint): the streamed inputs are marked
+// evict_first and the forward-sweep intermediates evict_last so that the latter survive in L2
+// until the back substitution reads them.
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ Vec<1> ld_hint(const double *p, uint64_t pol, Vec<1> *) {
+    Vec<1> r;
+    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(r.v) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ Vec<2> ld_hint(const double *p, uint64_t pol, Vec<2> *) {
+    Vec<2> r;
+    asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(r.v.x), "=d"(r.v.y) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ void st_hint(double *p, Vec<1> v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v.v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_hint(double *p, Vec<2> v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.v.x), "d"(v.v.y), "l"(pol) : "memory");
+}
+
 __device__ __forceinline__ Vec<1> fma_s(double a, Vec<1> x, Vec<1> y) { return {fma(a, x.v, y.v)}; }
 __device__ __forceinline__ Vec<2> fma_s(double a, Vec<2> x, Vec<2> y) {
     return {make_double2(fma(a, x.v.x, y.v.x), fma(a, x.v.y, y.v.y))};
@@ -101,6 +131,7 @@ struct ColPtrs {
     const double *tri4[TG];     // {ib, g, m, 0} of the tracer's class at (k, j)
     const double *src2;         // {frc(t_exp0), frc(t_exp1)} at (k, j)
     const double *light;
+    uint64_t pol_first, pol_last;  // L2 policies (0: no hints)
     ptrdiff_t dl, dr;           // offsets of the south / north neighbour column
     size_t stepk;               // one level down, state arrays
     size_t stepk4;              // one level down, packed [nz][ny][4] tables
@@ -122,10 +153,10 @@ __device__ __forceinline__ void forward_chunk(const StageArgs &p, ColPtrs<TG, NI
 #pragma unroll
             for (int g = 0; g < TG; ++g) {
                 const double *a = cp.uc[i][g] + q * cp.stepk;
-                c[q][i][g] = Vec<MPT>::ld(a);
+                c[q][i][g] = ld_hint(a, cp.pol_first, (Vec<MPT> *)nullptr);
                 if (has_e) {
-                    cl[q][i][g] = Vec<MPT>::ld(a + cp.dl);
-                    cr[q][i][g] = Vec<MPT>::ld(a + cp.dr);
+                    cl[q][i][g] = ld_hint(a + cp.dl, cp.pol_first, (Vec<MPT> *)nullptr);
+                    cr[q][i][g] = ld_hint(a + cp.dr, cp.pol_first, (Vec<MPT> *)nullptr);
                 }
             }
         }
@@ -177,7 +208,7 @@ __device__ __forceinline__ void forward_chunk(const StageArgs &p, ColPtrs<TG, NI
             if (k == 0) rhs[g] = add_v(rhs[g], Vec<MPT>::splat(aff[g]));
             yprev[g] = fma_s(-mk[q][g], yprev[g], rhs[g]);
             if (k < ksm) ys[(size_t)(g * ksm + k) * nthr + tid] = yprev[g];
-            else yprev[g].st(cp.out[g] + q * cp.stepk);
+            else st_hint(cp.out[g] + q * cp.stepk, yprev[g], cp.pol_last);
         }
     }
     // advance to the next chunk
@@ -226,7 +257,7 @@ __device__ __forceinline__ void backward_chunk(ColPtrs<TG, NIN> &cp, int khi, in
             xnext[g] = fma_s(-gk[q][g], xnext[g], mul_s(ib[q][g], y[q][g]));
             Vec<MPT> o = xnext[g];
             if (has_sub) o = sub_v(o, sb[q][g]);
-            o.st(cp.out[g] - q * cp.stepk);
+            st_hint(cp.out[g] - q * cp.stepk, o, cp.pol_first);
         }
     }
 #pragma unroll
@@ -258,6 +289,8 @@ __global__ void __launch_bounds__(256) stage_kernel(const StageArgs p) {
     ColPtrs<TG, NIN> cp;
     cp.stepk = (size_t)ny * ldb;
     cp.stepk4 = (size_t)ny * 4;
+    cp.pol_first = policy_evict_first();
+    cp.pol_last = policy_evict_last();
     cp.dl = (j > 0) ? -(ptrdiff_t)ldb : 0;
     cp.dr = (j < ny - 1) ? (ptrdiff_t)ldb : 0;
     double aff[TG];
@@ -389,7 +422,7 @@ static StageGeom pick_geometry(int nz, int ny, int T, int TG, int B, int ldb) {
     g.grid = dim3((lanes + bx - 1) / bx, ntile, T / TG);
     const size_t per_level = (size_t)TG * sizeof(double) * mpt * bx * jt;
     int ksm = (int)(smem_max / per_level);
-    const int ksm_env = env_int("NKB_KSM", 0);
+    const int ksm_env = env_int("NKB_KSM", 0);  // -1: as many levels as fit in NKB_SMEM_KB
     if (ksm_env >= 0) ksm = ksm_env;
     if (ksm > nz) ksm = nz;
     g.ksm = ksm;
@@ -429,6 +462,7 @@ int launch_stage(int kind, int nin, const StageArgs &a_in, cudaStream_t st) {
     const StageGeom g = pick_geometry(a_in.nz, a_in.ny, a_in.T, TG, a_in.B, a_in.ldb);
     StageArgs a = a_in;
     a.ksm = g.ksm;
+    a.hints = env_int("NKB_HINTS", 3);
     int rc = 0;
 #define NKB_DISPATCH(K, G)                                          \
     if (nin == 1) rc = launch_stage_t<K, G, 1>(a, g, st);           \

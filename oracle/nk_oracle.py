@@ -591,8 +591,8 @@ def comp_fcn_1d(module, x0, t_eval=None, rtol=1.0e-12, atol=1.0e-12, return_sol=
 
 
 def log_mean_mixing_coeff_1d(col, n_t=101):
-    """mixing_coeff_log_mean of the precond file: exp(mean_t log(mixing_coeff*dz_mid)) with
-    trapezoid time weights over the 101 hist times, end rows copied from neighbours
+    """mixing_coeff_log_mean of the precond file: exp(mean_t log(mixing_coeff*dz_mid)), plain mean
+    over the 101 hist times (model_state_base.py:463-466), end rows copied from neighbours
     (test_problem/model_state.py:200-225; model_state_base.py:580-616;
     tracer_module_state_base.py hist_time_mean_weights)"""
     times = np.linspace(col.time_range[0], col.time_range[1], n_t)
@@ -601,10 +601,7 @@ def log_mean_mixing_coeff_1d(col, n_t=101):
         vals[i, 1:-1] = col.mixing_coeff(t) * col.depth.delta_mid
     vals[:, 0] = vals[:, 1]
     vals[:, -1] = vals[:, -2]
-    w = np.ones(n_t)
-    w[0] = w[-1] = 0.5
-    w /= w.sum()
-    return np.exp(np.einsum("i,i...", w, np.log(vals)))
+    return np.exp(np.log(vals).mean(axis=0))
 
 
 # --------------------------------------------------------------------------------------

@@ -11,6 +11,7 @@ for p in (ROOT, os.path.join(ROOT, "newton-krylov_ooc_b200")):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
+    config.addinivalue_line("markers", "slow: takes more than a few seconds on one CPU core")
 
 
 @pytest.fixture(scope="session")
