@@ -49,7 +49,8 @@ def parse_args():
     ap.add_argument("--grid", default="refined125x150", choices=sorted(GRIDS))
     ap.add_argument("--module", default="forced", choices=sorted(TRACERS))
     ap.add_argument("--members", type=int, default=4096, help="members per GPU")
-    ap.add_argument("--nsteps", type=int, default=2400, help="time steps per model year")
+    ap.add_argument("--nsteps", type=int, default=0,
+                    help="uniform time steps per model year; 0 = the production graded schedule (2640 steps)")
     ap.add_argument("--cpu-sample-seconds", type=float, default=20.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -116,7 +117,10 @@ def build_model(args):
         model = modules.iage_model(tr)
     else:
         model = modules.phosphorus_model(tr)
-    model.set_uniform_schedule(args.nsteps)
+    if args.nsteps > 0:
+        model.set_uniform_schedule(args.nsteps)
+    else:
+        model.set_graded_schedule()
     return model, depth, ypos
 
 
@@ -327,7 +331,7 @@ def run_ours(args):
 
     ms_per_step = ms / args.steps
     value = world * B / (ms_per_step * 1e-3)
-    S, s = args.nsteps, 2
+    S, s = model.n_steps, 2
     bytes_alg_eval = 8.0 * N * (2 * s * S + 1)
     n_stage_launch = 2 * S
     avg_launch_ms = ms_per_step / n_stage_launch  # stage kernels run back to back on one stream

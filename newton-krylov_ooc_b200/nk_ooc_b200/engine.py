@@ -43,6 +43,20 @@ def piecewise_schedule(breaks, steps_per_piece, t0, t1):
     return np.concatenate(ts), np.concatenate(hs)
 
 
+def graded_schedule(t0, t1, flat=20, ramp=120, ramp_first=240):
+    """default py_driver_2d schedule: the year is cut into the 60 hist intervals
+    (py_driver_2d/model_state.py:81); `flat` steps per interval where the mixed-layer depth is
+    constant, `ramp` steps per interval while it moves (0.25-0.35 yr and 0.65-0.75 yr,
+    py_driver_2d/vert_mix.py:98-99) and `ramp_first` in the first interval of each ramp.
+    2640 steps/yr by default: meets the reference's CI tolerance (rtol 1e-3, atol 1e-6) on the
+    final state AND on all 61 hist snapshots of baselines/ci_py_driver_2d_iage."""
+    counts = [flat] * 60
+    for k in list(range(15, 21)) + list(range(39, 45)):
+        counts[k] = ramp
+    counts[15] = counts[39] = ramp_first
+    return piecewise_schedule([k / 60.0 for k in range(61)], counts, t0, t1)
+
+
 class Model:
     """one tracer module on one grid: owns the device tables (nkb_model handle)"""
 
@@ -81,6 +95,9 @@ class Model:
 
     def set_uniform_schedule(self, n_steps):
         self.set_schedule(*uniform_schedule(n_steps, self.t0, self.t1))
+
+    def set_graded_schedule(self, **kw):
+        self.set_schedule(*graded_schedule(self.t0, self.t1, **kw))
 
     def step_index_of_times(self, times):
         """step indices (0..n_steps) whose END time equals each requested time"""

@@ -1,0 +1,471 @@
+"""Host mirror of the reference's operator surface (nk_ooc/model_state_base.py,
+nk_ooc/tracer_module_state_base.py, nk_ooc/model_config.py) over the CUDA library.
+
+Same method names, argument meaning and error behaviour as the reference for the hot-path
+operators (comp_fcn, apply_precond_jacobian, comp_jacobian_fcn_state_prod, dot_prod, norm,
+mean, mod_gram_schmidt, lin_comb, arithmetic with per-(module, region) scalars, dump).  The
+values of a state live in HBM, one float64 tensor [tracer, depth(, ypos), member] per tracer
+module with the member index fastest; a state may carry B >= 1 independent members
+(B == 1 is the reference's single state).  Scalars are then arrays [n_modules, region_cnt]
+(B == 1, as in the reference) or [n_modules, region_cnt, B].
+
+State files are NETCDF3_64BIT_OFFSET with the reference's layout,
+read/written with scipy.io.netcdf_file; with B > 1 member 0 is written.
+"""
+
+import copy
+import logging
+import os
+from datetime import datetime
+
+import numpy as np
+import torch
+from scipy.io import netcdf_file
+
+from . import engine
+
+
+def _expand_defs(defs, names):
+    """tracer-module defs with `{suff}` templating: name `root:suff` (model_config.py:80-125)"""
+    out = {}
+    for full in names:
+        root, _, suff = full.partition(":")
+        if root not in defs:
+            raise ValueError(f"unknown tracer module name {root}")
+        src = copy.deepcopy(defs[root])
+
+        def subst(obj):
+            if isinstance(obj, str):
+                return obj.replace("{suff}", suff)
+            if isinstance(obj, dict):
+                return {subst(k): subst(v) for k, v in obj.items()}
+            if isinstance(obj, list):
+                return [subst(v) for v in obj]
+            return obj
+
+        out[subst(root) if suff else root] = subst(src)
+    return out
+
+
+class ModelConfig:
+    """modelinfo + tracer module definitions + region weights (nk_ooc/model_config.py:17-78,
+    249-315).  tracer_module_defs: dict as in input/<model>/tracer_module_defs.yaml."""
+
+    def __init__(self, modelinfo, tracer_module_defs, grid_vars=None):
+        self.modelinfo = modelinfo
+        names = modelinfo["tracer_module_names"].split(",")
+        self.tracer_module_defs = _expand_defs(tracer_module_defs, names)
+        # expanded names in the order given ("forced_{suff}:o2_like" -> "forced_o2_like")
+        self.tracer_module_names = list(self.tracer_module_defs)
+        if grid_vars is None:
+            grid_vars = read_grid_vars(modelinfo["grid_vars_fname"], "region_mask")
+        self.region_mask = grid_vars["region_mask"]
+        self.grid_weight = grid_vars["grid_weight"]
+        self.weights = engine.RegionWeights(self.region_mask, self.grid_weight)
+        self.region_cnt = self.weights.region_cnt
+
+
+def read_grid_vars(fname, region_mask_varname):
+    """region_mask and the weight variable named by its cell_measures attribute
+    (nk_ooc/model_config.py:249-289)"""
+    with netcdf_file(fname, "r", mmap=False) as fptr:
+        var = fptr.variables[region_mask_varname]
+        mask = np.array(var.data, dtype=np.int32)
+        cell_measures = var.cell_measures
+        if isinstance(cell_measures, bytes):
+            cell_measures = cell_measures.decode()
+        parts = cell_measures.split(":")
+        if len(parts) != 2:
+            raise RuntimeError(f"unexpected number of words in {region_mask_varname}:cell_measures")
+        wname = parts[-1].split()[0]
+        weight = np.array(fptr.variables[wname].data, dtype=np.float64)
+    return {"region_mask": mask, "grid_weight": weight}
+
+
+class TracerModuleStateBase:
+    """values of one tracer module for B members (nk_ooc/tracer_module_state_base.py:13-515)"""
+
+    def __init__(self, name, tracer_module_def, cell_shape, config, vals=None, members=1):
+        self.name = name
+        self._def = tracer_module_def
+        self.tracer_names = list(tracer_module_def["tracers"])
+        self.tracer_cnt = len(self.tracer_names)
+        self.cell_shape = tuple(cell_shape)
+        self.config = config
+        self.members = members
+        ldb = engine.padded_members(members)
+        if vals is None:
+            vals = torch.zeros((self.tracer_cnt,) + self.cell_shape + (ldb,), dtype=torch.float64, device="cuda")
+        self.vals = vals
+
+    # ---- host <-> device --------------------------------------------------------------
+    def tracer_index(self, tracer_name):
+        try:
+            return self.tracer_names.index(tracer_name)
+        except ValueError:
+            raise KeyError(f"unknown tracer_name={tracer_name}") from None
+
+    def get_tracer_vals(self, tracer_name, member=0):
+        return self.vals[self.tracer_index(tracer_name), ..., member].cpu().numpy()
+
+    def set_tracer_vals(self, tracer_name, vals, member=None):
+        t = torch.as_tensor(np.ascontiguousarray(vals), dtype=torch.float64).cuda()
+        if member is None:
+            self.vals[self.tracer_index(tracer_name), ..., : self.members] = t.unsqueeze(-1)
+        else:
+            self.vals[self.tracer_index(tracer_name), ..., member] = t
+
+    def get_tracer_vals_all(self, member=0):
+        return self.vals[..., member].cpu().numpy()
+
+    def set_tracer_vals_all(self, vals, member=None):
+        t = torch.as_tensor(np.ascontiguousarray(vals), dtype=torch.float64).cuda()
+        if member is None:
+            self.vals[..., : self.members] = t.unsqueeze(-1)
+        else:
+            self.vals[..., member] = t
+
+    def clone(self):
+        res = copy.copy(self)
+        res.vals = self.vals.clone()
+        return res
+
+    # ---- reductions (K5) --------------------------------------------------------------
+    def _flat(self, t):
+        return t.reshape(self.tracer_cnt, -1, t.shape[-1])
+
+    def dot_prod(self, other):
+        """[region_cnt, B] (tracer_module_state_base.py:379-388)"""
+        return self.config.weights.dot(self._flat(self.vals), self._flat(other.vals), self.members)
+
+    def mean(self):
+        """[region_cnt, B] (tracer_module_state_base.py:371-377)"""
+        return self.config.weights.dot(self._flat(self.vals), None, self.members)
+
+    # ---- elementwise with per-(region, member) scalars (K6) --------------------------------
+    def axpby(self, alpha, x, beta):
+        """self <- alpha*x + beta*self; alpha/beta float or device [region_cnt, B]"""
+        xv = None if x is None else self._flat(x.vals)
+        self.config.weights.axpby(alpha, xv, beta, self._flat(self.vals), self.members)
+        return self
+
+    def apply_region_mask(self):
+        """zero where region_mask == 0 (tracer_module_state_base.py:153-176)"""
+        R, B = self.config.region_cnt, self.members
+        ones = torch.ones((R, B), dtype=torch.float64, device="cuda")
+        self.config.weights.axpby(None, None, ones, self._flat(self.vals), B, fill_beta=0.0)
+        return self
+
+    def zero_extra_tracers(self):
+        """tracers not being solved for; none in the models of this package besides shadows
+        handled by the model classes (tracer_module_state_base.py:483-500)"""
+        return self
+
+    def shadow_pairs(self):
+        out = []
+        for name, meta in self._def["tracers"].items():
+            if "shadows" in meta:
+                out.append((self.tracer_index(name), self.tracer_index(meta["shadows"])))
+        return out
+
+    def precond_matrix_list(self):
+        res = []
+        for meta in self._def["tracers"].values():
+            pm = meta.get("precond_matrix")
+            if pm is not None and pm not in res:
+                res.append(pm)
+        return res
+
+
+class ModelStateBase:
+    """state space of a model (nk_ooc/model_state_base.py:24-577)"""
+
+    __array_priority__ = 100
+    model_config_obj = None
+
+    # ---- construction -----------------------------------------------------------------
+    def __init__(self, fname, members=1):
+        if self.model_config_obj is None:
+            raise RuntimeError("self.model_config_obj is None, it should be set in derived class")
+        engine.require_cuda()
+        cfg = self.model_config_obj
+        self.members = members
+        self.tracer_modules = np.empty(len(cfg.tracer_module_names), dtype=object)
+        for ind, name in enumerate(cfg.tracer_module_names):
+            tms = self._new_tracer_module(name, cfg.tracer_module_defs[name], members)
+            self._load(tms, fname)
+            self.tracer_modules[ind] = tms
+
+    def _new_tracer_module(self, name, tracer_module_def, members):
+        raise NotImplementedError("Method must be implemented in derived class")
+
+    def _gen_init_iterate(self, tms):
+        raise NotImplementedError("Method must be implemented in derived class")
+
+    def _load(self, tms, fname):
+        if isinstance(fname, dict):  # {tracer_name: ndarray} (convenience, not in the reference)
+            for tname in tms.tracer_names:
+                tms.set_tracer_vals(tname, np.asarray(fname[tname]).reshape(tms.cell_shape))
+            return
+        if fname == "zeros":
+            return
+        if fname == "gen_init_iterate":
+            self._gen_init_iterate(tms)
+            return
+        with netcdf_file(fname, "r", mmap=False) as fptr:
+            for tname in tms.tracer_names:
+                if tname not in fptr.variables:
+                    raise KeyError(f"{tname} not found in {fname}")
+                vals = np.array(fptr.variables[tname].data, dtype=np.float64)
+                if vals.size != int(np.prod(tms.cell_shape)):
+                    raise ValueError(f"unexpected dimension lengths for {tname} in {fname}")
+                tms.set_tracer_vals(tname, vals.reshape(tms.cell_shape))
+
+    def _like(self, clone_vals=True):
+        res = copy.copy(self)
+        res.tracer_modules = np.empty(len(self.tracer_modules), dtype=object)
+        for i, tms in enumerate(self.tracer_modules):
+            res.tracer_modules[i] = tms.clone() if clone_vals else copy.copy(tms)
+        return res
+
+    @classmethod
+    def from_members(cls, states):
+        """stack single-member states into one batched state (B = len(states))"""
+        res = cls("zeros", members=len(states))
+        for i, tms in enumerate(res.tracer_modules):
+            for b, st in enumerate(states):
+                tms.vals[..., b] = st.tracer_modules[i].vals[..., 0]
+        return res
+
+    def member(self, b):
+        """single-member state holding member b"""
+        res = type(self)("zeros", members=1)
+        for i, tms in enumerate(res.tracer_modules):
+            tms.vals[..., 0] = self.tracer_modules[i].vals[..., b]
+        return res
+
+    # ---- file output --------------------------------------------------------------------
+    def _axes(self):
+        raise NotImplementedError("Method must be implemented in derived class")
+
+    def dump(self, fname, caller=None):
+        """write the state (member 0) in the reference's state-file layout
+        (model_state_base.py:91-112; py_driver_2d/tracer_module_state.py:71-96)"""
+        if fname is None:
+            return self
+        if caller is None:
+            raise ValueError("caller unknown")
+        os.makedirs(os.path.dirname(os.path.abspath(fname)), exist_ok=True)
+        with netcdf_file(fname, "w", version=2) as fptr:
+            stamp = datetime.now().strftime("%Y-%m-%d %H:%M:%S")
+            fptr.history = f"{stamp}: created by {type(self).__module__}.{type(self).__name__}.dump called from {caller}"
+            axes = self._axes()
+            for axis in axes:
+                axis.define(fptr)
+            dims = tuple(axis.axisname for axis in axes)
+            for tms in self.tracer_modules:
+                for tname in tms.tracer_names:
+                    fptr.createVariable(tname, "f8", dims)
+            for axis in axes:
+                axis.write(fptr)
+            for tms in self.tracer_modules:
+                for tname in tms.tracer_names:
+                    fptr.variables[tname][:] = tms.get_tracer_vals(tname).reshape([len(a) for a in axes])
+        return self
+
+    def log(self, msg=None):
+        logger = logging.getLogger(__name__)
+        mean_vals, norm_vals = self.mean(), self.norm()
+        for ind, tms in enumerate(self.tracer_modules):
+            logger.info("%s[%s] mean=%s norm=%s", "" if msg is None else msg + ",", tms.name, mean_vals[ind], norm_vals[ind])
+
+    # ---- scalars ------------------------------------------------------------------------
+    def _scalar_shape(self):
+        n, R = len(self.tracer_modules), self.model_config_obj.region_cnt
+        return (n, R) if self.members == 1 else (n, R, self.members)
+
+    def _to_host(self, per_module):
+        """list of device [R, B] -> ndarray [n_modules, R] (B == 1) or [n_modules, R, B]"""
+        arr = torch.stack(per_module).cpu().numpy()
+        return arr[..., 0] if self.members == 1 else arr
+
+    def _module_scalars(self, arr, ind):
+        """host scalars (float | [n] | [n, R] | [n, R, B]) -> float or device [R, B] for module ind"""
+        if isinstance(arr, (int, float)):
+            return float(arr)
+        arr = np.asarray(arr, dtype=np.float64)
+        n, R, B = len(self.tracer_modules), self.model_config_obj.region_cnt, self.members
+        if arr.shape == (n,):
+            sel = np.full((R, B), arr[ind])
+        elif arr.shape == (n, R):
+            sel = np.repeat(arr[ind][:, None], B, axis=1)
+        elif arr.shape == (n, R, B):
+            sel = arr[ind]
+        else:
+            raise ValueError(f"unsupported scalar shape {arr.shape}")
+        return torch.from_numpy(np.ascontiguousarray(sel)).cuda()
+
+    def mean(self):
+        return self._to_host([tms.mean() for tms in self.tracer_modules])
+
+    def dot_prod(self, other):
+        return self._to_host([tms.dot_prod(o) for tms, o in zip(self.tracer_modules, other.tracer_modules)])
+
+    def norm(self):
+        return np.sqrt(self.dot_prod(self))
+
+    # ---- arithmetic (model_state_base.py:180-345) -------------------------------------------
+    def __neg__(self):
+        res = self._like()
+        for tms in res.tracer_modules:
+            tms.axpby(None, None, -1.0)
+        return res
+
+    def _iop_state(self, other, sign):
+        for tms, o in zip(self.tracer_modules, other.tracer_modules):
+            tms.axpby(sign, o, 1.0)
+        return self
+
+    def __iadd__(self, other):
+        if isinstance(other, ModelStateBase):
+            return self._iop_state(other, 1.0)
+        return NotImplemented
+
+    def __isub__(self, other):
+        if isinstance(other, ModelStateBase):
+            return self._iop_state(other, -1.0)
+        return NotImplemented
+
+    def __add__(self, other):
+        if isinstance(other, ModelStateBase):
+            return self._like().__iadd__(other)
+        return NotImplemented
+
+    def __sub__(self, other):
+        if isinstance(other, ModelStateBase):
+            return self._like().__isub__(other)
+        return NotImplemented
+
+    def _scale(self, other, reciprocal):
+        if isinstance(other, ModelStateBase):
+            return NotImplemented
+        if not isinstance(other, (int, float, np.ndarray)):
+            return NotImplemented
+        if reciprocal:
+            other = 1.0 / np.asarray(other, dtype=np.float64) if not isinstance(other, (int, float)) else 1.0 / other
+        for ind, tms in enumerate(self.tracer_modules):
+            tms.axpby(None, None, self._module_scalars(other, ind))
+        return self
+
+    def __imul__(self, other):
+        return self._scale(other, False)
+
+    def __itruediv__(self, other):
+        return self._scale(other, True)
+
+    def __mul__(self, other):
+        if isinstance(other, ModelStateBase):
+            return NotImplemented
+        return self._like().__imul__(other)
+
+    def __rmul__(self, other):
+        return self * other
+
+    def __truediv__(self, other):
+        if isinstance(other, ModelStateBase):
+            return NotImplemented
+        return self._like().__itruediv__(other)
+
+    # ---- Krylov building blocks -----------------------------------------------------------
+    def mod_gram_schmidt(self, basis_cnt, fname_fcn, quantity):
+        """in-place modified Gram-Schmidt against basis files (model_state_base.py:365-377).
+        fname_fcn may also return an in-memory ModelState (HBM-resident basis)."""
+        h_val = np.empty(self._scalar_shape()[:1] + (basis_cnt,) + self._scalar_shape()[1:])
+        for i_val in range(basis_cnt):
+            basis_i = fname_fcn(quantity, i_val)
+            if not isinstance(basis_i, ModelStateBase):
+                basis_i = type(self)(basis_i)
+            h_val[:, i_val] = self.dot_prod(basis_i)
+            self -= h_val[:, i_val] * basis_i
+        return h_val
+
+    def comp_jacobian_fcn_state_prod(self, fcn, direction, res_fname, solver_state):
+        """finite-difference Jacobian-vector product (model_state_base.py:492-527)"""
+        step = f"comp_jacobian_fcn_state_prod complete for {res_fname}"
+        if solver_state is not None and solver_state.step_logged(step):
+            return type(self)(res_fname)
+        sigma = 1.0e-4 * self.norm()
+        sigma = np.where(sigma == 0.0, 1.0, sigma)
+        perturb_ms = self + sigma * direction
+        perturb_fname = None
+        if res_fname is not None:
+            workdir = solver_state.get_workdir() if solver_state is not None else os.path.dirname(res_fname)
+            perturb_fname = os.path.join(workdir, f"perturb_fcn_{os.path.basename(res_fname)}")
+        perturb_fcn = perturb_ms.comp_fcn(perturb_fname, solver_state)
+        caller = f"{type(self).__name__}.comp_jacobian_fcn_state_prod"
+        res = ((perturb_fcn - fcn) / sigma).dump(res_fname, caller)
+        if solver_state is not None:
+            solver_state.log_step(step)
+        return res
+
+    def comp_fcn_postprocess(self, res_fname, caller):
+        """model_state_base.py:483-490"""
+        return self.zero_extra_tracers().apply_region_mask().dump(res_fname, f"comp_fcn_postprocess called from {caller}")
+
+    def get_tracer_vals(self, tracer_name):
+        for tms in self.tracer_modules:
+            try:
+                return tms.get_tracer_vals(tracer_name)
+            except KeyError:
+                pass
+        raise KeyError(f"unknown tracer_name={tracer_name}")
+
+    def set_tracer_vals(self, tracer_name, vals):
+        for tms in self.tracer_modules:
+            try:
+                tms.set_tracer_vals(tracer_name, vals)
+                return
+            except KeyError:
+                pass
+        raise KeyError(f"unknown tracer_name={tracer_name}")
+
+    def shadow_tracers_on(self):
+        return any(tms.shadow_pairs() for tms in self.tracer_modules)
+
+    def copy_shadow_tracers_to_real_tracers(self):
+        for tms in self.tracer_modules:
+            for shadow, real in tms.shadow_pairs():
+                tms.vals[real] = tms.vals[shadow]
+        return self
+
+    def copy_real_tracers_to_shadow_tracers(self):
+        for tms in self.tracer_modules:
+            for shadow, real in tms.shadow_pairs():
+                tms.vals[shadow] = tms.vals[real]
+        return self
+
+    def zero_extra_tracers(self):
+        for tms in self.tracer_modules:
+            tms.zero_extra_tracers()
+        return self
+
+    def apply_region_mask(self):
+        for tms in self.tracer_modules:
+            tms.apply_region_mask()
+        return self
+
+    def precond_matrix_list(self):
+        res = []
+        for tms in self.tracer_modules:
+            res.extend(tms.precond_matrix_list())
+        return res
+
+
+def lin_comb(res_type, coeff, fname_fcn, quantity):
+    """linear combination of model states in files (or in HBM) (model_state_base.py:619-624)"""
+    first = fname_fcn(quantity, 0)
+    res = coeff[:, 0] * (first if isinstance(first, ModelStateBase) else res_type(first))
+    for ind in range(1, coeff.shape[1]):
+        nxt = fname_fcn(quantity, ind)
+        res += coeff[:, ind] * (nxt if isinstance(nxt, ModelStateBase) else res_type(nxt))
+    return res

@@ -1,0 +1,408 @@
+"""py_driver_2d model specifics for ModelStateBase — mirror of
+nk_ooc/py_driver_2d/model_state.py with the model-year integration, the preconditioner solves
+and the vector algebra running on the device."""
+
+import logging
+import os
+from datetime import datetime
+
+import numpy as np
+import torch
+from scipy import sparse
+from scipy.io import netcdf_file
+
+from .. import engine
+from ..model_state_base import ModelConfig, ModelStateBase, TracerModuleStateBase
+from ..spatial_axis import spatial_axis_from_file
+from . import modules
+from .processes import SEC_PER_YEAR
+
+# input/py_driver_2d/tracer_module_defs.yaml of the reference, restated
+TRACER_MODULE_DEFS = {
+    "iage": {
+        "region_mask_varname": "region_mask",
+        "tracers": {
+            "iage": {"attrs": {"long_name": "ideal age", "units": "years"},
+                     "init_iterate_val_depths": [55.0, 200.0], "init_iterate_vals": [0.0, 2.0]},
+            "iage_slow_rest": {"attrs": {"long_name": "ideal age, slower surface restoring", "units": "years"},
+                               "init_iterate_val_depths": [55.0, 200.0], "init_iterate_vals": [0.0, 2.0]},
+        },
+    },
+    "phosphorus": {
+        "region_mask_varname": "region_mask",
+        "tracers": {
+            "po4": {"attrs": {"long_name": "phosphate", "units": "mmol / m^3"},
+                    "init_iterate_val_depths": [1.3e2, 2.6e2], "init_iterate_vals": [5.5e-3, 4.1e0],
+                    "precond_matrix": "phosphorus"},
+            "dop": {"attrs": {"long_name": "dissolved organic phosphorus", "units": "mmol / m^3"},
+                    "init_iterate_val_depths": [9.5e1, 1.4e2], "init_iterate_vals": [7.1e-2, 1.5e-4]},
+            "pop": {"attrs": {"long_name": "particulate organic phosphorus", "units": "mmol / m^3"},
+                    "init_iterate_val_depths": [1.7e2, 2.5e2], "init_iterate_vals": [1.8e-2, 7.9e-4]},
+        },
+    },
+    "forced_{suff}": {
+        "region_mask_varname": "region_mask",
+        "py_mod_name": "forced",
+        "tracers": {
+            "{suff}": {"attrs": {"long_name": "{suff} tracer", "units": "mmol / m^3"},
+                       "init_iterate_val_depths": [0.0], "init_iterate_vals": [1.0],
+                       "precond_matrix": "forced_{suff}", "bounds": {"lob": 0.0}},
+        },
+    },
+}
+
+# steps per model year of the fixed-schedule integrator: None = engine.graded_schedule (2640
+# steps, refined while the mixed layer moves), an int = that many uniform steps
+DEFAULT_STEPS_PER_YEAR = None
+
+
+def _eval_expr(expr):
+    """arithmetic strings of the cfg files, e.g. "1.0 / 3600.0" (nk_ooc/utils.py:138-164)"""
+    import ast
+    import operator as op
+
+    ops = {ast.Add: op.add, ast.Sub: op.sub, ast.Mult: op.mul, ast.Div: op.truediv, ast.Pow: op.pow,
+           ast.USub: op.neg, ast.UAdd: op.pos}
+
+    def ev(node):
+        if isinstance(node, ast.Constant) and isinstance(node.value, (int, float)):
+            return node.value
+        if isinstance(node, ast.BinOp):
+            return ops[type(node.op)](ev(node.left), ev(node.right))
+        if isinstance(node, ast.UnaryOp):
+            return ops[type(node.op)](ev(node.operand))
+        raise TypeError(f"unsupported expression {expr}")
+
+    return float(ev(ast.parse(str(expr), mode="eval").body))
+
+
+class ModelState(ModelStateBase):
+    """py_driver_2d model specifics for ModelStateBase"""
+
+    __array_priority__ = 100
+    class_vars_set = False
+    time_range = (0.0, SEC_PER_YEAR)
+    depth = None
+    ypos = None
+    transport = None
+    steps_per_year = DEFAULT_STEPS_PER_YEAR
+    _models = {}
+    _precond_cache = {}
+
+    # ---- class set-up (py_driver_2d/model_state.py:42-65) -------------------------------------
+    @classmethod
+    def configure(cls, modelinfo, tracer_module_defs=None, steps_per_year=None):
+        """set model_config_obj and the (time-invariant) class variables from modelinfo"""
+        cls.reset()
+        cls.model_config_obj = ModelConfig(modelinfo, tracer_module_defs or TRACER_MODULE_DEFS)
+        if steps_per_year is not None:
+            cls.steps_per_year = int(steps_per_year)
+        cls._set_class_vars(modelinfo)
+
+    @classmethod
+    def reset(cls):
+        cls.class_vars_set = False
+        cls.model_config_obj = None
+        cls._models = {}
+        cls._precond_cache = {}
+        cls.steps_per_year = DEFAULT_STEPS_PER_YEAR
+
+    @classmethod
+    def _set_class_vars(cls, modelinfo):
+        if cls.class_vars_set:
+            return
+        cls.depth = spatial_axis_from_file(modelinfo["grid_vars_fname"], modelinfo.get("depth_axisname", "depth"))
+        cls.ypos = spatial_axis_from_file(modelinfo["grid_vars_fname"], modelinfo.get("ypos_axisname", "ypos"))
+        cls.transport = modules.Transport2D(
+            cls.depth, cls.ypos, float(modelinfo.get("max_abs_vvel", 0.1)), float(modelinfo.get("horiz_mix_coeff", 1000.0))
+        )
+        cls.class_vars_set = True
+
+    def __init__(self, fname, members=1):
+        if ModelState.model_config_obj is None:
+            raise RuntimeError("ModelState.model_config_obj is None")
+        self._set_class_vars(self.model_config_obj.modelinfo)
+        super().__init__(fname, members)
+
+    def _new_tracer_module(self, name, tracer_module_def, members):
+        return TracerModuleStateBase(name, tracer_module_def, (len(self.depth), len(self.ypos)),
+                                     self.model_config_obj, members=members)
+
+    def _gen_init_iterate(self, tms):
+        """py_driver_2d/tracer_module_state.py:41-68"""
+        metas = tms._def["tracers"]
+        shape = (len(self.depth), len(self.ypos))
+        for tname, meta in metas.items():
+            if "init_iterate_vals" not in meta and "shadows" in meta:
+                meta = metas[meta["shadows"]]
+            if "init_iterate_vals" not in meta:
+                raise ValueError(f"gen_init_iterate failure for {tname}")
+            col = np.interp(self.depth.mid, meta["init_iterate_val_depths"], meta["init_iterate_vals"])
+            tms.set_tracer_vals(tname, np.broadcast_to(col[:, np.newaxis], shape))
+
+    def _axes(self):
+        return [self.depth, self.ypos]
+
+    # ---- device models -------------------------------------------------------------------
+    @classmethod
+    def model_for(cls, tms):
+        """device model (tables + schedule) of a tracer module; built once per class"""
+        if tms.name in cls._models:
+            return cls._models[tms.name]
+        info = cls.model_config_obj.modelinfo
+        kind = tms._def.get("py_mod_name", tms.name)
+        if kind == "iage":
+            model = modules.iage_model(cls.transport)
+        elif kind == "phosphorus":
+            params = {k: _eval_expr(info[k]) for k in ("po4_halfsat", "max_uptake_rate", "sigma", "dop_remin_rate",
+                                                       "pop_remin_rate", "pop_sink_vel") if k in info}
+            model = modules.phosphorus_model(cls.transport, params)
+        elif kind == "forced":
+            model = cls._forced_model(info)
+        else:
+            raise NotImplementedError(f"tracer module {tms.name} is not available in py_driver_2d")
+        if cls.steps_per_year is None:
+            model.set_graded_schedule()
+        else:
+            model.set_uniform_schedule(cls.steps_per_year)
+        cls._models[tms.name] = model
+        return model
+
+    @classmethod
+    def _forced_model(cls, info):
+        """forced.py:57-112: options from modelinfo (scripts/run_py_driver_2d_forced_*.sh)"""
+        kw = {"surf_restore_opt": info["forced_surf_restore_opt"], "sms_opt": info["forced_sms_opt"]}
+        if kw["surf_restore_opt"] == "file":
+            raise NotImplementedError("forced_surf_restore_opt=file is not on the B200 path yet")
+        if "forced_surf_restore_rate_10m" in info:
+            kw["surf_restore_rate_10m"] = _eval_expr(info["forced_surf_restore_rate_10m"])
+        if kw["surf_restore_opt"] == "const":
+            kw["surf_restore_const"] = _eval_expr(info["forced_surf_restore_const"])
+        if kw["sms_opt"] == "const":
+            kw["sms_const"] = _eval_expr(info["forced_sms_const"])
+        if kw["sms_opt"] == "decay":
+            kw["sms_decay_rate"] = _eval_expr(info["forced_sms_decay_rate"])
+        if kw["sms_opt"] == "file":
+            scalef = _eval_expr(info["forced_sms_scalef"]) if "forced_sms_scalef" in info else 1.0
+            kw["sms_times"], kw["sms_data"] = read_forcing(
+                info["forced_sms_fname"], info["forced_sms_varname"], [cls.depth.mid, cls.ypos.mid], scalef)
+            if "forced_sink_thres" in info:
+                kw["sink_thres"] = _eval_expr(info["forced_sink_thres"])
+        return modules.forced_model(cls.transport, **kw)
+
+    # ---- operators ------------------------------------------------------------------------
+    def comp_fcn(self, res_fname, solver_state, hist_fname=None):
+        """F(x) = x(T) - x(0) for every member (py_driver_2d/model_state.py:67-139)"""
+        logger = logging.getLogger(__name__)
+        logger.debug('res_fname="%s", hist_fname="%s"', res_fname, hist_fname)
+        step = f"comp_fcn complete for {res_fname}"
+        if solver_state is not None and solver_state.step_logged(step):
+            return ModelState(res_fname)
+        res_ms = self._like(clone_vals=False)
+        hist = {}
+        for ind, tms in enumerate(self.tracer_modules):
+            model = self.model_for(tms)
+            res_tms = res_ms.tracer_modules[ind]
+            if hist_fname is not None:
+                times = np.linspace(self.time_range[0], self.time_range[1], 61)
+                res_tms.vals, snaps = model.eval(tms.vals, self.members, hist_steps=model.step_index_of_times(times))
+                hist[tms.name] = (times, snaps)
+            else:
+                res_tms.vals = model.eval(tms.vals, self.members)
+        if hist_fname is not None:
+            self._write_hist(hist_fname, hist)
+        res_ms.comp_fcn_postprocess(res_fname, f"{type(self).__name__}.comp_fcn")
+        if solver_state is not None:
+            solver_state.log_step(step)
+        return res_ms
+
+    def _write_hist(self, hist_fname, hist):
+        """time, axes, process fields and the tracer snapshots of member 0
+        (py_driver_2d/model_state.py:141-233; derived *_time_mean/... variables: not yet)"""
+        os.makedirs(os.path.dirname(os.path.abspath(hist_fname)), exist_ok=True)
+        tr = self.transport
+        first = self.tracer_modules[0]
+        times = hist[first.name][0]
+        model = self.model_for(first)
+        with netcdf_file(hist_fname, "w", version=2) as fptr:
+            stamp = datetime.now().strftime("%Y-%m-%d %H:%M:%S")
+            fptr.history = f"{stamp}: created by {__name__}._gen_hist"
+            fptr.createDimension("time", None)
+            for axis in (self.depth, self.ypos):
+                axis.define(fptr)
+            dn, yn = self.depth.axisname, self.ypos.axisname
+            de, ye = self.depth.dump_names["edges"], self.ypos.dump_names["edges"]
+
+            def mkvar(name, dims, long_name, units, point=False):
+                var = fptr.createVariable(name, "f8", dims)
+                var.long_name = long_name
+                var.units = units
+                if point:
+                    var.cell_methods = "time: point"
+                return var
+
+            tv = mkvar("time", ("time",), "time", "seconds since 0001-01-01")
+            tv.calendar = "noleap"
+            mkvar("stream", (de, ye), "velocity streamfunction", "m^2 / s")
+            mkvar("vvel", (dn, ye), "velocity in ypos direction", "m / s")
+            mkvar("wvel", (de, yn), "velocity in depth direction", "m / s")
+            mkvar("horiz_mixing_coeff", (dn, ye), "horizontal mixing coefficient", "m^2 / s")
+            mkvar("bldepth", ("time", yn), "boundary layer depth", "m", True)
+            mkvar("vert_mixing_coeff", ("time", de, yn), "vertical mixing coefficient", "m^2 / s", True)
+            for tms in self.tracer_modules:
+                for tname, meta in tms._def["tracers"].items():
+                    mkvar(tname, ("time", dn, yn), meta["attrs"]["long_name"], meta["attrs"]["units"], True)
+            for axis in (self.depth, self.ypos):
+                axis.write(fptr)
+            fptr.variables["stream"][:] = tr.advection.stream
+            fptr.variables["vvel"][:] = tr.advection.vvel
+            fptr.variables["wvel"][:] = tr.advection.wvel
+            hm = np.empty((len(self.depth), len(self.ypos) + 1))
+            hm[:, 1:-1] = tr.horiz_mix.mixing_coeff * self.ypos.delta_mid
+            hm[:, 0], hm[:, -1] = hm[:, 1], hm[:, -2]
+            fptr.variables["horiz_mixing_coeff"][:] = hm
+            for ti, t in enumerate(times):
+                fptr.variables["time"][ti] = t
+                fptr.variables["bldepth"][ti, :] = tr.vert_mix.bldepth(t)
+                vm = np.empty((len(self.depth) + 1, len(self.ypos)))
+                vm[1:-1] = model.mixing_coeff(t).cpu().numpy() * self.depth.delta_mid[:, np.newaxis]
+                vm[0], vm[-1] = vm[1], vm[-2]
+                fptr.variables["vert_mixing_coeff"][ti, :] = vm
+            for tms in self.tracer_modules:
+                snaps = hist[tms.name][1].cpu().numpy()  # [n_time, T, nz, ny]
+                for ind, tname in enumerate(tms.tracer_names):
+                    fptr.variables[tname][:] = snaps[:, ind]
+
+    def gen_precond_jacobian(self, hist_fname, precond_fname, solver_state=None):
+        """hist -> precond file: time reductions of the hist variables listed in the precond
+        matrix definitions (model_state_base.py:404-481); py_driver_2d iage needs only `time`"""
+        os.makedirs(os.path.dirname(os.path.abspath(precond_fname)), exist_ok=True)
+        wanted = ["time"]
+        for tms in self.tracer_modules:
+            for tname, meta in tms._def["tracers"].items():
+                if "precond_matrix" in meta and tname not in wanted:
+                    wanted.append(tname)
+        with netcdf_file(hist_fname, "r", mmap=False) as fin, netcdf_file(precond_fname, "w", version=2) as fout:
+            stamp = datetime.now().strftime("%Y-%m-%d %H:%M:%S")
+            fout.history = f"{stamp}: created by {type(self).__name__}.gen_precond_jacobian"
+            for name in wanted:
+                var = fin.variables[name]
+                for dim, length in zip(var.dimensions, var.shape):
+                    if dim not in fout.dimensions:
+                        fout.createDimension(dim, length)
+                out = fout.createVariable(name, "f8", var.dimensions)
+                out[:] = np.array(var.data)
+
+    def apply_precond_jacobian(self, precond_fname, res_fname, solver_state):
+        """res = M^-1 self - self per tracer module (py_driver_2d/model_state.py:235-270)"""
+        step = f"apply_precond_jacobian complete for {res_fname}"
+        if solver_state is not None and solver_state.step_logged(step):
+            return ModelState(res_fname)
+        res_ms = self._like(clone_vals=False)
+        for ind, tms in enumerate(self.tracer_modules):
+            factors = self._precond_factors(tms, precond_fname)
+            out = torch.empty_like(tms.vals)
+            ncell = len(self.depth) * len(self.ypos)
+            for t in range(tms.tracer_cnt):
+                y = tms.vals[t].reshape(ncell, -1)
+                out[t] = factors[t].solve(y, self.members, 1.0, subtract_rhs=True).reshape(tms.vals[t].shape)
+            res_ms.tracer_modules[ind].vals = out
+        if solver_state is not None:
+            solver_state.log_step(step)
+        return res_ms.dump(res_fname, f"{type(self).__name__}.apply_precond_jacobian")
+
+    def _precond_factors(self, tms, precond_fname):
+        """banded LU of M = I - prod_i (I - dt J((i+1/2) dt)), dt = T/3, one per tracer
+        (py_driver_2d/iage.py:66-93, forced.py:204-241).  J is assembled on the host from the
+        device's vertical mixing coefficients; the factorisation and the solves run on the device."""
+        kind = tms._def.get("py_mod_name", tms.name)
+        if kind not in ("iage", "forced"):
+            raise NotImplementedError(f"preconditioner of {tms.name} is not on the B200 path yet")
+        key = (tms.name, precond_fname if kind == "forced" else None)
+        if key in self._precond_cache:
+            return self._precond_cache[key]
+        model = self.model_for(tms)
+        t0, t1 = self.time_range
+        n_t = 3
+        dt = (t1 - t0) / n_t
+        ncell = len(self.depth) * len(self.ypos)
+        factors = []
+        for t in range(tms.tracer_cnt):
+            ident = sparse.identity(ncell, format="csr")
+            mat = ident.copy()
+            for ti in range(n_t):
+                time_mid = t0 + (ti + 0.5) * dt
+                jac = self._jacobian_single_tracer(tms, model, t, time_mid, precond_fname, t0 + (ti + 1.0) * dt)
+                mat = mat @ (ident - dt * jac)
+            mat = (ident - mat).tocoo()
+            kl = int((mat.row - mat.col).max())
+            ku = int((mat.col - mat.row).max())
+            ab = np.zeros((kl + ku + 1, ncell))
+            ab[ku + mat.row - mat.col, mat.col] = mat.data
+            factors.append(engine.BandedFactor(ab, kl, ku))
+        self._precond_cache[key] = factors
+        return factors
+
+    def _jacobian_single_tracer(self, tms, model, tracer_ind, time, precond_fname, time_end):
+        """CSR Jacobian of one tracer's tendency, cell = j + ny*k (advection.py:111-179,
+        horiz_mix.py:100-149, vert_mix.py:140-188, iage.py:55-64, forced.py:156-202)"""
+        nz, ny = len(self.depth), len(self.ypos)
+        n = nz * ny
+        idx = np.arange(n).reshape(nz, ny)
+        tr = self.transport
+        dzr = self.depth.delta_r[:, np.newaxis]
+        mc = model.mixing_coeff(time).cpu().numpy()
+        w = tr.advection.wvel
+        e_l, e_c, e_r = tr.estencil
+        rows, cols, vals = [], [], []
+
+        def add(r, c, v):
+            rows.append(r.ravel())
+            cols.append(c.ravel())
+            vals.append(np.broadcast_to(v, r.shape).ravel())
+
+        diag = e_c.copy()
+        add(idx[:, 1:], idx[:, :-1], e_l[:, 1:])
+        add(idx[:, :-1], idx[:, 1:], e_r[:, :-1])
+        add(idx[1:], idx[:-1], (-0.5 * w[1:-1] + mc) * dzr[1:])
+        diag[1:] += (-0.5 * w[1:-1] - mc) * dzr[1:]
+        add(idx[:-1], idx[1:], (0.5 * w[1:-1] + mc) * dzr[:-1])
+        diag[:-1] += (0.5 * w[1:-1] - mc) * dzr[:-1]
+        desc = model.desc
+        cls_ind = desc.class_of[tracer_ind]
+        diag[0] += desc.surf_diag[cls_ind]
+        diag += desc.decay[cls_ind]
+        if desc.kind == engine._lib.MOD_FORCED_FILE and desc.sink_thres > 0.0:
+            # d sms / d tracer at the precond file's tracer snapshot nearest time_end (forced.py:190-202,221-229)
+            with netcdf_file(precond_fname, "r", mmap=False) as fptr:
+                ptimes = np.array(fptr.variables["time"].data)
+                snap = np.array(fptr.variables[tms.tracer_names[0]].data)[np.argmin(abs(time_end - ptimes))]
+            keep = model._keepalive
+            ft, fd = keep["ft"], keep["fd"]
+            i = int(np.clip(np.searchsorted(ft, time, side="right") - 1, 0, len(ft) - 2))
+            sms = fd[i] + (time - ft[i]) / (ft[i + 1] - ft[i]) * (fd[i + 1] - fd[i])
+            q = snap / desc.sink_thres
+            diag += np.where((sms < 0.0) & (q > 0.0) & (q < 1.0), sms / desc.sink_thres, 0.0)
+        add(idx, idx, diag)
+        return sparse.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n, n))
+
+
+def read_forcing(fname, varname, dims_out, scalef=1.0):
+    """forcing record [nt, ...] interpolated (linearly, with extrapolation) to the model axes
+    when they differ from the file's (nk_ooc/utils.py:488-537)"""
+    from scipy import interpolate
+
+    with netcdf_file(fname, "r", mmap=False) as fptr:
+        var = fptr.variables[varname]
+        if len(var.shape) not in (1, 2, 3):
+            raise ValueError(f"unexpected ndim={len(var.shape)}")
+        if len(dims_out) != len(var.shape) - 1:
+            raise ValueError(f"len(additional_dims_out) = {len(dims_out)} must be {len(var.shape) - 1}")
+        times = np.array(fptr.variables[var.dimensions[0]].data, dtype=np.float64)
+        data = scalef * np.array(var.data, dtype=np.float64)
+        for axis in range(1, len(var.shape)):
+            dim_in = np.array(fptr.variables[var.dimensions[axis]].data, dtype=np.float64)
+            dim_out = dims_out[axis - 1]
+            if len(dim_in) != len(dim_out) or (dim_in != dim_out).any():
+                data = interpolate.interp1d(dim_in, data, axis=axis, fill_value="extrapolate", assume_sorted=True)(dim_out)
+    return times, data
