@@ -96,6 +96,8 @@ int launch_pack(const double *src, double *dst, int n, int B, int ldb, cudaStrea
 int launch_unpack(const double *src, double *dst, int n, int B, int ldb, cudaStream_t st);
 int launch_stage(int kind, int nin, const StageArgs &a, cudaStream_t st);
 int launch_tend(int kind, const StageArgs &a, cudaStream_t st);
+bool tma_path_usable(const StageArgs &a);
+int launch_stage_tma(int kind, int nin, const StageArgs &a, cudaStream_t st);
 
 }  // namespace nkb
 
