@@ -30,6 +30,8 @@ int nkb_model_create(nkb_model **out, const nkb_model_desc *d) {
     NKB_REQUIRE(d->column_model == 1 || (d->h_bld_max && d->h_ypos_mid), "nkb_model_create: bld_max missing");
     NKB_REQUIRE(d->kind != NKB_MOD_PHOSPHORUS || (d->n_tracers == 3 && d->h_light),
                 "nkb_model_create: phosphorus needs 3 tracers and a light table");
+    NKB_REQUIRE(d->kind != NKB_MOD_PHOSPHORUS_1D || (d->n_tracers == 6 && d->h_light && d->ny == 1),
+                "nkb_model_create: test_problem phosphorus needs 6 tracers, ny == 1 and a light table");
     NKB_REQUIRE(d->kind != NKB_MOD_FORCED_FILE || (d->n_frc >= 2 && d->h_frc_time && d->h_frc_data),
                 "nkb_model_create: forced file module needs >= 2 forcing records");
     for (int t = 0; t < d->n_tracers; ++t)
@@ -126,7 +128,7 @@ int nkb_model_create(nkb_model **out, const nkb_model_desc *d) {
 
 void nkb_model_destroy(nkb_model *m) {
     if (!m) return;
-    cudaFree(m->arena); cudaFree(m->tri); cudaFree(m->aff); cudaFree(m->src);
+    cudaFree(m->arena); cudaFree(m->tri); cudaFree(m->aff); cudaFree(m->src); cudaFree(m->d_h);
     cudaFree(m->tri_raw); cudaFree(m->aff_raw); cudaFree(m->src_raw);
     cudaFree(m->d_stage_major); cudaFree(m->d_stage_x); cudaFree(m->d_stage_f); cudaFree(m->d_stage_work);
     if (m->graph) cudaGraphExecDestroy(m->graph);
@@ -183,6 +185,10 @@ int nkb_model_set_schedule(nkb_model *m, int n_steps, const double *h_t_start, c
             if (nkb::launch_forcing_tables(v, ns, d_t + s0, m->src + (size_t)s0 * plane, 0)) return 1;  // [step][cell][2]
         }
     }
+    cudaFree(m->d_h);
+    m->d_h = nullptr;
+    NKB_CUDA(cudaMalloc(&m->d_h, n_steps * sizeof(double)));
+    NKB_CUDA(cudaMemcpy(m->d_h, h_h, n_steps * sizeof(double), cudaMemcpyHostToDevice));
     NKB_CUDA(cudaDeviceSynchronize());
     cudaFree(d_t); cudaFree(d_hg);
     return 0;
@@ -242,6 +248,34 @@ int nkb_model_eval(nkb_model *m, const double *d_x0, double *d_f, double *d_work
     const int S = m->n_steps;
     const size_t tri_stride = (size_t)v.n_classes * 4 * plane, aff_stride = (size_t)v.n_classes * v.ny;
     const double a1 = (1.0 - nkb::kGamma) / nkb::kGamma, a0 = 1.0 - a1;
+
+    if (v.column_model == 1 && v.ny == 1) {
+        // test_problem: the whole year in one persistent kernel, state resident in shared memory
+        nkb::ColumnArgs c;
+        std::memset(&c, 0, sizeof(c));
+        c.x0 = d_x0; c.out = d_f; c.tri = m->tri; c.aff = m->aff; c.h = m->d_h; c.light = v.light;
+        c.nz = v.nz; c.B = B; c.ldb = ldb; c.T = v.T; c.n_steps = S; c.ncls = v.n_classes;
+        for (int t = 0; t < NKB_MAX_TRACERS; ++t) { c.class_of[t] = v.class_of[t]; c.src_const[t] = v.src_const[t]; }
+        c.restoring_opt = v.po4_s_restoring_opt;
+        int *d_slot = nullptr;
+        if (n_hist > 0) {
+            std::vector<int> slot(S + 1, -1);
+            for (int i = 0; i < n_hist; ++i) {
+                NKB_REQUIRE(h_hist_steps[i] >= 0 && h_hist_steps[i] <= S, "nkb_model_eval: hist step out of range");
+                slot[h_hist_steps[i]] = i;
+            }
+            NKB_CUDA(cudaMalloc(&d_slot, (S + 1) * sizeof(int)));
+            NKB_CUDA(cudaMemcpy(d_slot, slot.data(), (S + 1) * sizeof(int), cudaMemcpyHostToDevice));
+            c.hist_slot = d_slot;
+            c.hist = d_hist;
+        }
+        const int rc = nkb::launch_column_year(v.kind, c, st);
+        if (d_slot) {
+            NKB_CUDA(cudaStreamSynchronize(st));
+            cudaFree(d_slot);
+        }
+        return rc;
+    }
 
     StageArgs a;
     fill_args(m, a, B, ldb);

@@ -87,6 +87,23 @@ struct StageArgs {
     double halfsat, umax, sigma, rdop, rpop;
 };
 
+// arguments of the persistent column-model year kernel (nkb_column.cu)
+struct ColumnArgs {
+    const double *x0;      // [T][nz][ldb]
+    double *out;           // [T][nz][ldb]  F = x(T) - x(0)
+    const double *tri;     // [n_stages][ncls][nz][4] {ib, g, m, 0}
+    const double *aff;     // [n_stages][ncls]
+    const double *h;       // [n_steps]
+    const double *light;   // [nz] (phosphorus)
+    const int *hist_slot;  // [n_steps+1] slot index or -1 (nullptr: no hist)
+    double *hist;          // [n_hist][T][nz]
+    int nz, B, ldb, T, n_steps, ncls;
+    int class_of[NKB_MAX_TRACERS];
+    double src_const[NKB_MAX_TRACERS];
+    int restoring_opt;
+};
+
+int launch_column_year(int kind, const ColumnArgs &a, cudaStream_t st);
 int launch_stage_tables(const ModelDev &m, int n_stages, const double *d_t, const double *d_hg, int mode,
                         double *tri, double *aff, cudaStream_t st);
 int launch_mixing_coeff(const ModelDev &m, double time, double *out, cudaStream_t st);
@@ -108,6 +125,7 @@ struct nkb_model {
     // schedule
     int n_steps = 0;
     double *h_t_start = nullptr, *h_h = nullptr;  // host copies
+    double *d_h = nullptr;                         // device copy of the step sizes
     // per-stage tables, stage s = 2*step + {0,1}
     double *tri = nullptr;      // [n_stages][n_classes][nz][ny][4]  {ib, g, m, 0}
     double *aff = nullptr;      // [n_stages][n_classes][ny]  h*gamma*(affine surface source) per column

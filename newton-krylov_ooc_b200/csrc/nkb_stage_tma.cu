@@ -315,7 +315,10 @@ static int launch_tma_t(const StageArgs &a, cudaStream_t st) {
     for (int i = 0; i < NIN; ++i)
         if (make_map(&maps.u[i], a.u[i], a.T, a.nz, a.ny, a.ldb, rows, KC)) return 1;
     if (NIN == 1) maps.u[1] = maps.u[0];
-    const size_t smem = 128 + 128 + (size_t)NS * NIN * TG * KC * rows * kBM * sizeof(double);
+    size_t smem = 128 + 128 + (size_t)NS * NIN * TG * KC * rows * kBM * sizeof(double);
+    // optional cap on resident CTAs per SM (bounds the in-flight forward-sweep intermediates)
+    const size_t pad = (size_t)env_int_tma("NKB_TMA_MIN_SMEM_KB", 0) * 1024;
+    if (smem < pad) smem = pad;
     auto kern = stage_tma_kernel<KIND, TG, NIN, KC, NS>;
     static bool attr_set = false;
     if (!attr_set) {

@@ -225,3 +225,148 @@ def model_year_2d(mod, x0, nsteps=2400, snapshots=None, schedule=None):
         if snapshots is not None:
             snapshots.append((n + 1, u.copy()))
     return u - x0
+
+
+# --------------------------------------------------------------------------------------
+# test_problem (1-D column): everything is vertical, so the scheme reduces to the L-stable
+# SDIRK2 (gamma = 1 - 1/sqrt 2) with one tridiagonal solve per stage
+# --------------------------------------------------------------------------------------
+
+
+class Module1D:
+    """split of the test_problem tendencies (test_problem/{iage,dye_decay}.py) for the column
+    model; `kind` in {"iage", "dye_decay"}; the vertical operator carries mixing, the piston
+    velocity (iage) or the decay; the surface flux of dye_decay is an affine k=0 source"""
+
+    def __init__(self, kind, col, suff=None):
+        self.kind = kind
+        self.g = col
+        self.T = 1
+        self.suff = int(suff) if suff is not None else 0
+
+    def tridiag(self, time):
+        d = self.g.depth
+        nz = self.g.nz
+        mc = np.zeros(nz + 1)
+        mc[1:-1] = self.g.mixing_coeff(time)
+        sub = d.delta_r * mc[:-1]
+        sup = d.delta_r * mc[1:]
+        diag = -d.delta_r * (mc[1:] + mc[:-1])
+        aff = 0.0
+        if self.kind == "iage":
+            diag[0] -= 24.0 * (1.0 / 86400.0) * 10.0 * d.delta_r[0]
+        else:
+            diag -= self.suff * 0.001 * (1.0 / SEC_PER_YEAR)
+            flux = np.interp(time, SEC_PER_YEAR * np.array([0.1, 0.2, 0.6, 0.7]),
+                             (1.0 / SEC_PER_YEAR) * np.array([0.0, 2.0, 2.0, 0.0]))
+            aff = flux * d.delta_r[0]
+        return sub, diag, sup, aff
+
+    def src_const(self):
+        return 1.0 / SEC_PER_YEAR if self.kind == "iage" else 0.0
+
+
+def model_year_1d(mod, x0, nsteps=None, schedule=None):
+    """x0 [nz, B] -> x(T) - x(0) with SDIRK2 (ARS(2,2,2) without explicit transport)"""
+    g = mod.g
+    tstart, hs = schedule if schedule is not None else uniform_schedule(nsteps, *g.time_range)
+    nsteps = len(hs)
+    u = np.array(x0, dtype=np.float64)
+    a1 = (1.0 - GAMMA) / GAMMA
+    a0 = 1.0 - a1
+    sc = mod.src_const()
+    for n in range(nsteps):
+        t, h = tstart[n], hs[n]
+        hg = h * GAMMA
+        t1 = t + GAMMA * h
+        t2 = tstart[n + 1] if n + 1 < nsteps else g.time_range[1]
+        sub, diag, sup, aff = mod.tridiag(t1)
+        m, ib, gg = thomas_factor(sub, diag, sup, hg)
+        r = u + hg * sc
+        r[0] += hg * aff
+        u1 = thomas_solve(m, ib, gg, r)
+        sub, diag, sup, aff = mod.tridiag(t2)
+        m, ib, gg = thomas_factor(sub, diag, sup, hg)
+        r = a0 * u + a1 * u1 + h * (DELTA - 1.0 + GAMMA) * sc + h * (1.0 - DELTA) * sc
+        r[0] += hg * aff
+        u = thomas_solve(m, ib, gg, r)
+    return u - x0
+
+
+class Phosphorus1DSplit:
+    """test_problem phosphorus (test_problem/phosphorus.py:28-120) in IMEX form: mixing (all six
+    tracers) and pop / pop_s sinking (1 m/day, upwind) implicit; uptake, remineralisation and
+    the shadow restoring explicit"""
+
+    T = 6
+
+    def __init__(self, col, phos):
+        self.g = col
+        self.p = phos  # nk_oracle.Phosphorus1D
+
+    def tridiag(self, time, sinking):
+        d = self.g.depth
+        nz = self.g.nz
+        mc = np.zeros(nz + 1)
+        mc[1:-1] = self.g.mixing_coeff(time)
+        sub = d.delta_r * mc[:-1]
+        sup = d.delta_r * mc[1:]
+        diag = -d.delta_r * (mc[1:] + mc[:-1])
+        if sinking:
+            v = 1.0 / 86400.0
+            sub[1:] += v * d.delta_r[1:]
+            diag[:-1] -= v * d.delta_r[:-1]
+        return sub, diag, sup
+
+    def explicit(self, c):
+        """c [6, nz, B]"""
+        p = self.p
+        out = np.empty_like(c)
+        po4 = c[0]
+        u = (1.0 / 86400.0) * p.light[:, None] * (po4 / (po4 + 0.5))
+        rem = 0.01 * (1.0 / 86400.0)
+        for o3 in (0, 3):
+            out[o3 + 0] = -u + rem * c[o3 + 1] + rem * c[o3 + 2]
+            out[o3 + 1] = 0.67 * u - rem * c[o3 + 1]
+            out[o3 + 2] = (1.0 - 0.67) * u - rem * c[o3 + 2]
+        if p.opt == 0:
+            tau = np.zeros_like(po4)
+            tau[0] = 1.0 / 86400.0
+        else:
+            delta = 1.0e-3 * np.abs(po4)
+            delta[delta < 1.0e-8] = 1.0e-8
+            pd = po4 + delta
+            tau = ((1.0 / 86400.0) * p.light[:, None] * (pd / (pd + 0.5)) - u) / delta
+        rest = tau * (c[0] - c[3])
+        out[3] += rest
+        out[4] -= 0.67 * rest
+        out[5] -= 0.33 * rest
+        return out
+
+
+def model_year_1d_phosphorus(mod, x0, nsteps):
+    """x0 [6, nz, B]"""
+    g = mod.g
+    tstart, hs = uniform_schedule(nsteps, *g.time_range)
+    u = np.array(x0, dtype=np.float64)
+    a1 = (1.0 - GAMMA) / GAMMA
+    a0 = 1.0 - a1
+    sink = [False, False, True, False, False, True]
+
+    def solve(rhs, time, hg):
+        out = np.empty_like(rhs)
+        fac = {s: thomas_factor(*mod.tridiag(time, s), hg) for s in (False, True)}
+        for t in range(6):
+            out[t] = thomas_solve(*fac[sink[t]], rhs[t])
+        return out
+
+    for n in range(nsteps):
+        t, h = tstart[n], hs[n]
+        hg = h * GAMMA
+        t1 = t + GAMMA * h
+        t2 = tstart[n + 1] if n + 1 < nsteps else g.time_range[1]
+        e_n = mod.explicit(u)
+        u1 = solve(u + hg * e_n, t1, hg)
+        e_1 = mod.explicit(u1)
+        u = solve(a0 * u + a1 * u1 + h * (DELTA - 1.0 + GAMMA) * e_n + h * (1.0 - DELTA) * e_1, t2, hg)
+    return u - x0

@@ -1,0 +1,145 @@
+"""GPU parity tests of the test_problem (1-D column) path: K3 tables of the column model, the
+persistent column-year kernel against the numpy statement of the same scheme, and the host
+mirror against the reference's committed baselines (ci_short, ci_long_iage) with the tolerances
+of the reference's CI scripts."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def base(golden_dir):
+    return np.load(os.path.join(golden_dir, "baselines.npz"))
+
+
+def _dev(x):
+    from nk_ooc_b200.engine import padded_members
+
+    B = x.shape[-1]
+    out = torch.zeros(x.shape[:-1] + (padded_members(B),), dtype=torch.float64, device="cuda")
+    out[..., :B] = torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    return out
+
+
+def _depth(base):
+    from nk_ooc_b200.spatial_axis import SpatialAxis
+
+    return SpatialAxis("depth", base["ci_short/depth_axis/depth_edges"])
+
+
+def test_column_mixing_coeff_and_tend(base):
+    from nk_ooc_b200.test_problem import modules
+    from oracle import nk_oracle as o
+
+    depth = _depth(base)
+    col = o.Column1D(depth.edges)
+    rng = np.random.default_rng(0)
+    for name, model, om in (("iage", modules.iage_model(depth), o.Iage1D(col)),
+                            ("dye", modules.dye_decay_model(depth, "010"), o.DyeDecay1D(col, "010"))):
+        B = 7
+        x = np.abs(rng.normal(size=(1, 20, 1, B)))
+        for frac in (0.0, 0.15, 0.3, 0.65, 0.9):
+            t = frac * 365.0 * 86400.0
+            np.testing.assert_allclose(model.mixing_coeff(t).cpu().numpy()[:, 0], col.mixing_coeff(t), rtol=1e-13)
+            got = model.tend(t, _dev(x), B).cpu().numpy()[0, :, 0, :B]
+            want = np.stack([om.comp_tend(t, x[0, :, 0, b]) for b in range(B)], axis=-1)
+            np.testing.assert_allclose(got, want, rtol=0, atol=1e-12 * np.abs(want).max(), err_msg=name)
+
+
+@pytest.mark.parametrize("B", [1, 5, 200])
+def test_column_year_kernel_matches_scheme_oracle(base, B):
+    from nk_ooc_b200.test_problem import modules
+    from oracle import imex_oracle as im
+    from oracle import nk_oracle as o
+
+    depth = _depth(base)
+    col = o.Column1D(depth.edges)
+    rng = np.random.default_rng(B)
+    sched = modules.aligned_schedule(depth, 150, (0.1, 0.2, 0.6, 0.7))
+    for kind, model, mod in (("iage", modules.iage_model(depth), im.Module1D("iage", col)),
+                             ("dye", modules.dye_decay_model(depth, "010"), im.Module1D("dye_decay", col, "010"))):
+        x = np.abs(rng.normal(size=(20, B)))
+        model.set_schedule(*sched)
+        got = model.eval(_dev(x.reshape(1, 20, 1, B)), B).cpu().numpy()[0, :, 0, :B]
+        want = im.model_year_1d(mod, x, schedule=sched)
+        np.testing.assert_allclose(got, want, rtol=0, atol=1e-11 * np.abs(want).max(), err_msg=kind)
+    model = modules.phosphorus_model(depth)
+    model.set_uniform_schedule(400)
+    x = np.abs(rng.normal(size=(6, 20, min(B, 5)))) * 0.3
+    Bp = x.shape[-1]
+    got = model.eval(_dev(x.reshape(6, 20, 1, Bp)), Bp).cpu().numpy()[:, :, 0, :Bp]
+    want = im.model_year_1d_phosphorus(im.Phosphorus1DSplit(col, o.Phosphorus1D(col)), x, 400)
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-10 * np.abs(want).max())
+
+
+def _configure(tmp, names):
+    from nk_ooc_b200.spatial_axis import spatial_axis_from_defn
+    from nk_ooc_b200.test_problem.model_state import ModelState, gen_depth_axis_file
+
+    info = {"model_name": "test_problem", "tracer_module_names": names, "po4_s_restoring_opt": "1",
+            "grid_vars_fname": os.path.join(tmp, "depth_axis.nc"), "depth_axisname": "depth", "reinvoke": "False"}
+    depth = spatial_axis_from_defn("depth", nlevs=20)
+    gen_depth_axis_file(info, depth)
+    ModelState.configure(info)
+    return ModelState
+
+
+def test_ci_short(base, tmp_path):
+    """scripts/ci_short.sh: depth_axis.nc, init_iterate_00, fcn_00, init_iterate (rtol 1e-7, atol 2e-9)"""
+    from scipy.io import netcdf_file
+
+    ModelState = _configure(str(tmp_path), "iage,phosphorus")
+    with netcdf_file(str(tmp_path / "depth_axis.nc"), "r", mmap=False) as f:
+        for name in ("depth", "depth_edges", "depth_delta", "depth_bounds"):
+            np.testing.assert_allclose(np.array(f.variables[name].data), base["ci_short/depth_axis/" + name], rtol=1e-7, atol=2e-9)
+        np.testing.assert_array_equal(np.array(f.variables["region_mask"].data), base["ci_short/depth_axis/region_mask"])
+    names = ["iage", "po4", "dop", "pop", "po4_s", "dop_s", "pop_s"]
+    init = ModelState("gen_init_iterate")
+    for n in names:
+        np.testing.assert_allclose(init.get_tracer_vals(n), base["ci_short/init_iterate_00/" + n], rtol=1e-7, atol=2e-9)
+    x = ModelState({n: base["ci_short/init_iterate_00/" + n] for n in names})
+    fcn = x.comp_fcn(str(tmp_path / "fcn_00.nc"), None, str(tmp_path / "hist_00.nc"))
+    for n in names:
+        np.testing.assert_allclose(fcn.get_tracer_vals(n), base["ci_short/fcn_00/" + n], rtol=1e-7, atol=2e-9, err_msg=n)
+    x += fcn
+    x.copy_shadow_tracers_to_real_tracers()
+    for n in names:
+        np.testing.assert_allclose(x.get_tracer_vals(n), base["ci_short/init_iterate/" + n], rtol=1e-7, atol=2e-9, err_msg=n)
+    with netcdf_file(str(tmp_path / "hist_00.nc"), "r", mmap=False) as f:
+        for n in ("time", "bldepth", "mixing_coeff", "iage"):
+            np.testing.assert_allclose(np.array(f.variables[n].data), base["ci_short/hist_00/" + n], rtol=1e-7, atol=2e-9, err_msg=n)
+    ModelState.reset()
+
+
+def test_ci_long_iage_first_krylov_iteration(base, tmp_path):
+    """scripts/ci_long_iage.sh: precond_00, precond_fcn_00, basis_00, perturb_fcn_w_raw_00 (default
+    tolerance), w_raw_00, w_00 (rtol 2e-4)"""
+    from scipy.io import netcdf_file
+
+    ModelState = _configure(str(tmp_path), "iage")
+    pre = "ci_long_iage/"
+    iterate = ModelState({"iage": base["ci_short/init_iterate/iage"]})
+    fcn = iterate.comp_fcn(None, None, str(tmp_path / "hist_00.nc"))
+    iterate.gen_precond_jacobian(str(tmp_path / "hist_00.nc"), str(tmp_path / "precond_00.nc"))
+    with netcdf_file(str(tmp_path / "precond_00.nc"), "r", mmap=False) as f:
+        for n in ("mixing_coeff_mean", "mixing_coeff_log_mean"):
+            np.testing.assert_allclose(np.array(f.variables[n].data), base[pre + "precond_00/" + n], rtol=1e-7, atol=2e-9)
+    precond_fcn = fcn.apply_precond_jacobian(str(tmp_path / "precond_00.nc"), None, None)
+    np.testing.assert_allclose(precond_fcn.get_tracer_vals("iage"), base[pre + "precond_fcn_00/iage"], rtol=1e-7, atol=2e-9)
+    beta = precond_fcn.norm()
+    assert abs(beta[0, 0] - 140.4537919731353) < 1e-5
+    basis = -precond_fcn / beta
+    np.testing.assert_allclose(basis.get_tracer_vals("iage"), base[pre + "basis_00/iage"], rtol=1e-7, atol=2e-9)
+    w_raw = iterate.comp_jacobian_fcn_state_prod(fcn, basis, None, None)
+    sigma = 1.0e-4 * iterate.norm()
+    perturb_fcn = w_raw * sigma + fcn
+    np.testing.assert_allclose(perturb_fcn.get_tracer_vals("iage"), base[pre + "perturb_fcn_w_raw_00/iage"], rtol=1e-7, atol=2e-8)
+    np.testing.assert_allclose(w_raw.get_tracer_vals("iage"), base[pre + "w_raw_00/iage"], rtol=2e-4, atol=2e-9)
+    w0 = w_raw.apply_precond_jacobian(str(tmp_path / "precond_00.nc"), None, None)
+    np.testing.assert_allclose(w0.get_tracer_vals("iage"), base[pre + "w_00/iage"], rtol=2e-4, atol=2e-9)
+    ModelState.reset()
