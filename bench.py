@@ -273,6 +273,7 @@ def run_ours(args):
     engine.require_cuda()
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _lib.load()
 
@@ -370,7 +371,7 @@ def run_ours(args):
         },
         "e2e": {
             "value": world * B / e2e_s, "unit": "model-year evals/s",
-            "h2d_bytes_per_step": 8 * N * B, "d2h_bytes_per_step": 8 * N * B,
+            "h2d_bytes_per_step": 8 * N * B * world, "d2h_bytes_per_step": 8 * N * B * world,
             "api": "nkb_model_eval_host (C ABI, pinned host buffers)",
         },
         "gpu_launches": int(launches),

@@ -1,0 +1,58 @@
+"""Sharding of an ensemble over the GPUs of one box (one process per GPU, torch.distributed).
+
+Members (perturbed states, Armijo candidates, coloured probes) are independent for the whole
+model year, so the data path has NO collective: rank g owns the contiguous member block
+[lo, hi).  Collectives carry only (a) the gather of result columns to every rank (or to the
+owner of the Krylov basis) and (b) the all-reduce of [n_modules, region_cnt] partial dot
+products when one state is split by module/region, and (c) the broadcast of a new iterate.
+Backend: nccl over NVLink on GPUs, gloo in the CPU tests."""
+
+import torch
+import torch.distributed as dist
+
+
+def member_range(n_members, rank, world):
+    """contiguous, balanced block of members owned by `rank`: sizes differ by at most one"""
+    if not 0 <= rank < world:
+        raise ValueError(f"rank {rank} outside world of {world}")
+    base, rem = divmod(n_members, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def gather_members(local, n_members, group=None):
+    """all-gather member-major results: local [B_local, n] on every rank -> [n_members, n]"""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    lo, hi = member_range(n_members, rank, world)
+    if local.shape[0] != hi - lo:
+        raise ValueError(f"rank {rank} holds {local.shape[0]} members, expected {hi - lo}")
+    width = max(member_range(n_members, r, world)[1] - member_range(n_members, r, world)[0] for r in range(world))
+    padded = local.new_zeros((width,) + tuple(local.shape[1:]))
+    padded[: hi - lo] = local
+    out = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(out, padded, group=group)
+    parts = []
+    for r in range(world):
+        rlo, rhi = member_range(n_members, r, world)
+        parts.append(out[r][: rhi - rlo])
+    return torch.cat(parts, dim=0)
+
+
+def allreduce_sum(partial, group=None):
+    """sum of [n_modules, region_cnt(, k)] partial dot products over the ranks (in place)"""
+    dist.all_reduce(partial, op=dist.ReduceOp.SUM, group=group)
+    return partial
+
+
+def broadcast_state(vals, src=0, group=None):
+    """new iterate from the rank that owns it to everybody (in place)"""
+    dist.broadcast(vals, src=src, group=group)
+    return vals
+
+
+def max_over_ranks(value, device, group=None):
+    """device-timed durations are reported as the max over ranks"""
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return float(t[0])

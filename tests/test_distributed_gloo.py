@@ -1,0 +1,72 @@
+"""CPU tests of the N>1 path with the gloo backend, world_size 2 (and 3): member sharding,
+gather of result columns, all-reduce of partial dot products, broadcast of the iterate."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n_members, tmpdir):
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "newton-krylov_ooc_b200"))
+    from nk_ooc_b200 import distributed as D
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lo, hi = D.member_range(n_members, rank, world)
+        n = 11
+        full = torch.arange(n_members * n, dtype=torch.float64).reshape(n_members, n)
+        # every rank "evaluates" its own members (here: a deterministic function of the member id)
+        local = full[lo:hi] * 2.0 + 1.0
+        gathered = D.gather_members(local, n_members)
+        assert torch.equal(gathered, full * 2.0 + 1.0)
+        # partial dot products of a state split over ranks
+        part = torch.full((2, 3), float(rank + 1), dtype=torch.float64)
+        D.allreduce_sum(part)
+        assert torch.equal(part, torch.full((2, 3), float(sum(range(1, world + 1))), dtype=torch.float64))
+        it = torch.full((5,), float(rank), dtype=torch.float64)
+        D.broadcast_state(it, src=world - 1)
+        assert torch.equal(it, torch.full((5,), float(world - 1), dtype=torch.float64))
+        assert D.max_over_ranks(float(rank), "cpu") == float(world - 1)
+        open(os.path.join(tmpdir, f"ok_{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_members", [(2, 7), (2, 8), (3, 4)])
+def test_member_sharding_and_collectives_gloo(tmp_path, world, n_members):
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, n_members, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert (tmp_path / f"ok_{r}").exists()
+
+
+def test_member_range_partitions_exactly():
+    from nk_ooc_b200.distributed import member_range
+
+    for n in (0, 1, 5, 4096, 4099):
+        for world in (1, 2, 3, 8):
+            seen = []
+            for r in range(world):
+                lo, hi = member_range(n, r, world)
+                assert 0 <= lo <= hi <= n
+                seen.extend(range(lo, hi))
+            assert seen == list(range(n))
+            sizes = [member_range(n, r, world)[1] - member_range(n, r, world)[0] for r in range(world)]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        member_range(4, 2, 2)
