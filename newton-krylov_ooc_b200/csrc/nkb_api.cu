@@ -130,6 +130,7 @@ void nkb_model_destroy(nkb_model *m) {
     if (!m) return;
     cudaFree(m->arena); cudaFree(m->tri); cudaFree(m->aff); cudaFree(m->src); cudaFree(m->d_h);
     cudaFree(m->tri_raw); cudaFree(m->aff_raw); cudaFree(m->src_raw);
+    cudaFree(m->ftab); cudaFree(m->estp); cudaFree(m->srcp);
     cudaFree(m->d_stage_major); cudaFree(m->d_stage_x); cudaFree(m->d_stage_f); cudaFree(m->d_stage_work);
     if (m->graph) cudaGraphExecDestroy(m->graph);
     if (m->own_stream) cudaStreamDestroy(m->own_stream);
@@ -144,6 +145,8 @@ int nkb_model_set_schedule(nkb_model *m, int n_steps, const double *h_t_start, c
     const int n_stages = 2 * n_steps;
     cudaFree(m->tri); cudaFree(m->aff); cudaFree(m->src);
     m->tri = m->aff = m->src = nullptr;
+    cudaFree(m->ftab); cudaFree(m->estp); cudaFree(m->srcp);
+    m->ftab = m->estp = m->srcp = nullptr;
     if (m->graph) { cudaGraphExecDestroy(m->graph); m->graph = nullptr; }
     delete[] m->h_t_start; delete[] m->h_h;
     m->h_t_start = new double[n_steps]; m->h_h = new double[n_steps];
@@ -189,6 +192,59 @@ int nkb_model_set_schedule(nkb_model *m, int n_steps, const double *h_t_start, c
     m->d_h = nullptr;
     NKB_CUDA(cudaMalloc(&m->d_h, n_steps * sizeof(double)));
     NKB_CUDA(cudaMemcpy(m->d_h, h_h, n_steps * sizeof(double), cudaMemcpyHostToDevice));
+    NKB_CUDA(cudaDeviceSynchronize());
+    cudaFree(d_t); cudaFree(d_hg);
+    return 0;
+}
+
+// Tables of the fused step kernel, built on the first evaluation that uses it.
+static int ensure_fused_tables(nkb_model *m) {
+    if (m->ftab) return 0;
+    const ModelDev &v = m->dev;
+    const int n_steps = m->n_steps, n_stages = 2 * n_steps;
+    const int nyp = (v.ny + 2) & ~1;  // one zero column on the left, even pitch
+    m->nyp = nyp;
+    std::vector<double> t_imp(n_stages), hg(n_stages), t_exp(n_stages);
+    for (int n = 0; n < n_steps; ++n) {  // same stage times as nkb_model_set_schedule
+        const double t = m->h_t_start[n], h = m->h_h[n];
+        t_imp[2 * n] = t + nkb::kGamma * h;
+        t_imp[2 * n + 1] = (n + 1 < n_steps) ? m->h_t_start[n + 1] : v.t1;
+        hg[2 * n] = hg[2 * n + 1] = nkb::kGamma * h;
+        t_exp[2 * n] = t;
+        t_exp[2 * n + 1] = t + nkb::kGamma * h;
+    }
+    double *d_t = nullptr, *d_hg = nullptr;
+    NKB_CUDA(cudaMalloc(&d_t, n_stages * sizeof(double)));
+    NKB_CUDA(cudaMalloc(&d_hg, n_stages * sizeof(double)));
+    NKB_CUDA(cudaMemcpy(d_t, t_imp.data(), n_stages * sizeof(double), cudaMemcpyHostToDevice));
+    NKB_CUDA(cudaMemcpy(d_hg, hg.data(), n_stages * sizeof(double), cudaMemcpyHostToDevice));
+    const size_t pl = (size_t)v.nz * nyp;
+    const size_t per_step = (size_t)v.n_classes * 6 * pl;
+    NKB_CUDA(cudaMalloc(&m->ftab, (size_t)n_steps * per_step * sizeof(double)));
+    NKB_CUDA(cudaMemset(m->ftab, 0, (size_t)n_steps * per_step * sizeof(double)));
+    const int chunk = 32768;
+    for (int s0 = 0; s0 < n_steps; s0 += chunk) {
+        const int ns = (n_steps - s0 < chunk) ? n_steps - s0 : chunk;
+        if (nkb::launch_step_tables(v, ns, d_t + 2 * s0, d_hg + 2 * s0, nyp, m->ftab + (size_t)s0 * per_step, 0))
+            return 1;
+    }
+    if (nkb::fused_encode_plane_map(v.nz, v.ny, nyp, (size_t)n_steps * v.n_classes * 6, m->ftab, &m->map_ftab)) return 1;
+    if (v.estencil) {
+        NKB_CUDA(cudaMalloc(&m->estp, 3 * pl * sizeof(double)));
+        NKB_CUDA(cudaMemset(m->estp, 0, 3 * pl * sizeof(double)));
+        if (nkb::launch_est_planes(v, nyp, m->estp, 0)) return 1;
+        if (nkb::fused_encode_plane_map(v.nz, v.ny, nyp, 3, m->estp, &m->map_estp)) return 1;
+    }
+    if (v.kind == NKB_MOD_FORCED_FILE) {
+        NKB_CUDA(cudaMemcpy(d_t, t_exp.data(), n_stages * sizeof(double), cudaMemcpyHostToDevice));
+        NKB_CUDA(cudaMalloc(&m->srcp, (size_t)n_stages * pl * sizeof(double)));
+        NKB_CUDA(cudaMemset(m->srcp, 0, (size_t)n_stages * pl * sizeof(double)));
+        for (int s0 = 0; s0 < n_stages; s0 += chunk) {
+            const int ns = (n_stages - s0 < chunk) ? n_stages - s0 : chunk;
+            if (nkb::launch_forcing_planes(v, ns, d_t + s0, nyp, m->srcp + (size_t)s0 * pl, 0)) return 1;
+        }
+        if (nkb::fused_encode_plane_map(v.nz, v.ny, nyp, (size_t)n_stages, m->srcp, &m->map_srcp)) return 1;
+    }
     NKB_CUDA(cudaDeviceSynchronize());
     cudaFree(d_t); cudaFree(d_hg);
     return 0;
@@ -277,8 +333,6 @@ int nkb_model_eval(nkb_model *m, const double *d_x0, double *d_f, double *d_work
         return rc;
     }
 
-    StageArgs a;
-    fill_args(m, a, B, ldb);
     int hist_i = 0;
     auto emit_hist = [&](int step, const double *state) -> int {
         while (hist_i < n_hist && h_hist_steps[hist_i] == step) {
@@ -290,6 +344,34 @@ int nkb_model_eval(nkb_model *m, const double *d_x0, double *d_f, double *d_work
     };
     if (emit_hist(0, d_x0)) return 1;
 
+    if (nkb::fused_step_usable(v, B, ldb, d_x0, d_f, d_work)) {
+        // one launch per time step: both implicit stages fused (nkb_step_fused.cu)
+        if (ensure_fused_tables(m)) return 1;
+        CUtensorMap in_x0, in_f, out_f, in_w, out_w;
+        if (nkb::fused_encode_state_maps(v, B, ldb, d_x0, &in_x0, nullptr)) return 1;
+        if (nkb::fused_encode_state_maps(v, B, ldb, d_f, &in_f, &out_f)) return 1;
+        if (nkb::fused_encode_state_maps(v, B, ldb, w_alt, &in_w, &out_w)) return 1;
+        const double *un = d_x0;
+        for (int n = 0; n < S; ++n) {
+            const bool last = (n == S - 1);
+            double *dest = (((S - 1 - n) & 1) == 0) ? d_f : w_alt;
+            const CUtensorMap &mi = (un == d_x0) ? in_x0 : (un == d_f ? in_f : in_w);
+            const CUtensorMap &mo = (dest == d_f) ? out_f : out_w;
+            if (nkb::launch_step_fused(v, B, S, n, m->h_h[n], m->aff + (size_t)(2 * n) * aff_stride,
+                                       m->aff + (size_t)(2 * n + 1) * aff_stride, mi, mo,
+                                       m->estp ? &m->map_estp : nullptr, m->map_ftab,
+                                       m->srcp ? &m->map_srcp : nullptr, st))
+                return 1;
+            un = dest;
+            if (n_hist > 0 && !last && emit_hist(n + 1, dest)) return 1;
+        }
+        if (nkb::launch_sub_inplace(d_f, d_x0, nstate, st)) return 1;
+        NKB_CUDA(cudaGetLastError());
+        return 0;
+    }
+
+    StageArgs a;
+    fill_args(m, a, B, ldb);
     const double *un = d_x0;
     for (int n = 0; n < S; ++n) {
         const double h = m->h_h[n];

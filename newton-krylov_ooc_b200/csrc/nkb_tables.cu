@@ -82,6 +82,26 @@ __device__ __forceinline__ double surf_flux(const ModelDev &m, double time) {
     return interp_pw(time, m.flux_t, m.flux_v, m.n_flux_pts);
 }
 
+// raw coefficients (sub, diag, sup) of the vertical operator L of class c at level k, column j
+// (vert_mix.py:140-188 + vertical part of advection.py:111-179 + module extras)
+__device__ __forceinline__ void vert_coeffs(const ModelDev &m, int k, int j, int c, double mc_up, double mc_dn,
+                                            double &sub, double &diag, double &sup) {
+    const int nz = m.nz, ny = m.ny;
+    const double w_up = (k > 0 && m.wvel) ? m.wvel[k * ny + j] : 0.0;
+    const double w_dn = (k < nz - 1 && m.wvel) ? m.wvel[(k + 1) * ny + j] : 0.0;
+    const double dzr = m.dz_r[k];
+    sub = (k > 0) ? dzr * (-0.5 * w_up + mc_up) : 0.0;
+    sup = (k < nz - 1) ? dzr * (0.5 * w_dn + mc_dn) : 0.0;
+    diag = dzr * (0.5 * w_dn - 0.5 * w_up - mc_dn - mc_up);
+    if (k == 0) diag += m.surf_diag[c];
+    diag += m.decay[c];
+    const double sv = m.sink_vel[c];
+    if (sv != 0.0) {
+        if (k > 0) sub += sv * dzr;
+        if (k < nz - 1) diag -= sv * dzr;
+    }
+}
+
 // mode 0: raw (sub, diag, sup, aff);  mode 1: factored (m, ib, g, hg*aff) of I - hg*L
 // stage times/hg: t_stage[s], hg_stage[s]
 __global__ void stage_tables_kernel(ModelDev m, int n_stages, const double *__restrict__ t_stage,
@@ -100,20 +120,9 @@ __global__ void stage_tables_kernel(ModelDev m, int n_stages, const double *__re
     double prev_ib[NKB_MAX_CLASSES], prev_c[NKB_MAX_CLASSES];
     for (int k = 0; k < nz; ++k) {
         const double mc_dn = (k < nz - 1) ? mixing_coeff_edge(m, bld, k + 1, j) : 0.0;
-        const double w_up = (k > 0 && m.wvel) ? m.wvel[k * ny + j] : 0.0;
-        const double w_dn = (k < nz - 1 && m.wvel) ? m.wvel[(k + 1) * ny + j] : 0.0;
-        const double dzr = m.dz_r[k];
         for (int c = 0; c < nc; ++c) {
-            double sub = (k > 0) ? dzr * (-0.5 * w_up + mc_up) : 0.0;
-            double sup = (k < nz - 1) ? dzr * (0.5 * w_dn + mc_dn) : 0.0;
-            double diag = dzr * (0.5 * w_dn - 0.5 * w_up - mc_dn - mc_up);
-            if (k == 0) diag += m.surf_diag[c];
-            diag += m.decay[c];
-            const double sv = m.sink_vel[c];
-            if (sv != 0.0) {
-                if (k > 0) sub += sv * dzr;
-                if (k < nz - 1) diag -= sv * dzr;
-            }
+            double sub, diag, sup;
+            vert_coeffs(m, k, j, c, mc_up, mc_dn, sub, diag, sup);
             double *base = tri + ((((size_t)s * nc + c) * plane) + (size_t)k * ny + j) * 4;
             base[3] = 0.0;
             if (mode == 0) {
@@ -144,6 +153,100 @@ __global__ void stage_tables_kernel(ModelDev m, int n_stages, const double *__re
     }
 }
 
+// Tables of the fused step kernel (nkb_step_fused.cu): structure-of-arrays planes [nz][nyp]
+// (table column = j + 1: one zero column on the left; nyp >= ny + 1 even: 16-byte row pitch for TMA), per (step, class) the six planes
+//   0: m1  1: ib1  2: g1     LU (top-down) factors of I - hg*L(t_n + gamma h)   — same values as tri
+//   3: m2  4: ib2  5: g2     UL (bottom-up) factors of I - hg*L(t_n + h):
+//        elimination  y_k = r_k - m2_k y_{k+1} (k = nz-2..0),  substitution x_k = ib2_k y_k - g2_k x_{k-1}
+// The stage-2 system is eliminated upwards so that it can consume the stage-1 solution level by
+// level while that is being back-substituted upwards.
+__global__ void step_tables_kernel(ModelDev m, int n_steps, const double *__restrict__ t_stage,
+                                   const double *__restrict__ hg_stage, int nyp, double *__restrict__ ftab) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = blockIdx.y;
+    if (j >= m.ny || s >= n_steps) return;
+    const int nz = m.nz, nc = m.n_classes;
+    const size_t pl = (size_t)nz * nyp;
+    for (int stage = 0; stage < 2; ++stage) {
+        const double time = t_stage[2 * s + stage];
+        const double hg = hg_stage[2 * s + stage];
+        const double bld = bldepth(m, time, j);
+        double mc_up = 0.0;
+        double prev_ib[NKB_MAX_CLASSES], prev_c[NKB_MAX_CLASSES];
+        for (int k = 0; k < nz; ++k) {
+            const double mc_dn = (k < nz - 1) ? mixing_coeff_edge(m, bld, k + 1, j) : 0.0;
+            for (int c = 0; c < nc; ++c) {
+                double sub, diag, sup;
+                vert_coeffs(m, k, j, c, mc_up, mc_dn, sub, diag, sup);
+                const double a = -hg * sub, b = 1.0 - hg * diag, cc = -hg * sup;
+                double *base = ftab + ((size_t)s * nc + c) * 6 * pl + (size_t)k * nyp + j + 1;
+                if (stage == 0) {
+                    double mk = 0.0, beta = b;
+                    if (k > 0) {
+                        mk = a * prev_ib[c];
+                        beta = b - mk * prev_c[c];
+                    }
+                    const double ib = 1.0 / beta;
+                    base[0 * pl] = mk;
+                    base[1 * pl] = ib;
+                    base[2 * pl] = (k < nz - 1) ? cc * ib : 0.0;
+                    prev_ib[c] = ib;
+                    prev_c[c] = cc;
+                } else {  // raw rows first, factored bottom-up below
+                    base[3 * pl] = a;
+                    base[4 * pl] = b;
+                    base[5 * pl] = cc;
+                }
+            }
+            mc_up = mc_dn;
+        }
+    }
+    for (int c = 0; c < nc; ++c) {
+        double ib_next = 0.0, a_next = 0.0;
+        for (int k = nz - 1; k >= 0; --k) {
+            double *base = ftab + ((size_t)s * nc + c) * 6 * pl + (size_t)k * nyp + j + 1;
+            const double a = base[3 * pl], b = base[4 * pl], cc = base[5 * pl];
+            double mk = 0.0, beta = b;
+            if (k < nz - 1) {
+                mk = cc * ib_next;
+                beta = b - mk * a_next;
+            }
+            const double ib = 1.0 / beta;
+            base[3 * pl] = mk;
+            base[4 * pl] = ib;
+            base[5 * pl] = (k > 0) ? a * ib : 0.0;
+            ib_next = ib;
+            a_next = a;
+        }
+    }
+}
+
+// SoA copies of time-invariant / forcing tables with the padded row pitch nyp
+__global__ void est_planes_kernel(int nz, int ny, int nyp, const double *__restrict__ est4,
+                                  double *__restrict__ out /* [3][nz][nyp] */) {
+    const size_t cell = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= (size_t)nz * ny) return;
+    const int k = (int)(cell / ny), j = (int)(cell % ny);
+    for (int q = 0; q < 3; ++q) out[((size_t)q * nz + k) * nyp + j + 1] = est4[cell * 4 + q];
+}
+
+// forcing at the two explicit stage times of every step: out[step][2][nz][nyp]
+__global__ void forcing_planes_kernel(ModelDev m, int n_times, const double *__restrict__ t_eval, int nyp,
+                                      double *__restrict__ out) {
+    const size_t plane = (size_t)m.nz * m.ny;
+    const size_t cell = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = blockIdx.y;
+    if (cell >= plane || s >= n_times) return;
+    const double t = t_eval[s];
+    int i = 0;
+    while (i < m.n_frc - 2 && t >= m.frc_time[i + 1]) ++i;
+    const double lo = m.frc_data[(size_t)i * plane + cell];
+    const double hi = m.frc_data[(size_t)(i + 1) * plane + cell];
+    const double slope = (hi - lo) / (m.frc_time[i + 1] - m.frc_time[i]);
+    const int k = (int)(cell / m.ny), j = (int)(cell % m.ny);
+    out[((size_t)s * m.nz + k) * nyp + j + 1] = slope * (t - m.frc_time[i]) + lo;
+}
+
 __global__ void mixing_coeff_kernel(ModelDev m, double time, double *__restrict__ out) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= m.ny) return;
@@ -172,6 +275,32 @@ int launch_stage_tables(const ModelDev &m, int n_stages, const double *d_t, cons
                         double *tri, double *aff, cudaStream_t st) {
     dim3 block(64), grid((m.ny + 63) / 64, n_stages);
     stage_tables_kernel<<<grid, block, 0, st>>>(m, n_stages, d_t, d_hg, mode, tri, aff);
+    count_launch();
+    NKB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_step_tables(const ModelDev &m, int n_steps, const double *d_t, const double *d_hg, int nyp, double *ftab,
+                       cudaStream_t st) {
+    dim3 block(64), grid((m.ny + 63) / 64, n_steps);
+    step_tables_kernel<<<grid, block, 0, st>>>(m, n_steps, d_t, d_hg, nyp, ftab);
+    count_launch();
+    NKB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_est_planes(const ModelDev &m, int nyp, double *out, cudaStream_t st) {
+    const size_t plane = (size_t)m.nz * m.ny;
+    est_planes_kernel<<<(unsigned)((plane + 127) / 128), 128, 0, st>>>(m.nz, m.ny, nyp, m.estencil, out);
+    count_launch();
+    NKB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_forcing_planes(const ModelDev &m, int n_times, const double *d_t, int nyp, double *out, cudaStream_t st) {
+    const size_t plane = (size_t)m.nz * m.ny;
+    dim3 block(128), grid((unsigned)((plane + 127) / 128), n_times);
+    forcing_planes_kernel<<<grid, block, 0, st>>>(m, n_times, d_t, nyp, out);
     count_launch();
     NKB_CUDA(cudaGetLastError());
     return 0;

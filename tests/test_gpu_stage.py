@@ -134,3 +134,49 @@ def test_hist_snapshots_and_host_path():
     xm = np.ascontiguousarray(np.moveaxis(x, -1, 0))
     fh = m.eval_host(xm).numpy()
     np.testing.assert_allclose(np.moveaxis(fh, 0, -1), want, rtol=0, atol=1e-11 * np.abs(want).max())
+
+
+@pytest.mark.parametrize("kind", ["iage", "forced", "iage_columns"])
+@pytest.mark.parametrize("nz,ny,B", [(21, 33, 20), (37, 15, 50), (128, 16, 9), (10, 7, 70)])
+def test_fused_step_kernel_matches_scheme_oracle(kind, nz, ny, B, monkeypatch):
+    """the fused step kernel (one launch per time step: TMEM-resident intermediates, TMA-fed
+    sweeps; nkb_step_fused.cu) against the numpy statement of the scheme, and against the
+    stage-per-launch path.  Grids cover several column tiles (ny > 14), a partial last tile,
+    a level count that is not a multiple of the chunk (4) and the TMEM capacity limit (128)."""
+    from oracle import imex_oracle as im
+    from oracle import nk_oracle as o
+    from nk_ooc_b200 import _lib
+    from nk_ooc_b200.py_driver_2d import modules
+
+    rng = np.random.default_rng(21)
+    if kind == "iage_columns":
+        g, tr = _grid(nz, ny, vvel=0.0, kh=0.0)
+    else:
+        g, tr = _grid(nz, ny)
+    nsteps = 6
+    if kind in ("iage", "iage_columns"):
+        mod, m = im.Module2D("iage", g), modules.iage_model(tr)
+    else:
+        times, data = _forcing(g, rng)
+        f = o.Forced2D(g, restore_rate_10m=1.0 / 3600.0, restore_const=1.0, sms_opt="file", sms_times=times,
+                       sms_data=data, sink_thres=0.05)
+        mod = im.Module2D("forced", g, forced=f)
+        m = modules.forced_model(tr, "const", 1.0, 1.0 / 3600.0, "file", sms_times=times, sms_data=data,
+                                 sink_thres=0.05)
+    x = np.abs(rng.normal(size=(mod.T, g.nz, g.ny, B))) * 0.5
+    m.set_uniform_schedule(nsteps)
+    lib = _lib.load()
+    xd = _to_dev(x)
+    monkeypatch.setenv("NKB_FUSED", "1")
+    m.eval(xd, B)  # the first fused evaluation also builds the step tables
+    n0 = lib.nkb_launch_count()
+    got = m.eval(xd, B).cpu().numpy()[..., :B]
+    assert lib.nkb_launch_count() - n0 == nsteps + 1, "the fused step kernel did not run"
+    monkeypatch.setenv("NKB_FUSED", "0")
+    n0 = lib.nkb_launch_count()
+    unfused = m.eval(xd, B).cpu().numpy()[..., :B]
+    assert lib.nkb_launch_count() - n0 == 2 * nsteps
+    want = im.model_year_2d(mod, x, nsteps)
+    scale = np.abs(want).max()
+    np.testing.assert_allclose(got, want, rtol=0.0, atol=1e-10 * scale)
+    np.testing.assert_allclose(got, unfused, rtol=0.0, atol=1e-10 * scale)
