@@ -39,12 +39,11 @@
 
 namespace nkb {
 
-constexpr int FS_KC = 4;      // levels per chunk (one tcgen05 x16 access = 4 levels x 2 members)
-constexpr int FS_COLS = 16;   // stage-1 columns per tile (= lanes per member pair)
+constexpr int FS_KC = 4;      // levels per chunk
+constexpr int FS_COLS = 16;   // stage-1 columns per tile
 constexpr int FS_UCOLS = 18;  // state columns per tile (halo of 2)
 constexpr int FS_JT = 14;     // max interior columns per tile
-constexpr int FS_MEM = 16;    // members per tile
-constexpr int FS_NCW = 4;     // consumer warps (one per TMEM lane quarter)
+constexpr int FS_MEM = 16;    // members per tile (128-byte rows)
 constexpr int FS_NS = 8;      // load ring slots
 constexpr int FS_NO = 3;      // output staging slots
 constexpr int FS_UBYTES = FS_KC * FS_UCOLS * FS_MEM * 8;  // 9216
@@ -52,19 +51,22 @@ constexpr int FS_PLANE = FS_KC * FS_COLS * 8;             // 512
 constexpr int FS_NPLANES = 8;
 constexpr int FS_SLOT = FS_UBYTES + FS_NPLANES * FS_PLANE;  // 13312 = 13 * 1024
 constexpr int FS_OUT = FS_KC * FS_JT * FS_MEM * 8;          // 7168 = 7 * 1024
-constexpr int FS_SMEM = 1024 + FS_NS * FS_SLOT + FS_NO * FS_OUT + 1024;
-constexpr int FS_THREADS = (FS_NCW + 2) * 32;
+constexpr int FS_SMEM = 1024 + FS_NS * FS_SLOT + FS_NO * FS_OUT;
 static_assert(FS_SLOT % 1024 == 0 && FS_OUT % 1024 == 0, "swizzled boxes need 1024-byte aligned bases");
+// consumer warps: MPT members per thread; 256 (column, member) pairs per tile in both layouts
+//   MPT = 2: 4 warps, lane = column + 16*pair           (fewest instructions per member)
+//   MPT = 1: 8 warps, lane = 2*column + (member & 1)    (two warps per scheduler: latency hiding)
+__host__ __device__ constexpr int fs_ncw(int mpt) { return 8 / mpt; }
+__host__ __device__ constexpr int fs_threads(int mpt) { return (fs_ncw(mpt) + 2) * 32; }
 
 struct StepArgs {
     int nz, ny, B, T, ncls, n_steps;
     int nct, jt, nmb, ntiles;  // column tiles, interior columns per tile, member blocks, total
     int step;
-    int dbg;  // debug switches (NKB_FUSED_DBG): 1 no TMEM, 2 no TMA store, 4 single cache hint, 8 no alloc
     int class_of[NKB_MAX_TRACERS];
     double src_const[NKB_MAX_TRACERS];
     double sink_thres_r;
-    double hg, a0, a1, r, he1;  // gamma*h; stage-2 weights (see nkb_api.cu)
+    double hg, a0, a1, r, he1;  // gamma*h; stage-2 weights (see launch_step_fused)
     const double *aff1, *aff2;  // [ncls][ny] of the two stages of this step
 };
 
@@ -72,83 +74,92 @@ struct StepMaps {
     CUtensorMap uin, uout, est, ftab, src;
 };
 
-struct D2 {
-    double x, y;
-};
-
 // ---- PTX wrappers ------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t fs_smem_u32(const void *p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
-__device__ __forceinline__ void fs_mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(fs_smem_u32(bar)), "r"(count));
+__device__ __forceinline__ void fs_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-__device__ __forceinline__ void fs_mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fs_smem_u32(bar)), "r"(bytes)
-                 : "memory");
+__device__ __forceinline__ void fs_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void fs_mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(fs_smem_u32(bar)) : "memory");
+__device__ __forceinline__ void fs_mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void fs_mbar_wait(uint64_t *bar, uint32_t parity) {
+// try_wait with a suspend-time hint: the waiting warp sleeps in hardware instead of burning issue
+// slots of the consumer warps that share its scheduler
+template <int HINT_NS>
+__device__ __forceinline__ void fs_mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok = 0;
-    const uint32_t addr = fs_smem_u32(bar);
     do {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(ok)
-            : "r"(addr), "r"(parity)
+            : "r"(bar), "r"(parity), "r"(HINT_NS)
             : "memory");
     } while (!ok);
 }
-__device__ __forceinline__ void fs_tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1,
+__device__ __forceinline__ void fs_tma_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1,
                                                int c2, int c3, uint64_t hint) {
     asm volatile(
         "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
         " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
         :
-        : "r"(fs_smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(fs_smem_u32(bar)), "r"(c0), "r"(c1),
-          "r"(c2), "r"(c3), "l"(hint)
+        : "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(hint)
         : "memory");
 }
-__device__ __forceinline__ void fs_tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1,
+__device__ __forceinline__ void fs_tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1,
                                                int c2, uint64_t hint) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
         " [%0], [%1, {%3, %4, %5}], [%2], %6;"
         :
-        : "r"(fs_smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(fs_smem_u32(bar)), "r"(c0), "r"(c1),
-          "r"(c2), "l"(hint)
+        : "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(hint)
         : "memory");
 }
-__device__ __forceinline__ void fs_tma_store_4d(const CUtensorMap *map, const void *src, int c0, int c1, int c2,
+__device__ __forceinline__ void fs_tma_store_4d(const CUtensorMap *map, uint32_t src, int c0, int c1, int c2,
                                                 int c3) {
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                  :
-                 : "l"(reinterpret_cast<uint64_t>(map)), "r"(fs_smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                  : "memory");
 }
-__device__ __forceinline__ void fs_tmem_st16(uint32_t taddr, const D2 (&v)[FS_KC]) {
+
+// ---- tensor memory as a per-thread scratchpad: W 32-bit columns of this thread's TMEM lane --------
+template <int W>
+struct Raw {
+    uint32_t w[W];
+};
+__device__ __forceinline__ void fs_tmem_st(uint32_t taddr, const Raw<8> &r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 :
+                 : "r"(taddr), "r"(r.w[0]), "r"(r.w[1]), "r"(r.w[2]), "r"(r.w[3]), "r"(r.w[4]), "r"(r.w[5]),
+                   "r"(r.w[6]), "r"(r.w[7])
+                 : "memory");
+}
+__device__ __forceinline__ void fs_tmem_st(uint32_t taddr, const Raw<16> &r) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
         "%14, %15, %16};"
         :
-        : "r"(taddr), "r"(__double2loint(v[0].x)), "r"(__double2hiint(v[0].x)), "r"(__double2loint(v[0].y)),
-          "r"(__double2hiint(v[0].y)), "r"(__double2loint(v[1].x)), "r"(__double2hiint(v[1].x)),
-          "r"(__double2loint(v[1].y)), "r"(__double2hiint(v[1].y)), "r"(__double2loint(v[2].x)),
-          "r"(__double2hiint(v[2].x)), "r"(__double2loint(v[2].y)), "r"(__double2hiint(v[2].y)),
-          "r"(__double2loint(v[3].x)), "r"(__double2hiint(v[3].x)), "r"(__double2loint(v[3].y)),
-          "r"(__double2hiint(v[3].y))
+        : "r"(taddr), "r"(r.w[0]), "r"(r.w[1]), "r"(r.w[2]), "r"(r.w[3]), "r"(r.w[4]), "r"(r.w[5]), "r"(r.w[6]),
+          "r"(r.w[7]), "r"(r.w[8]), "r"(r.w[9]), "r"(r.w[10]), "r"(r.w[11]), "r"(r.w[12]), "r"(r.w[13]),
+          "r"(r.w[14]), "r"(r.w[15])
         : "memory");
 }
-// the load is asynchronous: the raw words are only valid after fs_tmem_wait_ld (which takes them
-// as in/out operands so that no use can be scheduled ahead of the wait)
-struct Raw16 {
-    uint32_t w[16];
-};
-__device__ __forceinline__ void fs_tmem_ld16(uint32_t taddr, Raw16 &r) {
+// the load is asynchronous: the words are only valid after fs_tmem_wait_ld, which takes them as
+// in/out operands so that no use can be scheduled ahead of the wait
+__device__ __forceinline__ void fs_tmem_ld(uint32_t taddr, Raw<8> &r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]),
+                   "=r"(r.w[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void fs_tmem_ld(uint32_t taddr, Raw<16> &r) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
         "%15}, [%16];"
@@ -158,7 +169,14 @@ __device__ __forceinline__ void fs_tmem_ld16(uint32_t taddr, Raw16 &r) {
         : "r"(taddr)
         : "memory");
 }
-__device__ __forceinline__ void fs_tmem_wait_ld(Raw16 &r) {
+__device__ __forceinline__ void fs_tmem_wait_ld(Raw<8> &r) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r.w[0]), "+r"(r.w[1]), "+r"(r.w[2]), "+r"(r.w[3]), "+r"(r.w[4]), "+r"(r.w[5]), "+r"(r.w[6]),
+                   "+r"(r.w[7])
+                 :
+                 : "memory");
+}
+__device__ __forceinline__ void fs_tmem_wait_ld(Raw<16> &r) {
     asm volatile("tcgen05.wait::ld.sync.aligned;"
                  : "+r"(r.w[0]), "+r"(r.w[1]), "+r"(r.w[2]), "+r"(r.w[3]), "+r"(r.w[4]), "+r"(r.w[5]), "+r"(r.w[6]),
                    "+r"(r.w[7]), "+r"(r.w[8]), "+r"(r.w[9]), "+r"(r.w[10]), "+r"(r.w[11]), "+r"(r.w[12]),
@@ -166,41 +184,110 @@ __device__ __forceinline__ void fs_tmem_wait_ld(Raw16 &r) {
                  :
                  : "memory");
 }
-__device__ __forceinline__ void fs_unpack(const Raw16 &r, D2 (&v)[FS_KC]) {
-#pragma unroll
-    for (int q = 0; q < FS_KC; ++q) {
-        v[q].x = __hiloint2double((int)r.w[4 * q + 1], (int)r.w[4 * q]);
-        v[q].y = __hiloint2double((int)r.w[4 * q + 3], (int)r.w[4 * q + 2]);
-    }
-}
 __device__ __forceinline__ void fs_tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ D2 fs_fma(double a, D2 x, D2 y) { return {fma(a, x.x, y.x), fma(a, x.y, y.y)}; }
-__device__ __forceinline__ D2 fs_mul(double a, D2 x) { return {a * x.x, a * x.y}; }
-__device__ __forceinline__ D2 fs_add(D2 x, D2 y) { return {x.x + y.x, x.y + y.y}; }
-__device__ __forceinline__ D2 fs_sub(D2 x, D2 y) { return {x.x - y.x, x.y - y.y}; }
-__device__ __forceinline__ D2 fs_ld(const unsigned char *p) {
-    const double2 v = *reinterpret_cast<const double2 *>(p);
-    return {v.x, v.y};
+// ---- MPT members of one (level, column) ---------------------------------------------------------
+template <int M>
+struct Vd {
+    double v[M];
+};
+template <int M>
+__device__ __forceinline__ Vd<M> fs_splat(double a) {
+    Vd<M> r;
+#pragma unroll
+    for (int i = 0; i < M; ++i) r.v[i] = a;
+    return r;
 }
-__device__ __forceinline__ D2 fs_shfl_up(D2 v) {
-    return {__shfl_up_sync(0xffffffffu, v.x, 1, 16), __shfl_up_sync(0xffffffffu, v.y, 1, 16)};
+template <int M>
+__device__ __forceinline__ Vd<M> fs_fma(double a, Vd<M> x, Vd<M> y) {
+    Vd<M> r;
+#pragma unroll
+    for (int i = 0; i < M; ++i) r.v[i] = fma(a, x.v[i], y.v[i]);
+    return r;
 }
-__device__ __forceinline__ D2 fs_shfl_down(D2 v) {
-    return {__shfl_down_sync(0xffffffffu, v.x, 1, 16), __shfl_down_sync(0xffffffffu, v.y, 1, 16)};
+template <int M>
+__device__ __forceinline__ Vd<M> fs_mul(double a, Vd<M> x) {
+    Vd<M> r;
+#pragma unroll
+    for (int i = 0; i < M; ++i) r.v[i] = a * x.v[i];
+    return r;
+}
+template <int M>
+__device__ __forceinline__ Vd<M> fs_add(Vd<M> x, Vd<M> y) {
+    Vd<M> r;
+#pragma unroll
+    for (int i = 0; i < M; ++i) r.v[i] = x.v[i] + y.v[i];
+    return r;
+}
+template <int M>
+__device__ __forceinline__ Vd<M> fs_sub(Vd<M> x, Vd<M> y) {
+    Vd<M> r;
+#pragma unroll
+    for (int i = 0; i < M; ++i) r.v[i] = x.v[i] - y.v[i];
+    return r;
+}
+__device__ __forceinline__ Vd<2> fs_ld(const unsigned char *p, Vd<2> *) {
+    const double2 t = *reinterpret_cast<const double2 *>(p);
+    return {{t.x, t.y}};
+}
+__device__ __forceinline__ Vd<1> fs_ld(const unsigned char *p, Vd<1> *) {
+    return {{*reinterpret_cast<const double *>(p)}};
+}
+__device__ __forceinline__ void fs_st(unsigned char *p, Vd<2> v) {
+    *reinterpret_cast<double2 *>(p) = make_double2(v.v[0], v.v[1]);
+}
+__device__ __forceinline__ void fs_st(unsigned char *p, Vd<1> v) { *reinterpret_cast<double *>(p) = v.v[0]; }
+// value of the neighbour column: lane - DELTA / lane + DELTA (lanes at the tile edge get their own)
+template <int M, int DELTA, int WIDTH>
+__device__ __forceinline__ Vd<M> fs_shfl_up(Vd<M> x) {
+    Vd<M> r;
+#pragma unroll
+    for (int i = 0; i < M; ++i) r.v[i] = __shfl_up_sync(0xffffffffu, x.v[i], DELTA, WIDTH);
+    return r;
+}
+template <int M, int DELTA, int WIDTH>
+__device__ __forceinline__ Vd<M> fs_shfl_down(Vd<M> x) {
+    Vd<M> r;
+#pragma unroll
+    for (int i = 0; i < M; ++i) r.v[i] = __shfl_down_sync(0xffffffffu, x.v[i], DELTA, WIDTH);
+    return r;
+}
+template <int M>
+__device__ __forceinline__ void fs_pack(const Vd<M> (&v)[FS_KC], Raw<FS_KC * 2 * M> &r) {
+#pragma unroll
+    for (int q = 0; q < FS_KC; ++q)
+#pragma unroll
+        for (int i = 0; i < M; ++i) {
+            r.w[(q * M + i) * 2] = (uint32_t)__double2loint(v[q].v[i]);
+            r.w[(q * M + i) * 2 + 1] = (uint32_t)__double2hiint(v[q].v[i]);
+        }
+}
+template <int M>
+__device__ __forceinline__ void fs_unpack(const Raw<FS_KC * 2 * M> &r, Vd<M> (&v)[FS_KC]) {
+#pragma unroll
+    for (int q = 0; q < FS_KC; ++q)
+#pragma unroll
+        for (int i = 0; i < M; ++i)
+            v[q].v[i] = __hiloint2double((int)r.w[(q * M + i) * 2 + 1], (int)r.w[(q * M + i) * 2]);
 }
 
 // explicit source of one tracer (iage.py:39 constant; forced.py:141-151 forcing record with the
 // sink_thres limiter) — same expressions as explicit_sources() in nkb_stage_dev.cuh
-template <int KIND>
-__device__ __forceinline__ D2 fs_source(double srcc, double thr_r, double frc, D2 c) {
+template <int KIND, int M>
+__device__ __forceinline__ Vd<M> fs_source(double srcc, double thr_r, double frc, Vd<M> c) {
+    Vd<M> r;
     if constexpr (KIND == NKB_MOD_LINEAR) {
-        return {srcc, srcc};
+#pragma unroll
+        for (int i = 0; i < M; ++i) r.v[i] = srcc;
     } else {
-        const double qx = thr_r * c.x, qy = thr_r * c.y;
         const bool lim = (thr_r > 0.0 && frc < 0.0);
-        return {(lim && qx > 0.0 && qx < 1.0) ? frc * qx : frc, (lim && qy > 0.0 && qy < 1.0) ? frc * qy : frc};
+#pragma unroll
+        for (int i = 0; i < M; ++i) {
+            const double q = thr_r * c.v[i];
+            r.v[i] = (lim && q > 0.0 && q < 1.0) ? frc * q : frc;
+        }
     }
+    return r;
 }
 
 constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
@@ -211,33 +298,38 @@ constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
 //   sweep A: 0 eL, 1 eC, 2 eR, 3 m1, 4 frc(t_n)
 //   sweep B: 0 eL, 1 eC, 2 eR, 3 ib1, 4 g1, 5 m1, 6 m2, 7 frc(t_n + gamma h)
 //   sweep C: 0 ib2, 1 g2
-template <int KIND, bool HAS_E>
-__global__ void __launch_bounds__(FS_THREADS, 1) step_fused_kernel(const StepArgs p,
-                                                                    const __grid_constant__ StepMaps maps) {
-    extern __shared__ unsigned char fs_smem[];
-    unsigned char *base =
-        reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(fs_smem) + 1023) & ~uintptr_t(1023));
-    uint64_t *full = reinterpret_cast<uint64_t *>(base);
-    uint64_t *empty = full + FS_NS;
-    uint64_t *ofull = empty + FS_NS;
-    uint64_t *oempty = ofull + FS_NO;
-    uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(base + 960);
-    unsigned char *ring = base + 1024;
+template <int KIND, bool HAS_E, int MPT>
+__global__ void __launch_bounds__(fs_threads(MPT), 1) step_fused_kernel(const StepArgs p,
+                                                                         const __grid_constant__ StepMaps maps) {
+    constexpr int NCW = fs_ncw(MPT);
+    constexpr int W = FS_KC * 2 * MPT;  // TMEM columns per chunk and thread
+    using V = Vd<MPT>;
+    // dynamic shared memory is the only shared allocation of this kernel: its window offset is a
+    // multiple of 1024 (checked), which the 128-byte-swizzled boxes rely on.  Offsets from the
+    // symbol keep the address space visible to the compiler (LDS/STS with immediate offsets).
+    extern __shared__ __align__(1024) unsigned char fs_smem[];
+    const uint32_t smem0 = fs_smem_u32(fs_smem);
+    if (smem0 & 1023u) __trap();
+    const uint32_t bar_full = smem0, bar_empty = smem0 + 8 * FS_NS, bar_ofull = smem0 + 16 * FS_NS,
+                   bar_oempty = smem0 + 16 * FS_NS + 8 * FS_NO;
+    uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(fs_smem + 960);
+    unsigned char *ring = fs_smem + 1024;
     unsigned char *oring = ring + FS_NS * FS_SLOT;
+    const uint32_t ring_a = smem0 + 1024, oring_a = ring_a + FS_NS * FS_SLOT;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < FS_NS; ++s) {
-            fs_mbar_init(&full[s], 1);
-            fs_mbar_init(&empty[s], FS_NCW);
+            fs_mbar_init(bar_full + 8 * s, 1);
+            fs_mbar_init(bar_empty + 8 * s, NCW);
         }
         for (int s = 0; s < FS_NO; ++s) {
-            fs_mbar_init(&ofull[s], FS_NCW);
-            fs_mbar_init(&oempty[s], 1);
+            fs_mbar_init(bar_ofull + 8 * s, NCW);
+            fs_mbar_init(bar_oempty + 8 * s, 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0 && !(p.dbg & 8)) {
+    if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(
                          fs_smem_u32(tmem_holder))
                      : "memory");
@@ -248,31 +340,15 @@ __global__ void __launch_bounds__(FS_THREADS, 1) step_fused_kernel(const StepArg
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(tmem_holder);
 
-    const uint64_t hN = (p.dbg & 4) ? kEvictFirst : kEvictNormal, hL = (p.dbg & 4) ? kEvictFirst : kEvictLast;
     const int nz = p.nz, ny = p.ny;
     const int nchunk = (nz + FS_KC - 1) / FS_KC;
     constexpr int NPA = (HAS_E ? 3 : 0) + 1 + (KIND == NKB_MOD_FORCED_FILE ? 1 : 0);
     constexpr int NPB = (HAS_E ? 3 : 0) + 4 + (KIND == NKB_MOD_FORCED_FILE ? 1 : 0);
 
-    if (warp == FS_NCW) {
+    if (warp == NCW) {
         // ===== producer: one lane issues every TMA load of this CTA, in consumption order =====
         if (lane == 0) {
             uint32_t g = 0;
-            const bool no4 = (p.dbg & 16) != 0, no3 = (p.dbg & 32) != 0;
-            auto fs_tma_load_4d = [&](void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3,
-                                      uint64_t hint) {
-                if (!no4) nkb::fs_tma_load_4d(dst, map, bar, c0, c1, c2, c3, hint);
-            };
-            auto fs_tma_load_3d = [&](void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2,
-                                      uint64_t hint) {
-                if (!no3) nkb::fs_tma_load_3d(dst, map, bar, c0, c1, c2, hint);
-            };
-            auto fs_mbar_expect_tx = [&](uint64_t *bar, uint32_t bytes) {
-                uint32_t b = 0;
-                if (!no4 && bytes > 2 * FS_PLANE) b += FS_UBYTES;
-                if (!no3) b += (bytes > 2 * FS_PLANE) ? bytes - FS_UBYTES : bytes;
-                nkb::fs_mbar_expect_tx(bar, b);
-            };
             for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
                 const int mb = tile % p.nmb;
                 const int ct = (tile / p.nmb) % p.nct;
@@ -284,47 +360,46 @@ __global__ void __launch_bounds__(FS_THREADS, 1) step_fused_kernel(const StepArg
                         const int c = (sweep == 1) ? nchunk - 1 - cc : cc;
                         const int k0 = c * FS_KC;
                         const uint32_t s = g % FS_NS, ph = (g / FS_NS) & 1;
-                        fs_mbar_wait(&empty[s], ph ^ 1);
-                        unsigned char *sb = ring + s * FS_SLOT;
-                        unsigned char *pl = sb + FS_UBYTES;
+                        fs_mbar_wait<2000>(bar_empty + 8 * s, ph ^ 1);
+                        const uint32_t sb = ring_a + s * FS_SLOT;
+                        const uint32_t pl = sb + FS_UBYTES;
+                        const uint32_t fb = bar_full + 8 * s;
                         if (sweep == 0) {
-                            fs_mbar_expect_tx(&full[s], FS_UBYTES + NPA * FS_PLANE);
-                            fs_tma_load_4d(sb, &maps.uin, &full[s], m0, j0 - 2, k0, tr, hN);
+                            fs_mbar_expect_tx(fb, FS_UBYTES + NPA * FS_PLANE);
+                            fs_tma_load_4d(sb, &maps.uin, fb, m0, j0 - 2, k0, tr, kEvictNormal);
                             if constexpr (HAS_E) {
 #pragma unroll
                                 for (int q = 0; q < 3; ++q)
-                                    fs_tma_load_3d(pl + q * FS_PLANE, &maps.est, &full[s], j0, k0, q, hL);
+                                    fs_tma_load_3d(pl + q * FS_PLANE, &maps.est, fb, j0, k0, q, kEvictLast);
                             }
-                            fs_tma_load_3d(pl + 3 * FS_PLANE, &maps.ftab, &full[s], j0, k0, zt + 0, hL);
+                            fs_tma_load_3d(pl + 3 * FS_PLANE, &maps.ftab, fb, j0, k0, zt + 0, kEvictLast);
                             if constexpr (KIND == NKB_MOD_FORCED_FILE)
-                                fs_tma_load_3d(pl + 4 * FS_PLANE, &maps.src, &full[s], j0, k0, 2 * p.step,
-                                               hL);
+                                fs_tma_load_3d(pl + 4 * FS_PLANE, &maps.src, fb, j0, k0, 2 * p.step, kEvictLast);
                         } else if (sweep == 1) {
-                            fs_mbar_expect_tx(&full[s], FS_UBYTES + NPB * FS_PLANE);
-                            fs_tma_load_4d(sb, &maps.uin, &full[s], m0, j0 - 2, k0, tr, kEvictFirst);
+                            fs_mbar_expect_tx(fb, FS_UBYTES + NPB * FS_PLANE);
+                            fs_tma_load_4d(sb, &maps.uin, fb, m0, j0 - 2, k0, tr, kEvictFirst);
                             if constexpr (HAS_E) {
 #pragma unroll
                                 for (int q = 0; q < 3; ++q)
-                                    fs_tma_load_3d(pl + q * FS_PLANE, &maps.est, &full[s], j0, k0, q, hL);
+                                    fs_tma_load_3d(pl + q * FS_PLANE, &maps.est, fb, j0, k0, q, kEvictLast);
                             }
-                            fs_tma_load_3d(pl + 3 * FS_PLANE, &maps.ftab, &full[s], j0, k0, zt + 1, hL);
-                            fs_tma_load_3d(pl + 4 * FS_PLANE, &maps.ftab, &full[s], j0, k0, zt + 2, hL);
-                            fs_tma_load_3d(pl + 5 * FS_PLANE, &maps.ftab, &full[s], j0, k0, zt + 0, hL);
-                            fs_tma_load_3d(pl + 6 * FS_PLANE, &maps.ftab, &full[s], j0, k0, zt + 3, hL);
+                            fs_tma_load_3d(pl + 3 * FS_PLANE, &maps.ftab, fb, j0, k0, zt + 1, kEvictLast);
+                            fs_tma_load_3d(pl + 4 * FS_PLANE, &maps.ftab, fb, j0, k0, zt + 2, kEvictLast);
+                            fs_tma_load_3d(pl + 5 * FS_PLANE, &maps.ftab, fb, j0, k0, zt + 0, kEvictLast);
+                            fs_tma_load_3d(pl + 6 * FS_PLANE, &maps.ftab, fb, j0, k0, zt + 3, kEvictLast);
                             if constexpr (KIND == NKB_MOD_FORCED_FILE)
-                                fs_tma_load_3d(pl + 7 * FS_PLANE, &maps.src, &full[s], j0, k0, 2 * p.step + 1,
-                                               hL);
+                                fs_tma_load_3d(pl + 7 * FS_PLANE, &maps.src, fb, j0, k0, 2 * p.step + 1, kEvictLast);
                         } else {
-                            fs_mbar_expect_tx(&full[s], 2 * FS_PLANE);
-                            fs_tma_load_3d(pl + 0 * FS_PLANE, &maps.ftab, &full[s], j0, k0, zt + 4, hL);
-                            fs_tma_load_3d(pl + 1 * FS_PLANE, &maps.ftab, &full[s], j0, k0, zt + 5, hL);
+                            fs_mbar_expect_tx(fb, 2 * FS_PLANE);
+                            fs_tma_load_3d(pl + 0 * FS_PLANE, &maps.ftab, fb, j0, k0, zt + 4, kEvictLast);
+                            fs_tma_load_3d(pl + 1 * FS_PLANE, &maps.ftab, fb, j0, k0, zt + 5, kEvictLast);
                         }
                         ++g;
                     }
                 }
             }
         }
-    } else if (warp == FS_NCW + 1) {
+    } else if (warp == NCW + 1) {
         // ===== store warp: drains the output staging ring with TMA stores =====
         if (lane == 0) {
             uint32_t go = 0;
@@ -334,11 +409,11 @@ __global__ void __launch_bounds__(FS_THREADS, 1) step_fused_kernel(const StepArg
                 const int tr = tile / (p.nmb * p.nct);
                 for (int c = 0; c < nchunk; ++c) {
                     const uint32_t s = go % FS_NO, ph = (go / FS_NO) & 1;
-                    fs_mbar_wait(&ofull[s], ph);
-                    if (!(p.dbg & 2)) fs_tma_store_4d(&maps.uout, oring + s * FS_OUT, mb * FS_MEM, ct * p.jt, c * FS_KC, tr);
+                    fs_mbar_wait<2000>(bar_ofull + 8 * s, ph);
+                    fs_tma_store_4d(&maps.uout, oring_a + s * FS_OUT, mb * FS_MEM, ct * p.jt, c * FS_KC, tr);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                    fs_mbar_arrive(&oempty[s]);
+                    fs_mbar_arrive(bar_oempty + 8 * s);
                     ++go;
                 }
             }
@@ -346,19 +421,23 @@ __global__ void __launch_bounds__(FS_THREADS, 1) step_fused_kernel(const StepArg
         }
     } else {
         // ===== consumers =====
-        const int col = lane & 15;
-        const int c16 = 2 * warp + (lane >> 4);  // 16-byte chunk (member pair) within the 128-byte row
-        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        constexpr int DELTA = (MPT == 2) ? 1 : 2;     // lane distance of the neighbour column
+        constexpr int WIDTH = (MPT == 2) ? 16 : 32;
+        const int col = (MPT == 2) ? (lane & 15) : (lane >> 1);
+        const int c16 = (MPT == 2) ? 2 * warp + (lane >> 4) : warp;  // 16-byte chunk within the 128-byte row
+        const int sub = (MPT == 2) ? 0 : 8 * (lane & 1);             // byte within the chunk
+        // TMEM: lane quarter warp % 4; with 8 warps the upper four use columns 256..511
+        const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 256);
         int offU[FS_KC][3], offO[FS_KC];
 #pragma unroll
         for (int q = 0; q < FS_KC; ++q) {
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
                 const int r = q * FS_UCOLS + col + d;
-                offU[q][d] = 128 * r + 16 * (c16 ^ (r & 7));
+                offU[q][d] = 128 * r + 16 * (c16 ^ (r & 7)) + sub;
             }
             const int ro = q * p.jt + col - 1;
-            offO[q] = 128 * ro + 16 * (c16 ^ (ro & 7));
+            offO[q] = 128 * ro + 16 * (c16 ^ (ro & 7)) + sub;
         }
         const bool interior = (col >= 1 && col <= p.jt);
         const double thr_r = p.sink_thres_r;
@@ -377,134 +456,133 @@ __global__ void __launch_bounds__(FS_THREADS, 1) step_fused_kernel(const StepArg
             const double srcc = p.src_const[tr];
 
             // ---------------- sweep A: stage-1 rhs + LU forward elimination, top -> bottom ----------------
-            D2 yprev = {0.0, 0.0};
+            V yprev = fs_splat<MPT>(0.0);
             for (int c = 0; c < nchunk; ++c) {
                 const uint32_t s = g % FS_NS, ph = (g / FS_NS) & 1;
-                fs_mbar_wait(&full[s], ph);
+                fs_mbar_wait<20>(bar_full + 8 * s, ph);
                 const unsigned char *sb = ring + s * FS_SLOT;
-                const double *pl = reinterpret_cast<const double *>(sb + FS_UBYTES);
-                D2 yb[FS_KC];
+                const double *pl = reinterpret_cast<const double *>(sb + FS_UBYTES) + col;
+                V yb[FS_KC];
 #pragma unroll
                 for (int q = 0; q < FS_KC; ++q) {
-                    const D2 cv = fs_ld(sb + offU[q][1]);
-                    D2 es;  // e + s
+                    const V cv = fs_ld(sb + offU[q][1], (V *)nullptr);
                     double frc = 0.0;
-                    if constexpr (KIND == NKB_MOD_FORCED_FILE) frc = pl[4 * 64 + q * 16 + col];
-                    const D2 sv = fs_source<KIND>(srcc, thr_r, frc, cv);
+                    if constexpr (KIND == NKB_MOD_FORCED_FILE) frc = pl[4 * 64 + q * 16];
+                    V es = fs_source<KIND, MPT>(srcc, thr_r, frc, cv);  // e + s
                     if constexpr (HAS_E) {
-                        const D2 cl = fs_ld(sb + offU[q][0]);
-                        const D2 cr = fs_ld(sb + offU[q][2]);
-                        const double eL = pl[q * 16 + col], eC = pl[64 + q * 16 + col], eR = pl[128 + q * 16 + col];
-                        es = fs_add(fs_fma(eL, cl, fs_fma(eR, cr, fs_mul(eC, cv))), sv);
+                        const V cl = fs_ld(sb + offU[q][0], (V *)nullptr);
+                        const V cr = fs_ld(sb + offU[q][2], (V *)nullptr);
+                        const double eL = pl[q * 16], eC = pl[64 + q * 16], eR = pl[128 + q * 16];
+                        es = fs_add(fs_fma(eL, cl, fs_fma(eR, cr, fs_mul(eC, cv))), es);
                     } else {
-                        es = fs_add(D2{0.0, 0.0}, sv);
+                        es = fs_add(fs_splat<MPT>(0.0), es);
                     }
-                    const double m1 = pl[3 * 64 + q * 16 + col];
-                    D2 rhs = fs_fma(p.hg, es, cv);
-                    if (c == 0 && q == 0) rhs = fs_add(rhs, D2{aff1, aff1});
+                    const double m1 = pl[3 * 64 + q * 16];
+                    V rhs = fs_fma(p.hg, es, cv);
+                    if (c == 0 && q == 0) rhs = fs_add(rhs, fs_splat<MPT>(aff1));
                     yprev = fs_fma(-m1, yprev, rhs);
                     yb[q] = yprev;
                 }
                 __syncwarp();
-                if (lane == 0) fs_mbar_arrive(&empty[s]);
-                if (!(p.dbg & 1)) fs_tmem_st16(taddr + c * 16, yb);
+                if (lane == 0) fs_mbar_arrive(bar_empty + 8 * s);
+                Raw<W> raw;
+                fs_pack(yb, raw);
+                fs_tmem_st(taddr + c * W, raw);
                 ++g;
             }
-            if (!(p.dbg & 1)) fs_tmem_wait_st();
+            fs_tmem_wait_st();
 
             // ------- sweep B: stage-1 back substitution + stage-2 rhs + UL elimination, bottom -> top -------
             {
-                Raw16 rcur, rnx;
-                D2 ycur[FS_KC], ynx[FS_KC];
-                for (int i = 0; i < 16; ++i) rcur.w[i] = rnx.w[i] = 0;
-                if (!(p.dbg & 1)) { fs_tmem_ld16(taddr + (nchunk - 1) * 16, rcur);
-                fs_tmem_wait_ld(rcur); }
+                Raw<W> rcur, rnx;
+                V ycur[FS_KC], ynx[FS_KC];
+                fs_tmem_ld(taddr + (nchunk - 1) * W, rcur);
+                fs_tmem_wait_ld(rcur);
                 fs_unpack(rcur, ycur);
-                D2 u1n = {0.0, 0.0}, y2n = {0.0, 0.0};
+                V u1n = fs_splat<MPT>(0.0), y2n = fs_splat<MPT>(0.0);
                 for (int c = nchunk - 1; c >= 0; --c) {
-                    if (c > 0 && !(p.dbg & 1)) fs_tmem_ld16(taddr + (c - 1) * 16, rnx);
+                    if (c > 0) fs_tmem_ld(taddr + (c - 1) * W, rnx);
                     const uint32_t s = g % FS_NS, ph = (g / FS_NS) & 1;
-                    fs_mbar_wait(&full[s], ph);
+                    fs_mbar_wait<20>(bar_full + 8 * s, ph);
                     if (c > 0) {
-                        if (!(p.dbg & 1)) fs_tmem_wait_ld(rnx);
+                        fs_tmem_wait_ld(rnx);
                         fs_unpack(rnx, ynx);
                     } else {
 #pragma unroll
-                        for (int q = 0; q < FS_KC; ++q) ynx[q] = D2{0.0, 0.0};
+                        for (int q = 0; q < FS_KC; ++q) ynx[q] = fs_splat<MPT>(0.0);
                     }
                     const unsigned char *sb = ring + s * FS_SLOT;
-                    const double *pl = reinterpret_cast<const double *>(sb + FS_UBYTES);
-                    D2 yb[FS_KC];
+                    const double *pl = reinterpret_cast<const double *>(sb + FS_UBYTES) + col;
+                    V yb[FS_KC];
 #pragma unroll
                     for (int q = FS_KC - 1; q >= 0; --q) {
-                        const D2 y1 = ycur[q];
-                        const D2 y1m = (q > 0) ? ycur[q > 0 ? q - 1 : 0] : ynx[FS_KC - 1];
-                        const double ib1 = pl[3 * 64 + q * 16 + col], g1 = pl[4 * 64 + q * 16 + col];
-                        const double m1 = pl[5 * 64 + q * 16 + col], m2 = pl[6 * 64 + q * 16 + col];
-                        const D2 u1 = fs_fma(-g1, u1n, fs_mul(ib1, y1));
+                        const V y1 = ycur[q];
+                        const V y1m = (q > 0) ? ycur[q > 0 ? q - 1 : 0] : ynx[FS_KC - 1];
+                        const double ib1 = pl[3 * 64 + q * 16], g1 = pl[4 * 64 + q * 16];
+                        const double m1 = pl[5 * 64 + q * 16], m2 = pl[6 * 64 + q * 16];
+                        const V u1 = fs_fma(-g1, u1n, fs_mul(ib1, y1));
                         u1n = u1;
-                        D2 rhs1 = fs_fma(m1, y1m, y1);
-                        if (c == 0 && q == 0) rhs1 = fs_sub(rhs1, D2{aff1, aff1});
-                        const D2 un = fs_ld(sb + offU[q][1]);
-                        const D2 pp = fs_fma(p.r, fs_sub(rhs1, un), fs_mul(p.a0, un));
+                        V rhs1 = fs_fma(m1, y1m, y1);  // = u_n + gamma h E(u_n) (+ aff1 at the surface)
+                        if (c == 0 && q == 0) rhs1 = fs_sub(rhs1, fs_splat<MPT>(aff1));
+                        const V un = fs_ld(sb + offU[q][1], (V *)nullptr);
+                        const V pp = fs_fma(p.r, fs_sub(rhs1, un), fs_mul(p.a0, un));
                         double frc = 0.0;
-                        if constexpr (KIND == NKB_MOD_FORCED_FILE) frc = pl[7 * 64 + q * 16 + col];
-                        const D2 sv = fs_source<KIND>(srcc, thr_r, frc, u1);
-                        D2 es;
+                        if constexpr (KIND == NKB_MOD_FORCED_FILE) frc = pl[7 * 64 + q * 16];
+                        V es = fs_source<KIND, MPT>(srcc, thr_r, frc, u1);
                         if constexpr (HAS_E) {
-                            const D2 ul = fs_shfl_up(u1), ur = fs_shfl_down(u1);
-                            const double eL = pl[q * 16 + col], eC = pl[64 + q * 16 + col],
-                                         eR = pl[128 + q * 16 + col];
-                            es = fs_add(fs_fma(eL, ul, fs_fma(eR, ur, fs_mul(eC, u1))), sv);
+                            const V ul = fs_shfl_up<MPT, DELTA, WIDTH>(u1), ur = fs_shfl_down<MPT, DELTA, WIDTH>(u1);
+                            const double eL = pl[q * 16], eC = pl[64 + q * 16], eR = pl[128 + q * 16];
+                            es = fs_add(fs_fma(eL, ul, fs_fma(eR, ur, fs_mul(eC, u1))), es);
                         } else {
-                            es = fs_add(D2{0.0, 0.0}, sv);
+                            es = fs_add(fs_splat<MPT>(0.0), es);
                         }
-                        D2 rhs2 = fs_fma(p.he1, es, fs_fma(p.a1, u1, pp));
-                        if (c == 0 && q == 0) rhs2 = fs_add(rhs2, D2{aff2, aff2});
+                        V rhs2 = fs_fma(p.he1, es, fs_fma(p.a1, u1, pp));
+                        if (c == 0 && q == 0) rhs2 = fs_add(rhs2, fs_splat<MPT>(aff2));
                         y2n = fs_fma(-m2, y2n, rhs2);
                         yb[q] = y2n;
                     }
                     __syncwarp();
-                    if (lane == 0) fs_mbar_arrive(&empty[s]);
-                    if (!(p.dbg & 1)) fs_tmem_st16(taddr + c * 16, yb);
+                    if (lane == 0) fs_mbar_arrive(bar_empty + 8 * s);
+                    Raw<W> raw;
+                    fs_pack(yb, raw);
+                    fs_tmem_st(taddr + c * W, raw);
 #pragma unroll
                     for (int q = 0; q < FS_KC; ++q) ycur[q] = ynx[q];
                     ++g;
                 }
-                if (!(p.dbg & 1)) fs_tmem_wait_st();
+                fs_tmem_wait_st();
             }
 
             // ---------------- sweep C: stage-2 substitution, top -> bottom, staged TMA store ----------------
             {
-                Raw16 rcur, rnx;
-                D2 ycur[FS_KC];
-                for (int i = 0; i < 16; ++i) rcur.w[i] = rnx.w[i] = 0;
-                if (!(p.dbg & 1)) { fs_tmem_ld16(taddr, rcur);
-                fs_tmem_wait_ld(rcur); }
+                Raw<W> rcur, rnx;
+                V ycur[FS_KC];
+                fs_tmem_ld(taddr, rcur);
+                fs_tmem_wait_ld(rcur);
                 fs_unpack(rcur, ycur);
-                D2 u2p = {0.0, 0.0};
+                V u2p = fs_splat<MPT>(0.0);
                 for (int c = 0; c < nchunk; ++c) {
-                    if (c + 1 < nchunk && !(p.dbg & 1)) fs_tmem_ld16(taddr + (c + 1) * 16, rnx);
+                    if (c + 1 < nchunk) fs_tmem_ld(taddr + (c + 1) * W, rnx);
                     const uint32_t s = g % FS_NS, ph = (g / FS_NS) & 1;
                     const uint32_t so = go % FS_NO, pho = (go / FS_NO) & 1;
-                    fs_mbar_wait(&full[s], ph);
-                    fs_mbar_wait(&oempty[so], pho ^ 1);
-                    const double *pl = reinterpret_cast<const double *>(ring + s * FS_SLOT + FS_UBYTES);
+                    fs_mbar_wait<20>(bar_full + 8 * s, ph);
+                    fs_mbar_wait<20>(bar_oempty + 8 * so, pho ^ 1);
+                    const double *pl = reinterpret_cast<const double *>(ring + s * FS_SLOT + FS_UBYTES) + col;
                     unsigned char *ob = oring + so * FS_OUT;
 #pragma unroll
                     for (int q = 0; q < FS_KC; ++q) {
-                        const double ib2 = pl[q * 16 + col], g2 = pl[64 + q * 16 + col];
+                        const double ib2 = pl[q * 16], g2 = pl[64 + q * 16];
                         u2p = fs_fma(-g2, u2p, fs_mul(ib2, ycur[q]));
-                        if (interior) *reinterpret_cast<double2 *>(ob + offO[q]) = make_double2(u2p.x, u2p.y);
+                        if (interior) fs_st(ob + offO[q], u2p);
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) {
-                        fs_mbar_arrive(&empty[s]);
-                        fs_mbar_arrive(&ofull[so]);
+                        fs_mbar_arrive(bar_empty + 8 * s);
+                        fs_mbar_arrive(bar_ofull + 8 * so);
                     }
                     if (c + 1 < nchunk) {
-                        if (!(p.dbg & 1)) fs_tmem_wait_ld(rnx);
+                        fs_tmem_wait_ld(rnx);
                         fs_unpack(rnx, ycur);
                     }
                     ++g;
@@ -516,7 +594,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) step_fused_kernel(const StepArg
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0 && !(p.dbg & 8)) {
+    if (warp == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
     }
@@ -625,17 +703,24 @@ struct FusedLaunch {
     const CUtensorMap *uin, *uout, *est, *ftab, *src;
 };
 
-template <int KIND, bool HAS_E>
-static int fs_launch_t(const StepArgs &a, const StepMaps &maps, int grid, cudaStream_t st) {
-    auto kern = step_fused_kernel<KIND, HAS_E>;
+template <int KIND, bool HAS_E, int MPT>
+static int fs_launch_m(const StepArgs &a, const StepMaps &maps, int grid, cudaStream_t st) {
+    auto kern = step_fused_kernel<KIND, HAS_E, MPT>;
     static bool attr_set = false;
     if (!attr_set) {
         NKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM));
         attr_set = true;
     }
-    kern<<<grid, FS_THREADS, FS_SMEM, st>>>(a, maps);
+    kern<<<grid, fs_threads(MPT), FS_SMEM, st>>>(a, maps);
     count_launch();
     return 0;
+}
+
+template <int KIND, bool HAS_E>
+static int fs_launch_t(const StepArgs &a, const StepMaps &maps, int grid, cudaStream_t st) {
+    // NKB_FUSED_MPT: members per thread (2: 4 consumer warps, 1: 8 consumer warps)
+    if (fs_env_int("NKB_FUSED_MPT", 1) == 2) return fs_launch_m<KIND, HAS_E, 2>(a, maps, grid, st);
+    return fs_launch_m<KIND, HAS_E, 1>(a, maps, grid, st);
 }
 
 int launch_step_fused(const ModelDev &v, int B, int n_steps, int step, double h, const double *aff1,
@@ -648,7 +733,6 @@ int launch_step_fused(const ModelDev &v, int B, int n_steps, int step, double h,
     a.nmb = (B + FS_MEM - 1) / FS_MEM;
     a.ntiles = a.nmb * a.nct * v.T;
     a.step = step;
-    a.dbg = fs_env_int("NKB_FUSED_DBG", 0);
     for (int t = 0; t < NKB_MAX_TRACERS; ++t) { a.class_of[t] = v.class_of[t]; a.src_const[t] = v.src_const[t]; }
     a.sink_thres_r = v.sink_thres > 0.0 ? 1.0 / v.sink_thres : 0.0;
     a.hg = kGamma * h;
