@@ -130,7 +130,7 @@ void nkb_model_destroy(nkb_model *m) {
     if (!m) return;
     cudaFree(m->arena); cudaFree(m->tri); cudaFree(m->aff); cudaFree(m->src); cudaFree(m->d_h);
     cudaFree(m->tri_raw); cudaFree(m->aff_raw); cudaFree(m->src_raw);
-    cudaFree(m->ftab); cudaFree(m->estp); cudaFree(m->srcp);
+    cudaFree(m->ctab);
     cudaFree(m->d_stage_major); cudaFree(m->d_stage_x); cudaFree(m->d_stage_f); cudaFree(m->d_stage_work);
     if (m->graph) cudaGraphExecDestroy(m->graph);
     if (m->own_stream) cudaStreamDestroy(m->own_stream);
@@ -145,8 +145,8 @@ int nkb_model_set_schedule(nkb_model *m, int n_steps, const double *h_t_start, c
     const int n_stages = 2 * n_steps;
     cudaFree(m->tri); cudaFree(m->aff); cudaFree(m->src);
     m->tri = m->aff = m->src = nullptr;
-    cudaFree(m->ftab); cudaFree(m->estp); cudaFree(m->srcp);
-    m->ftab = m->estp = m->srcp = nullptr;
+    cudaFree(m->ctab);
+    m->ctab = nullptr;
     if (m->graph) { cudaGraphExecDestroy(m->graph); m->graph = nullptr; }
     delete[] m->h_t_start; delete[] m->h_h;
     m->h_t_start = new double[n_steps]; m->h_h = new double[n_steps];
@@ -197,13 +197,11 @@ int nkb_model_set_schedule(nkb_model *m, int n_steps, const double *h_t_start, c
     return 0;
 }
 
-// Tables of the fused step kernel, built on the first evaluation that uses it.
+// Coefficient table of the fused step kernel, built on the first evaluation that uses it.
 static int ensure_fused_tables(nkb_model *m) {
-    if (m->ftab) return 0;
+    if (m->ctab) return 0;
     const ModelDev &v = m->dev;
     const int n_steps = m->n_steps, n_stages = 2 * n_steps;
-    const int nyp = (v.ny + 2) & ~1;  // one zero column on the left, even pitch
-    m->nyp = nyp;
     std::vector<double> t_imp(n_stages), hg(n_stages), t_exp(n_stages);
     for (int n = 0; n < n_steps; ++n) {  // same stage times as nkb_model_set_schedule
         const double t = m->h_t_start[n], h = m->h_h[n];
@@ -213,40 +211,25 @@ static int ensure_fused_tables(nkb_model *m) {
         t_exp[2 * n] = t;
         t_exp[2 * n + 1] = t + nkb::kGamma * h;
     }
-    double *d_t = nullptr, *d_hg = nullptr;
+    double *d_t = nullptr, *d_hg = nullptr, *d_te = nullptr;
     NKB_CUDA(cudaMalloc(&d_t, n_stages * sizeof(double)));
     NKB_CUDA(cudaMalloc(&d_hg, n_stages * sizeof(double)));
+    NKB_CUDA(cudaMalloc(&d_te, n_stages * sizeof(double)));
     NKB_CUDA(cudaMemcpy(d_t, t_imp.data(), n_stages * sizeof(double), cudaMemcpyHostToDevice));
     NKB_CUDA(cudaMemcpy(d_hg, hg.data(), n_stages * sizeof(double), cudaMemcpyHostToDevice));
-    const size_t pl = (size_t)v.nz * nyp;
-    const size_t per_step = (size_t)v.n_classes * 6 * pl;
-    NKB_CUDA(cudaMalloc(&m->ftab, (size_t)n_steps * per_step * sizeof(double)));
-    NKB_CUDA(cudaMemset(m->ftab, 0, (size_t)n_steps * per_step * sizeof(double)));
+    NKB_CUDA(cudaMemcpy(d_te, t_exp.data(), n_stages * sizeof(double), cudaMemcpyHostToDevice));
+    const size_t per_step = (size_t)v.n_classes * 8 * v.nz * 2 * (v.ny + 1);
+    NKB_CUDA(cudaMalloc(&m->ctab, (size_t)n_steps * per_step * sizeof(double)));
+    NKB_CUDA(cudaMemset(m->ctab, 0, (size_t)n_steps * per_step * sizeof(double)));
     const int chunk = 32768;
     for (int s0 = 0; s0 < n_steps; s0 += chunk) {
         const int ns = (n_steps - s0 < chunk) ? n_steps - s0 : chunk;
-        if (nkb::launch_step_tables(v, ns, d_t + 2 * s0, d_hg + 2 * s0, nyp, m->ftab + (size_t)s0 * per_step, 0))
+        if (nkb::launch_step_ctab(v, ns, d_t + 2 * s0, d_hg + 2 * s0, d_te + 2 * s0, m->ctab + (size_t)s0 * per_step, 0))
             return 1;
     }
-    if (nkb::fused_encode_plane_map(v.nz, v.ny, nyp, (size_t)n_steps * v.n_classes * 6, m->ftab, &m->map_ftab)) return 1;
-    if (v.estencil) {
-        NKB_CUDA(cudaMalloc(&m->estp, 3 * pl * sizeof(double)));
-        NKB_CUDA(cudaMemset(m->estp, 0, 3 * pl * sizeof(double)));
-        if (nkb::launch_est_planes(v, nyp, m->estp, 0)) return 1;
-        if (nkb::fused_encode_plane_map(v.nz, v.ny, nyp, 3, m->estp, &m->map_estp)) return 1;
-    }
-    if (v.kind == NKB_MOD_FORCED_FILE) {
-        NKB_CUDA(cudaMemcpy(d_t, t_exp.data(), n_stages * sizeof(double), cudaMemcpyHostToDevice));
-        NKB_CUDA(cudaMalloc(&m->srcp, (size_t)n_stages * pl * sizeof(double)));
-        NKB_CUDA(cudaMemset(m->srcp, 0, (size_t)n_stages * pl * sizeof(double)));
-        for (int s0 = 0; s0 < n_stages; s0 += chunk) {
-            const int ns = (n_stages - s0 < chunk) ? n_stages - s0 : chunk;
-            if (nkb::launch_forcing_planes(v, ns, d_t + s0, nyp, m->srcp + (size_t)s0 * pl, 0)) return 1;
-        }
-        if (nkb::fused_encode_plane_map(v.nz, v.ny, nyp, (size_t)n_stages, m->srcp, &m->map_srcp)) return 1;
-    }
+    if (nkb::fused_encode_ctab_map(v.nz, v.ny, (size_t)n_steps * v.n_classes * 8, m->ctab, &m->map_ctab)) return 1;
     NKB_CUDA(cudaDeviceSynchronize());
-    cudaFree(d_t); cudaFree(d_hg);
+    cudaFree(d_t); cudaFree(d_hg); cudaFree(d_te);
     return 0;
 }
 
@@ -358,9 +341,7 @@ int nkb_model_eval(nkb_model *m, const double *d_x0, double *d_f, double *d_work
             const CUtensorMap &mi = (un == d_x0) ? in_x0 : (un == d_f ? in_f : in_w);
             const CUtensorMap &mo = (dest == d_f) ? out_f : out_w;
             if (nkb::launch_step_fused(v, B, S, n, m->h_h[n], m->aff + (size_t)(2 * n) * aff_stride,
-                                       m->aff + (size_t)(2 * n + 1) * aff_stride, mi, mo,
-                                       m->estp ? &m->map_estp : nullptr, m->map_ftab,
-                                       m->srcp ? &m->map_srcp : nullptr, st))
+                                       m->aff + (size_t)(2 * n + 1) * aff_stride, mi, mo, m->map_ctab, st))
                 return 1;
             un = dest;
             if (n_hist > 0 && !last && emit_hist(n + 1, dest)) return 1;

@@ -114,17 +114,15 @@ int launch_pack(const double *src, double *dst, int n, int B, int ldb, cudaStrea
 int launch_unpack(const double *src, double *dst, int n, int B, int ldb, cudaStream_t st);
 int launch_stage(int kind, int nin, const StageArgs &a, cudaStream_t st);
 int launch_tend(int kind, const StageArgs &a, cudaStream_t st);
-int launch_step_tables(const ModelDev &m, int n_steps, const double *d_t, const double *d_hg, int nyp, double *ftab,
-                       cudaStream_t st);
-int launch_est_planes(const ModelDev &m, int nyp, double *out, cudaStream_t st);
-int launch_forcing_planes(const ModelDev &m, int n_times, const double *d_t, int nyp, double *out, cudaStream_t st);
+int launch_step_ctab(const ModelDev &m, int n_steps, const double *d_t, const double *d_hg, const double *d_texp,
+                     double *ctab, cudaStream_t st);
 // fused step kernel (nkb_step_fused.cu)
 bool fused_step_usable(const ModelDev &v, int B, int ldb, const double *x0, const double *f, const double *work);
 int fused_encode_state_maps(const ModelDev &v, int B, int ldb, const double *buf, CUtensorMap *in, CUtensorMap *out);
-int fused_encode_plane_map(int nz, int ny, int nyp, size_t nplanes, const double *buf, CUtensorMap *map);
+int fused_encode_ctab_map(int nz, int ny, size_t nplanes, const double *buf, CUtensorMap *map);
 int launch_step_fused(const ModelDev &v, int B, int n_steps, int step, double h, const double *aff1,
-                      const double *aff2, const CUtensorMap &uin, const CUtensorMap &uout, const CUtensorMap *est,
-                      const CUtensorMap &ftab, const CUtensorMap *src, cudaStream_t st);
+                      const double *aff2, const CUtensorMap &uin, const CUtensorMap &uout, const CUtensorMap &ctab,
+                      cudaStream_t st);
 int launch_sub_inplace(double *out, const double *x0, size_t n, cudaStream_t st);
 bool tma_path_usable(const StageArgs &a);
 int launch_stage_tma(int kind, int nin, const StageArgs &a, cudaStream_t st);
@@ -143,12 +141,9 @@ struct nkb_model {
     double *tri = nullptr;      // [n_stages][n_classes][nz][ny][4]  {ib, g, m, 0}
     double *aff = nullptr;      // [n_stages][n_classes][ny]  h*gamma*(affine surface source) per column
     double *src = nullptr;      // [n_steps][nz][ny][2] forcing at the two explicit stage times (or nullptr)
-    // fused-step tables (built on first use, nkb_step_fused.cu): SoA planes with row pitch nyp
-    int nyp = 0;
-    double *ftab = nullptr;     // [n_steps][n_classes][6][nz][nyp]
-    double *estp = nullptr;     // [3][nz][nyp]
-    double *srcp = nullptr;     // [n_steps][2][nz][nyp]
-    CUtensorMap map_ftab, map_estp, map_srcp;
+    // fused-step coefficient table (built on first use, nkb_tables.cu:step_ctab_kernel)
+    double *ctab = nullptr;     // [n_steps][n_classes][8][nz][2*(ny+1)]
+    CUtensorMap map_ctab;
     // scratch for tend()/mixing_coeff()
     double *tri_raw = nullptr;  // [n_classes][nz][ny][4]
     double *aff_raw = nullptr;  // [n_classes][ny]

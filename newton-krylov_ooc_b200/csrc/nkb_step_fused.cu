@@ -39,25 +39,30 @@
 
 namespace nkb {
 
-constexpr int FS_KC = 4;      // levels per chunk
 constexpr int FS_COLS = 16;   // stage-1 columns per tile
 constexpr int FS_UCOLS = 18;  // state columns per tile (halo of 2)
 constexpr int FS_JT = 14;     // max interior columns per tile
 constexpr int FS_MEM = 16;    // members per tile (128-byte rows)
-constexpr int FS_NS = 8;      // load ring slots
-constexpr int FS_NO = 3;      // output staging slots
-constexpr int FS_UBYTES = FS_KC * FS_UCOLS * FS_MEM * 8;  // 9216
-constexpr int FS_PLANE = FS_KC * FS_COLS * 8;             // 512
-constexpr int FS_NPLANES = 8;
-constexpr int FS_SLOT = FS_UBYTES + FS_NPLANES * FS_PLANE;  // 13312 = 13 * 1024
-constexpr int FS_OUT = FS_KC * FS_JT * FS_MEM * 8;          // 7168 = 7 * 1024
-constexpr int FS_SMEM = 1024 + FS_NS * FS_SLOT + FS_NO * FS_OUT;
-static_assert(FS_SLOT % 1024 == 0 && FS_OUT % 1024 == 0, "swizzled boxes need 1024-byte aligned bases");
-// consumer warps: MPT members per thread; 256 (column, member) pairs per tile in both layouts
-//   MPT = 2: 4 warps, lane = column + 16*pair           (fewest instructions per member)
-//   MPT = 1: 8 warps, lane = 2*column + (member & 1)    (two warps per scheduler: latency hiding)
-__host__ __device__ constexpr int fs_ncw(int mpt) { return 8 / mpt; }
-__host__ __device__ constexpr int fs_threads(int mpt) { return (fs_ncw(mpt) + 2) * 32; }
+constexpr int FS_NPP = 4;     // coefficient pair planes per ring slot
+// consumer warps: MPT members per thread, KC levels per chunk; 256 (column, member) pairs per tile
+//   MPT = 1, KC = 8: 8 warps, lane = 2*column + (member & 1)   (two warps per scheduler: default)
+//   MPT = 2, KC = 4: 4 warps, lane = column + 16*pair
+// either way one chunk of one thread is 16 32-bit TMEM columns (one tcgen05 x16 access)
+struct FsCfg {
+    int kc, ncw, threads, ns, no, ubytes, ppbytes, slot, out, smem;
+};
+__host__ __device__ constexpr FsCfg fs_cfg(int mpt) {
+    const int kc = (mpt == 1) ? 8 : 4;
+    const int ncw = 8 / mpt;
+    const int ns = (mpt == 1) ? 5 : 8, no = (mpt == 1) ? 2 : 3;
+    const int ubytes = kc * FS_UCOLS * FS_MEM * 8;  // 1024-byte multiple
+    const int ppbytes = kc * FS_COLS * 16;
+    const int slot = ubytes + FS_NPP * ppbytes;
+    const int out = kc * FS_JT * FS_MEM * 8;
+    return {kc, ncw, (ncw + 2) * 32, ns, no, ubytes, ppbytes, slot, out, 1024 + ns * slot + no * out};
+}
+static_assert(fs_cfg(1).slot % 1024 == 0 && fs_cfg(1).out % 1024 == 0, "swizzled boxes need 1024-byte aligned bases");
+static_assert(fs_cfg(2).slot % 1024 == 0 && fs_cfg(2).out % 1024 == 0, "swizzled boxes need 1024-byte aligned bases");
 
 struct StepArgs {
     int nz, ny, B, T, ncls, n_steps;
@@ -66,12 +71,12 @@ struct StepArgs {
     int class_of[NKB_MAX_TRACERS];
     double src_const[NKB_MAX_TRACERS];
     double sink_thres_r;
-    double hg, a0, a1, r, he1;  // gamma*h; stage-2 weights (see launch_step_fused)
+    double hg, he1, r, a0r;     // gamma*h, h*(1-delta); P = r*rhs1 + a0r*u_n (see launch_step_fused)
     const double *aff1, *aff2;  // [ncls][ny] of the two stages of this step
 };
 
 struct StepMaps {
-    CUtensorMap uin, uout, est, ftab, src;
+    CUtensorMap uin, uout, ctab;
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -252,39 +257,41 @@ __device__ __forceinline__ Vd<M> fs_shfl_down(Vd<M> x) {
     for (int i = 0; i < M; ++i) r.v[i] = __shfl_down_sync(0xffffffffu, x.v[i], DELTA, WIDTH);
     return r;
 }
-template <int M>
-__device__ __forceinline__ void fs_pack(const Vd<M> (&v)[FS_KC], Raw<FS_KC * 2 * M> &r) {
+template <int M, int KC>
+__device__ __forceinline__ void fs_pack(const Vd<M> (&v)[KC], Raw<KC * 2 * M> &r) {
 #pragma unroll
-    for (int q = 0; q < FS_KC; ++q)
+    for (int q = 0; q < KC; ++q)
 #pragma unroll
         for (int i = 0; i < M; ++i) {
             r.w[(q * M + i) * 2] = (uint32_t)__double2loint(v[q].v[i]);
             r.w[(q * M + i) * 2 + 1] = (uint32_t)__double2hiint(v[q].v[i]);
         }
 }
-template <int M>
-__device__ __forceinline__ void fs_unpack(const Raw<FS_KC * 2 * M> &r, Vd<M> (&v)[FS_KC]) {
+template <int M, int KC>
+__device__ __forceinline__ void fs_unpack(const Raw<KC * 2 * M> &r, Vd<M> (&v)[KC]) {
 #pragma unroll
-    for (int q = 0; q < FS_KC; ++q)
+    for (int q = 0; q < KC; ++q)
 #pragma unroll
         for (int i = 0; i < M; ++i)
             v[q].v[i] = __hiloint2double((int)r.w[(q * M + i) * 2 + 1], (int)r.w[(q * M + i) * 2]);
 }
 
-// explicit source of one tracer (iage.py:39 constant; forced.py:141-151 forcing record with the
-// sink_thres limiter) — same expressions as explicit_sources() in nkb_stage_dev.cuh
+// explicit source of one tracer times the stage weight w (w = gamma h or h (1 - delta)):
+// LINEAR: w * constant (iage.py:39), passed in ws.  FORCED_FILE: fw = w * forcing record with the
+// sink_thres limiter of forced.py:141-151 (sms scaled by c/thres where sms < 0 and 0 < c < thres)
 template <int KIND, int M>
-__device__ __forceinline__ Vd<M> fs_source(double srcc, double thr_r, double frc, Vd<M> c) {
+__device__ __forceinline__ Vd<M> fs_source(double ws, double thr_r, double fw, Vd<M> c) {
     Vd<M> r;
     if constexpr (KIND == NKB_MOD_LINEAR) {
 #pragma unroll
-        for (int i = 0; i < M; ++i) r.v[i] = srcc;
+        for (int i = 0; i < M; ++i) r.v[i] = ws;
     } else {
-        const bool lim = (thr_r > 0.0 && frc < 0.0);
+        const bool lim = (thr_r > 0.0) & (fw < 0.0);
 #pragma unroll
         for (int i = 0; i < M; ++i) {
             const double q = thr_r * c.v[i];
-            r.v[i] = (lim && q > 0.0 && q < 1.0) ? frc * q : frc;
+            const bool t = lim & (q > 0.0) & (q < 1.0);
+            r.v[i] = t ? fw * q : fw;
         }
     }
     return r;
@@ -294,15 +301,16 @@ constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
 constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
 
-// coefficient plane q of a ring slot: [FS_KC][FS_COLS] doubles
-//   sweep A: 0 eL, 1 eC, 2 eR, 3 m1, 4 frc(t_n)
-//   sweep B: 0 eL, 1 eC, 2 eR, 3 ib1, 4 g1, 5 m1, 6 m2, 7 frc(t_n + gamma h)
-//   sweep C: 0 ib2, 1 g2
-template <int KIND, bool HAS_E, int MPT>
-__global__ void __launch_bounds__(fs_threads(MPT), 1) step_fused_kernel(const StepArgs p,
-                                                                         const __grid_constant__ StepMaps maps) {
-    constexpr int NCW = fs_ncw(MPT);
-    constexpr int W = FS_KC * 2 * MPT;  // TMEM columns per chunk and thread
+// pair planes of a ring slot, [KC][FS_COLS] pairs each (see step_ctab_kernel in nkb_tables.cu):
+//   sweep A: 0 {aL,aC}  1 {aR,m1}  2 {fA,-}          sweep C: 0 {ib2,g2}
+//   sweep B: 0 {bL,bC}  1 {bR,ib1} 2 {g1,m1} 3 {m2,fB}
+template <int KIND, int MPT>
+__global__ void __launch_bounds__(fs_cfg(MPT).threads, 1) step_fused_kernel(const StepArgs p,
+                                                                             const __grid_constant__ StepMaps maps) {
+    constexpr FsCfg C = fs_cfg(MPT);
+    constexpr int KC = C.kc, NCW = C.ncw, NS = C.ns, NO = C.no;
+    constexpr int W = KC * 2 * MPT;  // TMEM columns per chunk and thread (16)
+    constexpr bool FRC = (KIND == NKB_MOD_FORCED_FILE);
     using V = Vd<MPT>;
     // dynamic shared memory is the only shared allocation of this kernel: its window offset is a
     // multiple of 1024 (checked), which the 128-byte-swizzled boxes rely on.  Offsets from the
@@ -310,20 +318,20 @@ __global__ void __launch_bounds__(fs_threads(MPT), 1) step_fused_kernel(const St
     extern __shared__ __align__(1024) unsigned char fs_smem[];
     const uint32_t smem0 = fs_smem_u32(fs_smem);
     if (smem0 & 1023u) __trap();
-    const uint32_t bar_full = smem0, bar_empty = smem0 + 8 * FS_NS, bar_ofull = smem0 + 16 * FS_NS,
-                   bar_oempty = smem0 + 16 * FS_NS + 8 * FS_NO;
+    const uint32_t bar_full = smem0, bar_empty = smem0 + 8 * NS, bar_ofull = smem0 + 16 * NS,
+                   bar_oempty = smem0 + 16 * NS + 8 * NO;
     uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(fs_smem + 960);
     unsigned char *ring = fs_smem + 1024;
-    unsigned char *oring = ring + FS_NS * FS_SLOT;
-    const uint32_t ring_a = smem0 + 1024, oring_a = ring_a + FS_NS * FS_SLOT;
+    unsigned char *oring = ring + NS * C.slot;
+    const uint32_t ring_a = smem0 + 1024, oring_a = ring_a + NS * C.slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < FS_NS; ++s) {
+        for (int s = 0; s < NS; ++s) {
             fs_mbar_init(bar_full + 8 * s, 1);
             fs_mbar_init(bar_empty + 8 * s, NCW);
         }
-        for (int s = 0; s < FS_NO; ++s) {
+        for (int s = 0; s < NO; ++s) {
             fs_mbar_init(bar_ofull + 8 * s, NCW);
             fs_mbar_init(bar_oempty + 8 * s, 1);
         }
@@ -341,9 +349,8 @@ __global__ void __launch_bounds__(fs_threads(MPT), 1) step_fused_kernel(const St
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(tmem_holder);
 
     const int nz = p.nz, ny = p.ny;
-    const int nchunk = (nz + FS_KC - 1) / FS_KC;
-    constexpr int NPA = (HAS_E ? 3 : 0) + 1 + (KIND == NKB_MOD_FORCED_FILE ? 1 : 0);
-    constexpr int NPB = (HAS_E ? 3 : 0) + 4 + (KIND == NKB_MOD_FORCED_FILE ? 1 : 0);
+    const int nchunk = (nz + KC - 1) / KC;
+    constexpr int NPA = FRC ? 3 : 2;
 
     if (warp == NCW) {
         // ===== producer: one lane issues every TMA load of this CTA, in consumption order =====
@@ -354,45 +361,31 @@ __global__ void __launch_bounds__(fs_threads(MPT), 1) step_fused_kernel(const St
                 const int ct = (tile / p.nmb) % p.nct;
                 const int tr = tile / (p.nmb * p.nct);
                 const int m0 = mb * FS_MEM, j0 = ct * p.jt;
-                const int zt = (p.step * p.ncls + p.class_of[tr]) * 6;
+                const int zt = (p.step * p.ncls + p.class_of[tr]) * 8;
                 for (int sweep = 0; sweep < 3; ++sweep) {
                     for (int cc = 0; cc < nchunk; ++cc) {
                         const int c = (sweep == 1) ? nchunk - 1 - cc : cc;
-                        const int k0 = c * FS_KC;
-                        const uint32_t s = g % FS_NS, ph = (g / FS_NS) & 1;
+                        const int k0 = c * KC;
+                        const uint32_t s = g % NS, ph = (g / NS) & 1;
                         fs_mbar_wait<2000>(bar_empty + 8 * s, ph ^ 1);
-                        const uint32_t sb = ring_a + s * FS_SLOT;
-                        const uint32_t pl = sb + FS_UBYTES;
+                        const uint32_t sb = ring_a + s * C.slot;
+                        const uint32_t pl = sb + C.ubytes;
                         const uint32_t fb = bar_full + 8 * s;
                         if (sweep == 0) {
-                            fs_mbar_expect_tx(fb, FS_UBYTES + NPA * FS_PLANE);
+                            fs_mbar_expect_tx(fb, C.ubytes + NPA * C.ppbytes);
                             fs_tma_load_4d(sb, &maps.uin, fb, m0, j0 - 2, k0, tr, kEvictNormal);
-                            if constexpr (HAS_E) {
 #pragma unroll
-                                for (int q = 0; q < 3; ++q)
-                                    fs_tma_load_3d(pl + q * FS_PLANE, &maps.est, fb, j0, k0, q, kEvictLast);
-                            }
-                            fs_tma_load_3d(pl + 3 * FS_PLANE, &maps.ftab, fb, j0, k0, zt + 0, kEvictLast);
-                            if constexpr (KIND == NKB_MOD_FORCED_FILE)
-                                fs_tma_load_3d(pl + 4 * FS_PLANE, &maps.src, fb, j0, k0, 2 * p.step, kEvictLast);
+                            for (int q = 0; q < NPA; ++q)
+                                fs_tma_load_3d(pl + q * C.ppbytes, &maps.ctab, fb, 2 * j0, k0, zt + q, kEvictLast);
                         } else if (sweep == 1) {
-                            fs_mbar_expect_tx(fb, FS_UBYTES + NPB * FS_PLANE);
+                            fs_mbar_expect_tx(fb, C.ubytes + 4 * C.ppbytes);
                             fs_tma_load_4d(sb, &maps.uin, fb, m0, j0 - 2, k0, tr, kEvictFirst);
-                            if constexpr (HAS_E) {
 #pragma unroll
-                                for (int q = 0; q < 3; ++q)
-                                    fs_tma_load_3d(pl + q * FS_PLANE, &maps.est, fb, j0, k0, q, kEvictLast);
-                            }
-                            fs_tma_load_3d(pl + 3 * FS_PLANE, &maps.ftab, fb, j0, k0, zt + 1, kEvictLast);
-                            fs_tma_load_3d(pl + 4 * FS_PLANE, &maps.ftab, fb, j0, k0, zt + 2, kEvictLast);
-                            fs_tma_load_3d(pl + 5 * FS_PLANE, &maps.ftab, fb, j0, k0, zt + 0, kEvictLast);
-                            fs_tma_load_3d(pl + 6 * FS_PLANE, &maps.ftab, fb, j0, k0, zt + 3, kEvictLast);
-                            if constexpr (KIND == NKB_MOD_FORCED_FILE)
-                                fs_tma_load_3d(pl + 7 * FS_PLANE, &maps.src, fb, j0, k0, 2 * p.step + 1, kEvictLast);
+                            for (int q = 0; q < 4; ++q)
+                                fs_tma_load_3d(pl + q * C.ppbytes, &maps.ctab, fb, 2 * j0, k0, zt + 3 + q, kEvictLast);
                         } else {
-                            fs_mbar_expect_tx(fb, 2 * FS_PLANE);
-                            fs_tma_load_3d(pl + 0 * FS_PLANE, &maps.ftab, fb, j0, k0, zt + 4, kEvictLast);
-                            fs_tma_load_3d(pl + 1 * FS_PLANE, &maps.ftab, fb, j0, k0, zt + 5, kEvictLast);
+                            fs_mbar_expect_tx(fb, C.ppbytes);
+                            fs_tma_load_3d(pl, &maps.ctab, fb, 2 * j0, k0, zt + 7, kEvictLast);
                         }
                         ++g;
                     }
@@ -408,9 +401,9 @@ __global__ void __launch_bounds__(fs_threads(MPT), 1) step_fused_kernel(const St
                 const int ct = (tile / p.nmb) % p.nct;
                 const int tr = tile / (p.nmb * p.nct);
                 for (int c = 0; c < nchunk; ++c) {
-                    const uint32_t s = go % FS_NO, ph = (go / FS_NO) & 1;
+                    const uint32_t s = go % NO, ph = (go / NO) & 1;
                     fs_mbar_wait<2000>(bar_ofull + 8 * s, ph);
-                    fs_tma_store_4d(&maps.uout, oring_a + s * FS_OUT, mb * FS_MEM, ct * p.jt, c * FS_KC, tr);
+                    fs_tma_store_4d(&maps.uout, oring_a + s * C.out, mb * FS_MEM, ct * p.jt, c * KC, tr);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                     fs_mbar_arrive(bar_oempty + 8 * s);
@@ -421,16 +414,17 @@ __global__ void __launch_bounds__(fs_threads(MPT), 1) step_fused_kernel(const St
         }
     } else {
         // ===== consumers =====
-        constexpr int DELTA = (MPT == 2) ? 1 : 2;     // lane distance of the neighbour column
+        constexpr int DELTA = (MPT == 2) ? 1 : 2;  // lane distance of the neighbour column
         constexpr int WIDTH = (MPT == 2) ? 16 : 32;
+        constexpr int PP = KC * FS_COLS;           // pairs per plane
         const int col = (MPT == 2) ? (lane & 15) : (lane >> 1);
         const int c16 = (MPT == 2) ? 2 * warp + (lane >> 4) : warp;  // 16-byte chunk within the 128-byte row
         const int sub = (MPT == 2) ? 0 : 8 * (lane & 1);             // byte within the chunk
         // TMEM: lane quarter warp % 4; with 8 warps the upper four use columns 256..511
         const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 256);
-        int offU[FS_KC][3], offO[FS_KC];
+        int offU[KC][3], offO[KC];
 #pragma unroll
-        for (int q = 0; q < FS_KC; ++q) {
+        for (int q = 0; q < KC; ++q) {
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
                 const int r = q * FS_UCOLS + col + d;
@@ -453,40 +447,34 @@ __global__ void __launch_bounds__(fs_threads(MPT), 1) step_fused_kernel(const St
                 aff1 = __ldg(p.aff1 + (size_t)cls * ny + j);
                 aff2 = __ldg(p.aff2 + (size_t)cls * ny + j);
             }
-            const double srcc = p.src_const[tr];
+            const double ws1 = p.hg * p.src_const[tr], ws2 = p.he1 * p.src_const[tr];
 
             // ---------------- sweep A: stage-1 rhs + LU forward elimination, top -> bottom ----------------
             V yprev = fs_splat<MPT>(0.0);
             for (int c = 0; c < nchunk; ++c) {
-                const uint32_t s = g % FS_NS, ph = (g / FS_NS) & 1;
+                const uint32_t s = g % NS, ph = (g / NS) & 1;
                 fs_mbar_wait<20>(bar_full + 8 * s, ph);
-                const unsigned char *sb = ring + s * FS_SLOT;
-                const double *pl = reinterpret_cast<const double *>(sb + FS_UBYTES) + col;
-                V yb[FS_KC];
+                const unsigned char *sb = ring + s * C.slot;
+                const double2 *pl = reinterpret_cast<const double2 *>(sb + C.ubytes) + col;
+                V yb[KC];
 #pragma unroll
-                for (int q = 0; q < FS_KC; ++q) {
+                for (int q = 0; q < KC; ++q) {
                     const V cv = fs_ld(sb + offU[q][1], (V *)nullptr);
-                    double frc = 0.0;
-                    if constexpr (KIND == NKB_MOD_FORCED_FILE) frc = pl[4 * 64 + q * 16];
-                    V es = fs_source<KIND, MPT>(srcc, thr_r, frc, cv);  // e + s
-                    if constexpr (HAS_E) {
-                        const V cl = fs_ld(sb + offU[q][0], (V *)nullptr);
-                        const V cr = fs_ld(sb + offU[q][2], (V *)nullptr);
-                        const double eL = pl[q * 16], eC = pl[64 + q * 16], eR = pl[128 + q * 16];
-                        es = fs_add(fs_fma(eL, cl, fs_fma(eR, cr, fs_mul(eC, cv))), es);
-                    } else {
-                        es = fs_add(fs_splat<MPT>(0.0), es);
-                    }
-                    const double m1 = pl[3 * 64 + q * 16];
-                    V rhs = fs_fma(p.hg, es, cv);
+                    const V cl = fs_ld(sb + offU[q][0], (V *)nullptr);
+                    const V cr = fs_ld(sb + offU[q][2], (V *)nullptr);
+                    const double2 lc = pl[q * FS_COLS], rm = pl[PP + q * FS_COLS];
+                    double fw = 0.0;
+                    if constexpr (FRC) fw = pl[2 * PP + q * FS_COLS].x;
+                    const V sv = fs_source<KIND, MPT>(ws1, thr_r, fw, cv);
+                    V rhs = fs_fma(lc.x, cl, fs_fma(rm.x, cr, fs_fma(lc.y, cv, sv)));
                     if (c == 0 && q == 0) rhs = fs_add(rhs, fs_splat<MPT>(aff1));
-                    yprev = fs_fma(-m1, yprev, rhs);
+                    yprev = fs_fma(-rm.y, yprev, rhs);
                     yb[q] = yprev;
                 }
                 __syncwarp();
                 if (lane == 0) fs_mbar_arrive(bar_empty + 8 * s);
                 Raw<W> raw;
-                fs_pack(yb, raw);
+                fs_pack<MPT, KC>(yb, raw);
                 fs_tmem_st(taddr + c * W, raw);
                 ++g;
             }
@@ -495,59 +483,56 @@ __global__ void __launch_bounds__(fs_threads(MPT), 1) step_fused_kernel(const St
             // ------- sweep B: stage-1 back substitution + stage-2 rhs + UL elimination, bottom -> top -------
             {
                 Raw<W> rcur, rnx;
-                V ycur[FS_KC], ynx[FS_KC];
+                V ycur[KC], ynx[KC];
                 fs_tmem_ld(taddr + (nchunk - 1) * W, rcur);
                 fs_tmem_wait_ld(rcur);
-                fs_unpack(rcur, ycur);
+                fs_unpack<MPT, KC>(rcur, ycur);
                 V u1n = fs_splat<MPT>(0.0), y2n = fs_splat<MPT>(0.0);
                 for (int c = nchunk - 1; c >= 0; --c) {
                     if (c > 0) fs_tmem_ld(taddr + (c - 1) * W, rnx);
-                    const uint32_t s = g % FS_NS, ph = (g / FS_NS) & 1;
+                    const uint32_t s = g % NS, ph = (g / NS) & 1;
                     fs_mbar_wait<20>(bar_full + 8 * s, ph);
                     if (c > 0) {
                         fs_tmem_wait_ld(rnx);
-                        fs_unpack(rnx, ynx);
+                        fs_unpack<MPT, KC>(rnx, ynx);
                     } else {
 #pragma unroll
-                        for (int q = 0; q < FS_KC; ++q) ynx[q] = fs_splat<MPT>(0.0);
+                        for (int q = 0; q < KC; ++q) ynx[q] = fs_splat<MPT>(0.0);
                     }
-                    const unsigned char *sb = ring + s * FS_SLOT;
-                    const double *pl = reinterpret_cast<const double *>(sb + FS_UBYTES) + col;
-                    V yb[FS_KC];
+                    const unsigned char *sb = ring + s * C.slot;
+                    const double2 *pl = reinterpret_cast<const double2 *>(sb + C.ubytes) + col;
+                    V yb[KC];
 #pragma unroll
-                    for (int q = FS_KC - 1; q >= 0; --q) {
+                    for (int q = KC - 1; q >= 0; --q) {
                         const V y1 = ycur[q];
-                        const V y1m = (q > 0) ? ycur[q > 0 ? q - 1 : 0] : ynx[FS_KC - 1];
-                        const double ib1 = pl[3 * 64 + q * 16], g1 = pl[4 * 64 + q * 16];
-                        const double m1 = pl[5 * 64 + q * 16], m2 = pl[6 * 64 + q * 16];
-                        const V u1 = fs_fma(-g1, u1n, fs_mul(ib1, y1));
+                        const V y1m = (q > 0) ? ycur[q > 0 ? q - 1 : 0] : ynx[KC - 1];
+                        const double2 lc = pl[q * FS_COLS], ri = pl[PP + q * FS_COLS], gm = pl[2 * PP + q * FS_COLS],
+                                      mf = pl[3 * PP + q * FS_COLS];
+                        const V u1 = fs_fma(-gm.x, u1n, fs_mul(ri.y, y1));
                         u1n = u1;
-                        V rhs1 = fs_fma(m1, y1m, y1);  // = u_n + gamma h E(u_n) (+ aff1 at the surface)
+                        V rhs1 = fs_fma(gm.y, y1m, y1);  // = u_n + gamma h E(u_n) (+ aff1 at the surface)
                         if (c == 0 && q == 0) rhs1 = fs_sub(rhs1, fs_splat<MPT>(aff1));
                         const V un = fs_ld(sb + offU[q][1], (V *)nullptr);
-                        const V pp = fs_fma(p.r, fs_sub(rhs1, un), fs_mul(p.a0, un));
-                        double frc = 0.0;
-                        if constexpr (KIND == NKB_MOD_FORCED_FILE) frc = pl[7 * 64 + q * 16];
-                        V es = fs_source<KIND, MPT>(srcc, thr_r, frc, u1);
-                        if constexpr (HAS_E) {
-                            const V ul = fs_shfl_up<MPT, DELTA, WIDTH>(u1), ur = fs_shfl_down<MPT, DELTA, WIDTH>(u1);
-                            const double eL = pl[q * 16], eC = pl[64 + q * 16], eR = pl[128 + q * 16];
-                            es = fs_add(fs_fma(eL, ul, fs_fma(eR, ur, fs_mul(eC, u1))), es);
+                        // a0 u_n + h (delta - 1 + gamma) E(u_n) + he1 * source(u1)
+                        V pp;
+                        if constexpr (FRC) {
+                            pp = fs_add(fs_fma(p.r, rhs1, fs_mul(p.a0r, un)), fs_source<KIND, MPT>(ws2, thr_r, mf.y, u1));
                         } else {
-                            es = fs_add(fs_splat<MPT>(0.0), es);
+                            pp = fs_fma(p.r, rhs1, fs_fma(p.a0r, un, fs_splat<MPT>(ws2)));
                         }
-                        V rhs2 = fs_fma(p.he1, es, fs_fma(p.a1, u1, pp));
+                        const V ul = fs_shfl_up<MPT, DELTA, WIDTH>(u1), ur = fs_shfl_down<MPT, DELTA, WIDTH>(u1);
+                        V rhs2 = fs_fma(lc.x, ul, fs_fma(ri.x, ur, fs_fma(lc.y, u1, pp)));
                         if (c == 0 && q == 0) rhs2 = fs_add(rhs2, fs_splat<MPT>(aff2));
-                        y2n = fs_fma(-m2, y2n, rhs2);
+                        y2n = fs_fma(-mf.x, y2n, rhs2);
                         yb[q] = y2n;
                     }
                     __syncwarp();
                     if (lane == 0) fs_mbar_arrive(bar_empty + 8 * s);
                     Raw<W> raw;
-                    fs_pack(yb, raw);
+                    fs_pack<MPT, KC>(yb, raw);
                     fs_tmem_st(taddr + c * W, raw);
 #pragma unroll
-                    for (int q = 0; q < FS_KC; ++q) ycur[q] = ynx[q];
+                    for (int q = 0; q < KC; ++q) ycur[q] = ynx[q];
                     ++g;
                 }
                 fs_tmem_wait_st();
@@ -556,23 +541,23 @@ __global__ void __launch_bounds__(fs_threads(MPT), 1) step_fused_kernel(const St
             // ---------------- sweep C: stage-2 substitution, top -> bottom, staged TMA store ----------------
             {
                 Raw<W> rcur, rnx;
-                V ycur[FS_KC];
+                V ycur[KC];
                 fs_tmem_ld(taddr, rcur);
                 fs_tmem_wait_ld(rcur);
-                fs_unpack(rcur, ycur);
+                fs_unpack<MPT, KC>(rcur, ycur);
                 V u2p = fs_splat<MPT>(0.0);
                 for (int c = 0; c < nchunk; ++c) {
                     if (c + 1 < nchunk) fs_tmem_ld(taddr + (c + 1) * W, rnx);
-                    const uint32_t s = g % FS_NS, ph = (g / FS_NS) & 1;
-                    const uint32_t so = go % FS_NO, pho = (go / FS_NO) & 1;
+                    const uint32_t s = g % NS, ph = (g / NS) & 1;
+                    const uint32_t so = go % NO, pho = (go / NO) & 1;
                     fs_mbar_wait<20>(bar_full + 8 * s, ph);
                     fs_mbar_wait<20>(bar_oempty + 8 * so, pho ^ 1);
-                    const double *pl = reinterpret_cast<const double *>(ring + s * FS_SLOT + FS_UBYTES) + col;
-                    unsigned char *ob = oring + so * FS_OUT;
+                    const double2 *pl = reinterpret_cast<const double2 *>(ring + s * C.slot + C.ubytes) + col;
+                    unsigned char *ob = oring + so * C.out;
 #pragma unroll
-                    for (int q = 0; q < FS_KC; ++q) {
-                        const double ib2 = pl[q * 16], g2 = pl[64 + q * 16];
-                        u2p = fs_fma(-g2, u2p, fs_mul(ib2, ycur[q]));
+                    for (int q = 0; q < KC; ++q) {
+                        const double2 ig = pl[q * FS_COLS];
+                        u2p = fs_fma(-ig.y, u2p, fs_mul(ig.x, ycur[q]));
                         if (interior) fs_st(ob + offO[q], u2p);
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -583,7 +568,7 @@ __global__ void __launch_bounds__(fs_threads(MPT), 1) step_fused_kernel(const St
                     }
                     if (c + 1 < nchunk) {
                         fs_tmem_wait_ld(rnx);
-                        fs_unpack(rnx, ycur);
+                        fs_unpack<MPT, KC>(rnx, ycur);
                     }
                     ++g;
                     ++go;
@@ -655,6 +640,9 @@ static int fs_encode(CUtensorMap *map, const void *ptr, int rank, const cuuint64
     return 0;
 }
 
+// members per thread of the consumer layout (NKB_FUSED_MPT: 1 = 8 warps x 8-level chunks, 2 = 4 warps x 4)
+static int fs_mpt() { return fs_env_int("NKB_FUSED_MPT", 1) == 2 ? 2 : 1; }
+
 // geometry of the column tiling: nct tiles of jt <= 14 interior columns
 static void fs_col_tiles(int ny, int &nct, int &jt) {
     int jmax = fs_env_int("NKB_FUSED_JT", FS_JT);
@@ -662,14 +650,13 @@ static void fs_col_tiles(int ny, int &nct, int &jt) {
     if (jmax > FS_JT) jmax = FS_JT;
     nct = (ny + jmax - 1) / jmax;
     jt = (ny + nct - 1) / nct;
-    jt = (jt + 1) & ~1;  // even: the plane boxes start at table column j0 = ct*jt, which TMA wants 16-byte aligned
 }
 
 bool fused_step_usable(const ModelDev &v, int B, int ldb, const double *x0, const double *f, const double *work) {
     if (fs_env_int("NKB_FUSED", 1) == 0) return false;
     if (v.column_model == 1 && v.ny == 1) return false;
     if (v.kind != NKB_MOD_LINEAR && v.kind != NKB_MOD_FORCED_FILE) return false;
-    if ((v.nz + FS_KC - 1) / FS_KC * 16 > 512) return false;  // TMEM: 4 columns per level
+    if (v.nz > 128) return false;  // TMEM: 2 x 32-bit columns per level and member, 256 per thread
     if (B < fs_env_int("NKB_FUSED_MIN_B", 8) || (ldb % 2) != 0) return false;
     if (((uintptr_t)x0 | (uintptr_t)f | (uintptr_t)work) & 15) return false;
     return fs_encode_fn() != nullptr;
@@ -678,54 +665,46 @@ bool fused_step_usable(const ModelDev &v, int B, int ldb, const double *x0, cons
 int fused_encode_state_maps(const ModelDev &v, int B, int ldb, const double *buf, CUtensorMap *in, CUtensorMap *out) {
     int nct, jt;
     fs_col_tiles(v.ny, nct, jt);
+    const cuuint32_t kc = (cuuint32_t)fs_cfg(fs_mpt()).kc;
+    // members beyond B are never read (zero-filled) nor written (clipped)
     const cuuint64_t dims[4] = {(cuuint64_t)B, (cuuint64_t)v.ny, (cuuint64_t)v.nz, (cuuint64_t)v.T};
     const cuuint64_t strides[3] = {(cuuint64_t)ldb * 8, (cuuint64_t)v.ny * ldb * 8, (cuuint64_t)v.nz * v.ny * ldb * 8};
-    const cuuint32_t box_in[4] = {FS_MEM, FS_UCOLS, FS_KC, 1};
-    const cuuint32_t box_out[4] = {FS_MEM, (cuuint32_t)jt, FS_KC, 1};
+    const cuuint32_t box_in[4] = {FS_MEM, FS_UCOLS, kc, 1};
+    const cuuint32_t box_out[4] = {FS_MEM, (cuuint32_t)jt, kc, 1};
     if (in && fs_encode(in, buf, 4, dims, strides, box_in, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
     if (out && fs_encode(out, buf, 4, dims, strides, box_out, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
     return 0;
 }
 
-int fused_encode_plane_map(int nz, int ny, int nyp, size_t nplanes, const double *buf, CUtensorMap *map) {
-    // plane tables carry one zero column on the left (table column = j + 1): the box of a tile starts
-    // at column j0 - 1, and TMA faults ("illegal instruction") on a box whose innermost start
-    // address is not 16-byte aligned (odd float64 coordinate), measured on B200
-    const cuuint64_t dims[3] = {(cuuint64_t)(ny + 1), (cuuint64_t)nz, (cuuint64_t)nplanes};
-    const cuuint64_t strides[2] = {(cuuint64_t)nyp * 8, (cuuint64_t)nz * nyp * 8};
-    const cuuint32_t box[3] = {FS_COLS, FS_KC, 1};
+int fused_encode_ctab_map(int nz, int ny, size_t nplanes, const double *buf, CUtensorMap *map) {
+    // rows of (ny + 1) coefficient pairs, one zero pair on the left: the box of a column tile starts at
+    // column j0 - 1 = pair index j0, double index 2*j0 — always even.  TMA faults ("illegal
+    // instruction") on a box whose innermost start address is not 16-byte aligned (an odd float64
+    // coordinate), measured on B200.
+    const cuuint64_t np = 2 * ((cuuint64_t)ny + 1);
+    const cuuint64_t dims[3] = {np, (cuuint64_t)nz, (cuuint64_t)nplanes};
+    const cuuint64_t strides[2] = {np * 8, (cuuint64_t)nz * np * 8};
+    const cuuint32_t box[3] = {2 * FS_COLS, (cuuint32_t)fs_cfg(fs_mpt()).kc, 1};
     return fs_encode(map, buf, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
 }
 
-struct FusedLaunch {
-    const ModelDev *v;
-    int B, n_steps;
-    const CUtensorMap *uin, *uout, *est, *ftab, *src;
-};
-
-template <int KIND, bool HAS_E, int MPT>
+template <int KIND, int MPT>
 static int fs_launch_m(const StepArgs &a, const StepMaps &maps, int grid, cudaStream_t st) {
-    auto kern = step_fused_kernel<KIND, HAS_E, MPT>;
+    auto kern = step_fused_kernel<KIND, MPT>;
+    constexpr FsCfg C = fs_cfg(MPT);
     static bool attr_set = false;
     if (!attr_set) {
-        NKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM));
+        NKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C.smem));
         attr_set = true;
     }
-    kern<<<grid, fs_threads(MPT), FS_SMEM, st>>>(a, maps);
+    kern<<<grid, C.threads, C.smem, st>>>(a, maps);
     count_launch();
     return 0;
 }
 
-template <int KIND, bool HAS_E>
-static int fs_launch_t(const StepArgs &a, const StepMaps &maps, int grid, cudaStream_t st) {
-    // NKB_FUSED_MPT: members per thread (2: 4 consumer warps, 1: 8 consumer warps)
-    if (fs_env_int("NKB_FUSED_MPT", 1) == 2) return fs_launch_m<KIND, HAS_E, 2>(a, maps, grid, st);
-    return fs_launch_m<KIND, HAS_E, 1>(a, maps, grid, st);
-}
-
 int launch_step_fused(const ModelDev &v, int B, int n_steps, int step, double h, const double *aff1,
-                      const double *aff2, const CUtensorMap &uin, const CUtensorMap &uout, const CUtensorMap *est,
-                      const CUtensorMap &ftab, const CUtensorMap *src, cudaStream_t st) {
+                      const double *aff2, const CUtensorMap &uin, const CUtensorMap &uout, const CUtensorMap &ctab,
+                      cudaStream_t st) {
     StepArgs a;
     std::memset(&a, 0, sizeof(a));
     a.nz = v.nz; a.ny = v.ny; a.B = B; a.T = v.T; a.ncls = v.n_classes; a.n_steps = n_steps;
@@ -735,17 +714,16 @@ int launch_step_fused(const ModelDev &v, int B, int n_steps, int step, double h,
     a.step = step;
     for (int t = 0; t < NKB_MAX_TRACERS; ++t) { a.class_of[t] = v.class_of[t]; a.src_const[t] = v.src_const[t]; }
     a.sink_thres_r = v.sink_thres > 0.0 ? 1.0 / v.sink_thres : 0.0;
+    // stage 2 (nkb_api.cu): rhs2 = a0 u_n + a1 u1 + h (delta - 1 + gamma) E(u_n) + h (1 - delta) E(u1); with
+    // rhs1 = u_n + gamma h E(u_n) the u_n terms are P = r rhs1 + (a0 - r) u_n, r = (delta - 1 + gamma)/gamma
+    const double a1 = (1.0 - kGamma) / kGamma, a0 = 1.0 - a1;
     a.hg = kGamma * h;
-    a.a1 = (1.0 - kGamma) / kGamma;
-    a.a0 = 1.0 - a.a1;
-    a.r = (kDelta - 1.0 + kGamma) / kGamma;
     a.he1 = h * (1.0 - kDelta);
+    a.r = (kDelta - 1.0 + kGamma) / kGamma;
+    a.a0r = a0 - a.r;
     a.aff1 = aff1; a.aff2 = aff2;
     StepMaps maps;
-    std::memset(&maps, 0, sizeof(maps));
-    maps.uin = uin; maps.uout = uout; maps.ftab = ftab;
-    if (est) maps.est = *est;
-    if (src) maps.src = *src;
+    maps.uin = uin; maps.uout = uout; maps.ctab = ctab;
     static int n_sm = 0;
     if (n_sm == 0) {
         int dev = 0;
@@ -754,16 +732,12 @@ int launch_step_fused(const ModelDev &v, int B, int n_steps, int step, double h,
     }
     int grid = fs_env_int("NKB_FUSED_GRID", n_sm);
     if (grid > a.ntiles) grid = a.ntiles;
-    const bool has_e = (est != nullptr);
-    if (v.kind == NKB_MOD_LINEAR) {
-        return has_e ? fs_launch_t<NKB_MOD_LINEAR, true>(a, maps, grid, st)
-                     : fs_launch_t<NKB_MOD_LINEAR, false>(a, maps, grid, st);
-    }
-    if (v.kind == NKB_MOD_FORCED_FILE) {
-        NKB_REQUIRE(src != nullptr, "launch_step_fused: forcing planes missing");
-        return has_e ? fs_launch_t<NKB_MOD_FORCED_FILE, true>(a, maps, grid, st)
-                     : fs_launch_t<NKB_MOD_FORCED_FILE, false>(a, maps, grid, st);
-    }
+    const int mpt = fs_mpt();
+    if (v.kind == NKB_MOD_LINEAR)
+        return mpt == 2 ? fs_launch_m<NKB_MOD_LINEAR, 2>(a, maps, grid, st) : fs_launch_m<NKB_MOD_LINEAR, 1>(a, maps, grid, st);
+    if (v.kind == NKB_MOD_FORCED_FILE)
+        return mpt == 2 ? fs_launch_m<NKB_MOD_FORCED_FILE, 2>(a, maps, grid, st)
+                        : fs_launch_m<NKB_MOD_FORCED_FILE, 1>(a, maps, grid, st);
     set_error("launch_step_fused: unsupported module kind");
     return 2;
 }

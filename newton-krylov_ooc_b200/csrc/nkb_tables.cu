@@ -153,33 +153,67 @@ __global__ void stage_tables_kernel(ModelDev m, int n_stages, const double *__re
     }
 }
 
-// Tables of the fused step kernel (nkb_step_fused.cu): structure-of-arrays planes [nz][nyp]
-// (table column = j + 1: one zero column on the left; nyp >= ny + 1 even: 16-byte row pitch for TMA), per (step, class) the six planes
-//   0: m1  1: ib1  2: g1     LU (top-down) factors of I - hg*L(t_n + gamma h)   — same values as tri
-//   3: m2  4: ib2  5: g2     UL (bottom-up) factors of I - hg*L(t_n + h):
-//        elimination  y_k = r_k - m2_k y_{k+1} (k = nz-2..0),  substitution x_k = ib2_k y_k - g2_k x_{k-1}
-// The stage-2 system is eliminated upwards so that it can consume the stage-1 solution level by
-// level while that is being back-substituted upwards.
-__global__ void step_tables_kernel(ModelDev m, int n_steps, const double *__restrict__ t_stage,
-                                   const double *__restrict__ hg_stage, int nyp, double *__restrict__ ftab) {
+// forcing record interpolated to time t at one cell (utils.py:533-535: interp1d, linear,
+// fill_value="extrapolate")
+__device__ __forceinline__ double forcing_at(const ModelDev &m, double t, size_t cell) {
+    const size_t plane = (size_t)m.nz * m.ny;
+    int i = 0;
+    while (i < m.n_frc - 2 && t >= m.frc_time[i + 1]) ++i;
+    const double lo = m.frc_data[(size_t)i * plane + cell];
+    const double hi = m.frc_data[(size_t)(i + 1) * plane + cell];
+    const double slope = (hi - lo) / (m.frc_time[i + 1] - m.frc_time[i]);
+    return slope * (t - m.frc_time[i]) + lo;
+}
+
+// Tables of the fused step kernel (nkb_step_fused.cu).  Everything member independent that a
+// time step needs at (level k, column j) is folded here, once per schedule, into 16-byte pairs
+// so that a thread of the step kernel gets two coefficients per shared-memory load:
+//   pair plane   contents                                   used by
+//   0  {aL, aC}  hg*eL, 1 + hg*eC                            sweep A: rhs1 = aL c_{j-1} + aC c_j + aR c_{j+1} + hg*s
+//   1  {aR, m1}  hg*eR, LU multiplier of stage 1
+//   2  {fA, 0}   hg*frc(t_n)                       (forcing record, FORCED_FILE)
+//   3  {bL, bC}  he1*eL, a1 + he1*eC                         sweep B: rhs2 = P + bL u1_{j-1} + bC u1_j + bR u1_{j+1} + he1*s
+//   4  {bR, ib1} he1*eR, 1/beta of stage 1
+//   5  {g1, m1}  U factor and L multiplier of stage 1
+//   6  {m2, fB}  UL multiplier of stage 2, he1*frc(t_n + gamma h)
+//   7  {ib2, g2} UL factors of stage 2                       sweep C
+// with hg = gamma h, he1 = h (1 - delta), a1 = (1 - gamma)/gamma (ARS(2,2,2)).  Stage 1 is factored
+// top-down (LU, same values as the tri tables), stage 2 bottom-up (UL):
+//   elimination  y_k = r_k - m2_k y_{k+1} (k = nz-2..0),  substitution x_k = ib2_k y_k - g2_k x_{k-1}
+// so that it can consume the stage-1 solution level by level while that is being back-substituted
+// upwards.  Layout ctab[step][class][8][nz][np], np = 2*(ny + 1) doubles: pair of column j at
+// [2*(j+1)], one zero pair on the left (the box of a column tile starts at column j0 - 1).
+__global__ void step_ctab_kernel(ModelDev m, int n_steps, const double *__restrict__ t_stage,
+                                 const double *__restrict__ hg_stage, const double *__restrict__ t_exp,
+                                 double *__restrict__ ctab) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int s = blockIdx.y;
     if (j >= m.ny || s >= n_steps) return;
-    const int nz = m.nz, nc = m.n_classes;
-    const size_t pl = (size_t)nz * nyp;
+    const int nz = m.nz, ny = m.ny, nc = m.n_classes;
+    const int np = 2 * (ny + 1);
+    const size_t pl = (size_t)nz * np;
+    const double hg = hg_stage[2 * s];
+    const double he1 = hg / kGamma * (1.0 - kDelta);
+    const double a1 = (1.0 - kGamma) / kGamma;
     for (int stage = 0; stage < 2; ++stage) {
         const double time = t_stage[2 * s + stage];
-        const double hg = hg_stage[2 * s + stage];
         const double bld = bldepth(m, time, j);
         double mc_up = 0.0;
         double prev_ib[NKB_MAX_CLASSES], prev_c[NKB_MAX_CLASSES];
         for (int k = 0; k < nz; ++k) {
             const double mc_dn = (k < nz - 1) ? mixing_coeff_edge(m, bld, k + 1, j) : 0.0;
+            const size_t cell = (size_t)k * ny + j;
+            double eL = 0.0, eC = 0.0, eR = 0.0;
+            if (m.estencil) {
+                eL = m.estencil[cell * 4 + 0];
+                eC = m.estencil[cell * 4 + 1];
+                eR = m.estencil[cell * 4 + 2];
+            }
             for (int c = 0; c < nc; ++c) {
                 double sub, diag, sup;
                 vert_coeffs(m, k, j, c, mc_up, mc_dn, sub, diag, sup);
                 const double a = -hg * sub, b = 1.0 - hg * diag, cc = -hg * sup;
-                double *base = ftab + ((size_t)s * nc + c) * 6 * pl + (size_t)k * nyp + j + 1;
+                double *base = ctab + ((size_t)s * nc + c) * 8 * pl + (size_t)k * np + 2 * (j + 1);
                 if (stage == 0) {
                     double mk = 0.0, beta = b;
                     if (k > 0) {
@@ -187,15 +221,26 @@ __global__ void step_tables_kernel(ModelDev m, int n_steps, const double *__rest
                         beta = b - mk * prev_c[c];
                     }
                     const double ib = 1.0 / beta;
-                    base[0 * pl] = mk;
-                    base[1 * pl] = ib;
-                    base[2 * pl] = (k < nz - 1) ? cc * ib : 0.0;
+                    base[0 * pl + 0] = hg * eL;
+                    base[0 * pl + 1] = 1.0 + hg * eC;
+                    base[1 * pl + 0] = hg * eR;
+                    base[1 * pl + 1] = mk;
+                    base[2 * pl + 0] = (m.kind == NKB_MOD_FORCED_FILE) ? hg * forcing_at(m, t_exp[2 * s], cell) : 0.0;
+                    base[2 * pl + 1] = 0.0;
+                    base[3 * pl + 0] = he1 * eL;
+                    base[3 * pl + 1] = a1 + he1 * eC;
+                    base[4 * pl + 0] = he1 * eR;
+                    base[4 * pl + 1] = ib;
+                    base[5 * pl + 0] = (k < nz - 1) ? cc * ib : 0.0;
+                    base[5 * pl + 1] = mk;
                     prev_ib[c] = ib;
                     prev_c[c] = cc;
-                } else {  // raw rows first, factored bottom-up below
-                    base[3 * pl] = a;
-                    base[4 * pl] = b;
-                    base[5 * pl] = cc;
+                } else {  // raw rows first (parked in planes 6 and 7), factored bottom-up below
+                    base[6 * pl + 0] = a;
+                    base[7 * pl + 0] = b;
+                    base[7 * pl + 1] = cc;
+                    base[6 * pl + 1] =
+                        (m.kind == NKB_MOD_FORCED_FILE) ? he1 * forcing_at(m, t_exp[2 * s + 1], cell) : 0.0;
                 }
             }
             mc_up = mc_dn;
@@ -204,47 +249,21 @@ __global__ void step_tables_kernel(ModelDev m, int n_steps, const double *__rest
     for (int c = 0; c < nc; ++c) {
         double ib_next = 0.0, a_next = 0.0;
         for (int k = nz - 1; k >= 0; --k) {
-            double *base = ftab + ((size_t)s * nc + c) * 6 * pl + (size_t)k * nyp + j + 1;
-            const double a = base[3 * pl], b = base[4 * pl], cc = base[5 * pl];
+            double *base = ctab + ((size_t)s * nc + c) * 8 * pl + (size_t)k * np + 2 * (j + 1);
+            const double a = base[6 * pl + 0], b = base[7 * pl + 0], cc = base[7 * pl + 1];
             double mk = 0.0, beta = b;
             if (k < nz - 1) {
                 mk = cc * ib_next;
                 beta = b - mk * a_next;
             }
             const double ib = 1.0 / beta;
-            base[3 * pl] = mk;
-            base[4 * pl] = ib;
-            base[5 * pl] = (k > 0) ? a * ib : 0.0;
+            base[6 * pl + 0] = mk;
+            base[7 * pl + 0] = ib;
+            base[7 * pl + 1] = (k > 0) ? a * ib : 0.0;
             ib_next = ib;
             a_next = a;
         }
     }
-}
-
-// SoA copies of time-invariant / forcing tables with the padded row pitch nyp
-__global__ void est_planes_kernel(int nz, int ny, int nyp, const double *__restrict__ est4,
-                                  double *__restrict__ out /* [3][nz][nyp] */) {
-    const size_t cell = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (cell >= (size_t)nz * ny) return;
-    const int k = (int)(cell / ny), j = (int)(cell % ny);
-    for (int q = 0; q < 3; ++q) out[((size_t)q * nz + k) * nyp + j + 1] = est4[cell * 4 + q];
-}
-
-// forcing at the two explicit stage times of every step: out[step][2][nz][nyp]
-__global__ void forcing_planes_kernel(ModelDev m, int n_times, const double *__restrict__ t_eval, int nyp,
-                                      double *__restrict__ out) {
-    const size_t plane = (size_t)m.nz * m.ny;
-    const size_t cell = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int s = blockIdx.y;
-    if (cell >= plane || s >= n_times) return;
-    const double t = t_eval[s];
-    int i = 0;
-    while (i < m.n_frc - 2 && t >= m.frc_time[i + 1]) ++i;
-    const double lo = m.frc_data[(size_t)i * plane + cell];
-    const double hi = m.frc_data[(size_t)(i + 1) * plane + cell];
-    const double slope = (hi - lo) / (m.frc_time[i + 1] - m.frc_time[i]);
-    const int k = (int)(cell / m.ny), j = (int)(cell % m.ny);
-    out[((size_t)s * m.nz + k) * nyp + j + 1] = slope * (t - m.frc_time[i]) + lo;
 }
 
 __global__ void mixing_coeff_kernel(ModelDev m, double time, double *__restrict__ out) {
@@ -280,27 +299,10 @@ int launch_stage_tables(const ModelDev &m, int n_stages, const double *d_t, cons
     return 0;
 }
 
-int launch_step_tables(const ModelDev &m, int n_steps, const double *d_t, const double *d_hg, int nyp, double *ftab,
-                       cudaStream_t st) {
+int launch_step_ctab(const ModelDev &m, int n_steps, const double *d_t, const double *d_hg, const double *d_texp,
+                     double *ctab, cudaStream_t st) {
     dim3 block(64), grid((m.ny + 63) / 64, n_steps);
-    step_tables_kernel<<<grid, block, 0, st>>>(m, n_steps, d_t, d_hg, nyp, ftab);
-    count_launch();
-    NKB_CUDA(cudaGetLastError());
-    return 0;
-}
-
-int launch_est_planes(const ModelDev &m, int nyp, double *out, cudaStream_t st) {
-    const size_t plane = (size_t)m.nz * m.ny;
-    est_planes_kernel<<<(unsigned)((plane + 127) / 128), 128, 0, st>>>(m.nz, m.ny, nyp, m.estencil, out);
-    count_launch();
-    NKB_CUDA(cudaGetLastError());
-    return 0;
-}
-
-int launch_forcing_planes(const ModelDev &m, int n_times, const double *d_t, int nyp, double *out, cudaStream_t st) {
-    const size_t plane = (size_t)m.nz * m.ny;
-    dim3 block(128), grid((unsigned)((plane + 127) / 128), n_times);
-    forcing_planes_kernel<<<grid, block, 0, st>>>(m, n_times, d_t, nyp, out);
+    step_ctab_kernel<<<grid, block, 0, st>>>(m, n_steps, d_t, d_hg, d_texp, ctab);
     count_launch();
     NKB_CUDA(cudaGetLastError());
     return 0;
