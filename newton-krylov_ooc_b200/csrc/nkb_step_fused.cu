@@ -278,7 +278,9 @@ __device__ __forceinline__ void fs_unpack(const Raw<KC * 2 * M> &r, Vd<M> (&v)[K
 
 // explicit source of one tracer times the stage weight w (w = gamma h or h (1 - delta)):
 // LINEAR: w * constant (iage.py:39), passed in ws.  FORCED_FILE: fw = w * forcing record with the
-// sink_thres limiter of forced.py:141-151 (sms scaled by c/thres where sms < 0 and 0 < c < thres)
+// sink_thres limiter of forced.py:141-151 (sms scaled by c/thres where sms < 0 and 0 < c < thres;
+// thr_r = 1/thres, or 0 when the limiter is off so that q = 0 fails the test).  The three
+// comparisons are chained into one predicate (DSETP .AND) and a single select.
 template <int KIND, int M>
 __device__ __forceinline__ Vd<M> fs_source(double ws, double thr_r, double fw, Vd<M> c) {
     Vd<M> r;
@@ -286,12 +288,17 @@ __device__ __forceinline__ Vd<M> fs_source(double ws, double thr_r, double fw, V
 #pragma unroll
         for (int i = 0; i < M; ++i) r.v[i] = ws;
     } else {
-        const bool lim = (thr_r > 0.0) & (fw < 0.0);
 #pragma unroll
         for (int i = 0; i < M; ++i) {
-            const double q = thr_r * c.v[i];
-            const bool t = lim & (q > 0.0) & (q < 1.0);
-            r.v[i] = t ? fw * q : fw;
+            asm("{\n\t.reg .pred pl, p1, p2;\n\t.reg .f64 q, fq;\n\t"
+                "setp.lt.f64 pl, %2, 0d0000000000000000;\n\t"
+                "mul.f64 q, %3, %1;\n\t"
+                "setp.gt.and.f64 p1, q, 0d0000000000000000, pl;\n\t"
+                "setp.lt.and.f64 p2, q, 0d3FF0000000000000, p1;\n\t"
+                "mul.f64 fq, %2, q;\n\t"
+                "selp.f64 %0, fq, %2, p2;\n\t}"
+                : "=d"(r.v[i])
+                : "d"(c.v[i]), "d"(fw), "d"(thr_r));
         }
     }
     return r;
@@ -482,22 +489,22 @@ __global__ void __launch_bounds__(fs_cfg(MPT).threads, 1) step_fused_kernel(cons
 
             // ------- sweep B: stage-1 back substitution + stage-2 rhs + UL elimination, bottom -> top -------
             {
-                Raw<W> rcur, rnx;
-                V ycur[KC], ynx[KC];
-                fs_tmem_ld(taddr + (nchunk - 1) * W, rcur);
-                fs_tmem_wait_ld(rcur);
-                fs_unpack<MPT, KC>(rcur, ycur);
+                Raw<W> ra, rb;  // chunk c and chunk c-1 (prefetched), alternating roles: no register copies
                 V u1n = fs_splat<MPT>(0.0), y2n = fs_splat<MPT>(0.0);
-                for (int c = nchunk - 1; c >= 0; --c) {
-                    if (c > 0) fs_tmem_ld(taddr + (c - 1) * W, rnx);
+                auto chunk_b = [&](Raw<W> &cur, Raw<W> &nxt, int c) {
+                    if (c > 0) fs_tmem_ld(taddr + (c - 1) * W, nxt);
                     const uint32_t s = g % NS, ph = (g / NS) & 1;
                     fs_mbar_wait<20>(bar_full + 8 * s, ph);
+                    V ycur[KC], y1top;
+                    fs_unpack<MPT, KC>(cur, ycur);
                     if (c > 0) {
-                        fs_tmem_wait_ld(rnx);
-                        fs_unpack<MPT, KC>(rnx, ynx);
-                    } else {
+                        fs_tmem_wait_ld(nxt);
 #pragma unroll
-                        for (int q = 0; q < KC; ++q) ynx[q] = fs_splat<MPT>(0.0);
+                        for (int i = 0; i < MPT; ++i)
+                            y1top.v[i] = __hiloint2double((int)nxt.w[((KC - 1) * MPT + i) * 2 + 1],
+                                                          (int)nxt.w[((KC - 1) * MPT + i) * 2]);
+                    } else {
+                        y1top = fs_splat<MPT>(0.0);
                     }
                     const unsigned char *sb = ring + s * C.slot;
                     const double2 *pl = reinterpret_cast<const double2 *>(sb + C.ubytes) + col;
@@ -505,7 +512,7 @@ __global__ void __launch_bounds__(fs_cfg(MPT).threads, 1) step_fused_kernel(cons
 #pragma unroll
                     for (int q = KC - 1; q >= 0; --q) {
                         const V y1 = ycur[q];
-                        const V y1m = (q > 0) ? ycur[q > 0 ? q - 1 : 0] : ynx[KC - 1];
+                        const V y1m = (q > 0) ? ycur[q > 0 ? q - 1 : 0] : y1top;
                         const double2 lc = pl[q * FS_COLS], ri = pl[PP + q * FS_COLS], gm = pl[2 * PP + q * FS_COLS],
                                       mf = pl[3 * PP + q * FS_COLS];
                         const V u1 = fs_fma(-gm.x, u1n, fs_mul(ri.y, y1));
@@ -531,29 +538,33 @@ __global__ void __launch_bounds__(fs_cfg(MPT).threads, 1) step_fused_kernel(cons
                     Raw<W> raw;
                     fs_pack<MPT, KC>(yb, raw);
                     fs_tmem_st(taddr + c * W, raw);
-#pragma unroll
-                    for (int q = 0; q < KC; ++q) ycur[q] = ynx[q];
                     ++g;
+                };
+                fs_tmem_ld(taddr + (nchunk - 1) * W, ra);
+                fs_tmem_wait_ld(ra);
+                int c = nchunk - 1;
+                for (; c >= 1; c -= 2) {
+                    chunk_b(ra, rb, c);
+                    chunk_b(rb, ra, c - 1);
                 }
+                if (c == 0) chunk_b(ra, rb, 0);
                 fs_tmem_wait_st();
             }
 
             // ---------------- sweep C: stage-2 substitution, top -> bottom, staged TMA store ----------------
             {
-                Raw<W> rcur, rnx;
-                V ycur[KC];
-                fs_tmem_ld(taddr, rcur);
-                fs_tmem_wait_ld(rcur);
-                fs_unpack<MPT, KC>(rcur, ycur);
+                Raw<W> ra, rb;
                 V u2p = fs_splat<MPT>(0.0);
-                for (int c = 0; c < nchunk; ++c) {
-                    if (c + 1 < nchunk) fs_tmem_ld(taddr + (c + 1) * W, rnx);
+                auto chunk_c = [&](Raw<W> &cur, Raw<W> &nxt, int c) {
+                    if (c + 1 < nchunk) fs_tmem_ld(taddr + (c + 1) * W, nxt);
                     const uint32_t s = g % NS, ph = (g / NS) & 1;
                     const uint32_t so = go % NO, pho = (go / NO) & 1;
                     fs_mbar_wait<20>(bar_full + 8 * s, ph);
                     fs_mbar_wait<20>(bar_oempty + 8 * so, pho ^ 1);
                     const double2 *pl = reinterpret_cast<const double2 *>(ring + s * C.slot + C.ubytes) + col;
                     unsigned char *ob = oring + so * C.out;
+                    V ycur[KC];
+                    fs_unpack<MPT, KC>(cur, ycur);
 #pragma unroll
                     for (int q = 0; q < KC; ++q) {
                         const double2 ig = pl[q * FS_COLS];
@@ -566,13 +577,18 @@ __global__ void __launch_bounds__(fs_cfg(MPT).threads, 1) step_fused_kernel(cons
                         fs_mbar_arrive(bar_empty + 8 * s);
                         fs_mbar_arrive(bar_ofull + 8 * so);
                     }
-                    if (c + 1 < nchunk) {
-                        fs_tmem_wait_ld(rnx);
-                        fs_unpack<MPT, KC>(rnx, ycur);
-                    }
+                    if (c + 1 < nchunk) fs_tmem_wait_ld(nxt);
                     ++g;
                     ++go;
+                };
+                fs_tmem_ld(taddr, ra);
+                fs_tmem_wait_ld(ra);
+                int c = 0;
+                for (; c + 1 < nchunk; c += 2) {
+                    chunk_c(ra, rb, c);
+                    chunk_c(rb, ra, c + 1);
                 }
+                if (c < nchunk) chunk_c(ra, rb, c);
             }
         }
     }
