@@ -563,13 +563,21 @@ __global__ void __launch_bounds__(fs_cfg(MPT).threads, 1) step_fused_kernel(cons
                     fs_mbar_wait<20>(bar_oempty + 8 * so, pho ^ 1);
                     const double2 *pl = reinterpret_cast<const double2 *>(ring + s * C.slot + C.ubytes) + col;
                     unsigned char *ob = oring + so * C.out;
-                    V ycur[KC];
+                    V ycur[KC], u2[KC];
                     fs_unpack<MPT, KC>(cur, ycur);
+                    // all coefficient loads first: the compiler cannot move a shared load across the
+                    // staging stores below (it cannot prove the two ring slots disjoint)
+                    double2 ig[KC];
+#pragma unroll
+                    for (int q = 0; q < KC; ++q) ig[q] = pl[q * FS_COLS];
 #pragma unroll
                     for (int q = 0; q < KC; ++q) {
-                        const double2 ig = pl[q * FS_COLS];
-                        u2p = fs_fma(-ig.y, u2p, fs_mul(ig.x, ycur[q]));
-                        if (interior) fs_st(ob + offO[q], u2p);
+                        u2p = fs_fma(-ig[q].y, u2p, fs_mul(ig[q].x, ycur[q]));
+                        u2[q] = u2p;
+                    }
+                    if (interior) {
+#pragma unroll
+                        for (int q = 0; q < KC; ++q) fs_st(ob + offO[q], u2[q]);
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
