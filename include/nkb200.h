@@ -164,6 +164,16 @@ int nkb_axpby(const int32_t *d_region, int R, int T, int ncell, const double *d_
  *   sigma[r][b] = 1e-4*norm (1 where 0);  perturb = x + sigma*v;  jvp = (fp - f0)/sigma */
 int nkb_fd_sigma(const double *d_norm, double *d_sigma, int n, void *stream);
 
+/* limiter of the Newton increment (tracer_module_state_base.py:115-151 apply_limiter ->
+ * utils.py:544-600 comp_scalef_lob / comp_scalef_upb / min_by_region): per (region, member) the
+ * largest scale factor in [0, 1] such that base + scalef*inc stays inside [lob, upb] for every
+ * tracer and cell of the region.  d_out [R][B] must be pre-filled by the caller with the value
+ * for regions that hold no cell (+inf in the reference); it is lowered by an exact atomic min.
+ * d_flag[0] is set to 1 when base itself is out of bounds (the reference raises ValueError). */
+int nkb_limiter_scalef(const int32_t *d_region, int R, int T, int ncell, const double *d_base,
+                       const double *d_inc, double lob, int has_lob, double upb, int has_upb, int B,
+                       int ldb, double *d_out /* [R][B] */, int32_t *d_flag, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

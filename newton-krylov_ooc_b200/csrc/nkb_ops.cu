@@ -127,9 +127,56 @@ __global__ void fd_sigma_kernel(const double *__restrict__ nrm, double *__restri
     sigma[i] = (s == 0.0) ? 1.0 : s;
 }
 
+// ---- limiter -------------------------------------------------------------------------------
+// out[r][b] = min over tracers and cells of region r of the largest scale factor in [0, 1] that
+// keeps base + scalef*inc inside [lob, upb] (utils.py:561-600 comp_scalef_lob/upb +
+// min_by_region :544-558).  Scale factors are non-negative doubles, whose bit patterns order like
+// unsigned integers: atomicMin on the bits is exact and order independent (deterministic).
+// flag[0] is set when base itself violates a bound (the reference raises ValueError).
+__global__ void limiter_scalef_kernel(const int *__restrict__ region, int T, size_t ncell,
+                                      const double *__restrict__ base, const double *__restrict__ inc, double lob,
+                                      int has_lob, double upb, int has_upb, int B, size_t ldb,
+                                      unsigned long long *__restrict__ out_bits, int *__restrict__ flag) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t cell = (size_t)blockIdx.y * blockDim.y + threadIdx.y;
+    if (b >= B || cell >= ncell) return;
+    const int r = region[cell];
+    if (r <= 0) return;
+    double sc = 1.0;
+    for (int t = 0; t < T; ++t) {
+        const size_t off = ((size_t)t * ncell + cell) * ldb + b;
+        const double x = base[off], d = inc[off];
+        if (has_lob) {
+            if (x < lob) flag[0] = 1;
+            if (x + d < lob) sc = fmin(sc, fabs((lob - x) / d));
+        }
+        if (has_upb) {
+            if (x > upb) flag[0] = 1;
+            if (x + d > upb) sc = fmin(sc, fabs((upb - x) / d));
+        }
+    }
+    atomicMin(out_bits + (size_t)(r - 1) * B + b, (unsigned long long)__double_as_longlong(sc));
+}
+
 }  // namespace nkb
 
 extern "C" {
+
+int nkb_limiter_scalef(const int32_t *d_region, int R, int T, int ncell, const double *d_base, const double *d_inc,
+                       double lob, int has_lob, double upb, int has_upb, int B, int ldb, double *d_out,
+                       int32_t *d_flag, void *stream) {
+    NKB_REQUIRE(d_region && d_base && d_inc && d_out && d_flag, "nkb_limiter_scalef: null argument");
+    NKB_REQUIRE(R >= 1 && T >= 1 && ncell >= 1 && B >= 1 && ldb >= B, "nkb_limiter_scalef: bad size");
+    int bx = 1;
+    while (bx < B && bx < 32) bx <<= 1;
+    dim3 block(bx, 256 / bx), grid((B + bx - 1) / bx, (ncell + block.y - 1) / block.y);
+    nkb::limiter_scalef_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(
+        d_region, T, (size_t)ncell, d_base, d_inc, lob, has_lob, upb, has_upb, B, (size_t)ldb,
+        reinterpret_cast<unsigned long long *>(d_out), d_flag);
+    nkb::count_launch();
+    NKB_CUDA(cudaGetLastError());
+    return 0;
+}
 
 int nkb_pack_members(const double *d_src_major, double *d_dst_fast, int n, int B, int ldb, void *stream) {
     NKB_REQUIRE(d_src_major && d_dst_fast && n > 0 && B > 0 && ldb >= B, "nkb_pack_members: bad argument");

@@ -97,6 +97,11 @@ SYMBOLS = {
          c_int, c_void_p],
     ),
     "nkb_fd_sigma": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "nkb_limiter_scalef": (
+        c_int,
+        [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_double, c_int, c_double, c_int, c_int, c_int,
+         c_void_p, c_void_p, c_void_p],
+    ),
 }
 
 _lib = None

@@ -260,6 +260,26 @@ class RegionWeights:
         return y
 
 
+    def limiter_scalef(self, base, inc, lob, upb, B):
+        """[region_cnt, B] largest scale factors in [0, 1] keeping base + scalef*inc in [lob, upb]
+        (utils.py:561-600); raises ValueError when base itself is out of bounds"""
+        lib = _lib.load()
+        ldb = base.shape[-1]
+        T = base.shape[0]
+        out = torch.full((self.region_cnt, B), float("inf"), dtype=torch.float64, device="cuda")
+        flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+        check(
+            lib.nkb_limiter_scalef(self.region.data_ptr(), self.region_cnt, T, self.ncell, base.data_ptr(),
+                                   inc.data_ptr(), 0.0 if lob is None else float(lob), 0 if lob is None else 1,
+                                   0.0 if upb is None else float(upb), 0 if upb is None else 1, B, ldb,
+                                   out.data_ptr(), flag.data_ptr(), _stream_ptr()),
+            "nkb_limiter_scalef",
+        )
+        if int(flag.item()) != 0:
+            raise ValueError("base < lob" if lob is not None else "base > upb")
+        return out
+
+
 class BandedFactor:
     """member-shared banded LU (nkb_banded)"""
 

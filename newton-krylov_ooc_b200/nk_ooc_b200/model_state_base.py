@@ -149,6 +149,41 @@ class TracerModuleStateBase:
         self.config.weights.axpby(alpha, xv, beta, self._flat(self.vals), self.members)
         return self
 
+    # ---- limiter (tracer_module_state_base.py:115-176) ----------------------------------------
+    def has_bounds(self):
+        if "bounds" in self._def:
+            return True
+        return any("bounds" in meta for meta in self._def["tracers"].values())
+
+    def get_bounds(self, tracer_name):
+        lob, upb = None, None
+        for metadata in (self._def, self._def["tracers"][tracer_name]):
+            if "bounds" in metadata:
+                lob = metadata["bounds"].get("lob", lob)
+                upb = metadata["bounds"].get("upb", upb)
+        return lob, upb
+
+    def apply_limiter(self, base):
+        """scale self so that base + scalef*self is within bounds; returns scalef [region_cnt, B]
+        on the host (1.0 without bounds), as tracer_module_state_base.py:115-151"""
+        R, B = self.config.region_cnt, self.members
+        if not self.has_bounds():
+            return np.ones((R, B))
+        scalef = np.ones((R, B))
+        for tname in self.tracer_names:
+            lob, upb = self.get_bounds(tname)
+            if lob is None and upb is None:
+                continue
+            t = self.tracer_index(tname)
+            got = self.config.weights.limiter_scalef(self._flat(base.vals[t : t + 1]), self._flat(self.vals[t : t + 1]),
+                                                     lob, upb, B).cpu().numpy()
+            # regions without cells come back as +inf (min_by_region, utils.py:557); the running
+            # minimum starts from ones (tracer_module_state_base.py:123-124), so they end at 1.0
+            scalef = np.minimum(scalef, got)
+        if (scalef < 1.0).any():
+            self.axpby(None, None, torch.from_numpy(np.ascontiguousarray(scalef)).cuda())
+        return scalef
+
     def apply_region_mask(self):
         """zero where region_mask == 0 (tracer_module_state_base.py:153-176)"""
         R, B = self.config.region_cnt, self.members
@@ -375,6 +410,13 @@ class ModelStateBase:
         if isinstance(other, ModelStateBase):
             return NotImplemented
         return self._like().__itruediv__(other)
+
+    def apply_limiter(self, base):
+        """scale self so that base + scalef*self is within bounds (model_state_base.py:76-84);
+        returns scalef [n_modules, region_cnt(, B)]"""
+        per = [tms.apply_limiter(b) for tms, b in zip(self.tracer_modules, base.tracer_modules)]
+        arr = np.stack(per)
+        return arr[..., 0] if self.members == 1 else arr
 
     # ---- Krylov building blocks -----------------------------------------------------------
     def mod_gram_schmidt(self, basis_cnt, fname_fcn, quantity):

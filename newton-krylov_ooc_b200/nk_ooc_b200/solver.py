@@ -1,0 +1,243 @@
+"""GPU-resident Newton-Krylov driver.
+
+The loops of the reference's NewtonSolver.step (nk_ooc/newton_solver.py:140-334) and
+KrylovSolver.solve (nk_ooc/krylov_solver.py:86-182, left-preconditioned GMRES, Saad alg. 9.4,
+x0 = 0) over the device operator surface of this package.  Differences from the reference are in
+WHERE the data lives, not in the algorithm:
+
+* the Krylov basis v_j, the preconditioned products w_j and the right-hand side stay in HBM as
+  ModelState objects; modified Gram-Schmidt and the linear combinations read them there instead of
+  re-reading basis_jj.nc / w_jj.nc for every inner product (j + 1 file reads per iteration in the
+  reference);
+* Armijo candidates can be evaluated speculatively: `armijo_batch` = k evaluates the factors
+  1, 1/2, ..., 2^-(k-1) as k members of ONE batched model-year evaluation and takes the first that
+  satisfies the Armijo condition for every (tracer module, region) — identical to the reference's
+  sequence whenever all regions accept/reject together (always the case with one region);
+  `armijo_batch` = 1 is the reference's sequential per-region halving;
+* when `workdir` is given the same files as the reference are written (krylov_NN/precond_fcn_00.nc,
+  basis_jj.nc, w_raw_jj.nc, w_jj.nc, krylov_res_jj.nc, increment_NN.nc, iterate_NN.nc, fcn_NN.nc,
+  hist_NN.nc), so that baseline_cmp-style comparisons keep working.
+
+The small dense least-squares problem (numpy.linalg.lstsq, krylov_solver.py:168-182) stays on the
+host: it is (j+2) x (j+1) per (module, region).
+"""
+
+import logging
+import os
+import tempfile
+
+import numpy as np
+
+from . import model_state_base
+
+
+def comp_krylov_basis_coeffs(beta, h_mat):
+    """least-squares coefficients of the Krylov basis per (tracer module, region)
+    (krylov_solver.py:168-182).  beta [n_modules, R], h_mat [n_modules, j+2, j+1, R]"""
+    h_shape = h_mat.shape
+    coeff = np.zeros((h_shape[0], h_shape[2], h_shape[3]))
+    lstsq_rhs = np.zeros(h_shape[1])
+    for m in range(h_shape[0]):
+        for r in range(h_shape[3]):
+            lstsq_rhs[0] = beta[m, r]
+            coeff[m, :, r] = np.linalg.lstsq(h_mat[m, :, :, r], lstsq_rhs, rcond=None)[0]
+    return coeff
+
+
+class KrylovSolver:
+    """left-preconditioned GMRES for  J(iterate) x = -fcn  with the basis resident in HBM"""
+
+    def __init__(self, iterate, solverinfo, hist_fname, workdir, max_iter=50):
+        self._iterate = iterate
+        self._info = solverinfo
+        self._workdir = workdir
+        self._max_iter = max_iter
+        self.iteration = 0
+        self.basis, self.w = [], []
+        self.beta = None
+        self.h_mat = None
+        self.precond_resid_norm = []
+        os.makedirs(workdir, exist_ok=True)
+        self.precond_fname = self._fname("precond", 0)
+        iterate.gen_precond_jacobian(hist_fname, self.precond_fname, solver_state=None)
+
+    def _fname(self, quantity, iteration=None):
+        iteration = self.iteration if iteration is None else iteration
+        return os.path.join(self._workdir, f"{quantity}_{iteration:02}.nc")
+
+    def _rel_tol(self):
+        return float(self._info["krylov_rel_tol"])
+
+    def _min_iter(self):
+        return int(self._info.get("krylov_min_iter", 0))
+
+    def converged(self, precond_resid_norm):
+        """krylov_solver.py:76-84"""
+        return (self.iteration >= self._min_iter()) & (precond_resid_norm < self._rel_tol() * self.beta)
+
+    def _resident(self, quantity, ind):
+        return self.basis[ind] if quantity == "basis" else self.w[ind]
+
+    def solve(self, res_fname, fcn, dump=True):
+        logger = logging.getLogger(__name__)
+        caller = f"{type(self).__name__}.solve"
+        fn = self._fname if dump else (lambda *a, **k: None)
+        # step 1 of alg. 9.4: r0 = -M^-1 fcn, beta = ||r0||, v0 = r0 / beta
+        precond_fcn = fcn.apply_precond_jacobian(self.precond_fname, fn("precond_fcn"), None)
+        self.beta = precond_fcn.norm()
+        self.basis.append((-precond_fcn / self.beta).dump(fn("basis"), caller))
+        n_mod, region_cnt = self.beta.shape[0], self.beta.shape[1]
+        while True:
+            j_val = self.iteration
+            h_mat = np.zeros((n_mod, j_val + 2, j_val + 1, region_cnt))
+            if j_val > 0:
+                h_mat[:, :-1, :-1, :] = self.h_mat
+            w_raw = self._iterate.comp_jacobian_fcn_state_prod(fcn, self.basis[j_val], fn("w_raw"), None)
+            w_j = w_raw.apply_precond_jacobian(self.precond_fname, fn("w"), None)
+            self.w.append(w_j._like())  # un-orthogonalised M^-1 J v_j: needed for the residual below
+            h_mat[:, :-1, -1, :] = w_j.mod_gram_schmidt(j_val + 1, self._resident, "basis")
+            h_mat[:, -1, -1, :] = w_j.norm()
+            w_j /= h_mat[:, -1, -1, :]
+            self.h_mat = h_mat
+            coeff = comp_krylov_basis_coeffs(self.beta, h_mat)
+            res = model_state_base.lin_comb(type(self._iterate), coeff, self._resident, "basis")
+            res.dump(fn("krylov_res", j_val), caller)
+            precond_resid = model_state_base.lin_comb(type(self._iterate), coeff, self._resident, "w")
+            precond_resid += precond_fcn
+            resid_norm = precond_resid.norm()
+            self.precond_resid_norm.append(resid_norm)
+            logger.info("Krylov iteration %d: precond_resid_norm/beta = %s", j_val, resid_norm / self.beta)
+            self.iteration += 1
+            if self.converged(resid_norm).all():
+                logger.info("Krylov convergence criterion satisfied")
+                break
+            if self.iteration >= self._max_iter:
+                raise RuntimeError("number of maximum Krylov iterations exceeded")
+            self.basis.append(w_j.dump(fn("basis"), caller))
+        return res.dump(res_fname, caller)
+
+
+class NewtonSolver:
+    """Newton's method with Armijo damping and post-Newton fixed-point iterations
+    (newton_solver.py:22-334) on a device-resident iterate"""
+
+    def __init__(self, iterate, solverinfo, workdir=None, armijo_batch=1, dump=True):
+        self._info = dict(solverinfo)
+        self._workdir = workdir or tempfile.mkdtemp(prefix="nkb200_newton_")
+        os.makedirs(self._workdir, exist_ok=True)
+        self._armijo_batch = int(armijo_batch)
+        self._dump = dump
+        self.iteration = 0
+        self._iterate = iterate
+        caller = f"{type(self).__name__}.__init__"
+        iterate.dump(self._fname("iterate") if dump else None, caller)
+        self._fcn = iterate.comp_fcn(self._fname("fcn") if dump else None, None, self._fname("hist"))
+        self.history = []  # per iteration: dict(fcn_norm, iterate_norm, krylov_iterations, armijo_factor, ...)
+        self._record()
+
+    # ---- bookkeeping --------------------------------------------------------------------
+    def _fname(self, quantity, iteration=None):
+        iteration = self.iteration if iteration is None else iteration
+        return os.path.join(self._workdir, f"{quantity}_{iteration:02}.nc")
+
+    def _record(self, **extra):
+        rec = {"iteration": self.iteration, "fcn_norm": self._fcn.norm(), "iterate_norm": self._iterate.norm()}
+        rec.update(extra)
+        self.history.append(rec)
+        logging.getLogger(__name__).info("Newton iteration %02d: |fcn|/|iterate| = %s", self.iteration,
+                                         rec["fcn_norm"] / np.where(rec["iterate_norm"] == 0, 1, rec["iterate_norm"]))
+
+    @property
+    def iterate(self):
+        return self._iterate
+
+    @property
+    def fcn(self):
+        return self._fcn
+
+    def converged(self):
+        """newton_solver.py:133-138"""
+        rel_tol = float(self._info["newton_rel_tol"])
+        min_iter = int(self._info.get("newton_min_iter", 0))
+        return (self.iteration >= min_iter) & (self._fcn.norm() < rel_tol * self._iterate.norm())
+
+    def converged_flat(self):
+        return self.converged().all()
+
+    # ---- one Newton step ------------------------------------------------------------------
+    def _comp_increment(self):
+        krylov_dir = os.path.join(self._workdir, f"krylov_{self.iteration:02}")
+        krylov = KrylovSolver(self._iterate, self._info, self._fname("hist"), krylov_dir)
+        increment = krylov.solve(self._fname("increment") if self._dump else None, self._fcn, dump=self._dump)
+        return increment, krylov
+
+    def _armijo_candidates(self, increment, armijo_factor):
+        """prov = iterate + factor*increment and F(prov) for one factor array [n_modules, R]"""
+        prov = self._iterate + armijo_factor * increment
+        return prov, prov.comp_fcn(None, None, self._fname("prov_hist_Armijo"))
+
+    def _comp_next_iterate(self, increment):
+        """Armijo damping, Eq. (A.1) of Kelley 2003 (newton_solver.py:183-258)"""
+        alpha = 1.0e-4
+        armijo_factor = np.where(self.converged(), 0.0, 1.0)
+        fcn_norm = self._fcn.norm()
+        armijo_ind = 0
+        if self._armijo_batch > 1:
+            # speculative: k candidates as k members of one batched evaluation
+            k = self._armijo_batch
+            factors = [armijo_factor * 0.5 ** i for i in range(k)]
+            provs = [self._iterate + f * increment for f in factors]
+            batched_fcn = type(self._iterate).from_members(provs).comp_fcn(None, None)
+            norms = batched_fcn.norm()  # [n_modules, R, k]
+            for i in range(k):
+                cond = (factors[i] == 0.0) | (norms[..., i] <= (1.0 - alpha * factors[i]) * fcn_norm)
+                if cond.all():
+                    return provs[i], batched_fcn.member(i), factors[i], i
+            armijo_factor, armijo_ind = factors[-1] * 0.5, k
+        while True:
+            prov, prov_fcn = self._armijo_candidates(increment, armijo_factor)
+            prov_fcn_norm = prov_fcn.norm()
+            armijo_cond = (armijo_factor == 0.0) | (prov_fcn_norm <= (1.0 - alpha * armijo_factor) * fcn_norm)
+            if armijo_cond.all():
+                return prov, prov_fcn, armijo_factor, armijo_ind
+            armijo_factor = np.where(armijo_cond, armijo_factor, 0.5 * armijo_factor)
+            armijo_ind += 1
+            if armijo_ind > 10:
+                raise RuntimeError("Armijo_ind exceeds limit")
+
+    def step(self):
+        """newton_solver.py:260-334"""
+        if self.iteration >= int(self._info["newton_max_iter"]):
+            raise RuntimeError("number of maximum Newton iterations exceeded")
+        caller = f"{type(self).__name__}.step"
+        increment, krylov = self._comp_increment()
+        scalef = increment.apply_limiter(self._iterate)
+        prov, prov_fcn, armijo_factor, armijo_ind = self._comp_next_iterate(increment)
+        prov.copy_shadow_tracers_to_real_tracers()
+        if prov.shadow_tracers_on():
+            prov_fcn = prov.comp_fcn(None, None, self._fname("prov_hist_fp"))
+        n_fp = int(self._info.get("post_newton_fp_iter", 0))
+        if n_fp == 0:
+            self.iteration += 1
+            prov.dump(self._fname("iterate") if self._dump else None, caller)
+            prov_fcn = prov.comp_fcn(self._fname("fcn") if self._dump else None, None, self._fname("hist"))
+        for fp_iter in range(n_fp):
+            prov += prov_fcn
+            prov.copy_shadow_tracers_to_real_tracers()
+            if fp_iter + 1 < n_fp:
+                prov_fcn = prov.comp_fcn(None, None, self._fname("prov_hist_fp"))
+            else:
+                self.iteration += 1
+                prov.dump(self._fname("iterate") if self._dump else None, caller)
+                prov_fcn = prov.comp_fcn(self._fname("fcn") if self._dump else None, None, self._fname("hist"))
+        self._iterate, self._fcn = prov, prov_fcn
+        self._record(krylov_iterations=krylov.iteration, krylov_precond_resid_norm=krylov.precond_resid_norm,
+                     krylov_beta=krylov.beta, increment_scalef=scalef, armijo_factor=armijo_factor,
+                     armijo_ind=armijo_ind)
+        return increment
+
+    def solve(self):
+        """iterate until converged (nk_driver.py main loop)"""
+        while not self.converged_flat():
+            self.step()
+        return self._iterate

@@ -657,6 +657,47 @@ def fd_sigma(w, x):
 # --------------------------------------------------------------------------------------
 
 
+def min_by_region(region_cnt, region_mask, vals):
+    """utils.py:544-558"""
+    out = np.empty(region_cnt)
+    for region_ind in range(region_cnt):
+        out[region_ind] = np.amin(vals, initial=np.inf, where=region_mask == region_ind + 1)
+    return out
+
+
+def comp_scalef_lob(region_cnt, region_mask, base, increment, lob):
+    """largest 0 <= scalef <= 1 by region with base + scalef*increment >= lob (utils.py:561-579)"""
+    if lob is None or (base + increment >= lob).all():
+        return np.ones(region_cnt)
+    if (base < lob).any():
+        raise ValueError("base < lob")
+    scalef_all = np.ones(base.shape)
+    np.divide(lob - base, increment, out=scalef_all, where=base + increment < lob)
+    return min_by_region(region_cnt, region_mask, scalef_all)
+
+
+def comp_scalef_upb(region_cnt, region_mask, base, increment, upb):
+    """utils.py:582-600"""
+    if upb is None or (base + increment <= upb).all():
+        return np.ones(region_cnt)
+    if (base > upb).any():
+        raise ValueError("base > upb")
+    scalef_all = np.ones(base.shape)
+    np.divide(upb - base, increment, out=scalef_all, where=base + increment > upb)
+    return min_by_region(region_cnt, region_mask, scalef_all)
+
+
+def apply_limiter(region_cnt, region_mask, base, increment, lob, upb):
+    """scalef of one tracer module, tracers stacked in front (tracer_module_state_base.py:115-151)"""
+    scalef = np.ones(region_cnt)
+    for t in range(base.shape[0]):
+        if lob is not None:
+            scalef = np.minimum(scalef, comp_scalef_lob(region_cnt, region_mask, base[t], increment[t], lob))
+        if upb is not None:
+            scalef = np.minimum(scalef, comp_scalef_upb(region_cnt, region_mask, base[t], increment[t], upb))
+    return scalef
+
+
 def column_region_mask(nz, ny, max_abs_vvel, horiz_mix_coeff):
     if max_abs_vvel == 0.0 and horiz_mix_coeff == 0.0:
         mask = np.empty((nz, ny), dtype=np.int32)

@@ -97,3 +97,42 @@ def test_banded_solve_matches_scipy(n, kl, ku):
     np.testing.assert_allclose(got, want, rtol=0, atol=1e-9 * np.abs(want).max())
     got = f.solve(_dev(y), B, scale=0.25, subtract_rhs=True).cpu().numpy()[:, :B]
     np.testing.assert_allclose(got, 0.25 * want - y, rtol=0, atol=1e-9 * np.abs(want).max())
+
+
+@pytest.mark.parametrize("B", [1, 7])
+def test_limiter_scalef_matches_oracle(B):
+    """nkb_limiter_scalef against the restated comp_scalef_lob/upb (utils.py:561-600), incl. the
+    reference's own known-answer cases (tests/test_utils.py:144-224) in member 0"""
+    from oracle import nk_oracle as o
+    from nk_ooc_b200 import engine
+
+    rng = np.random.default_rng(13)
+    region_cnt = 7
+    shape = (3, region_cnt)
+    mask = np.zeros(shape, dtype=np.int32)
+    for r in range(region_cnt):
+        mask[:, r] = r + 1
+    base = np.ones((1,) + shape + (B,))
+    inc = np.ones((1,) + shape + (B,))
+    inc[0, 0, 1, 0] = -0.5
+    inc[0, 0, 2, 0], inc[0, 1, 2, 0] = -0.5, -1.0
+    inc[0, 0, 3, 0], inc[0, 1, 3, 0], inc[0, 2, 3, 0] = -0.5, -1.0, -2.0
+    base[0, :, 4:, 0] = 0.0
+    inc[0, 0, 5, 0] = 0.0
+    inc[0, 0, 6, 0], inc[0, 1, 6, 0] = 0.0, -1.0
+    for b in range(1, B):
+        base[..., b] = rng.random(size=(1,) + shape) + 0.1
+        inc[..., b] = rng.normal(size=(1,) + shape)
+    rw = engine.RegionWeights(mask, np.ones(shape))
+    got = rw.limiter_scalef(_dev(base), _dev(inc), 0.0, None, B).cpu().numpy()
+    assert (got[:, 0] == np.array([1.0, 1.0, 1.0, 0.5, 1.0, 1.0, 0.0])).all()
+    for b in range(B):
+        want = o.comp_scalef_lob(region_cnt, mask, base[0, ..., b], inc[0, ..., b], 0.0)
+        np.testing.assert_array_equal(np.minimum(got[:, b], 1.0), want)
+        want = o.comp_scalef_upb(region_cnt, mask, -base[0, ..., b], -inc[0, ..., b], 0.0)
+        gotu = rw.limiter_scalef(_dev(-base), _dev(-inc), None, 0.0, B).cpu().numpy()
+        np.testing.assert_array_equal(np.minimum(gotu[:, b], 1.0), want)
+    bad = base.copy()
+    bad[0, 1, 1, 0] = -1.0
+    with pytest.raises(ValueError):
+        rw.limiter_scalef(_dev(bad), _dev(inc), 0.0, None, B)

@@ -1,0 +1,103 @@
+"""GPU tests of the device-resident Newton-Krylov driver (nk_ooc_b200/solver.py) against the
+reference's committed baselines of a complete Newton step (krylov_res_00, increment_00,
+iterate_01) with the tolerances of the reference's own CI scripts, and to convergence."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from test_gpu_model_state import _modelinfo, _state, _vals, _want  # noqa: E402
+from test_gpu_test_problem import _configure  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def base(golden_dir):
+    return np.load(os.path.join(golden_dir, "baselines.npz"))
+
+
+TP_SOLVERINFO = {"newton_rel_tol": "1.0e-8", "newton_max_iter": "5", "post_newton_fp_iter": "1",
+                 "krylov_rel_tol": "0.01"}  # input/test_problem/newton_krylov.cfg:32-43
+PD_SOLVERINFO = {"newton_rel_tol": "1.0e-5", "newton_max_iter": "5", "post_newton_fp_iter": "1",
+                 "krylov_rel_tol": "0.01"}  # input/py_driver_2d/newton_krylov.cfg:32-43
+
+
+def test_ci_long_iage_newton_step_and_convergence(base, tmp_path):
+    """scripts/ci_long_iage.sh: krylov_res_00, increment_00, iterate_01 at rtol 2e-4; the reference run
+    stops at Newton iteration 3 (baselines/ci_long_iage/Newton_state.json)"""
+    from scipy.io import netcdf_file
+
+    from nk_ooc_b200.solver import NewtonSolver
+
+    ModelState = _configure(str(tmp_path), "iage")
+    pre = "ci_long_iage/"
+    iterate = ModelState({"iage": base["ci_short/init_iterate/iage"]})
+    solver = NewtonSolver(iterate, TP_SOLVERINFO, workdir=str(tmp_path / "work"))
+    assert not solver.converged_flat()
+    increment = solver.step()
+    np.testing.assert_allclose(increment.get_tracer_vals("iage"), base[pre + "increment_00/iage"], rtol=2e-4, atol=2e-9)
+    np.testing.assert_allclose(solver.iterate.get_tracer_vals("iage"), base[pre + "iterate_01/iage"], rtol=2e-4,
+                               atol=2e-9)
+    # the files the reference's CI compares are written with the reference's names
+    with netcdf_file(str(tmp_path / "work" / "krylov_00" / "krylov_res_00.nc"), "r", mmap=False) as f:
+        np.testing.assert_allclose(np.array(f.variables["iage"].data), base[pre + "krylov_res_00/iage"], rtol=2e-4,
+                                   atol=2e-9)
+    for name in ("increment_00.nc", "iterate_01.nc", "fcn_01.nc", "hist_01.nc"):
+        assert os.path.exists(str(tmp_path / "work" / name)), name
+    rec = solver.history[-1]
+    assert rec["krylov_iterations"] >= 1 and (rec["armijo_factor"] == 1.0).all() and rec["armijo_ind"] == 0
+    assert (rec["krylov_precond_resid_norm"][-1] < 0.01 * rec["krylov_beta"]).all()
+    solver.solve()
+    assert solver.converged_flat() and solver.iteration == 3
+    norms = [float(r["fcn_norm"][0, 0]) for r in solver.history]
+    assert all(b < a for a, b in zip(norms[:-1], norms[1:])), norms
+    ModelState.reset()
+
+
+def test_speculative_armijo_equals_sequential(base, tmp_path):
+    """armijo_batch = 3 (three candidates as members of one batched evaluation) gives the
+    sequential result; a deliberately overshooting increment exercises the halving"""
+    from nk_ooc_b200.solver import NewtonSolver
+
+    ModelState = _configure(str(tmp_path), "iage")
+    x0 = ModelState({"iage": base["ci_short/init_iterate_00/iage"]})
+    out = []
+    for k in (1, 3):
+        solver = NewtonSolver(x0._like(), TP_SOLVERINFO, workdir=str(tmp_path / f"w{k}"), armijo_batch=k, dump=False)
+        inc = solver.fcn * 40.0  # far too long a step along F: needs damping
+        prov, prov_fcn, factor, ind = solver._comp_next_iterate(inc)
+        out.append((prov.get_tracer_vals("iage"), prov_fcn.get_tracer_vals("iage"), factor, ind))
+    assert out[0][3] == out[1][3] and out[0][3] >= 1
+    np.testing.assert_array_equal(out[0][2], out[1][2])
+    np.testing.assert_allclose(out[0][0], out[1][0], rtol=0, atol=1e-13 * np.abs(out[0][0]).max())
+    np.testing.assert_allclose(out[0][1], out[1][1], rtol=0, atol=1e-12 * np.abs(out[0][1]).max())
+    ModelState.reset()
+
+
+def test_ci_py_driver_2d_iage_column_regions_newton_step(base, tmp_path):
+    """scripts/ci_py_driver_2d_iage_column_regions.sh: krylov_res_00, increment_00, iterate_01 at
+    rtol 1.9e-2 (3 column regions: per-region Krylov coefficients and Armijo factors)"""
+    from scipy.io import netcdf_file
+
+    from nk_ooc_b200.py_driver_2d.model_state import ModelState
+    from nk_ooc_b200.py_driver_2d.setup_solver import gen_grid_vars_file
+    from nk_ooc_b200.solver import NewtonSolver
+
+    info = _modelinfo(str(tmp_path), 20, 3, "0.0", "0.0")
+    gen_grid_vars_file(info)
+    ModelState.configure(info)
+    pre = "ci_py_driver_2d_iage_column_regions/"
+    iterate = _state(ModelState, base, pre + "init_iterate")
+    solver = NewtonSolver(iterate, PD_SOLVERINFO, workdir=str(tmp_path / "work"))
+    increment = solver.step()
+    np.testing.assert_allclose(_vals(increment), _want(base, pre + "increment_00"), rtol=1.9e-2, atol=1e-9)
+    np.testing.assert_allclose(_vals(solver.iterate), _want(base, pre + "iterate_01"), rtol=1.9e-2, atol=1e-9)
+    with netcdf_file(str(tmp_path / "work" / "krylov_00" / "krylov_res_00.nc"), "r", mmap=False) as f:
+        got = np.stack([np.array(f.variables[n].data) for n in ("iage", "iage_slow_rest")])
+    np.testing.assert_allclose(got, _want(base, pre + "krylov_res_00"), rtol=1.9e-2, atol=1e-9)
+    rec = solver.history[-1]
+    assert rec["krylov_beta"].shape == (1, 3) and (rec["armijo_factor"] == 1.0).all()
+    ModelState.reset()
