@@ -768,3 +768,70 @@ def dimacs_edges(mask, offsets):
                 edges.append((i, j))
     lines = [f"p edge {len(cells)} {len(edges)}"] + [f"e {i} {j}" for i, j in edges]
     return lines
+
+
+# ---- notebook-faithful connectivity (IRF_coloring_dev.ipynb cells 4-13, 23) --------------------
+def ind_wrap(mask_shape, ind):
+    """cell 4: periodic in the last dimension, tripole fold beyond the end of the second-to-last"""
+    ind_list = list(ind)
+    if ind_list[-1] < 0:
+        ind_list[-1] += mask_shape[-1]
+    if ind_list[-1] >= mask_shape[-1]:
+        ind_list[-1] -= mask_shape[-1]
+    if ind_list[-2] >= mask_shape[-2]:
+        ind_list[-1] = mask_shape[-1] - 1 - ind_list[-1]
+        ind_list[-2] = 2 * mask_shape[-2] - 1 - ind_list[-2]
+    return tuple(ind_list)
+
+
+def apply_ind_offsets(mask, inds, ind_offsets):
+    """cell 4: wet cells reached from `inds` by `ind_offsets` (after ind_wrap)"""
+    ret_val = set()
+    for ind in inds:
+        for ind_offset in ind_offsets:
+            nb = ind_wrap(mask.shape, tuple(i + o for i, o in zip(ind, ind_offset[-mask.ndim:])))
+            if all(0 <= nb[n] < mask.shape[n] for n in range(mask.ndim)) and mask[nb]:
+                ret_val.add(nb)
+    return ret_val
+
+
+def gen_conn_nd(mask, ind):
+    """cell 4: MOM6's computational stencil around ind"""
+    if mask[ind] == 0:
+        return set()
+    ret_val = set()
+    if mask.ndim == 3 and ind[-3] > 0:
+        ret_val.update(apply_ind_offsets(mask, [ind], [(-1, -1, 0), (-1, 0, -1), (-1, 0, 0), (-1, 0, 1), (-1, 1, 0)]))
+    offs_x = [(0, 0, -1), (0, 0, 0), (0, 0, 1)]
+    offs_y = [(0, -1, 0), (0, 0, 0), (0, 1, 0)]
+    ret_val.update(apply_ind_offsets(mask, apply_ind_offsets(mask, [ind], offs_x), offs_y))
+    ret_val.update(apply_ind_offsets(mask, apply_ind_offsets(mask, [ind], offs_y), offs_x))
+    if mask.ndim == 3 and ind[-3] < mask.shape[-3] - 1:
+        ret_val.update(apply_ind_offsets(mask, [ind], [(1, -1, 0), (1, 0, -1), (1, 0, 0), (1, 0, 1), (1, 1, 0)]))
+    return ret_val
+
+
+def conn_mom6(mask):
+    """cells 5-7: conn_nd and conn2_nd as dicts of sets over the wet cells"""
+    cells = [ind for ind in np.ndindex(mask.shape) if mask[ind]]
+    conn = {c: gen_conn_nd(mask, c) for c in cells}
+    conn2 = {}
+    for c in cells:
+        s2 = set()
+        for nb in conn[c]:
+            s2.update(conn[nb])
+        conn2[c] = s2
+    return cells, conn, conn2
+
+
+def greedy_colouring_sets(mask, cells, conn2, order=None):
+    """cells 9-13: first-fit over `order` (default: C order); 0-based colours, -1 where masked"""
+    color = np.full(mask.shape, -1)
+    for ind in (cells if order is None else order):
+        used = [color[nb] for nb in conn2[ind]]
+        val = 0
+        while val in used:
+            val += 1
+        color[ind] = val
+    return color
+

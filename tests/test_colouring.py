@@ -1,0 +1,127 @@
+"""CPU tests of the product-side colouring / index maps (nk_ooc_b200/colouring.py)
+against the notebook-faithful restatement in oracle/nk_oracle.py (integers: bit-exact) and the
+answers printed in the reference's notebooks/IRF_coloring_dev.ipynb."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+from oracle import nk_oracle as o
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# the module is pure numpy/scipy: load it without importing the package (which needs torch + CUDA lib)
+_spec = importlib.util.spec_from_file_location(
+    "nkb_colouring", os.path.join(ROOT, "newton-krylov_ooc_b200", "nk_ooc_b200", "colouring.py"))
+col = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(col)
+
+
+def _notebook_mask():
+    """IRF_coloring_dev.ipynb cell 2"""
+    ni, nj = 120, 100
+    mask = np.ones((nj, ni))
+    mask[nj // 5:3 * nj // 5, 0:ni // 6] = 0
+    mask[nj // 5:3 * nj // 5, 3 * ni // 6:4 * ni // 6] = 0
+    mask[4 * nj // 5:nj, 0:ni // 6] = 0
+    mask[4 * nj // 5:nj, 2 * ni // 6:4 * ni // 6] = 0
+    mask[4 * nj // 5:nj, 5 * ni // 6:ni] = 0
+    return mask
+
+
+def test_notebook_printed_answers():
+    """cell 5: conn_nd_cnt.max() = 9; cell 7: conn2_nd_cnt.max() = 25; cell 17: flat_len = 8800;
+    greedy colour counts 12 (C order, cell 9), 12 (reverse, cell 11), 13 (largest degree first, cell 13)"""
+    mask = _notebook_mask()
+    conn = col.connectivity_mom6(mask)
+    conn2 = col.distance2(conn)
+    assert conn.shape[0] == 8800
+    assert np.diff(conn.indptr).max() == 9 and np.diff(conn2.indptr).max() == 25
+    n = conn2.shape[0]
+    c_fwd = col.greedy_colouring(conn2)
+    assert c_fwd.max() + 1 == 12
+    assert col.greedy_colouring(conn2, order=range(n - 1, -1, -1)).max() + 1 == 12
+    assert col.greedy_colouring(conn2, order=col.degree_order(conn2)).max() + 1 == 13
+    col.check_proper(c_fwd, conn2)
+    lines = col.dimacs_lines(conn2)
+    assert lines[1] == f"p edge 8800 {(np.diff(conn2.indptr).sum() - 8800) // 2}"  # cell 19
+    assert len(lines) == 2 + int(lines[1].split()[3])
+
+
+@pytest.mark.parametrize("shape", [(7, 9), (3, 6, 8)])
+def test_mom6_connectivity_and_colouring_equal_notebook_restatement(shape):
+    rng = np.random.default_rng(4)
+    mask = (rng.random(shape) > 0.25).astype(np.int32)
+    cells, conn_o, conn2_o = o.conn_mom6(mask)
+    nd_to_flat, flat_to_nd = col.index_maps(mask)
+    nd_o, flat_o = o.index_maps(mask)
+    assert nd_to_flat.dtype == np.int32 and flat_to_nd.dtype == np.int32
+    np.testing.assert_array_equal(nd_to_flat, nd_o)
+    np.testing.assert_array_equal(flat_to_nd, flat_o)
+    conn = col.connectivity_mom6(mask)
+    conn2 = col.distance2(conn)
+    for c in cells:
+        a = int(nd_to_flat[c])
+        for mat, ref in ((conn, conn_o), (conn2, conn2_o)):
+            got = set(mat.indices[mat.indptr[a]:mat.indptr[a + 1]].tolist())
+            assert got == {int(nd_to_flat[nb]) for nb in ref[c]}, c
+    want = o.greedy_colouring_sets(mask, cells, conn2_o)
+    np.testing.assert_array_equal(col.to_nd(mask, col.greedy_colouring(conn2)), want)
+    order = sorted(cells, key=lambda ind: len(conn2_o[ind]), reverse=True)
+    want = o.greedy_colouring_sets(mask, cells, conn2_o, order=order)
+    np.testing.assert_array_equal(col.to_nd(mask, col.greedy_colouring(conn2, order=col.degree_order(conn2))), want)
+
+
+def test_offset_stencil_equals_oracle_and_dimacs_edges():
+    rng = np.random.default_rng(3)
+    mask = (rng.random((9, 8)) > 0.2).astype(np.int32)
+    offsets = [(-1, 0), (1, 0), (0, -1), (0, 1)]
+    colour_o, n_o = o.greedy_colouring(mask, offsets)  # 1-based, 0 where masked; conn2 without self
+    conn = col.connectivity_offsets(mask, offsets + [(0, 0)])
+    conn2 = col.distance2(conn)
+    colour = col.to_nd(mask, col.greedy_colouring(conn2), fill=-1) + 1
+    np.testing.assert_array_equal(colour, colour_o)
+    want = o.dimacs_edges(mask, offsets)
+    got = col.dimacs_lines(conn2)[1:]
+    assert got[0] == want[0] and sorted(got[1:]) == sorted(want[1:])
+    # solution reader: accepts a proper colouring, rejects an improper one (notebook cell 23)
+    flat = col.greedy_colouring(conn2)
+    lines = ["header"] + [str(int(v)) for v in flat]
+    np.testing.assert_array_equal(col.read_solution(lines, conn2), flat)
+    bad = flat.copy()
+    i = int(np.argmax(np.diff(conn2.indptr) > 1))
+    nb = [j for j in conn2.indices[conn2.indptr[i]:conn2.indptr[i + 1]] if j != i][0]
+    bad[i] = bad[nb]
+    with pytest.raises(ValueError):
+        col.read_solution(["header"] + [str(int(v)) for v in bad], conn2)
+
+
+def test_column_probes_recover_a_banded_jacobian():
+    """3-point y stencil: 3 colours; probes of all (tracer, level) of every column in
+    3*T*nz members recover the column blocks of a linear map exactly"""
+    rng = np.random.default_rng(8)
+    T, nz, ny = 2, 5, 10
+    colour = col.column_colouring(ny)
+    assert (colour == np.arange(ny) % 3).all()
+    n = T * nz
+    blocks = rng.normal(size=(ny, 3, n, n))  # F[:, :, j] = sum_d blocks[j+d-1 -> j] x[:, :, j+d-1]
+
+    def fcn(x):  # x [T, nz, ny]
+        out = np.zeros_like(x)
+        for j in range(ny):
+            for d in (-1, 0, 1):
+                if 0 <= j + d < ny:
+                    out[:, :, j] += (blocks[j, d + 1] @ x[:, :, j + d].reshape(-1)).reshape(T, nz)
+        return out
+
+    x0 = rng.normal(size=(T, nz, ny))
+    eps = 0.5
+    probes = col.probe_batch(x0, colour, eps)
+    assert probes.shape == (3 * n, T, nz, ny)
+    f0 = fcn(x0)
+    fp = np.stack([fcn(p) for p in probes])
+    jac = col.decode_probes(f0, fp, colour, eps, reach=1)
+    for j in range(ny):
+        for d in (-1, 0, 1):
+            if 0 <= j + d < ny:  # response of column j+d to a probe in column j = blocks[j+d][-d]
+                np.testing.assert_allclose(jac[j, d + 1], blocks[j + d, 1 - d], rtol=0, atol=1e-12)

@@ -101,3 +101,43 @@ def test_ci_py_driver_2d_iage_column_regions_newton_step(base, tmp_path):
     rec = solver.history[-1]
     assert rec["krylov_beta"].shape == (1, 3) and (rec["armijo_factor"] == 1.0).all()
     ModelState.reset()
+
+
+def test_coloured_column_probes_give_the_jacobian(base, tmp_path):
+    """all (tracer, level) unit perturbations of all columns in ONE batched evaluation
+    (3 colours x 2 tracers x 20 levels = 120 members, nk_ooc_b200/colouring.py): the decoded
+    column blocks reproduce the finite-difference Jacobian-vector product of
+    comp_jacobian_fcn_state_prod; without lateral processes the off-column blocks vanish"""
+    from nk_ooc_b200 import colouring as col
+    from nk_ooc_b200.py_driver_2d.model_state import ModelState
+    from nk_ooc_b200.py_driver_2d.setup_solver import gen_grid_vars_file
+
+    info = _modelinfo(str(tmp_path), 20, 3, "0.0", "0.0")
+    gen_grid_vars_file(info)
+    ModelState.configure(info)
+    pre = "ci_py_driver_2d_iage_column_regions/"
+    iterate = _state(ModelState, base, pre + "init_iterate")
+    x0 = _vals(iterate)  # [T, nz, ny]
+    T, nz, ny = x0.shape
+    colour = col.column_colouring(ny)
+    eps = 1.0e-2
+    probes = col.probe_batch(x0, colour, eps)
+    B = probes.shape[0]
+    assert B == 3 * T * nz
+    batched = ModelState("zeros", members=B)
+    tms = batched.tracer_modules[0]
+    tms.vals[..., :B] = torch.from_numpy(np.ascontiguousarray(np.moveaxis(probes, 0, -1))).cuda()
+    fb = batched.comp_fcn(None, None)
+    fprobe = np.moveaxis(fb.tracer_modules[0].vals[..., :B].cpu().numpy(), -1, 0)
+    f0 = _vals(iterate.comp_fcn(None, None))
+    jac = col.decode_probes(f0, fprobe, colour, eps, reach=1)
+    scale = np.abs(jac[:, 1]).max()
+    assert np.abs(jac[:, 0]).max() <= 1e-9 * scale and np.abs(jac[:, 2]).max() <= 1e-9 * scale
+    rng = np.random.default_rng(2)
+    v = rng.normal(size=x0.shape)
+    direction = ModelState({"iage": v[0], "iage_slow_rest": v[1]})
+    fcn = iterate.comp_fcn(None, None)
+    jv = _vals(iterate.comp_jacobian_fcn_state_prod(fcn, direction, None, None))
+    want = np.stack([(jac[j, 1] @ v[:, :, j].reshape(-1)).reshape(T, nz) for j in range(ny)], axis=-1)
+    np.testing.assert_allclose(jv, want, rtol=0, atol=1e-6 * np.abs(want).max())
+    ModelState.reset()
