@@ -204,6 +204,14 @@ class ModelState(ModelStateBase):
                     var = fptr.createVariable(tname, "f8", ("time", dn))
                     var.long_name, var.units = meta["attrs"]["long_name"], meta["attrs"]["units"]
                     var.cell_methods = "time: point"
+                if tms._def.get("py_mod_name", tms.name) == "phosphorus":
+                    # test_problem/phosphorus.py:122-160 hist_vars_metadata_tracer_like / write_hist_vars
+                    po4_units = tms._def["tracers"]["po4"]["attrs"]["units"]
+                    var = fptr.createVariable("po4_uptake", "f8", ("time", dn))
+                    var.long_name, var.units, var.cell_methods = "uptake of po4", f"{po4_units} / s", "time: point"
+                    var = fptr.createVariable("po4_s_restore_tau_r", "f8", ("time", dn))
+                    var.long_name, var.units = "inverse timescale for po4_s restoring", "1 / s"
+                    var.cell_methods = "time: point"
             self.depth.write(fptr)
             for ti, t in enumerate(times):
                 fptr.variables["time"][ti] = t
@@ -216,6 +224,12 @@ class ModelState(ModelStateBase):
                 snaps = hist[tms.name].cpu().numpy()  # [n_time, T, nz, 1]
                 for ind, tname in enumerate(tms.tracer_names):
                     fptr.variables[tname][:] = snaps[:, ind, :, 0]
+                if tms._def.get("py_mod_name", tms.name) == "phosphorus":
+                    po4 = snaps[:, tms.tracer_index("po4"), :, 0]
+                    uptake = modules.po4_uptake(self.depth, po4)
+                    fptr.variables["po4_uptake"][:] = uptake
+                    opt = int(self.model_config_obj.modelinfo.get("po4_s_restoring_opt", 1))
+                    fptr.variables["po4_s_restore_tau_r"][:] = modules.po4_s_restore_tau_r(self.depth, po4, uptake, opt)
 
     def gen_precond_jacobian(self, hist_fname, precond_fname, solver_state=None):
         """mixing_coeff:mean and mixing_coeff:log_mean over the hist times
@@ -233,6 +247,14 @@ class ModelState(ModelStateBase):
             var[:] = mc.mean(axis=0)
             var = fout.createVariable("mixing_coeff_log_mean", "f8", (de,))
             var[:] = np.exp(np.log(mc).mean(axis=0))
+            if "phosphorus" in self.precond_matrix_list():
+                # precond_matrix_defs.phosphorus: 'po4_s_restore_tau_r:mean'
+                # (input/test_problem/tracer_module_defs.yaml:62-64)
+                dn = self.depth.axisname
+                tau = np.array(fin.variables["po4_s_restore_tau_r"].data)
+                fout.createDimension(dn, tau.shape[1])
+                var = fout.createVariable("po4_s_restore_tau_r_mean", "f8", (dn,))
+                var[:] = tau.mean(axis=0)
 
     def apply_precond_jacobian(self, precond_fname, res_fname, solver_state):
         """res = A^-1 (self / T) - self, A the tridiagonal Jacobian with the log-mean mixing
@@ -246,6 +268,9 @@ class ModelState(ModelStateBase):
         t0, t1 = self.time_range
         for ind, tms in enumerate(self.tracer_modules):
             kind = tms._def.get("py_mod_name", tms.name)
+            if kind == "phosphorus":
+                res_ms.tracer_modules[ind].vals = self._apply_precond_phosphorus(tms, precond_fname, mca)
+                continue
             if kind not in ("iage", "dye_decay"):
                 raise NotImplementedError(f"preconditioner of {tms.name} is not on the B200 path yet")
             key = (tms.name, precond_fname)
@@ -267,6 +292,77 @@ class ModelState(ModelStateBase):
         if solver_state is not None:
             solver_state.log_step(step)
         return res_ms.dump(res_fname, f"{type(self).__name__}.apply_precond_jacobian")
+
+    def _apply_precond_phosphorus(self, tms, precond_fname, mca):
+        """preconditioner of the shadow phosphorus tracers (test_problem/phosphorus.py:169-211):
+        two regularised solves (shifts 1e-11, 0.5e-11) + Richardson extrapolation, removal of the
+        null vector weighted by layer thickness, minus the input.  The member-independent pieces
+        (band matrices, SVD null vector) are set up on the host once per precond file; the solves,
+        the weighted sums and the updates of all members run in the library's kernels (K4-K6)."""
+        nz, B = len(self.depth), self.members
+        weights = self.model_config_obj.weights
+        key = (tms.name, precond_fname)
+        if key not in self._precond_cache:
+            with netcdf_file(precond_fname, "r", mmap=False) as fptr:
+                tau_r = np.array(fptr.variables["po4_s_restore_tau_r_mean"].data)
+            ab_a, kl, ku, _ = _phosphorus_precond_band(self.depth, mca, tau_r, 1.0e-11)
+            ab_b, _, _, _ = _phosphorus_precond_band(self.depth, mca, tau_r, 0.5e-11)
+            _, _, _, dense = _phosphorus_precond_band(self.depth, mca, tau_r, 0.0)
+            _, sing_vals, r_sing_vects = np.linalg.svd(dense)
+            null_vect = r_sing_vects[sing_vals.argmin(), :]
+            dz3 = np.concatenate((self.depth.delta,) * 3)
+            # region-weighted "mean" of K5 = sum_k dz_k/sum(dz) * (.) summed over the 3 tracers
+            denom_mean = (null_vect * dz3).sum() / self.depth.delta.sum()
+            self._precond_cache[key] = (engine.BandedFactor(ab_a, kl, ku), engine.BandedFactor(ab_b, kl, ku),
+                                        null_vect.reshape(3, nz), denom_mean)
+        fac_a, fac_b, null_vect, denom_mean = self._precond_cache[key]
+        t0, t1 = self.time_range
+        ldb = tms.vals.shape[-1]
+        y3 = tms.vals[3:6].reshape(3 * nz, ldb)
+        res_a = fac_a.solve(y3, B, 1.0 / (t1 - t0))
+        res = fac_b.solve(y3, B, 1.0 / (t1 - t0))
+        weights.axpby(-1.0, res_a.reshape(3, nz, ldb), 2.0, res.reshape(3, nz, ldb), B)  # 2 b - a
+        numer_mean = weights.dot(res.reshape(3, nz, ldb), None, B)  # [1, B]
+        nv = torch.zeros((3, nz, ldb), dtype=torch.float64, device="cuda")
+        nv[..., :B] = torch.from_numpy(null_vect).cuda().unsqueeze(-1)
+        weights.axpby(-numer_mean / denom_mean, nv, 1.0, res.reshape(3, nz, ldb), B)
+        weights.axpby(-1.0, y3.reshape(3, nz, ldb), 1.0, res.reshape(3, nz, ldb), B)
+        out = tms.vals.clone()  # real tracers keep their values (res_ms = deepcopy(self), :237)
+        out[3:6] = res.reshape(out[3:6].shape)
+        return out
+
+
+def _phosphorus_precond_band(depth, mca, tau_r, shift):
+    """banded storage [kl+ku+1, 3nz] (kl = ku = 2nz) of the 7-diagonal preconditioner matrix of the
+    shadow phosphorus tracers minus shift*I (test_problem/phosphorus.py:177-290)"""
+    nz = len(depth)
+    day_per_sec = 1.0 / 86400.0
+    single = np.zeros(nz)
+    single[:-1] -= mca * depth.delta_mid_r * depth.delta_r[:-1]
+    single[1:] -= mca * depth.delta_mid_r * depth.delta_r[1:]
+    d0 = np.concatenate((single - tau_r, single - 0.01 * day_per_sec, single - 0.01 * day_per_sec))
+    d0[2 * nz:3 * nz - 1] -= day_per_sec * depth.delta_r[:-1]  # pop_s sinking loss to the layer below
+    up = mca * depth.delta_mid_r * depth.delta_r[:-1]
+    lo = mca * depth.delta_mid_r * depth.delta_r[1:]
+    zero = np.zeros(1)
+    diags = {
+        0: d0 - shift,
+        1: np.concatenate((up, zero, up, zero, up)),
+        -1: np.concatenate((lo, zero, lo, zero, lo + day_per_sec * depth.delta_r[1:])),
+        nz: np.concatenate((0.01 * day_per_sec * np.ones(nz), np.zeros(nz))),
+        -nz: np.concatenate((0.67 * tau_r, np.zeros(nz))),
+        2 * nz: 0.01 * day_per_sec * np.ones(nz),
+        -2 * nz: 0.33 * tau_r,
+    }
+    n, kl, ku = 3 * nz, 2 * nz, 2 * nz
+    ab = np.zeros((kl + ku + 1, n))
+    dense = np.zeros((n, n))
+    for off, vals in diags.items():
+        rows = np.arange(len(vals)) + max(0, -off)
+        cols = rows + off
+        ab[ku + rows - cols, cols] = vals
+        dense[rows, cols] = vals
+    return ab, kl, ku, dense
 
 
 def gen_depth_axis_file(modelinfo, depth):

@@ -65,6 +65,25 @@ def phosphorus_model(depth, po4_s_restoring_opt=1):
     return Model(d, keep)
 
 
+def po4_uptake(depth, po4):
+    """test_problem/phosphorus.py:78-85: po4 [..., nz]; light e-folding depth 25 m, half saturation 0.5,
+    maximum rate 1/day"""
+    light = np.exp((-1.0 / 25.0) * depth.mid)
+    return (1.0 / SEC_PER_DAY) * light * (po4 / (po4 + 0.5))
+
+
+def po4_s_restore_tau_r(depth, po4, uptake, opt=1):
+    """inverse time scale of the po4_s restoring (test_problem/phosphorus.py:58-76): opt 0: 1/day in
+    the surface layer; opt 1: finite-difference d uptake / d po4"""
+    if opt == 0:
+        res = np.zeros(np.shape(po4))
+        res[..., 0] = 1.0 / SEC_PER_DAY
+        return res
+    delta = 1.0e-3 * np.abs(po4)
+    delta = np.where(delta < 1.0e-8, 1.0e-8, delta)
+    return (po4_uptake(depth, po4 + delta) - uptake) / delta
+
+
 def bldepth(time):
     """test_problem/vert_mix.py:50-57 (host copy for hist output)"""
     frac = 0.5 + 0.5 * np.cos((2 * np.pi) * ((1.0 / SEC_PER_YEAR) * time - 0.25))

@@ -202,6 +202,30 @@ def test_problem_cases():
             tm.apply_precond_jacobian((0.0, YEAR), res, mca)
             out[f"{name}/mca"] = mca
             out[f"{name}/precond"] = res.vals
+    # phosphorus: derived hist variables and the 3nz x 3nz preconditioner of the shadow tracers
+    # (test_problem/phosphorus.py:60-120,169-290)
+    tm = rh.make_tp_module("phosphorus", depth, "phosphorus")
+    x = out["phosphorus/x"]
+    uptake = tm.po4_uptake(x[0])
+    tau_r = tm.po4_s_restore_tau_r(x[0], uptake)
+    out["phosphorus/po4_uptake"] = uptake
+    out["phosphorus/po4_s_restore_tau_r"] = tau_r
+    mca = np.abs(rng.normal(size=nz - 1)) * 1.0e-3
+    y = rng.normal(size=(6, nz))
+
+    class _ResP:
+        def __init__(self):
+            self.vals = {}
+
+        def set_tracer_vals(self, name, vals):
+            self.vals[name] = np.array(vals)
+
+    tm.get_tracer_vals_all = lambda y=y: y
+    res = _ResP()
+    tm.apply_precond_jacobian((0.0, YEAR), res, mca, tau_r)
+    out["phosphorus/precond_mca"] = mca
+    out["phosphorus/precond_y"] = y
+    out["phosphorus/precond"] = np.stack([res.vals[n] for n in ("po4_s", "dop_s", "pop_s")])
     np.savez_compressed(os.path.join(OUT, "test_problem.npz"), **out)
     print("test_problem.npz:", len(out), "arrays")
 

@@ -580,6 +580,60 @@ class Phosphorus1D:
         return out.reshape(-1)
 
 
+    def precond_matrix(self, mca, tau_r):
+        """3nz x 3nz, 7 diagonals, unknowns [po4_s, dop_s, pop_s] (test_problem/phosphorus.py:213-290)"""
+        d = self.g.depth
+        nz = self.g.nz
+        day_per_sec = 1.0 / 86400.0
+        single = np.zeros(nz)
+        single[:-1] -= mca * d.delta_mid_r * d.delta_r[:-1]
+        single[1:] -= mca * d.delta_mid_r * d.delta_r[1:]
+        d0_po4 = single - tau_r
+        d0_dop = single - 0.01 * day_per_sec
+        d0_pop = single - 0.01 * day_per_sec
+        d0_pop[:-1] -= day_per_sec * d.delta_r[:-1]
+        zero = np.zeros(1)
+        up = mca * d.delta_mid_r * d.delta_r[:-1]
+        lo = mca * d.delta_mid_r * d.delta_r[1:]
+        lo_pop = lo + day_per_sec * d.delta_r[1:]
+        return sparse.diags(
+            [
+                np.concatenate((d0_po4, d0_dop, d0_pop)),
+                np.concatenate((up, zero, up, zero, up)),
+                np.concatenate((lo, zero, lo, zero, lo_pop)),
+                np.concatenate((0.01 * day_per_sec * np.ones(nz), np.zeros(nz))),
+                np.concatenate((0.67 * tau_r, np.zeros(nz))),
+                0.01 * day_per_sec * np.ones(nz),
+                0.33 * tau_r,
+            ],
+            [0, 1, -1, nz, -nz, 2 * nz, -2 * nz],
+            format="csr",
+        )
+
+    def apply_precond_jacobian(self, y_shadow, mca, tau_r):
+        """res for the shadow tracers [3, nz] (test_problem/phosphorus.py:169-211): two regularised
+        sparse solves + Richardson extrapolation, removal of the null vector (smallest singular
+        value) weighted by layer thickness, minus the input"""
+        from scipy import linalg
+        from scipy.sparse import linalg as sp_linalg
+
+        nz = self.g.nz
+        self_vals = np.asarray(y_shadow, dtype=np.float64).reshape(-1)
+        t0, t1 = self.g.time_range
+        rhs_vals = (1.0 / (t1 - t0)) * self_vals
+        matrix = self.precond_matrix(mca, tau_r)
+        res_a = sp_linalg.spsolve(matrix - 1.0e-11 * sparse.eye(3 * nz), rhs_vals)
+        res_b = sp_linalg.spsolve(matrix - 0.5e-11 * sparse.eye(3 * nz), rhs_vals)
+        res_vals = 2.0 * res_b - res_a
+        _, sing_vals, r_sing_vects = linalg.svd(matrix.todense())
+        min_ind = sing_vals.argmin()
+        dz3 = np.concatenate((self.g.depth.delta,) * 3)
+        numer = (res_vals * dz3).sum()
+        denom = (r_sing_vects[min_ind, :] * dz3).sum()
+        res_vals -= numer / denom * r_sing_vects[min_ind, :]
+        return (res_vals - self_vals).reshape(3, nz)
+
+
 def comp_fcn_1d(module, x0, t_eval=None, rtol=1.0e-12, atol=1.0e-12, return_sol=False):
     """test_problem/model_state.py:83-103"""
     flat0 = np.asarray(x0, dtype=np.float64).reshape(-1)
