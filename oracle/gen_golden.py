@@ -154,6 +154,9 @@ def py_driver_2d_cases():
             [phos.comp_tend(t, x.reshape(-1), procs).reshape(x.shape) for t in times[:4]]
         )
 
+        out[f"{tag}/phosphorus/jac_dense_t3"] = phos.comp_jacobian(times[3], x.reshape(-1), procs).toarray()
+        out.update(phosphorus_2d_precond_case(tag, depth, ypos, procs, rng))
+
         ft, fd = synthetic_forcing(nz, ny, 300)
         fname = f"/tmp/golden_forcing_{tag}.nc"
         write_forcing_nc(fname, ft, fd, depth.mid, ypos.mid)
@@ -172,6 +175,89 @@ def py_driver_2d_cases():
         out[f"{tag}/forced/tend"] = np.stack([forced.comp_tend(t, x.reshape(-1), procs).reshape(x.shape) for t in tt])
     np.savez_compressed(os.path.join(OUT, "py_driver_2d.npz"), **out)
     print("py_driver_2d.npz:", len(out), "arrays")
+
+
+def phosphorus_2d_precond_case(tag, depth, ypos, procs, rng):
+    """the reference's py_driver_2d phosphorus.apply_precond_jacobian (phosphorus.py:197-274) run
+    unmodified; only the xarray-backed base-class plumbing it touches (value access, region mean,
+    the three in-place operators, the null-space file dump) is replaced by numpy equivalents with
+    the semantics of tracer_module_state_base.py:255-388 for ONE region covering the grid"""
+    import nk_ooc.py_driver_2d.phosphorus as ref_mod
+
+    nz, ny = len(depth), len(ypos)
+    weight = np.outer(depth.delta, ypos.delta)
+    weight = weight / weight.sum()  # region_comp_mean_matrix row (model_config.py:292-315)
+
+    class _P(ref_mod.phosphorus):  # pylint: disable=invalid-name
+        def get_tracer_vals_all(self):
+            return self._v
+
+        def set_tracer_vals_all(self, vals, reseat_vals=False):
+            self._v = vals if reseat_vals else np.array(vals)
+
+        def mean(self):  # tracer_module_state_base.py:371-377: sum over tracers of the region means
+            return np.array([(weight[None] * self._v).sum()])
+
+        def __itruediv__(self, other):
+            self._v /= float(np.asarray(other).reshape(-1)[0])
+            return self
+
+        def __rmul__(self, other):
+            res = copy.copy(self)
+            res._v = float(np.asarray(other).reshape(-1)[0]) * self._v
+            return res
+
+        def __isub__(self, other):
+            self._v -= other._v
+            return self
+
+        def dump(self, fptr, action):
+            pass
+
+    import copy
+
+    class _NullDataset:
+        def __init__(self, *a, **k):
+            pass
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *exc):
+            return False
+
+    class _Var:
+        def __init__(self, arr):
+            self._a = arr
+
+        def __getitem__(self, key):
+            return self._a[key]
+
+    class _Precond:
+        def __init__(self, times, po4):
+            self.variables = {"time": _Var(times), "po4": _Var(po4)}
+
+        def filepath(self):
+            return "/tmp/golden_precond/precond_00.nc"
+
+    ref_mod.Dataset = _NullDataset
+    base = rh.make_2d_phosphorus(depth, ypos)
+    tm = object.__new__(_P)
+    tm.__dict__.update(base.__dict__)
+    y = rng.normal(size=(3, nz, ny)) * np.array([1.0, 0.05, 0.01])[:, None, None]
+    tm._v = y.copy()
+    n_t = 4
+    ptimes = YEAR * np.linspace(0.0, 1.0, n_t)
+    po4 = np.abs(rng.normal(size=(n_t, nz, ny))) * 2.0
+
+    class _Res:
+        def set_tracer_vals_all(self, vals, reseat_vals=False):
+            self.vals = np.array(vals)
+
+    res = _Res()
+    tm.apply_precond_jacobian((0.0, YEAR), res, procs, _Precond(ptimes, po4))
+    return {f"{tag}/phosphorus/precond_y": y, f"{tag}/phosphorus/precond_times": ptimes,
+            f"{tag}/phosphorus/precond_po4": po4, f"{tag}/phosphorus/precond": res.vals}
 
 
 def test_problem_cases():

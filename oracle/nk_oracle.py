@@ -360,6 +360,38 @@ class Phosphorus2D:
         return (jac.tocsr() + sparse.bmat(blocks, format="csr")).tocsr()
 
 
+    def apply_precond_jacobian(self, y, precond_times, precond_po4, weight=None):
+        """res [3, nz, ny] (phosphorus.py:197-274): one interval of length T, Jacobian at T/2 with po4
+        from the precond snapshot nearest T; null vector and shift from ARPACK shift-invert
+        (sigma = 0); two shifted sparse solves + Richardson extrapolation; the multiple of the
+        null vector that makes the region mean of the result vanish is removed; minus the input.
+        weight: normalised cell weights of the (single) region; default layer thickness x width."""
+        g = self.g
+        shape = (3, g.nz, g.ny)
+        if weight is None:
+            weight = np.outer(g.depth.delta, g.ypos.delta)
+            weight = weight / weight.sum()
+        self_vals = np.asarray(y, dtype=np.float64).reshape(-1)
+        t0, t1 = g.time_range
+        time_delta = t1 - t0
+        tracer_vals = np.zeros(shape)
+        tracer_vals[0] = precond_po4[np.argmin(abs(t1 - precond_times))]
+        mat_id = sparse.identity(self_vals.size)
+        mat = mat_id - (mat_id - time_delta * self.comp_jacobian(t0 + 0.5 * time_delta, tracer_vals.reshape(-1)))
+        e_vals, e_vects = sp_linalg.eigs(mat, k=5, sigma=0.0)
+        null_comp = e_vects[:, 0]
+        if max(abs(null_comp.imag)) > 1.0e-10 * max(abs(null_comp.real)):
+            raise RuntimeError("1st eigenvector has non-trivial imaginary part")
+        null_vect = null_comp.real.reshape(shape)
+        shift = 0.5 * e_vals[1].real
+        solve_tmp = sp_linalg.spsolve(mat - shift * mat_id, self_vals)
+        solve_vals = sp_linalg.spsolve(mat - (0.5 * shift) * mat_id, self_vals)
+        solve_vals = (2.0 * solve_vals - solve_tmp).reshape(shape)
+        e_vect = null_vect / (weight[None] * null_vect).sum()
+        solve_vals = solve_vals - (weight[None] * solve_vals).sum() * e_vect
+        return solve_vals - self_vals.reshape(shape)
+
+
 class Forced2D:
     """forced.py:11-202; forcing interpolation utils.py:488-537.
 
