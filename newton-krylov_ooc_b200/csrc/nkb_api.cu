@@ -130,7 +130,8 @@ void nkb_model_destroy(nkb_model *m) {
     if (!m) return;
     cudaFree(m->arena); cudaFree(m->tri); cudaFree(m->aff); cudaFree(m->src); cudaFree(m->d_h);
     cudaFree(m->tri_raw); cudaFree(m->aff_raw); cudaFree(m->src_raw);
-    cudaFree(m->ctab);
+    cudaFree(m->ctab); cudaFree(m->d_done);
+    if (m->h_err) cudaFreeHost(m->h_err);
     cudaFree(m->d_stage_major); cudaFree(m->d_stage_x); cudaFree(m->d_stage_f); cudaFree(m->d_stage_work);
     if (m->graph) cudaGraphExecDestroy(m->graph);
     if (m->own_stream) cudaStreamDestroy(m->own_stream);
@@ -328,23 +329,47 @@ int nkb_model_eval(nkb_model *m, const double *d_x0, double *d_f, double *d_work
     if (emit_hist(0, d_x0)) return 1;
 
     if (nkb::fused_step_usable(v, B, ldb, d_x0, d_f, d_work)) {
-        // one launch per time step: both implicit stages fused (nkb_step_fused.cu)
+        // fused step kernel (nkb_step_fused.cu): both implicit stages of a time step in one pass; by
+        // default ONE persistent launch integrates all steps between two hist snapshots (CTAs wait
+        // on per-tile step counters instead of kernel boundaries), NKB_FUSED_PERSIST=0: one launch
+        // per step
         if (ensure_fused_tables(m)) return 1;
-        CUtensorMap in_x0, in_f, out_f, in_w, out_w;
-        if (nkb::fused_encode_state_maps(v, B, ldb, d_x0, &in_x0, nullptr)) return 1;
-        if (nkb::fused_encode_state_maps(v, B, ldb, d_f, &in_f, &out_f)) return 1;
-        if (nkb::fused_encode_state_maps(v, B, ldb, w_alt, &in_w, &out_w)) return 1;
-        const double *un = d_x0;
-        for (int n = 0; n < S; ++n) {
-            const bool last = (n == S - 1);
-            double *dest = (((S - 1 - n) & 1) == 0) ? d_f : w_alt;
-            const CUtensorMap &mi = (un == d_x0) ? in_x0 : (un == d_f ? in_f : in_w);
-            const CUtensorMap &mo = (dest == d_f) ? out_f : out_w;
-            if (nkb::launch_step_fused(v, B, S, n, m->h_h[n], m->aff + (size_t)(2 * n) * aff_stride,
-                                       m->aff + (size_t)(2 * n + 1) * aff_stride, mi, mo, m->map_ctab, st))
-                return 1;
-            un = dest;
-            if (n_hist > 0 && !last && emit_hist(n + 1, dest)) return 1;
+        if (m->h_err && *m->h_err) {
+            *m->h_err = 0;
+            nkb::set_error("nkb_model_eval: a previous persistent step launch timed out waiting for a tile");
+            return 1;
+        }
+        if (!m->h_err) {
+            NKB_CUDA(cudaHostAlloc(&m->h_err, sizeof(int), cudaHostAllocMapped));
+            *m->h_err = 0;
+            NKB_CUDA(cudaHostGetDevicePointer(&m->d_err, m->h_err, 0));
+        }
+        const size_t ntiles = (size_t)nkb::fused_tile_count(v, B);
+        if (ntiles > m->done_cap) {
+            cudaFree(m->d_done);
+            m->d_done = nullptr;
+            NKB_CUDA(cudaMalloc(&m->d_done, ntiles * sizeof(int)));
+            m->done_cap = ntiles;
+        }
+        NKB_CUDA(cudaMemsetAsync(m->d_done, 0, ntiles * sizeof(int), st));
+        nkb::FusedMaps fm;
+        if (nkb::fused_encode_state_maps(v, B, ldb, d_x0, &fm.in_x0, nullptr)) return 1;
+        if (nkb::fused_encode_state_maps(v, B, ldb, d_f, &fm.in_f, &fm.out_f)) return 1;
+        if (nkb::fused_encode_state_maps(v, B, ldb, w_alt, &fm.in_w, &fm.out_w)) return 1;
+        fm.ctab = m->map_ctab;
+        const bool persist = nkb::fused_persistent();
+        int n = 0;
+        while (n < S) {
+            // the segment ends after the next step whose result is a hist snapshot (or at S)
+            int end = S;
+            if (!persist) end = n + 1;
+            else if (hist_i < n_hist && h_hist_steps[hist_i] < S) end = h_hist_steps[hist_i] > n ? h_hist_steps[hist_i] : n + 1;
+            if (nkb::launch_steps_fused(v, B, S, n, end, m->d_h, m->aff, fm, m->d_done, m->d_err, st)) return 1;
+            n = end;
+            if (n_hist > 0 && n < S) {
+                double *dest = (((S - n) & 1) == 0) ? d_f : w_alt;  // buffer written by step n - 1
+                if (emit_hist(n, dest)) return 1;
+            }
         }
         if (nkb::launch_sub_inplace(d_f, d_x0, nstate, st)) return 1;
         NKB_CUDA(cudaGetLastError());

@@ -120,9 +120,13 @@ int launch_step_ctab(const ModelDev &m, int n_steps, const double *d_t, const do
 bool fused_step_usable(const ModelDev &v, int B, int ldb, const double *x0, const double *f, const double *work);
 int fused_encode_state_maps(const ModelDev &v, int B, int ldb, const double *buf, CUtensorMap *in, CUtensorMap *out);
 int fused_encode_ctab_map(int nz, int ny, size_t nplanes, const double *buf, CUtensorMap *map);
-int launch_step_fused(const ModelDev &v, int B, int n_steps, int step, double h, const double *aff1,
-                      const double *aff2, const CUtensorMap &uin, const CUtensorMap &uout, const CUtensorMap &ctab,
-                      cudaStream_t st);
+struct FusedMaps {
+    CUtensorMap in_x0, in_f, in_w, out_f, out_w, ctab;
+};
+int launch_steps_fused(const ModelDev &v, int B, int n_steps, int step0, int step1, const double *d_h,
+                       const double *d_aff, const FusedMaps &fm, int *d_done, int *d_err, cudaStream_t st);
+bool fused_persistent();
+int fused_tile_count(const ModelDev &v, int B);
 int launch_sub_inplace(double *out, const double *x0, size_t n, cudaStream_t st);
 bool tma_path_usable(const StageArgs &a);
 int launch_stage_tma(int kind, int nin, const StageArgs &a, cudaStream_t st);
@@ -144,6 +148,9 @@ struct nkb_model {
     // fused-step coefficient table (built on first use, nkb_tables.cu:step_ctab_kernel)
     double *ctab = nullptr;     // [n_steps][n_classes][8][nz][2*(ny+1)]
     CUtensorMap map_ctab;
+    int *d_done = nullptr;      // per-tile step counters of the persistent step kernel
+    size_t done_cap = 0;
+    int *h_err = nullptr, *d_err = nullptr;  // host-mapped error flag (dependency-wait timeout)
     // scratch for tend()/mixing_coeff()
     double *tri_raw = nullptr;  // [n_classes][nz][ny][4]
     double *aff_raw = nullptr;  // [n_classes][ny]

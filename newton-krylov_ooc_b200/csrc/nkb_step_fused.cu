@@ -67,16 +67,22 @@ static_assert(fs_cfg(2).slot % 1024 == 0 && fs_cfg(2).out % 1024 == 0, "swizzled
 struct StepArgs {
     int nz, ny, B, T, ncls, n_steps;
     int nct, jt, nmb, ntiles;  // column tiles, interior columns per tile, member blocks, total
-    int step;
+    int step0, step1;          // this launch integrates the time steps [step0, step1)
+    int rot;                   // tile -> CTA assignment is rotated by rot CTAs per step (load balance)
     int class_of[NKB_MAX_TRACERS];
     double src_const[NKB_MAX_TRACERS];
     double sink_thres_r;
-    double hg, he1, r, a0r;     // gamma*h, h*(1-delta); P = r*rhs1 + a0r*u_n (see launch_step_fused)
-    const double *aff1, *aff2;  // [ncls][ny] of the two stages of this step
+    double r, a0r;             // P = r*rhs1 + a0r*u_n (see launch_steps_fused)
+    const double *h;           // [n_steps] step sizes
+    const double *aff;         // [2*n_steps][ncls][ny]: gamma*h*(affine surface source) of every stage
+    int *done;                 // [ntiles] number of time steps completed for the tile (inter-CTA dependencies)
+    int *err;                  // set when a dependency wait timed out (host-mapped)
 };
 
+// state buffers of a model-year evaluation: x0 (read by step 0 only) and the two buffers the steps
+// alternate between (the last step writes f)
 struct StepMaps {
-    CUtensorMap uin, uout, ctab;
+    CUtensorMap in_x0, in_f, in_w, out_f, out_w, ctab;
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -106,6 +112,20 @@ __device__ __forceinline__ void fs_mbar_wait(uint32_t bar, uint32_t parity) {
             : "r"(bar), "r"(parity), "r"(HINT_NS)
             : "memory");
     } while (!ok);
+}
+// spin until *flag >= want (acquire); gives up after ~2e9 cycles and raises *err instead of hanging
+__device__ __forceinline__ void fs_wait_done(const int *flag, int want, int *err) {
+    int v;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (v >= want) return;
+        __nanosleep(200);
+        if (clock64() - t0 > 2000000000ll) {
+            *reinterpret_cast<volatile int *>(err) = 1;
+            return;
+        }
+    }
 }
 __device__ __forceinline__ void fs_tma_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1,
                                                int c2, int c3, uint64_t hint) {
@@ -363,38 +383,53 @@ __global__ void __launch_bounds__(fs_cfg(MPT).threads, 1) step_fused_kernel(cons
         // ===== producer: one lane issues every TMA load of this CTA, in consumption order =====
         if (lane == 0) {
             uint32_t g = 0;
-            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-                const int mb = tile % p.nmb;
-                const int ct = (tile / p.nmb) % p.nct;
-                const int tr = tile / (p.nmb * p.nct);
-                const int m0 = mb * FS_MEM, j0 = ct * p.jt;
-                const int zt = (p.step * p.ncls + p.class_of[tr]) * 8;
-                for (int sweep = 0; sweep < 3; ++sweep) {
-                    for (int cc = 0; cc < nchunk; ++cc) {
-                        const int c = (sweep == 1) ? nchunk - 1 - cc : cc;
-                        const int k0 = c * KC;
-                        const uint32_t s = g % NS, ph = (g / NS) & 1;
-                        fs_mbar_wait<2000>(bar_empty + 8 * s, ph ^ 1);
-                        const uint32_t sb = ring_a + s * C.slot;
-                        const uint32_t pl = sb + C.ubytes;
-                        const uint32_t fb = bar_full + 8 * s;
-                        if (sweep == 0) {
-                            fs_mbar_expect_tx(fb, C.ubytes + NPA * C.ppbytes);
-                            fs_tma_load_4d(sb, &maps.uin, fb, m0, j0 - 2, k0, tr, kEvictNormal);
+            for (int n = p.step0; n < p.step1; ++n) {
+                const bool to_f = (((p.n_steps - 1 - n) & 1) == 0);  // this step writes f (else w)
+                const CUtensorMap *uin = (n == 0) ? &maps.in_x0 : (to_f ? &maps.in_w : &maps.in_f);
+                const int first = (int)((blockIdx.x + (unsigned)n * (unsigned)p.rot) % gridDim.x);
+                for (int tile = first; tile < p.ntiles; tile += gridDim.x) {
+                    const int mb = tile % p.nmb;
+                    const int ct = (tile / p.nmb) % p.nct;
+                    const int tr = tile / (p.nmb * p.nct);
+                    const int m0 = mb * FS_MEM, j0 = ct * p.jt;
+                    const int zt = (n * p.ncls + p.class_of[tr]) * 8;
+                    // the tile and its two column neighbours must have completed step n - 1: their
+                    // output is this step's input (halo included), and this step's output buffer is
+                    // what they read during step n - 1
+                    if (n > 0) {
+                        fs_wait_done(p.done + tile, n, p.err);
+                        if (ct > 0) fs_wait_done(p.done + tile - p.nmb, n, p.err);
+                        if (ct + 1 < p.nct) fs_wait_done(p.done + tile + p.nmb, n, p.err);
+                        asm volatile("fence.proxy.async;" ::: "memory");
+                    }
+                    for (int sweep = 0; sweep < 3; ++sweep) {
+                        for (int cc = 0; cc < nchunk; ++cc) {
+                            const int c = (sweep == 1) ? nchunk - 1 - cc : cc;
+                            const int k0 = c * KC;
+                            const uint32_t s = g % NS, ph = (g / NS) & 1;
+                            fs_mbar_wait<2000>(bar_empty + 8 * s, ph ^ 1);
+                            const uint32_t sb = ring_a + s * C.slot;
+                            const uint32_t pl = sb + C.ubytes;
+                            const uint32_t fb = bar_full + 8 * s;
+                            if (sweep == 0) {
+                                fs_mbar_expect_tx(fb, C.ubytes + NPA * C.ppbytes);
+                                fs_tma_load_4d(sb, uin, fb, m0, j0 - 2, k0, tr, kEvictNormal);
 #pragma unroll
-                            for (int q = 0; q < NPA; ++q)
-                                fs_tma_load_3d(pl + q * C.ppbytes, &maps.ctab, fb, 2 * j0, k0, zt + q, kEvictLast);
-                        } else if (sweep == 1) {
-                            fs_mbar_expect_tx(fb, C.ubytes + 4 * C.ppbytes);
-                            fs_tma_load_4d(sb, &maps.uin, fb, m0, j0 - 2, k0, tr, kEvictFirst);
+                                for (int q = 0; q < NPA; ++q)
+                                    fs_tma_load_3d(pl + q * C.ppbytes, &maps.ctab, fb, 2 * j0, k0, zt + q, kEvictLast);
+                            } else if (sweep == 1) {
+                                fs_mbar_expect_tx(fb, C.ubytes + 4 * C.ppbytes);
+                                fs_tma_load_4d(sb, uin, fb, m0, j0 - 2, k0, tr, kEvictFirst);
 #pragma unroll
-                            for (int q = 0; q < 4; ++q)
-                                fs_tma_load_3d(pl + q * C.ppbytes, &maps.ctab, fb, 2 * j0, k0, zt + 3 + q, kEvictLast);
-                        } else {
-                            fs_mbar_expect_tx(fb, C.ppbytes);
-                            fs_tma_load_3d(pl, &maps.ctab, fb, 2 * j0, k0, zt + 7, kEvictLast);
+                                for (int q = 0; q < 4; ++q)
+                                    fs_tma_load_3d(pl + q * C.ppbytes, &maps.ctab, fb, 2 * j0, k0, zt + 3 + q,
+                                                   kEvictLast);
+                            } else {
+                                fs_mbar_expect_tx(fb, C.ppbytes);
+                                fs_tma_load_3d(pl, &maps.ctab, fb, 2 * j0, k0, zt + 7, kEvictLast);
+                            }
+                            ++g;
                         }
-                        ++g;
                     }
                 }
             }
@@ -403,21 +438,30 @@ __global__ void __launch_bounds__(fs_cfg(MPT).threads, 1) step_fused_kernel(cons
         // ===== store warp: drains the output staging ring with TMA stores =====
         if (lane == 0) {
             uint32_t go = 0;
-            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-                const int mb = tile % p.nmb;
-                const int ct = (tile / p.nmb) % p.nct;
-                const int tr = tile / (p.nmb * p.nct);
-                for (int c = 0; c < nchunk; ++c) {
-                    const uint32_t s = go % NO, ph = (go / NO) & 1;
-                    fs_mbar_wait<2000>(bar_ofull + 8 * s, ph);
-                    fs_tma_store_4d(&maps.uout, oring_a + s * C.out, mb * FS_MEM, ct * p.jt, c * KC, tr);
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                    fs_mbar_arrive(bar_oempty + 8 * s);
-                    ++go;
+            for (int n = p.step0; n < p.step1; ++n) {
+                const bool to_f = (((p.n_steps - 1 - n) & 1) == 0);
+                const CUtensorMap *uout = to_f ? &maps.out_f : &maps.out_w;
+                const int first = (int)((blockIdx.x + (unsigned)n * (unsigned)p.rot) % gridDim.x);
+                for (int tile = first; tile < p.ntiles; tile += gridDim.x) {
+                    const int mb = tile % p.nmb;
+                    const int ct = (tile / p.nmb) % p.nct;
+                    const int tr = tile / (p.nmb * p.nct);
+                    for (int c = 0; c < nchunk; ++c) {
+                        const uint32_t s = go % NO, ph = (go / NO) & 1;
+                        fs_mbar_wait<2000>(bar_ofull + 8 * s, ph);
+                        fs_tma_store_4d(uout, oring_a + s * C.out, mb * FS_MEM, ct * p.jt, c * KC, tr);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        fs_mbar_arrive(bar_oempty + 8 * s);
+                        ++go;
+                    }
+                    // publish: the tile has completed step n (its stores are performed)
+                    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                    __threadfence();
+                    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.done + tile), "r"(n + 1) : "memory");
                 }
             }
-            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         }
     } else {
         // ===== consumers =====
@@ -444,17 +488,21 @@ __global__ void __launch_bounds__(fs_cfg(MPT).threads, 1) step_fused_kernel(cons
         const double thr_r = p.sink_thres_r;
         uint32_t g = 0, go = 0;
 
-        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        for (int n = p.step0; n < p.step1; ++n) {
+        const double hstep = __ldg(p.h + n);
+        const double *aff_n = p.aff + (size_t)(2 * n) * p.ncls * ny;
+        const int first = (int)((blockIdx.x + (unsigned)n * (unsigned)p.rot) % gridDim.x);
+        for (int tile = first; tile < p.ntiles; tile += gridDim.x) {
             const int ct = (tile / p.nmb) % p.nct;
             const int tr = tile / (p.nmb * p.nct);
             const int j = ct * p.jt - 1 + col;
             const int cls = p.class_of[tr];
             double aff1 = 0.0, aff2 = 0.0;
             if (j >= 0 && j < ny) {
-                aff1 = __ldg(p.aff1 + (size_t)cls * ny + j);
-                aff2 = __ldg(p.aff2 + (size_t)cls * ny + j);
+                aff1 = __ldg(aff_n + (size_t)cls * ny + j);
+                aff2 = __ldg(aff_n + (size_t)(p.ncls + cls) * ny + j);
             }
-            const double ws1 = p.hg * p.src_const[tr], ws2 = p.he1 * p.src_const[tr];
+            const double ws1 = kGamma * hstep * p.src_const[tr], ws2 = hstep * (1.0 - kDelta) * p.src_const[tr];
 
             // ---------------- sweep A: stage-1 rhs + LU forward elimination, top -> bottom ----------------
             V yprev = fs_splat<MPT>(0.0);
@@ -599,6 +647,7 @@ __global__ void __launch_bounds__(fs_cfg(MPT).threads, 1) step_fused_kernel(cons
                 if (c < nchunk) chunk_c(ra, rb, c);
             }
         }
+        }
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -713,7 +762,7 @@ int fused_encode_ctab_map(int nz, int ny, size_t nplanes, const double *buf, CUt
 }
 
 template <int KIND, int MPT>
-static int fs_launch_m(const StepArgs &a, const StepMaps &maps, int grid, cudaStream_t st) {
+static int fs_launch_m(const StepArgs &a, const StepMaps &maps, int grid, bool cooperative, cudaStream_t st) {
     auto kern = step_fused_kernel<KIND, MPT>;
     constexpr FsCfg C = fs_cfg(MPT);
     static bool attr_set = false;
@@ -721,33 +770,43 @@ static int fs_launch_m(const StepArgs &a, const StepMaps &maps, int grid, cudaSt
         NKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C.smem));
         attr_set = true;
     }
-    kern<<<grid, C.threads, C.smem, st>>>(a, maps);
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(C.threads);
+    cfg.dynamicSmemBytes = C.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;  // all CTAs co-resident: they wait on each other's tiles
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = cooperative ? 1 : 0;
+    NKB_CUDA(cudaLaunchKernelEx(&cfg, kern, a, maps));
     count_launch();
     return 0;
 }
 
-int launch_step_fused(const ModelDev &v, int B, int n_steps, int step, double h, const double *aff1,
-                      const double *aff2, const CUtensorMap &uin, const CUtensorMap &uout, const CUtensorMap &ctab,
-                      cudaStream_t st) {
+// integrates the time steps [step0, step1) in one launch
+int launch_steps_fused(const ModelDev &v, int B, int n_steps, int step0, int step1, const double *d_h,
+                       const double *d_aff, const FusedMaps &fm, int *d_done, int *d_err, cudaStream_t st) {
     StepArgs a;
     std::memset(&a, 0, sizeof(a));
     a.nz = v.nz; a.ny = v.ny; a.B = B; a.T = v.T; a.ncls = v.n_classes; a.n_steps = n_steps;
     fs_col_tiles(v.ny, a.nct, a.jt);
     a.nmb = (B + FS_MEM - 1) / FS_MEM;
     a.ntiles = a.nmb * a.nct * v.T;
-    a.step = step;
+    a.step0 = step0; a.step1 = step1;
     for (int t = 0; t < NKB_MAX_TRACERS; ++t) { a.class_of[t] = v.class_of[t]; a.src_const[t] = v.src_const[t]; }
     a.sink_thres_r = v.sink_thres > 0.0 ? 1.0 / v.sink_thres : 0.0;
     // stage 2 (nkb_api.cu): rhs2 = a0 u_n + a1 u1 + h (delta - 1 + gamma) E(u_n) + h (1 - delta) E(u1); with
     // rhs1 = u_n + gamma h E(u_n) the u_n terms are P = r rhs1 + (a0 - r) u_n, r = (delta - 1 + gamma)/gamma
     const double a1 = (1.0 - kGamma) / kGamma, a0 = 1.0 - a1;
-    a.hg = kGamma * h;
-    a.he1 = h * (1.0 - kDelta);
     a.r = (kDelta - 1.0 + kGamma) / kGamma;
     a.a0r = a0 - a.r;
-    a.aff1 = aff1; a.aff2 = aff2;
+    a.h = d_h; a.aff = d_aff; a.done = d_done; a.err = d_err;
     StepMaps maps;
-    maps.uin = uin; maps.uout = uout; maps.ctab = ctab;
+    maps.in_x0 = fm.in_x0; maps.in_f = fm.in_f; maps.in_w = fm.in_w;
+    maps.out_f = fm.out_f; maps.out_w = fm.out_w; maps.ctab = fm.ctab;
     static int n_sm = 0;
     if (n_sm == 0) {
         int dev = 0;
@@ -755,15 +814,29 @@ int launch_step_fused(const ModelDev &v, int B, int n_steps, int step, double h,
         NKB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     }
     int grid = fs_env_int("NKB_FUSED_GRID", n_sm);
+    if (grid > n_sm) grid = n_sm;  // one CTA per SM (shared memory, 512 TMEM columns): all co-resident
     if (grid > a.ntiles) grid = a.ntiles;
+    // rotate the tile -> CTA assignment by the number of left-over tiles per step so that the CTAs that
+    // get one tile more than the others change from step to step
+    a.rot = (step1 - step0 > 1) ? a.ntiles % grid : 0;
+    const bool coop = (step1 - step0 > 1);
     const int mpt = fs_mpt();
     if (v.kind == NKB_MOD_LINEAR)
-        return mpt == 2 ? fs_launch_m<NKB_MOD_LINEAR, 2>(a, maps, grid, st) : fs_launch_m<NKB_MOD_LINEAR, 1>(a, maps, grid, st);
+        return mpt == 2 ? fs_launch_m<NKB_MOD_LINEAR, 2>(a, maps, grid, coop, st)
+                        : fs_launch_m<NKB_MOD_LINEAR, 1>(a, maps, grid, coop, st);
     if (v.kind == NKB_MOD_FORCED_FILE)
-        return mpt == 2 ? fs_launch_m<NKB_MOD_FORCED_FILE, 2>(a, maps, grid, st)
-                        : fs_launch_m<NKB_MOD_FORCED_FILE, 1>(a, maps, grid, st);
-    set_error("launch_step_fused: unsupported module kind");
+        return mpt == 2 ? fs_launch_m<NKB_MOD_FORCED_FILE, 2>(a, maps, grid, coop, st)
+                        : fs_launch_m<NKB_MOD_FORCED_FILE, 1>(a, maps, grid, coop, st);
+    set_error("launch_steps_fused: unsupported module kind");
     return 2;
+}
+
+bool fused_persistent() { return fs_env_int("NKB_FUSED_PERSIST", 1) != 0; }
+
+int fused_tile_count(const ModelDev &v, int B) {
+    int nct, jt;
+    fs_col_tiles(v.ny, nct, jt);
+    return ((B + FS_MEM - 1) / FS_MEM) * nct * v.T;
 }
 
 int launch_sub_inplace(double *out, const double *x0, size_t n, cudaStream_t st) {

@@ -171,7 +171,14 @@ def test_fused_step_kernel_matches_scheme_oracle(kind, nz, ny, B, monkeypatch):
     m.eval(xd, B)  # the first fused evaluation also builds the step tables
     n0 = lib.nkb_launch_count()
     got = m.eval(xd, B).cpu().numpy()[..., :B]
-    assert lib.nkb_launch_count() - n0 == nsteps + 1, "the fused step kernel did not run"
+    assert lib.nkb_launch_count() - n0 == 2, "the persistent fused step kernel did not run"
+    # one launch per step instead of one persistent launch with per-tile dependencies: same bits
+    monkeypatch.setenv("NKB_FUSED_PERSIST", "0")
+    n0 = lib.nkb_launch_count()
+    per_step = m.eval(xd, B).cpu().numpy()[..., :B]
+    assert lib.nkb_launch_count() - n0 == nsteps + 1
+    np.testing.assert_array_equal(got, per_step)
+    monkeypatch.delenv("NKB_FUSED_PERSIST")
     monkeypatch.setenv("NKB_FUSED", "0")
     n0 = lib.nkb_launch_count()
     unfused = m.eval(xd, B).cpu().numpy()[..., :B]
