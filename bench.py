@@ -334,9 +334,13 @@ def run_ours(args):
     value = world * B / (ms_per_step * 1e-3)
     S, s = model.n_steps, 2
     bytes_alg_eval = 8.0 * N * (2 * s * S + 1)
-    # launches per evaluation, counted by the library: S fused step launches (+1 final difference) on the
-    # fused path, 2*S stage launches otherwise; the kernels run back to back on one stream
-    n_stage_launch = max(1, int(round(launches / args.steps)))
+    # launches per evaluation, counted by the library: the persistent fused step kernel integrates all S
+    # time steps in ONE launch (+1 for the final difference); NKB_FUSED_PERSIST=0: S step launches;
+    # stage-per-launch path: 2*S.  The roofline unit of work is one TIME STEP of the fused kernel
+    # (one pass of the kernel's tile loop over the whole state batch) or one stage launch.
+    launches_per_eval = max(1, int(round(launches / args.steps)))
+    fused = launches_per_eval < 2 * S
+    n_stage_launch = S if fused else 2 * S
     avg_launch_ms = ms_per_step / n_stage_launch
     peak, how = measured_peak_gbs()
     achieved = (bytes_alg_eval * B / n_stage_launch) / (avg_launch_ms * 1e-3) / 1e9
@@ -369,11 +373,14 @@ def run_ours(args):
         "roofline": {
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": traffic, "peak_source": how,
-            "kernel": "nkb::step_fused_kernel" if n_stage_launch < 2 * S else "nkb::stage_tma_kernel",
-            "launches_per_eval": n_stage_launch,
+            "kernel": "nkb::step_fused_kernel" if fused else "nkb::stage_tma_kernel",
+            "launches_per_eval": launches_per_eval,
+            "unit_of_work": "one time step of the persistent fused step kernel (all members)" if fused
+                            else "one stage launch",
             "alg_bytes_model": "8*N*(2*s*S+1) per member (SURVEY.md 8d: one read + one write of the state per "
                                "implicit stage); the fused step kernel moves less than that (see traffic)",
             "alg_bytes_per_launch": bytes_alg_eval * B / n_stage_launch, "avg_launch_ms": avg_launch_ms,
+            "traffic_unit": "dram bytes per unit of work (ncu, profiles/traffic.json)",
         },
         "e2e": {
             "value": world * B / e2e_s, "unit": "model-year evals/s",

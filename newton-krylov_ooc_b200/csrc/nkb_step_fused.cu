@@ -69,6 +69,7 @@ struct StepArgs {
     int nct, jt, nmb, ntiles;  // column tiles, interior columns per tile, member blocks, total
     int step0, step1;          // this launch integrates the time steps [step0, step1)
     int rot;                   // tile -> CTA assignment is rotated by rot CTAs per step (load balance)
+    int cross_step_fuse;       // sweep C of a step's last tile may share a pass with sweep A of the next step
     int class_of[NKB_MAX_TRACERS];
     double src_const[NKB_MAX_TRACERS];
     double sink_thres_r;
@@ -329,7 +330,7 @@ constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
 constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
 
 // pair planes of a ring slot, [KC][FS_COLS] pairs each (see step_ctab_kernel in nkb_tables.cu):
-//   sweep A: 0 {aL,aC}  1 {aR,m1}  2 {fA,-}          sweep C: 0 {ib2,g2}
+//   sweep A: 0 {aL,aC}  1 {aR,m1}  2 {fA,-}          sweep C: 3 {ib2,g2}  (C may share a slot with A)
 //   sweep B: 0 {bL,bC}  1 {bR,ib1} 2 {g1,m1} 3 {m2,fB}
 template <int KIND, int MPT>
 __global__ void __launch_bounds__(fs_cfg(MPT).threads, 1) step_fused_kernel(const StepArgs p,
@@ -379,58 +380,120 @@ __global__ void __launch_bounds__(fs_cfg(MPT).threads, 1) step_fused_kernel(cons
     const int nchunk = (nz + KC - 1) / KC;
     constexpr int NPA = FRC ? 3 : 2;
 
+    // ---- the (step, tile) items of this CTA, in processing order (identical in the three roles) ----
+    // item i+1 is "independent" of item i when it does not need item i's result: then the last sweep
+    // of item i (C, output heavy) and the first sweep of item i+1 (A, input heavy) — both top-down —
+    // run as ONE pass over depth: C reads chunk c of the TMEM scratch, A overwrites it.
+    struct Item {
+        int n, tile;
+    };
+    auto item_first = [&](int n) { return (int)((blockIdx.x + (unsigned)n * (unsigned)p.rot) % gridDim.x); };
+    auto item_valid = [&](const Item &it) { return it.n < p.step1; };
+    auto item_next = [&](const Item &it) {
+        Item nx = {it.n, it.tile + (int)gridDim.x};
+        if (nx.tile >= p.ntiles) {
+            nx.n = it.n + 1;
+            nx.tile = item_first(nx.n);
+        }
+        return nx;
+    };
+    auto item_depends = [&](const Item &nx, const Item &it) {
+        if (nx.n == it.n) return false;  // tiles of one step are independent
+        // Fusing across a step boundary makes the completion of a CTA's last tile of step n wait for the
+        // step-n neighbours of its first tile of step n+1.  That is free of cycles only when those
+        // neighbours cannot themselves be last-round tiles (ntiles > 2*grid + nmb, decided by the host).
+        if (!p.cross_step_fuse) return true;
+        const int d = nx.tile - it.tile;
+        // neighbours in the column direction are nmb apart (a tracer boundary only makes this conservative)
+        return d == 0 || d == p.nmb || d == -p.nmb;
+    };
+    Item it0 = {p.step0, item_first(p.step0)};
+    if (it0.tile >= p.ntiles) it0.n = p.step1;  // (grid <= ntiles: does not happen)
+
     if (warp == NCW) {
         // ===== producer: one lane issues every TMA load of this CTA, in consumption order =====
         if (lane == 0) {
             uint32_t g = 0;
-            for (int n = p.step0; n < p.step1; ++n) {
-                const bool to_f = (((p.n_steps - 1 - n) & 1) == 0);  // this step writes f (else w)
-                const CUtensorMap *uin = (n == 0) ? &maps.in_x0 : (to_f ? &maps.in_w : &maps.in_f);
-                const int first = (int)((blockIdx.x + (unsigned)n * (unsigned)p.rot) % gridDim.x);
-                for (int tile = first; tile < p.ntiles; tile += gridDim.x) {
-                    const int mb = tile % p.nmb;
-                    const int ct = (tile / p.nmb) % p.nct;
-                    const int tr = tile / (p.nmb * p.nct);
-                    const int m0 = mb * FS_MEM, j0 = ct * p.jt;
-                    const int zt = (n * p.ncls + p.class_of[tr]) * 8;
-                    // the tile and its two column neighbours must have completed step n - 1: their
-                    // output is this step's input (halo included), and this step's output buffer is
-                    // what they read during step n - 1
-                    if (n > 0) {
-                        fs_wait_done(p.done + tile, n, p.err);
-                        if (ct > 0) fs_wait_done(p.done + tile - p.nmb, n, p.err);
-                        if (ct + 1 < p.nct) fs_wait_done(p.done + tile + p.nmb, n, p.err);
-                        asm volatile("fence.proxy.async;" ::: "memory");
-                    }
-                    for (int sweep = 0; sweep < 3; ++sweep) {
-                        for (int cc = 0; cc < nchunk; ++cc) {
-                            const int c = (sweep == 1) ? nchunk - 1 - cc : cc;
-                            const int k0 = c * KC;
-                            const uint32_t s = g % NS, ph = (g / NS) & 1;
-                            fs_mbar_wait<2000>(bar_empty + 8 * s, ph ^ 1);
-                            const uint32_t sb = ring_a + s * C.slot;
-                            const uint32_t pl = sb + C.ubytes;
-                            const uint32_t fb = bar_full + 8 * s;
-                            if (sweep == 0) {
-                                fs_mbar_expect_tx(fb, C.ubytes + NPA * C.ppbytes);
-                                fs_tma_load_4d(sb, uin, fb, m0, j0 - 2, k0, tr, kEvictNormal);
+            struct TileP {
+                const CUtensorMap *uin;
+                int m0, j0, tr, zt, ct;
+            };
+            auto tile_p = [&](const Item &it) {
+                TileP t;
+                const bool to_f = (((p.n_steps - 1 - it.n) & 1) == 0);  // this step writes f (else w)
+                t.uin = (it.n == 0) ? &maps.in_x0 : (to_f ? &maps.in_w : &maps.in_f);
+                const int mb = it.tile % p.nmb;
+                t.ct = (it.tile / p.nmb) % p.nct;
+                t.tr = it.tile / (p.nmb * p.nct);
+                t.m0 = mb * FS_MEM;
+                t.j0 = t.ct * p.jt;
+                t.zt = (it.n * p.ncls + p.class_of[t.tr]) * 8;
+                return t;
+            };
+            // the tile and its two column neighbours must have completed step n - 1: their output is
+            // this step's input (halo included), and this step's output buffer is what they read then
+            auto dep_wait = [&](const Item &it, const TileP &t) {
+                if (it.n > 0) {
+                    fs_wait_done(p.done + it.tile, it.n, p.err);
+                    if (t.ct > 0) fs_wait_done(p.done + it.tile - p.nmb, it.n, p.err);
+                    if (t.ct + 1 < p.nct) fs_wait_done(p.done + it.tile + p.nmb, it.n, p.err);
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                }
+            };
+            // sweep: 0 = A (tile ta), 1 = B (ta), 2 = C (tc), 3 = C (tc) fused with A (ta)
+            auto issue = [&](int sweep, const TileP &ta, const TileP &tc) {
+                for (int cc = 0; cc < nchunk; ++cc) {
+                    const int c = (sweep == 1) ? nchunk - 1 - cc : cc;
+                    const int k0 = c * KC;
+                    const uint32_t s = g % NS, ph = (g / NS) & 1;
+                    fs_mbar_wait<2000>(bar_empty + 8 * s, ph ^ 1);
+                    const uint32_t sb = ring_a + s * C.slot;
+                    const uint32_t pl = sb + C.ubytes;
+                    const uint32_t fb = bar_full + 8 * s;
+                    if (sweep == 0 || sweep == 3) {
+                        fs_mbar_expect_tx(fb, C.ubytes + (NPA + (sweep == 3 ? 1 : 0)) * C.ppbytes);
+                        fs_tma_load_4d(sb, ta.uin, fb, ta.m0, ta.j0 - 2, k0, ta.tr, kEvictNormal);
 #pragma unroll
-                                for (int q = 0; q < NPA; ++q)
-                                    fs_tma_load_3d(pl + q * C.ppbytes, &maps.ctab, fb, 2 * j0, k0, zt + q, kEvictLast);
-                            } else if (sweep == 1) {
-                                fs_mbar_expect_tx(fb, C.ubytes + 4 * C.ppbytes);
-                                fs_tma_load_4d(sb, uin, fb, m0, j0 - 2, k0, tr, kEvictFirst);
+                        for (int q = 0; q < NPA; ++q)
+                            fs_tma_load_3d(pl + q * C.ppbytes, &maps.ctab, fb, 2 * ta.j0, k0, ta.zt + q, kEvictLast);
+                        if (sweep == 3)
+                            fs_tma_load_3d(pl + 3 * C.ppbytes, &maps.ctab, fb, 2 * tc.j0, k0, tc.zt + 7, kEvictLast);
+                    } else if (sweep == 1) {
+                        fs_mbar_expect_tx(fb, C.ubytes + 4 * C.ppbytes);
+                        fs_tma_load_4d(sb, ta.uin, fb, ta.m0, ta.j0 - 2, k0, ta.tr, kEvictFirst);
 #pragma unroll
-                                for (int q = 0; q < 4; ++q)
-                                    fs_tma_load_3d(pl + q * C.ppbytes, &maps.ctab, fb, 2 * j0, k0, zt + 3 + q,
-                                                   kEvictLast);
-                            } else {
-                                fs_mbar_expect_tx(fb, C.ppbytes);
-                                fs_tma_load_3d(pl, &maps.ctab, fb, 2 * j0, k0, zt + 7, kEvictLast);
-                            }
-                            ++g;
-                        }
+                        for (int q = 0; q < 4; ++q)
+                            fs_tma_load_3d(pl + q * C.ppbytes, &maps.ctab, fb, 2 * ta.j0, k0, ta.zt + 3 + q, kEvictLast);
+                    } else {
+                        fs_mbar_expect_tx(fb, C.ppbytes);
+                        fs_tma_load_3d(pl + 3 * C.ppbytes, &maps.ctab, fb, 2 * tc.j0, k0, tc.zt + 7, kEvictLast);
                     }
+                    ++g;
+                }
+            };
+            Item it = it0;
+            if (item_valid(it)) {
+                TileP t = tile_p(it);
+                dep_wait(it, t);
+                issue(0, t, t);
+                while (true) {
+                    issue(1, t, t);
+                    const Item nx = item_next(it);
+                    if (!item_valid(nx)) {
+                        issue(2, t, t);
+                        break;
+                    }
+                    const TileP tn = tile_p(nx);
+                    if (!item_depends(nx, it)) {
+                        dep_wait(nx, tn);
+                        issue(3, tn, t);
+                    } else {
+                        issue(2, t, t);
+                        dep_wait(nx, tn);
+                        issue(0, tn, tn);
+                    }
+                    it = nx;
+                    t = tn;
                 }
             }
         }
@@ -438,29 +501,26 @@ __global__ void __launch_bounds__(fs_cfg(MPT).threads, 1) step_fused_kernel(cons
         // ===== store warp: drains the output staging ring with TMA stores =====
         if (lane == 0) {
             uint32_t go = 0;
-            for (int n = p.step0; n < p.step1; ++n) {
-                const bool to_f = (((p.n_steps - 1 - n) & 1) == 0);
+            for (Item it = it0; item_valid(it); it = item_next(it)) {
+                const bool to_f = (((p.n_steps - 1 - it.n) & 1) == 0);
                 const CUtensorMap *uout = to_f ? &maps.out_f : &maps.out_w;
-                const int first = (int)((blockIdx.x + (unsigned)n * (unsigned)p.rot) % gridDim.x);
-                for (int tile = first; tile < p.ntiles; tile += gridDim.x) {
-                    const int mb = tile % p.nmb;
-                    const int ct = (tile / p.nmb) % p.nct;
-                    const int tr = tile / (p.nmb * p.nct);
-                    for (int c = 0; c < nchunk; ++c) {
-                        const uint32_t s = go % NO, ph = (go / NO) & 1;
-                        fs_mbar_wait<2000>(bar_ofull + 8 * s, ph);
-                        fs_tma_store_4d(uout, oring_a + s * C.out, mb * FS_MEM, ct * p.jt, c * KC, tr);
-                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                        fs_mbar_arrive(bar_oempty + 8 * s);
-                        ++go;
-                    }
-                    // publish: the tile has completed step n (its stores are performed)
-                    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-                    asm volatile("fence.proxy.async;" ::: "memory");
-                    __threadfence();
-                    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.done + tile), "r"(n + 1) : "memory");
+                const int mb = it.tile % p.nmb;
+                const int ct = (it.tile / p.nmb) % p.nct;
+                const int tr = it.tile / (p.nmb * p.nct);
+                for (int c = 0; c < nchunk; ++c) {
+                    const uint32_t s = go % NO, ph = (go / NO) & 1;
+                    fs_mbar_wait<2000>(bar_ofull + 8 * s, ph);
+                    fs_tma_store_4d(uout, oring_a + s * C.out, mb * FS_MEM, ct * p.jt, c * KC, tr);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    fs_mbar_arrive(bar_oempty + 8 * s);
+                    ++go;
                 }
+                // publish: the tile has completed step n (its stores are performed)
+                asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                asm volatile("fence.proxy.async;" ::: "memory");
+                __threadfence();
+                asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.done + it.tile), "r"(it.n + 1) : "memory");
             }
         }
     } else {
@@ -488,43 +548,130 @@ __global__ void __launch_bounds__(fs_cfg(MPT).threads, 1) step_fused_kernel(cons
         const double thr_r = p.sink_thres_r;
         uint32_t g = 0, go = 0;
 
-        for (int n = p.step0; n < p.step1; ++n) {
-        const double hstep = __ldg(p.h + n);
-        const double *aff_n = p.aff + (size_t)(2 * n) * p.ncls * ny;
-        const int first = (int)((blockIdx.x + (unsigned)n * (unsigned)p.rot) % gridDim.x);
-        for (int tile = first; tile < p.ntiles; tile += gridDim.x) {
-            const int ct = (tile / p.nmb) % p.nct;
-            const int tr = tile / (p.nmb * p.nct);
+        struct TileC {  // per-thread parameters of a (step, tile) item
+            double aff1, aff2, ws1, ws2;
+        };
+        auto tile_c = [&](const Item &it) {
+            TileC t;
+            const double hstep = __ldg(p.h + it.n);
+            const double *aff_n = p.aff + (size_t)(2 * it.n) * p.ncls * ny;
+            const int ct = (it.tile / p.nmb) % p.nct;
+            const int tr = it.tile / (p.nmb * p.nct);
             const int j = ct * p.jt - 1 + col;
             const int cls = p.class_of[tr];
-            double aff1 = 0.0, aff2 = 0.0;
+            t.aff1 = t.aff2 = 0.0;
             if (j >= 0 && j < ny) {
-                aff1 = __ldg(aff_n + (size_t)cls * ny + j);
-                aff2 = __ldg(aff_n + (size_t)(p.ncls + cls) * ny + j);
+                t.aff1 = __ldg(aff_n + (size_t)cls * ny + j);
+                t.aff2 = __ldg(aff_n + (size_t)(p.ncls + cls) * ny + j);
             }
-            const double ws1 = kGamma * hstep * p.src_const[tr], ws2 = hstep * (1.0 - kDelta) * p.src_const[tr];
+            t.ws1 = kGamma * hstep * p.src_const[tr];
+            t.ws2 = hstep * (1.0 - kDelta) * p.src_const[tr];
+            return t;
+        };
 
-            // ---------------- sweep A: stage-1 rhs + LU forward elimination, top -> bottom ----------------
+        // stage-1 right-hand side + LU forward elimination of one chunk (top -> bottom); y1 -> raw
+        auto chunk_a = [&](const TileC &t, const unsigned char *sb, int c, V &yprev, Raw<W> &raw) {
+            const double2 *pl = reinterpret_cast<const double2 *>(sb + C.ubytes) + col;
+            V yb[KC];
+#pragma unroll
+            for (int q = 0; q < KC; ++q) {
+                const V cv = fs_ld(sb + offU[q][1], (V *)nullptr);
+                const V cl = fs_ld(sb + offU[q][0], (V *)nullptr);
+                const V cr = fs_ld(sb + offU[q][2], (V *)nullptr);
+                const double2 lc = pl[q * FS_COLS], rm = pl[PP + q * FS_COLS];
+                double fw = 0.0;
+                if constexpr (FRC) fw = pl[2 * PP + q * FS_COLS].x;
+                const V sv = fs_source<KIND, MPT>(t.ws1, thr_r, fw, cv);
+                V rhs = fs_fma(lc.x, cl, fs_fma(rm.x, cr, fs_fma(lc.y, cv, sv)));
+                if (c == 0 && q == 0) rhs = fs_add(rhs, fs_splat<MPT>(t.aff1));
+                yprev = fs_fma(-rm.y, yprev, rhs);
+                yb[q] = yprev;
+            }
+            fs_pack<MPT, KC>(yb, raw);
+        };
+        // stage-2 substitution of one chunk (top -> bottom) into the output staging slot
+        auto chunk_c = [&](const unsigned char *sb, unsigned char *ob, const Raw<W> &cur, V &u2p) {
+            const double2 *pl = reinterpret_cast<const double2 *>(sb + C.ubytes) + col;
+            V ycur[KC], u2[KC];
+            fs_unpack<MPT, KC>(cur, ycur);
+            // all coefficient loads first: the compiler cannot move a shared load across the staging
+            // stores below (it cannot prove the two ring slots disjoint)
+            double2 ig[KC];
+#pragma unroll
+            for (int q = 0; q < KC; ++q) ig[q] = pl[3 * PP + q * FS_COLS];
+#pragma unroll
+            for (int q = 0; q < KC; ++q) {
+                u2p = fs_fma(-ig[q].y, u2p, fs_mul(ig[q].x, ycur[q]));
+                u2[q] = u2p;
+            }
+            if (interior) {
+#pragma unroll
+                for (int q = 0; q < KC; ++q) fs_st(ob + offO[q], u2[q]);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        };
+
+        // ---- sweep A alone (first item of the launch, or when the item needs its predecessor's result) ----
+        auto sweep_a = [&](const TileC &t) {
             V yprev = fs_splat<MPT>(0.0);
             for (int c = 0; c < nchunk; ++c) {
                 const uint32_t s = g % NS, ph = (g / NS) & 1;
                 fs_mbar_wait<20>(bar_full + 8 * s, ph);
+                Raw<W> raw;
+                chunk_a(t, ring + s * C.slot, c, yprev, raw);
+                __syncwarp();
+                if (lane == 0) fs_mbar_arrive(bar_empty + 8 * s);
+                fs_tmem_st(taddr + c * W, raw);
+                ++g;
+            }
+            fs_tmem_wait_st();
+        };
+
+        // ---- sweep B: stage-1 back substitution + stage-2 rhs + UL elimination, bottom -> top ----
+        auto sweep_b = [&](const TileC &t) {
+            Raw<W> ra, rb;  // chunk c and chunk c-1 (prefetched), alternating roles: no register copies
+            V u1n = fs_splat<MPT>(0.0), y2n = fs_splat<MPT>(0.0);
+            auto chunk_b = [&](Raw<W> &cur, Raw<W> &nxt, int c) {
+                if (c > 0) fs_tmem_ld(taddr + (c - 1) * W, nxt);
+                const uint32_t s = g % NS, ph = (g / NS) & 1;
+                fs_mbar_wait<20>(bar_full + 8 * s, ph);
+                V ycur[KC], y1top;
+                fs_unpack<MPT, KC>(cur, ycur);
+                if (c > 0) {
+                    fs_tmem_wait_ld(nxt);
+#pragma unroll
+                    for (int i = 0; i < MPT; ++i)
+                        y1top.v[i] = __hiloint2double((int)nxt.w[((KC - 1) * MPT + i) * 2 + 1],
+                                                      (int)nxt.w[((KC - 1) * MPT + i) * 2]);
+                } else {
+                    y1top = fs_splat<MPT>(0.0);
+                }
                 const unsigned char *sb = ring + s * C.slot;
                 const double2 *pl = reinterpret_cast<const double2 *>(sb + C.ubytes) + col;
                 V yb[KC];
 #pragma unroll
-                for (int q = 0; q < KC; ++q) {
-                    const V cv = fs_ld(sb + offU[q][1], (V *)nullptr);
-                    const V cl = fs_ld(sb + offU[q][0], (V *)nullptr);
-                    const V cr = fs_ld(sb + offU[q][2], (V *)nullptr);
-                    const double2 lc = pl[q * FS_COLS], rm = pl[PP + q * FS_COLS];
-                    double fw = 0.0;
-                    if constexpr (FRC) fw = pl[2 * PP + q * FS_COLS].x;
-                    const V sv = fs_source<KIND, MPT>(ws1, thr_r, fw, cv);
-                    V rhs = fs_fma(lc.x, cl, fs_fma(rm.x, cr, fs_fma(lc.y, cv, sv)));
-                    if (c == 0 && q == 0) rhs = fs_add(rhs, fs_splat<MPT>(aff1));
-                    yprev = fs_fma(-rm.y, yprev, rhs);
-                    yb[q] = yprev;
+                for (int q = KC - 1; q >= 0; --q) {
+                    const V y1 = ycur[q];
+                    const V y1m = (q > 0) ? ycur[q > 0 ? q - 1 : 0] : y1top;
+                    const double2 lc = pl[q * FS_COLS], ri = pl[PP + q * FS_COLS], gm = pl[2 * PP + q * FS_COLS],
+                                  mf = pl[3 * PP + q * FS_COLS];
+                    const V u1 = fs_fma(-gm.x, u1n, fs_mul(ri.y, y1));
+                    u1n = u1;
+                    V rhs1 = fs_fma(gm.y, y1m, y1);  // = u_n + gamma h E(u_n) (+ aff1 at the surface)
+                    if (c == 0 && q == 0) rhs1 = fs_sub(rhs1, fs_splat<MPT>(t.aff1));
+                    const V un = fs_ld(sb + offU[q][1], (V *)nullptr);
+                    // a0 u_n + h (delta - 1 + gamma) E(u_n) + he1 * source(u1)
+                    V pp;
+                    if constexpr (FRC) {
+                        pp = fs_add(fs_fma(p.r, rhs1, fs_mul(p.a0r, un)), fs_source<KIND, MPT>(t.ws2, thr_r, mf.y, u1));
+                    } else {
+                        pp = fs_fma(p.r, rhs1, fs_fma(p.a0r, un, fs_splat<MPT>(t.ws2)));
+                    }
+                    const V ul = fs_shfl_up<MPT, DELTA, WIDTH>(u1), ur = fs_shfl_down<MPT, DELTA, WIDTH>(u1);
+                    V rhs2 = fs_fma(lc.x, ul, fs_fma(ri.x, ur, fs_fma(lc.y, u1, pp)));
+                    if (c == 0 && q == 0) rhs2 = fs_add(rhs2, fs_splat<MPT>(t.aff2));
+                    y2n = fs_fma(-mf.x, y2n, rhs2);
+                    yb[q] = y2n;
                 }
                 __syncwarp();
                 if (lane == 0) fs_mbar_arrive(bar_empty + 8 * s);
@@ -532,121 +679,75 @@ __global__ void __launch_bounds__(fs_cfg(MPT).threads, 1) step_fused_kernel(cons
                 fs_pack<MPT, KC>(yb, raw);
                 fs_tmem_st(taddr + c * W, raw);
                 ++g;
+            };
+            fs_tmem_ld(taddr + (nchunk - 1) * W, ra);
+            fs_tmem_wait_ld(ra);
+            int c = nchunk - 1;
+            for (; c >= 1; c -= 2) {
+                chunk_b(ra, rb, c);
+                chunk_b(rb, ra, c - 1);
             }
+            if (c == 0) chunk_b(ra, rb, 0);
             fs_tmem_wait_st();
+        };
 
-            // ------- sweep B: stage-1 back substitution + stage-2 rhs + UL elimination, bottom -> top -------
-            {
-                Raw<W> ra, rb;  // chunk c and chunk c-1 (prefetched), alternating roles: no register copies
-                V u1n = fs_splat<MPT>(0.0), y2n = fs_splat<MPT>(0.0);
-                auto chunk_b = [&](Raw<W> &cur, Raw<W> &nxt, int c) {
-                    if (c > 0) fs_tmem_ld(taddr + (c - 1) * W, nxt);
-                    const uint32_t s = g % NS, ph = (g / NS) & 1;
-                    fs_mbar_wait<20>(bar_full + 8 * s, ph);
-                    V ycur[KC], y1top;
-                    fs_unpack<MPT, KC>(cur, ycur);
-                    if (c > 0) {
-                        fs_tmem_wait_ld(nxt);
-#pragma unroll
-                        for (int i = 0; i < MPT; ++i)
-                            y1top.v[i] = __hiloint2double((int)nxt.w[((KC - 1) * MPT + i) * 2 + 1],
-                                                          (int)nxt.w[((KC - 1) * MPT + i) * 2]);
-                    } else {
-                        y1top = fs_splat<MPT>(0.0);
-                    }
-                    const unsigned char *sb = ring + s * C.slot;
-                    const double2 *pl = reinterpret_cast<const double2 *>(sb + C.ubytes) + col;
-                    V yb[KC];
-#pragma unroll
-                    for (int q = KC - 1; q >= 0; --q) {
-                        const V y1 = ycur[q];
-                        const V y1m = (q > 0) ? ycur[q > 0 ? q - 1 : 0] : y1top;
-                        const double2 lc = pl[q * FS_COLS], ri = pl[PP + q * FS_COLS], gm = pl[2 * PP + q * FS_COLS],
-                                      mf = pl[3 * PP + q * FS_COLS];
-                        const V u1 = fs_fma(-gm.x, u1n, fs_mul(ri.y, y1));
-                        u1n = u1;
-                        V rhs1 = fs_fma(gm.y, y1m, y1);  // = u_n + gamma h E(u_n) (+ aff1 at the surface)
-                        if (c == 0 && q == 0) rhs1 = fs_sub(rhs1, fs_splat<MPT>(aff1));
-                        const V un = fs_ld(sb + offU[q][1], (V *)nullptr);
-                        // a0 u_n + h (delta - 1 + gamma) E(u_n) + he1 * source(u1)
-                        V pp;
-                        if constexpr (FRC) {
-                            pp = fs_add(fs_fma(p.r, rhs1, fs_mul(p.a0r, un)), fs_source<KIND, MPT>(ws2, thr_r, mf.y, u1));
-                        } else {
-                            pp = fs_fma(p.r, rhs1, fs_fma(p.a0r, un, fs_splat<MPT>(ws2)));
-                        }
-                        const V ul = fs_shfl_up<MPT, DELTA, WIDTH>(u1), ur = fs_shfl_down<MPT, DELTA, WIDTH>(u1);
-                        V rhs2 = fs_fma(lc.x, ul, fs_fma(ri.x, ur, fs_fma(lc.y, u1, pp)));
-                        if (c == 0 && q == 0) rhs2 = fs_add(rhs2, fs_splat<MPT>(aff2));
-                        y2n = fs_fma(-mf.x, y2n, rhs2);
-                        yb[q] = y2n;
-                    }
-                    __syncwarp();
-                    if (lane == 0) fs_mbar_arrive(bar_empty + 8 * s);
-                    Raw<W> raw;
-                    fs_pack<MPT, KC>(yb, raw);
-                    fs_tmem_st(taddr + c * W, raw);
-                    ++g;
-                };
-                fs_tmem_ld(taddr + (nchunk - 1) * W, ra);
-                fs_tmem_wait_ld(ra);
-                int c = nchunk - 1;
-                for (; c >= 1; c -= 2) {
-                    chunk_b(ra, rb, c);
-                    chunk_b(rb, ra, c - 1);
+        // ---- sweep C (stage-2 substitution, staged TMA store), optionally fused with sweep A of the next
+        //      item: both run top -> bottom; A's y1 of chunk c replaces the y2 that C has just consumed ----
+        auto sweep_c = [&](bool with_a, const TileC &ta) {
+            Raw<W> ra, rb;
+            V u2p = fs_splat<MPT>(0.0), yprev = fs_splat<MPT>(0.0);
+            auto chunk_ca = [&](Raw<W> &cur, Raw<W> &nxt, int c) {
+                if (c + 1 < nchunk) fs_tmem_ld(taddr + (c + 1) * W, nxt);
+                const uint32_t s = g % NS, ph = (g / NS) & 1;
+                const uint32_t so = go % NO, pho = (go / NO) & 1;
+                fs_mbar_wait<20>(bar_full + 8 * s, ph);
+                fs_mbar_wait<20>(bar_oempty + 8 * so, pho ^ 1);
+                const unsigned char *sb = ring + s * C.slot;
+                chunk_c(sb, oring + so * C.out, cur, u2p);
+                Raw<W> raw;
+                if (with_a) chunk_a(ta, sb, c, yprev, raw);
+                __syncwarp();
+                if (lane == 0) {
+                    fs_mbar_arrive(bar_empty + 8 * s);
+                    fs_mbar_arrive(bar_ofull + 8 * so);
                 }
-                if (c == 0) chunk_b(ra, rb, 0);
-                fs_tmem_wait_st();
+                if (with_a) fs_tmem_st(taddr + c * W, raw);
+                if (c + 1 < nchunk) fs_tmem_wait_ld(nxt);
+                ++g;
+                ++go;
+            };
+            fs_tmem_ld(taddr, ra);
+            fs_tmem_wait_ld(ra);
+            int c = 0;
+            for (; c + 1 < nchunk; c += 2) {
+                chunk_ca(ra, rb, c);
+                chunk_ca(rb, ra, c + 1);
             }
+            if (c < nchunk) chunk_ca(ra, rb, c);
+            if (with_a) fs_tmem_wait_st();
+        };
 
-            // ---------------- sweep C: stage-2 substitution, top -> bottom, staged TMA store ----------------
-            {
-                Raw<W> ra, rb;
-                V u2p = fs_splat<MPT>(0.0);
-                auto chunk_c = [&](Raw<W> &cur, Raw<W> &nxt, int c) {
-                    if (c + 1 < nchunk) fs_tmem_ld(taddr + (c + 1) * W, nxt);
-                    const uint32_t s = g % NS, ph = (g / NS) & 1;
-                    const uint32_t so = go % NO, pho = (go / NO) & 1;
-                    fs_mbar_wait<20>(bar_full + 8 * s, ph);
-                    fs_mbar_wait<20>(bar_oempty + 8 * so, pho ^ 1);
-                    const double2 *pl = reinterpret_cast<const double2 *>(ring + s * C.slot + C.ubytes) + col;
-                    unsigned char *ob = oring + so * C.out;
-                    V ycur[KC], u2[KC];
-                    fs_unpack<MPT, KC>(cur, ycur);
-                    // all coefficient loads first: the compiler cannot move a shared load across the
-                    // staging stores below (it cannot prove the two ring slots disjoint)
-                    double2 ig[KC];
-#pragma unroll
-                    for (int q = 0; q < KC; ++q) ig[q] = pl[q * FS_COLS];
-#pragma unroll
-                    for (int q = 0; q < KC; ++q) {
-                        u2p = fs_fma(-ig[q].y, u2p, fs_mul(ig[q].x, ycur[q]));
-                        u2[q] = u2p;
-                    }
-                    if (interior) {
-#pragma unroll
-                        for (int q = 0; q < KC; ++q) fs_st(ob + offO[q], u2[q]);
-                    }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) {
-                        fs_mbar_arrive(bar_empty + 8 * s);
-                        fs_mbar_arrive(bar_ofull + 8 * so);
-                    }
-                    if (c + 1 < nchunk) fs_tmem_wait_ld(nxt);
-                    ++g;
-                    ++go;
-                };
-                fs_tmem_ld(taddr, ra);
-                fs_tmem_wait_ld(ra);
-                int c = 0;
-                for (; c + 1 < nchunk; c += 2) {
-                    chunk_c(ra, rb, c);
-                    chunk_c(rb, ra, c + 1);
+        Item it = it0;
+        if (item_valid(it)) {
+            TileC t = tile_c(it);
+            sweep_a(t);
+            while (true) {
+                sweep_b(t);
+                const Item nx = item_next(it);
+                if (!item_valid(nx)) {
+                    sweep_c(false, t);
+                    break;
                 }
-                if (c < nchunk) chunk_c(ra, rb, c);
+                const TileC tn = tile_c(nx);
+                if (!item_depends(nx, it)) {
+                    sweep_c(true, tn);
+                } else {
+                    sweep_c(false, t);
+                    sweep_a(tn);
+                }
+                it = nx;
+                t = tn;
             }
-        }
         }
     }
 
@@ -819,6 +920,7 @@ int launch_steps_fused(const ModelDev &v, int B, int n_steps, int step0, int ste
     // rotate the tile -> CTA assignment by the number of left-over tiles per step so that the CTAs that
     // get one tile more than the others change from step to step
     a.rot = (step1 - step0 > 1) ? a.ntiles % grid : 0;
+    a.cross_step_fuse = (a.ntiles > 2 * grid + a.nmb) ? 1 : 0;
     const bool coop = (step1 - step0 > 1);
     const int mpt = fs_mpt();
     if (v.kind == NKB_MOD_LINEAR)
