@@ -381,6 +381,9 @@ def run_ours(args):
                                "implicit stage); the fused step kernel moves less than that (see traffic)",
             "alg_bytes_per_launch": bytes_alg_eval * B / n_stage_launch, "avg_launch_ms": avg_launch_ms,
             "traffic_unit": "dram bytes per unit of work (ncu, profiles/traffic.json)",
+            "limiter": "shared-memory LSU data pipe at 84 % of peak (ncu l1tex__data_pipe_lsu_wavefronts), DRAM at 46 %: "
+                       "the fused kernel moves 0.57 of the algorithmic bytes (profiles/r01_ncu_full_step_fused_persistent_*.txt)"
+                       if fused else "L2 round trip of the elimination intermediates",
         },
         "e2e": {
             "value": world * B / e2e_s, "unit": "model-year evals/s",
