@@ -356,15 +356,21 @@ int nkb_model_eval(nkb_model *m, const double *d_x0, double *d_f, double *d_work
         if (nkb::fused_encode_state_maps(v, B, ldb, d_x0, &fm.in_x0, nullptr)) return 1;
         if (nkb::fused_encode_state_maps(v, B, ldb, d_f, &fm.in_f, &fm.out_f)) return 1;
         if (nkb::fused_encode_state_maps(v, B, ldb, w_alt, &fm.in_w, &fm.out_w)) return 1;
-        fm.ctab = m->map_ctab;
-        const bool persist = nkb::fused_persistent();
+        // encoded per evaluation: the box shape follows the thread layout in use (NKB_FUSED_MPT)
+        if (nkb::fused_encode_ctab_map(v.nz, v.ny, (size_t)S * v.n_classes * 8, m->ctab, &fm.ctab)) return 1;
+        bool persist = nkb::fused_persistent();
         int n = 0;
         while (n < S) {
             // the segment ends after the next step whose result is a hist snapshot (or at S)
             int end = S;
             if (!persist) end = n + 1;
             else if (hist_i < n_hist && h_hist_steps[hist_i] < S) end = h_hist_steps[hist_i] > n ? h_hist_steps[hist_i] : n + 1;
-            if (nkb::launch_steps_fused(v, B, S, n, end, m->d_h, m->aff, fm, m->d_done, m->d_err, st)) return 1;
+            const int rc = nkb::launch_steps_fused(v, B, S, n, end, m->d_h, m->aff, fm, m->d_done, m->d_err, st);
+            if (rc == -1) {  // cooperative launch refused (SMs in use by someone else): one launch per step
+                persist = false;
+                continue;
+            }
+            if (rc) return 1;
             n = end;
             if (n_hist > 0 && n < S) {
                 double *dest = (((S - n) & 1) == 0) ? d_f : w_alt;  // buffer written by step n - 1

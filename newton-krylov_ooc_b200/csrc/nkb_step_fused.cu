@@ -882,7 +882,12 @@ static int fs_launch_m(const StepArgs &a, const StepMaps &maps, int grid, bool c
     attr[0].val.cooperative = 1;
     cfg.attrs = attr;
     cfg.numAttrs = cooperative ? 1 : 0;
-    NKB_CUDA(cudaLaunchKernelEx(&cfg, kern, a, maps));
+    const cudaError_t err = cudaLaunchKernelEx(&cfg, kern, a, maps);
+    if (cooperative && err == cudaErrorCooperativeLaunchTooLarge) {
+        cudaGetLastError();  // the SMs are not all available: the caller falls back to one launch per step
+        return -1;
+    }
+    NKB_CUDA(err);
     count_launch();
     return 0;
 }

@@ -187,3 +187,40 @@ def test_fused_step_kernel_matches_scheme_oracle(kind, nz, ny, B, monkeypatch):
     scale = np.abs(want).max()
     np.testing.assert_allclose(got, want, rtol=0.0, atol=1e-10 * scale)
     np.testing.assert_allclose(got, unfused, rtol=0.0, atol=1e-10 * scale)
+
+
+def test_fused_kernel_hist_snapshots_and_two_members_per_thread(monkeypatch):
+    """B >= 8: hist snapshots cut the persistent launch into segments (one cooperative launch per
+    interval between snapshots); the alternative thread layout (NKB_FUSED_MPT=2: 4 consumer warps x 2
+    members, 4-level chunks) gives the same result to rounding"""
+    from oracle import imex_oracle as im
+    from nk_ooc_b200 import _lib
+    from nk_ooc_b200.py_driver_2d import modules
+
+    rng = np.random.default_rng(31)
+    g, tr = _grid(13, 19)
+    m = modules.iage_model(tr)
+    m.set_uniform_schedule(12)
+    B = 21
+    x = rng.normal(size=(2, g.nz, g.ny, B))
+    snaps = []
+    want = im.model_year_2d(im.Module2D("iage", g), x, 12, snapshots=snaps)
+    lib = _lib.load()
+    xd = _to_dev(x)
+    m.eval(xd, B)
+    n0 = lib.nkb_launch_count()
+    f, hist = m.eval(xd, B, hist_steps=[0, 4, 8, 12])
+    # gathers of member 0 (4) + persistent segments [0,4) [4,8) [8,12) + final difference
+    assert lib.nkb_launch_count() - n0 <= 4 + 3 + 1
+    hist = hist.cpu().numpy()
+    scale = np.abs(want).max()
+    np.testing.assert_allclose(hist[0], x[..., 0], rtol=0, atol=0)
+    np.testing.assert_allclose(hist[1], snaps[3][1][..., 0], rtol=0, atol=1e-11 * scale)
+    np.testing.assert_allclose(hist[2], snaps[7][1][..., 0], rtol=0, atol=1e-11 * scale)
+    np.testing.assert_allclose(f.cpu().numpy()[..., :B], want, rtol=0, atol=1e-10 * scale)
+    monkeypatch.setenv("NKB_FUSED_MPT", "2")
+    m2 = modules.iage_model(tr)  # box shapes depend on the layout: fresh tables
+    m2.set_uniform_schedule(12)
+    got2 = m2.eval(xd, B).cpu().numpy()[..., :B]
+    np.testing.assert_allclose(got2, want, rtol=0, atol=1e-10 * scale)
+
