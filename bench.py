@@ -272,8 +272,12 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     engine.require_cuda()
     torch.cuda.set_device(local)
+    # stdout carries ONE JSON line: everything else a library writes to fd 1 (NCCL's version banner, ...)
+    # goes to stderr; the JSON line is written to the saved descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _lib.load()
 
@@ -396,7 +400,8 @@ def run_ours(args):
     }
     if not args.no_cpu_baseline and world == 1:
         out["cpu_baseline"] = cpu_baseline(args, 1, args.cpu_sample_seconds)
-    print(json.dumps(out), flush=True)
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
