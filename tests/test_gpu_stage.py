@@ -224,3 +224,64 @@ def test_fused_kernel_hist_snapshots_and_two_members_per_thread(monkeypatch):
     got2 = m2.eval(xd, B).cpu().numpy()[..., :B]
     np.testing.assert_allclose(got2, want, rtol=0, atol=1e-10 * scale)
 
+
+
+def test_full_size_properties_refined_grid():
+    """BASELINE.json's headline size (refined 125 x 150 grid, 4096 members; 8 steps instead of a year)
+    through size-independent properties, since the numpy oracle takes minutes there:
+    (i) members are independent — a permutation of the members permutes the results, bit for bit;
+    (ii) the linear module is affine — F(a x + b y) - F(0) = a (F(x) - F(0)) + b (F(y) - F(0));
+    (iii) the persistent fused kernel, one launch per step and the stage-per-launch kernels agree;
+    (iv) one member against the numpy statement of the scheme."""
+    import os
+
+    from oracle import imex_oracle as im
+    from oracle import nk_oracle as o
+    from nk_ooc_b200.py_driver_2d import modules
+    from nk_ooc_b200.spatial_axis import SpatialAxis, edges_from_defn
+
+    nz, ny, B, nsteps = 125, 150, 4096, 8
+    ze = edges_from_defn(nz, 0.0, 4000.0, 11.8)
+    ye = edges_from_defn(ny, 0.0, 50.0e5, 1.0)
+    tr = modules.Transport2D(SpatialAxis("depth", ze), SpatialAxis("ypos", ye), 0.1, 1000.0)
+    m = modules.iage_model(tr)
+    # the first 8 steps of the production schedule (h = 1/1200 yr): stable for non-smooth random states
+    from nk_ooc_b200.engine import graded_schedule
+
+    t_all, h_all = graded_schedule(0.0, 365.0 * 86400.0)
+    sched = (t_all[:nsteps].copy(), h_all[:nsteps].copy())
+    m.set_schedule(*sched)
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.randn((2, nz, ny, B), dtype=torch.float64, device="cuda", generator=gen)
+    f = m.eval(x, B).clone()
+    # (i)
+    perm = torch.randperm(B, device="cuda", generator=gen)
+    fp = m.eval(x[..., perm].contiguous(), B)
+    assert torch.equal(fp, f[..., perm])
+    # (ii) members 0..B/2-1 = x, B/2.. = y; third batch = a x + b y; F(0) from a zero batch
+    h = B // 2
+    a, b = 0.75, -1.5
+    z = torch.zeros_like(x)
+    z[..., :h] = a * x[..., :h] + b * x[..., h:]
+    fz = m.eval(z, B)
+    f0 = fz[..., h:h + 1]  # members h.. of z are zero states
+    lhs = fz[..., :h] - f0
+    rhs = a * (f[..., :h] - f0) + b * (f[..., h:] - f0)
+    scale = float(f.abs().max())
+    assert float((lhs - rhs).abs().max()) <= 1e-11 * scale
+    # (iii)
+    os.environ["NKB_FUSED_PERSIST"] = "0"
+    try:
+        assert torch.equal(m.eval(x, B), f)
+    finally:
+        del os.environ["NKB_FUSED_PERSIST"]
+    os.environ["NKB_FUSED"] = "0"
+    try:
+        fu = m.eval(x, B)
+    finally:
+        del os.environ["NKB_FUSED"]
+    assert float((fu - f).abs().max()) <= 1e-11 * scale
+    # (iv)
+    g = o.Grid2D(ze, ye, 0.1, 1000.0)
+    want = im.model_year_2d(im.Module2D("iage", g), x[..., 5:6].cpu().numpy(), schedule=sched)
+    np.testing.assert_allclose(f[..., 5:6].cpu().numpy(), want, rtol=0, atol=1e-11 * np.abs(want).max())
