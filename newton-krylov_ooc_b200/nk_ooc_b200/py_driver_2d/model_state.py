@@ -12,6 +12,7 @@ from scipy import sparse
 from scipy.io import netcdf_file
 
 from .. import engine
+from .. import hist as hist_mod
 from ..model_state_base import ModelConfig, ModelStateBase, TracerModuleStateBase
 from ..spatial_axis import spatial_axis_from_file
 from . import modules
@@ -216,9 +217,18 @@ class ModelState(ModelStateBase):
             solver_state.log_step(step)
         return res_ms
 
+    @staticmethod
+    def _hist_tracer_like(tms):
+        """{name: attrs} of the tracer-like hist variables (tracer_module_state.py:197-202;
+        phosphorus adds po4_uptake, phosphorus.py:174-181)"""
+        res = {tname: meta["attrs"] for tname, meta in tms._def["tracers"].items()}
+        if tms._def.get("py_mod_name", tms.name) == "phosphorus":
+            res["po4_uptake"] = {"long_name": "uptake of po4", "units": f"{res['po4']['units']} / s"}
+        return res
+
     def _write_hist(self, hist_fname, hist):
-        """time, axes, process fields and the tracer snapshots of member 0
-        (py_driver_2d/model_state.py:141-233; derived *_time_mean/... variables: not yet)"""
+        """time, axes, process fields, the tracer snapshots of member 0 and their derived variables
+        (py_driver_2d/model_state.py:141-233; tracer_module_state.py:110-260)"""
         os.makedirs(os.path.dirname(os.path.abspath(hist_fname)), exist_ok=True)
         tr = self.transport
         first = self.tracer_modules[0]
@@ -250,8 +260,9 @@ class ModelState(ModelStateBase):
             mkvar("bldepth", ("time", yn), "boundary layer depth", "m", True)
             mkvar("vert_mixing_coeff", ("time", de, yn), "vertical mixing coefficient", "m^2 / s", True)
             for tms in self.tracer_modules:
-                for tname, meta in tms._def["tracers"].items():
-                    mkvar(tname, ("time", dn, yn), meta["attrs"]["long_name"], meta["attrs"]["units"], True)
+                for tname, attrs in self._hist_tracer_like(tms).items():
+                    mkvar(tname, ("time", dn, yn), attrs["long_name"], attrs["units"], True)
+                    hist_mod.define_derived(fptr, tname, attrs, self.depth, self.ypos)
             for axis in (self.depth, self.ypos):
                 axis.write(fptr)
             fptr.variables["stream"][:] = tr.advection.stream
@@ -270,8 +281,16 @@ class ModelState(ModelStateBase):
                 fptr.variables["vert_mixing_coeff"][ti, :] = vm
             for tms in self.tracer_modules:
                 snaps = hist[tms.name][1].cpu().numpy()  # [n_time, T, nz, ny]
-                for ind, tname in enumerate(tms.tracer_names):
-                    fptr.variables[tname][:] = snaps[:, ind]
+                like = {tname: snaps[:, ind] for ind, tname in enumerate(tms.tracer_names)}
+                if tms._def.get("py_mod_name", tms.name) == "phosphorus":
+                    # po4_uptake (py_driver_2d/phosphorus.py:97-103,174-195)
+                    desc = self.model_for(tms).desc
+                    light = self.model_for(tms)._keepalive["light"]
+                    po4 = like["po4"]
+                    like["po4_uptake"] = desc.max_uptake_rate * light * (po4 / (po4 + desc.po4_halfsat))
+                for tname, vals in like.items():
+                    fptr.variables[tname][:] = vals
+                    hist_mod.write_derived(fptr, tname, vals, self.depth, self.ypos)
 
     def gen_precond_jacobian(self, hist_fname, precond_fname, solver_state=None):
         """hist -> precond file: time reductions of the hist variables listed in the precond

@@ -12,6 +12,7 @@ import torch
 from scipy.io import netcdf_file
 
 from .. import engine
+from .. import hist as hist_mod
 from ..model_state_base import ModelConfig, ModelStateBase, TracerModuleStateBase
 from ..spatial_axis import spatial_axis_from_file
 from . import modules
@@ -182,9 +183,19 @@ class ModelState(ModelStateBase):
                 tms.vals[real] = 0.0
         return self
 
+    @staticmethod
+    def _hist_tracer_like(tms):
+        """{name: attrs} of the tracer-like hist variables (test_problem/tracer_module_state.py:149-154;
+        phosphorus adds po4_uptake and po4_s_restore_tau_r, phosphorus.py:122-135)"""
+        res = {tname: meta["attrs"] for tname, meta in tms._def["tracers"].items()}
+        if tms._def.get("py_mod_name", tms.name) == "phosphorus":
+            res["po4_uptake"] = {"long_name": "uptake of po4", "units": f"{res['po4']['units']} / s"}
+            res["po4_s_restore_tau_r"] = {"long_name": "inverse timescale for po4_s restoring", "units": "1 / s"}
+        return res
+
     def _write_hist(self, hist_fname, times, hist):
-        """time, depth axis, bldepth, mixing_coeff and tracer snapshots of member 0
-        (test_problem/model_state.py:119-225; derived *_time_mean/... variables: not yet)"""
+        """time, depth axis, bldepth, mixing_coeff, tracer snapshots of member 0 and their derived
+        variables (test_problem/model_state.py:119-225; tracer_module_state.py:96-199)"""
         os.makedirs(os.path.dirname(os.path.abspath(hist_fname)), exist_ok=True)
         model = self.models_for(self.tracer_modules[0])[0]
         dn, de = self.depth.axisname, self.depth.dump_names["edges"]
@@ -200,18 +211,11 @@ class ModelState(ModelStateBase):
             var = fptr.createVariable("mixing_coeff", "f8", ("time", de))
             var.long_name, var.units, var.cell_methods = "vertical mixing coefficient", "m^2 / s", "time: point"
             for tms in self.tracer_modules:
-                for tname, meta in tms._def["tracers"].items():
+                for tname, attrs in self._hist_tracer_like(tms).items():
                     var = fptr.createVariable(tname, "f8", ("time", dn))
-                    var.long_name, var.units = meta["attrs"]["long_name"], meta["attrs"]["units"]
+                    var.long_name, var.units = attrs["long_name"], attrs["units"]
                     var.cell_methods = "time: point"
-                if tms._def.get("py_mod_name", tms.name) == "phosphorus":
-                    # test_problem/phosphorus.py:122-160 hist_vars_metadata_tracer_like / write_hist_vars
-                    po4_units = tms._def["tracers"]["po4"]["attrs"]["units"]
-                    var = fptr.createVariable("po4_uptake", "f8", ("time", dn))
-                    var.long_name, var.units, var.cell_methods = "uptake of po4", f"{po4_units} / s", "time: point"
-                    var = fptr.createVariable("po4_s_restore_tau_r", "f8", ("time", dn))
-                    var.long_name, var.units = "inverse timescale for po4_s restoring", "1 / s"
-                    var.cell_methods = "time: point"
+                    hist_mod.define_derived(fptr, tname, attrs, self.depth)
             self.depth.write(fptr)
             for ti, t in enumerate(times):
                 fptr.variables["time"][ti] = t
@@ -222,14 +226,15 @@ class ModelState(ModelStateBase):
                 fptr.variables["mixing_coeff"][ti, :] = mc
             for tms in self.tracer_modules:
                 snaps = hist[tms.name].cpu().numpy()  # [n_time, T, nz, 1]
-                for ind, tname in enumerate(tms.tracer_names):
-                    fptr.variables[tname][:] = snaps[:, ind, :, 0]
+                like = {tname: snaps[:, ind, :, 0] for ind, tname in enumerate(tms.tracer_names)}
                 if tms._def.get("py_mod_name", tms.name) == "phosphorus":
-                    po4 = snaps[:, tms.tracer_index("po4"), :, 0]
-                    uptake = modules.po4_uptake(self.depth, po4)
-                    fptr.variables["po4_uptake"][:] = uptake
+                    po4 = like["po4"]
+                    like["po4_uptake"] = modules.po4_uptake(self.depth, po4)
                     opt = int(self.model_config_obj.modelinfo.get("po4_s_restoring_opt", 1))
-                    fptr.variables["po4_s_restore_tau_r"][:] = modules.po4_s_restore_tau_r(self.depth, po4, uptake, opt)
+                    like["po4_s_restore_tau_r"] = modules.po4_s_restore_tau_r(self.depth, po4, like["po4_uptake"], opt)
+                for tname, vals in like.items():
+                    fptr.variables[tname][:] = vals
+                    hist_mod.write_derived(fptr, tname, vals, self.depth)
 
     def gen_precond_jacobian(self, hist_fname, precond_fname, solver_state=None):
         """mixing_coeff:mean and mixing_coeff:log_mean over the hist times

@@ -42,11 +42,13 @@ def baselines():
                 out[f"{cfg}/{f}/{var}"] = vals
     # a few hist variables (process fields, pinned at rtol 1e-3/atol 1e-6 by the CI script)
     hist = rh.read_nc(os.path.join(base, "ci_py_driver_2d_iage", "hist_0000.nc"))
+    derived = ["time_mean", "time_std", "time_delta", "depth_int"]  # (time_anom is large and redundant)
     for var in ["time", "stream", "vvel", "wvel", "horiz_mixing_coeff", "bldepth", "vert_mixing_coeff", "iage",
-                "iage_slow_rest"]:
+                "iage_slow_rest"] + [f"iage_{d}" for d in derived + ["ypos_mean", "depth_ypos_int"]]:
         out[f"ci_py_driver_2d_iage/hist_0000/{var}"] = hist[var]
     hist = rh.read_nc(os.path.join(base, "ci_short", "hist_00.nc"))
-    for var in ["time", "bldepth", "mixing_coeff", "iage"]:
+    for var in (["time", "bldepth", "mixing_coeff", "iage", "po4", "po4_uptake", "po4_s_restore_tau_r"]
+                + [f"{v}_{d}" for v in ("iage", "po4", "po4_uptake", "po4_s_restore_tau_r") for d in derived]):
         out[f"ci_short/hist_00/{var}"] = hist[var]
     np.savez_compressed(os.path.join(OUT, "baselines.npz"), **out)
     print("baselines.npz:", len(out), "arrays")

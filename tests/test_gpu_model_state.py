@@ -71,7 +71,8 @@ def test_ci_py_driver_2d_iage(base, tmp_path):
     # hist file: 61 snapshots + process fields
     with netcdf_file(str(tmp_path / "hist_0000.nc"), "r", mmap=False) as f:
         for name in ("time", "stream", "vvel", "wvel", "horiz_mixing_coeff", "bldepth", "vert_mixing_coeff", "iage",
-                     "iage_slow_rest"):
+                     "iage_slow_rest", "iage_time_mean", "iage_time_std", "iage_time_delta", "iage_depth_int",
+                     "iage_ypos_mean", "iage_depth_ypos_int"):
             np.testing.assert_allclose(np.array(f.variables[name].data), base[pre + "hist_0000/" + name], rtol=1e-3,
                                        atol=1e-6, err_msg=name)
     ModelState.reset()

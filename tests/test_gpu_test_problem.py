@@ -111,8 +111,13 @@ def test_ci_short(base, tmp_path):
     for n in names:
         np.testing.assert_allclose(x.get_tracer_vals(n), base["ci_short/init_iterate/" + n], rtol=1e-7, atol=2e-9, err_msg=n)
     with netcdf_file(str(tmp_path / "hist_00.nc"), "r", mmap=False) as f:
-        for n in ("time", "bldepth", "mixing_coeff", "iage"):
-            np.testing.assert_allclose(np.array(f.variables[n].data), base["ci_short/hist_00/" + n], rtol=1e-7, atol=2e-9, err_msg=n)
+        for n in (["time", "bldepth", "mixing_coeff", "iage", "po4", "po4_uptake", "po4_s_restore_tau_r"]
+                  + [f"{v}_{d}" for v in ("iage", "po4", "po4_uptake", "po4_s_restore_tau_r")
+                     for d in ("time_mean", "time_std", "time_delta", "depth_int")]):
+            want = base["ci_short/hist_00/" + n]
+            # atol scaled to the variable: the integrals are O(1e3), po4_uptake O(1e-6)
+            np.testing.assert_allclose(np.array(f.variables[n].data), want, rtol=1e-7,
+                                       atol=2e-9 * max(1.0, np.abs(want).max()), err_msg=n)
     ModelState.reset()
 
 
