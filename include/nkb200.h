@@ -119,6 +119,12 @@ size_t nkb_model_work_doubles(const nkb_model *m, int B, int ldb);
 int nkb_model_eval(nkb_model *m, const double *d_x0, double *d_f, double *d_work, int B, int ldb,
                    int n_hist, const int *h_hist_steps, double *d_hist, void *stream);
 
+/* Non-blocking health check of the persistent step kernel: returns 1 (and clears the flag) when a
+ * CTA of an earlier nkb_model_eval gave up waiting for a neighbour tile (its results are then
+ * invalid), else 0.  Meaningful after the stream of that evaluation has been synchronised;
+ * nkb_model_eval and nkb_model_eval_host check it themselves. */
+int nkb_model_poll_error(nkb_model *m);
+
 /* Same through HOST buffers: h_x0/h_f are [B][T][nz][ny] (member-major, the reference's
  * per-state layout); does H2D, pack, eval, unpack, D2H and synchronises.  Host buffers
  * should be pinned for full PCIe rate. */

@@ -412,6 +412,13 @@ int nkb_model_eval(nkb_model *m, const double *d_x0, double *d_f, double *d_work
     return 0;
 }
 
+int nkb_model_poll_error(nkb_model *m) {
+    if (!m || !m->h_err) return 0;
+    const int e = *reinterpret_cast<volatile int *>(m->h_err);
+    if (e) *m->h_err = 0;
+    return e ? 1 : 0;
+}
+
 int nkb_model_eval_host(nkb_model *m, const double *h_x0, double *h_f, int B) {
     NKB_REQUIRE(m && h_x0 && h_f && B >= 1, "nkb_model_eval_host: bad argument");
     const ModelDev &v = m->dev;
@@ -436,6 +443,10 @@ int nkb_model_eval_host(nkb_model *m, const double *h_x0, double *h_f, int B) {
     if (nkb::launch_unpack(m->d_stage_f, m->d_stage_major, (int)n, B, ldb, st)) return 1;
     NKB_CUDA(cudaMemcpyAsync(h_f, m->d_stage_major, n * (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));
     NKB_CUDA(cudaStreamSynchronize(st));
+    if (nkb_model_poll_error(m)) {
+        nkb::set_error("nkb_model_eval_host: the persistent step kernel timed out waiting for a tile");
+        return 1;
+    }
     return 0;
 }
 

@@ -80,6 +80,7 @@ SYMBOLS = {
         [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, POINTER(c_int), c_void_p, c_void_p],
     ),
     "nkb_model_eval_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),
+    "nkb_model_poll_error": (c_int, [c_void_p]),
     "nkb_banded_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, POINTER(c_double)]),
     "nkb_banded_destroy": (None, [c_void_p]),
     "nkb_banded_solve": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_int, c_void_p]),

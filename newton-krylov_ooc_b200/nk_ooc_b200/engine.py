@@ -159,6 +159,11 @@ class Model:
             return out, hist
         return out
 
+    def check_health(self):
+        """after a synchronisation: raise if the persistent step kernel reported a dependency time-out"""
+        if self.lib.nkb_model_poll_error(self.handle):
+            raise _lib.NkbError("the persistent step kernel timed out waiting for a tile: results are invalid")
+
     def eval_host(self, x_host, out_host=None):
         """F for member-major host arrays [B, T, nz, ny] (pinned torch tensors or numpy)"""
         xt = x_host if isinstance(x_host, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x_host))
