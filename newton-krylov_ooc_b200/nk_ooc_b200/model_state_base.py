@@ -26,24 +26,28 @@ from . import engine
 
 
 def _expand_defs(defs, names):
-    """tracer-module defs with `{suff}` templating: name `root:suff` (model_config.py:80-125)"""
+    """tracer-module defs with `{suff}` templating: a name `root:suff1:suff2...` gives one module
+    per suffix (model_config.py:80-125)"""
+
+    def subst(obj, suff):
+        if isinstance(obj, str):
+            return obj.replace("{suff}", suff)
+        if isinstance(obj, dict):
+            return {subst(k, suff): subst(v, suff) for k, v in obj.items()}
+        if isinstance(obj, list):
+            return [subst(v, suff) for v in obj]
+        return obj
+
     out = {}
     for full in names:
-        root, _, suff = full.partition(":")
+        root, _, suffs = full.partition(":")
         if root not in defs:
             raise ValueError(f"unknown tracer module name {root}")
-        src = copy.deepcopy(defs[root])
-
-        def subst(obj):
-            if isinstance(obj, str):
-                return obj.replace("{suff}", suff)
-            if isinstance(obj, dict):
-                return {subst(k): subst(v) for k, v in obj.items()}
-            if isinstance(obj, list):
-                return [subst(v) for v in obj]
-            return obj
-
-        out[subst(root) if suff else root] = subst(src)
+        if not suffs:
+            out[root] = copy.deepcopy(defs[root])
+            continue
+        for suff in suffs.split(":"):
+            out[subst(root, suff)] = subst(copy.deepcopy(defs[root]), suff)
     return out
 
 

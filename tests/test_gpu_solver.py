@@ -141,3 +141,23 @@ def test_coloured_column_probes_give_the_jacobian(base, tmp_path):
     want = np.stack([(jac[j, 1] @ v[:, :, j].reshape(-1)).reshape(T, nz) for j in range(ny)], axis=-1)
     np.testing.assert_allclose(jv, want, rtol=0, atol=1e-6 * np.abs(want).max())
     ModelState.reset()
+
+
+def test_ci_long_dye_decay_newton_convergence(tmp_path):
+    """scripts/ci_long_dye_decay.sh: two parameterised modules (dye_decay_{suff}:001:010), init iterate
+    = gen_init_iterate + one fixed-point iteration, newton_rel_tol 1e-6.  The reference's committed
+    Newton_state.json stops at iteration 2 with Armijo factor 1 for both modules."""
+    from nk_ooc_b200.solver import NewtonSolver
+
+    ModelState = _configure(str(tmp_path), "dye_decay_{suff}:001:010")
+    assert ModelState.model_config_obj.tracer_module_names == ["dye_decay_001", "dye_decay_010"]
+    x = ModelState("gen_init_iterate")
+    x += x.comp_fcn(None, None)  # --fp_cnt 1 (test_problem/setup_solver.py:137-155)
+    info = dict(TP_SOLVERINFO, newton_rel_tol="1.0e-6")
+    solver = NewtonSolver(x, info, workdir=str(tmp_path / "work"), dump=False)
+    solver.solve()
+    assert solver.iteration == 2
+    for rec in solver.history[1:]:
+        assert rec["armijo_factor"].shape == (2, 1) and (rec["armijo_factor"] == 1.0).all()
+    assert (solver.fcn.norm() < 1.0e-6 * solver.iterate.norm()).all()
+    ModelState.reset()
