@@ -44,10 +44,81 @@ def comp_krylov_basis_coeffs(beta, h_mat):
     return coeff
 
 
-class KrylovSolver:
-    """left-preconditioned GMRES for  J(iterate) x = -fcn  with the basis resident in HBM"""
+class ProbePreconditioner:
+    """Preconditioner built from coloured perturbation probes (the third batched workload of the
+    north star): ONE batched function evaluation with n_colours * T * nz members
+    (colouring.probe_batch: a unit perturbation of level k, tracer t in every column of one colour)
+    gives, per ypos column, the Jacobian block of F with respect to the column itself and to its
+    `reach` neighbours (colouring.decode_probes).  M = that block-(tri)diagonal matrix; applying the
+    preconditioner is a member-batched banded solve on the device (K4) in column-major ordering.
+    For a linear module without lateral processes M is the exact Jacobian of F.
 
-    def __init__(self, iterate, solverinfo, hist_fname, workdir, max_iter=50):
+    Two-dimensional models with ONE tracer module (py_driver_2d)."""
+
+    def __init__(self, iterate, fcn=None, eps=None, reach=1, couple_neighbours=True):
+        import torch
+
+        from . import colouring, engine
+
+        if len(iterate.tracer_modules) != 1:
+            raise NotImplementedError("ProbePreconditioner handles states with one tracer module")
+        tms = iterate.tracer_modules[0]
+        if len(tms.cell_shape) != 2:
+            raise NotImplementedError("ProbePreconditioner needs a (depth, ypos) grid")
+        T, (nz, ny) = tms.tracer_cnt, tms.cell_shape
+        x0 = tms.vals[..., 0].cpu().numpy()
+        if fcn is None:
+            fcn = iterate.comp_fcn(None, None)
+        f0 = fcn.tracer_modules[0].vals[..., 0].cpu().numpy()
+        if eps is None:
+            eps = 1.0e-4 * max(float(np.abs(x0).max()), 1.0e-30)
+        colour = colouring.column_colouring(ny, reach)
+        probes = colouring.probe_batch(x0, colour, eps)
+        B = probes.shape[0]
+        batched = type(iterate)("zeros", members=B)
+        batched.tracer_modules[0].vals[..., :B] = torch.from_numpy(
+            np.ascontiguousarray(np.moveaxis(probes, 0, -1))).cuda()
+        fprobe = np.moveaxis(batched.comp_fcn(None, None).tracer_modules[0].vals[..., :B].cpu().numpy(), -1, 0)
+        jac = colouring.decode_probes(f0, fprobe, colour, eps, reach)  # [ny, 2*reach+1, n, n]
+        self.members_probed = B
+        n = T * nz
+        self._shape = (T, nz, ny)
+        # column-major ordering (column slowest): block (j, j+d) sits at rows j*n.., columns (j+d)*n..
+        # jac[j, d+reach][:, c] = d F[:, column j+d] / d x[c, column j]  ->  block (row j+d, column j)
+        reach_used = reach if couple_neighbours else 0
+        kl = ku = (reach_used + 1) * n - 1
+        N = ny * n
+        ab = np.zeros((kl + ku + 1, N))
+        for j in range(ny):
+            for d in range(-reach_used, reach_used + 1):
+                jj = j + d
+                if 0 <= jj < ny:
+                    blk = jac[j, d + reach]
+                    rows = jj * n + np.arange(n)[:, None]
+                    cols = j * n + np.arange(n)[None, :]
+                    ab[ku + rows - cols, cols] = blk
+        self._factor = engine.BandedFactor(ab, kl, ku)
+        self.jac_blocks = jac
+
+    def __call__(self, y):
+        """M^-1 y for every member of y"""
+        T, nz, ny = self._shape
+        res = y._like(clone_vals=False)
+        tms = y.tracer_modules[0]
+        ldb = tms.vals.shape[-1]
+        yp = tms.vals.permute(2, 0, 1, 3).reshape(ny * T * nz, ldb).contiguous()  # layout conversion only
+        sol = self._factor.solve(yp, y.members)
+        res.tracer_modules[0].vals = sol.reshape(ny, T, nz, ldb).permute(1, 2, 0, 3).contiguous()
+        return res
+
+
+class KrylovSolver:
+    """left-preconditioned GMRES for  J(iterate) x = -fcn  with the basis resident in HBM.
+    `precond`: optional callable ModelState -> ModelState applying M^-1 (e.g. ProbePreconditioner)
+    instead of the model's apply_precond_jacobian."""
+
+    def __init__(self, iterate, solverinfo, hist_fname, workdir, max_iter=50, precond=None):
+        self._precond = precond
         self._iterate = iterate
         self._info = solverinfo
         self._workdir = workdir
@@ -59,7 +130,13 @@ class KrylovSolver:
         self.precond_resid_norm = []
         os.makedirs(workdir, exist_ok=True)
         self.precond_fname = self._fname("precond", 0)
-        iterate.gen_precond_jacobian(hist_fname, self.precond_fname, solver_state=None)
+        if precond is None:
+            iterate.gen_precond_jacobian(hist_fname, self.precond_fname, solver_state=None)
+
+    def _apply_precond(self, state, res_fname, caller):
+        if self._precond is None:
+            return state.apply_precond_jacobian(self.precond_fname, res_fname, None)
+        return self._precond(state).dump(res_fname, caller)
 
     def _fname(self, quantity, iteration=None):
         iteration = self.iteration if iteration is None else iteration
@@ -83,7 +160,7 @@ class KrylovSolver:
         caller = f"{type(self).__name__}.solve"
         fn = self._fname if dump else (lambda *a, **k: None)
         # step 1 of alg. 9.4: r0 = -M^-1 fcn, beta = ||r0||, v0 = r0 / beta
-        precond_fcn = fcn.apply_precond_jacobian(self.precond_fname, fn("precond_fcn"), None)
+        precond_fcn = self._apply_precond(fcn, fn("precond_fcn"), caller)
         self.beta = precond_fcn.norm()
         self.basis.append((-precond_fcn / self.beta).dump(fn("basis"), caller))
         n_mod, region_cnt = self.beta.shape[0], self.beta.shape[1]
@@ -93,7 +170,7 @@ class KrylovSolver:
             if j_val > 0:
                 h_mat[:, :-1, :-1, :] = self.h_mat
             w_raw = self._iterate.comp_jacobian_fcn_state_prod(fcn, self.basis[j_val], fn("w_raw"), None)
-            w_j = w_raw.apply_precond_jacobian(self.precond_fname, fn("w"), None)
+            w_j = self._apply_precond(w_raw, fn("w"), caller)
             self.w.append(w_j._like())  # un-orthogonalised M^-1 J v_j: needed for the residual below
             h_mat[:, :-1, -1, :] = w_j.mod_gram_schmidt(j_val + 1, self._resident, "basis")
             h_mat[:, -1, -1, :] = w_j.norm()
@@ -121,7 +198,10 @@ class NewtonSolver:
     """Newton's method with Armijo damping and post-Newton fixed-point iterations
     (newton_solver.py:22-334) on a device-resident iterate"""
 
-    def __init__(self, iterate, solverinfo, workdir=None, armijo_batch=1, dump=True):
+    def __init__(self, iterate, solverinfo, workdir=None, armijo_batch=1, dump=True, precond_factory=None):
+        """precond_factory: optional callable (iterate, fcn) -> preconditioner callable, called once per
+        Newton iteration (e.g. ProbePreconditioner)"""
+        self._precond_factory = precond_factory
         self._info = dict(solverinfo)
         self._workdir = workdir or tempfile.mkdtemp(prefix="nkb200_newton_")
         os.makedirs(self._workdir, exist_ok=True)
@@ -167,7 +247,8 @@ class NewtonSolver:
     # ---- one Newton step ------------------------------------------------------------------
     def _comp_increment(self):
         krylov_dir = os.path.join(self._workdir, f"krylov_{self.iteration:02}")
-        krylov = KrylovSolver(self._iterate, self._info, self._fname("hist"), krylov_dir)
+        precond = None if self._precond_factory is None else self._precond_factory(self._iterate, self._fcn)
+        krylov = KrylovSolver(self._iterate, self._info, self._fname("hist"), krylov_dir, precond=precond)
         increment = krylov.solve(self._fname("increment") if self._dump else None, self._fcn, dump=self._dump)
         return increment, krylov
 

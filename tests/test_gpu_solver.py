@@ -161,3 +161,35 @@ def test_ci_long_dye_decay_newton_convergence(tmp_path):
         assert rec["armijo_factor"].shape == (2, 1) and (rec["armijo_factor"] == 1.0).all()
     assert (solver.fcn.norm() < 1.0e-6 * solver.iterate.norm()).all()
     ModelState.reset()
+
+
+def test_probe_preconditioner_newton_in_one_step(base, tmp_path):
+    """the preconditioner built from ONE batched evaluation of coloured column probes
+    (solver.ProbePreconditioner; 3 colours x 2 tracers x 20 levels = 120 members): on the grid
+    without lateral processes and for the linear iage module M is the exact Jacobian of F, so GMRES
+    converges in its first iteration and Newton in one step"""
+    from nk_ooc_b200.py_driver_2d.model_state import ModelState
+    from nk_ooc_b200.py_driver_2d.setup_solver import gen_grid_vars_file
+    from nk_ooc_b200.solver import NewtonSolver, ProbePreconditioner
+
+    info = _modelinfo(str(tmp_path), 20, 3, "0.0", "0.0")
+    gen_grid_vars_file(info)
+    ModelState.configure(info)
+    pre = "ci_py_driver_2d_iage_column_regions/"
+    iterate = _state(ModelState, base, pre + "init_iterate")
+    made = []
+
+    def factory(it, fcn):
+        made.append(ProbePreconditioner(it, fcn))
+        return made[-1]
+
+    solver = NewtonSolver(iterate, dict(PD_SOLVERINFO, post_newton_fp_iter="0"), workdir=str(tmp_path / "w0"),
+                          dump=False, precond_factory=factory)
+    n0 = solver.history[0]["fcn_norm"]
+    solver.step()
+    rec = solver.history[-1]
+    assert made[0].members_probed == 120 and rec["krylov_iterations"] == 1
+    # limited by the finite-difference step of the probes and of the Jacobian-vector product
+    assert (rec["krylov_precond_resid_norm"][0] < 1e-5 * rec["krylov_beta"]).all()
+    assert (rec["fcn_norm"] < 1e-4 * n0).all() and solver.converged_flat()
+    ModelState.reset()
