@@ -1,6 +1,7 @@
-// Fused IMEX step kernel — one launch per ARS(2,2,2) time step (both implicit stages), so that a
-// model state is read from HBM once (+ halo) and written once per step instead of 3 reads and
-// 2 writes with one launch per stage (nkb_stage_tma.cu).
+// Fused IMEX step kernel — both implicit stages of an ARS(2,2,2) time step in one pass over the
+// state, and ALL time steps of a model year in ONE persistent cooperative launch.  A state is read
+// from HBM once (+ halo) and written once per step instead of 3 reads and 2 writes with one launch
+// per stage (nkb_stage_tma.cu); the elimination intermediates never leave the SM.
 //
 // Replaces, per step and for all members at once, what the reference does inside
 // solve_ivp(Radau) for py_driver_2d (nk_ooc/py_driver_2d/model_state.py:94-121):
@@ -8,13 +9,13 @@
 // horiz_mix.py:48-67, vert_mix.py:24-41, iage.py:22-41 / forced.py:114-154) and the implicit
 // solves of its Jacobian (vert_mix.py:140-188).
 //
-// Work decomposition (B200: 148 SMs, one persistent CTA per SM, static tile round-robin)
+// Work decomposition (B200: 148 SMs, one persistent CTA per SM)
 //   tile  = 16 members x 14 interior columns (+1 halo column each side for the stage-1 solution,
 //           +2 for the state) x all levels of one tracer;  rows of 16 members = 128 bytes.
-//   warp  = 16 columns x 2 member pairs; thread = (column, 2 adjacent members), lane = column +
-//           16*pair.  Warps are self-contained: the only cross-thread exchange (stage-1 solution
-//           of the neighbour columns) is a warp shuffle.
-//   three sweeps over depth per tile:
+//   warp  = 16 columns x 2 members, lane = 2*column + (member & 1), 8 consumer warps (default
+//           layout; the other one is 4 warps x 2 members per thread).  Warps are self-contained: the
+//           only cross-thread exchange (stage-1 solution of the neighbour columns) is a warp shuffle.
+//   sweeps over depth per (time step, tile) item:
 //     A (top->bottom)  stage-1 right-hand side (explicit horizontal stencil + sources) and LU
 //                      forward elimination;  intermediates y1_k -> TMEM
 //     B (bottom->top)  stage-1 back substitution u1_k, exchange with the neighbour columns,
@@ -22,13 +23,19 @@
 //                      y1_k + m1_k y1_{k-1} and a re-read of the state, which hits L2) and UL
 //                      elimination upwards;  y2_k overwrites y1_k in TMEM
 //     C (top->bottom)  stage-2 substitution u2_k -> shared-memory staging -> TMA store
-//   Tensor memory is used as a per-lane scratchpad (tcgen05.st/ld 32x32b): 512 columns x 4 B =
-//   2 members x 128 levels of float64 per thread — the forward-sweep intermediates never leave
-//   the SM.  No tcgen05.mma is issued: nothing here is a contraction.
+//   C of an item and A of the next item run as ONE pass (chunk c of the TMEM scratch is read by C
+//   and overwritten by A) unless the next item needs this one's result: two passes per tile.
+//   Tensor memory is used as a per-lane scratchpad (tcgen05.st/ld 32x32b.x16): 256 32-bit columns
+//   per thread = 128 levels of float64, two warps per lane quarter; 512 columns x 128 lanes hold the
+//   256 (column, member) pairs of a tile.  No tcgen05.mma is issued: nothing here is a contraction.
 //   All state and coefficient traffic global->shared goes through TMA (cp.async.bulk.tensor,
-//   128-byte swizzle for the state boxes so that lane=column accesses are bank-conflict free)
-//   into one mbarrier full/empty ring shared by the three sweeps; a producer warp runs ahead of
-//   the consumers across sweeps and tiles, a store warp drains the output staging ring.
+//   128-byte swizzle for the state boxes so that lane = column accesses are bank-conflict free)
+//   into one mbarrier full/empty ring shared by all sweeps; a producer lane runs ahead of the
+//   consumers across sweeps, tiles and time steps, a store lane drains the output staging ring.
+//   Time steps are chained inside the launch: the store lane publishes a per-tile step counter
+//   (release), the producer lane acquires the counters of the tile and of its two column neighbours
+//   before the first load of the next step; the tile -> CTA assignment rotates from step to step so
+//   that the left-over tiles of a step do not always land on the same CTAs.
 
 #include <cuda.h>
 
