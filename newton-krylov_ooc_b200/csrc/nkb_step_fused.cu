@@ -121,7 +121,7 @@ __device__ __forceinline__ void fs_mbar_wait(uint32_t bar, uint32_t parity) {
             : "memory");
     } while (!ok);
 }
-// spin until *flag >= want (acquire); gives up after ~2e9 cycles and raises *err instead of hanging
+// spin until *flag >= want (acquire); gives up after 2e10 cycles (~10 s) and raises *err instead of hanging
 __device__ __forceinline__ void fs_wait_done(const int *flag, int want, int *err) {
     int v;
     const long long t0 = clock64();
@@ -129,7 +129,7 @@ __device__ __forceinline__ void fs_wait_done(const int *flag, int want, int *err
         asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
         if (v >= want) return;
         __nanosleep(200);
-        if (clock64() - t0 > 2000000000ll) {
+        if (clock64() - t0 > 20000000000ll) {
             *reinterpret_cast<volatile int *>(err) = 1;
             return;
         }
