@@ -193,3 +193,42 @@ def test_probe_preconditioner_newton_in_one_step(base, tmp_path):
     assert (rec["krylov_precond_resid_norm"][0] < 1e-5 * rec["krylov_beta"]).all()
     assert (rec["fcn_norm"] < 1e-4 * n0).all() and solver.converged_flat()
     ModelState.reset()
+
+
+def test_cli_setup_solver_and_nk_driver_column_regions(base, tmp_path):
+    """scripts/ci_py_driver_2d_iage_column_regions.sh through the command line: setup_solver (grid
+    file, gen_init_iterate + 1 fixed-point iteration) and nk_driver write the reference's files;
+    grid_vars, init_iterate (rtol 1e-3 / atol 1e-6) and iterate_01 (rtol 1.9e-2) against the
+    baselines; run_cmd comp_fcn file-to-file"""
+    from scipy.io import netcdf_file
+
+    from nk_ooc_b200 import cli
+    from nk_ooc_b200.py_driver_2d.model_state import ModelState
+
+    work = str(tmp_path / "work")
+    common = ["--model_name", "py_driver_2d", "--workdir", work, "--depth_nlevs", "20", "--ypos_nlevs", "3",
+              "--max_abs_vvel", "0.0", "--horiz_mix_coeff", "0.0"]
+    assert cli.main(["setup_solver", "--fp_cnt", "1"] + common) == 0
+    pre = "ci_py_driver_2d_iage_column_regions/"
+
+    def read(fname, names=("iage", "iage_slow_rest")):
+        with netcdf_file(fname, "r", mmap=False) as f:
+            return np.stack([np.array(f.variables[n].data) for n in names])
+
+    with netcdf_file(os.path.join(work, "grid_vars.nc"), "r", mmap=False) as f:
+        np.testing.assert_array_equal(np.array(f.variables["region_mask"].data), base[pre + "grid_vars/region_mask"])
+    np.testing.assert_allclose(read(os.path.join(work, "gen_init_iterate", "init_iterate_00.nc")),
+                               _want(base, pre + "init_iterate_0000"), rtol=1e-7, atol=2e-9)
+    np.testing.assert_allclose(read(os.path.join(work, "gen_init_iterate", "init_iterate.nc")),
+                               _want(base, pre + "init_iterate"), rtol=1e-3, atol=1e-6)
+    ModelState.reset()
+    assert cli.main(["nk_driver", "--newton_max_iter", "5"] + common) == 0
+    np.testing.assert_allclose(read(os.path.join(work, "iterate_01.nc")), _want(base, pre + "iterate_01"),
+                               rtol=1.9e-2, atol=1e-9)
+    assert os.path.exists(os.path.join(work, "krylov_00", "krylov_res_00.nc"))
+    # file-to-file function evaluation
+    assert cli.main(["comp_fcn", "--fname_dir", work, "--in_fname", "gen_init_iterate/init_iterate_00.nc",
+                     "--res_fname", "fcn_cli.nc"] + common) == 0
+    np.testing.assert_allclose(read(os.path.join(work, "fcn_cli.nc")), _want(base, pre + "fcn_0000"), rtol=1e-3,
+                               atol=1e-6)
+    ModelState.reset()
