@@ -139,6 +139,10 @@ int nkb_model_eval_host(nkb_model *m, const double *h_x0, double *h_f, int B);
 typedef struct nkb_banded nkb_banded;
 int nkb_banded_create(nkb_banded **out, int n, int kl, int ku, const double *h_ab /* [kl+ku+1][n] */);
 void nkb_banded_destroy(nkb_banded *f);
+/* number of independent diagonal blocks found in the matrix (rows that no band entry couples, e.g.
+ * the per-column systems of a grid without lateral processes): they are factored and solved in
+ * parallel */
+int nkb_banded_blocks(const nkb_banded *f);
 /* d_y, d_x: [n][ldb]; x = A^-1 y (in place allowed); if subtract_rhs, x = A^-1 (scale*y) - y */
 int nkb_banded_solve(nkb_banded *f, const double *d_y, double *d_x, int B, int ldb, double scale,
                      int subtract_rhs, void *stream);

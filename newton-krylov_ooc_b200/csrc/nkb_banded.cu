@@ -1,13 +1,28 @@
 // K4 — member-shared banded LU with partial pivoting + batched member-fastest solves.
 //
 // The preconditioner matrix is member-independent, so it is factored ONCE on the device
-// (one CTA, LAPACK dgbtf2-style right-looking elimination inside the band) and the factor is
-// then applied to every member's right-hand side, one thread per member, coalesced across
-// members.  Replaces scipy.linalg.solve_banded((1,1), ...) (test_problem/iage.py:50,
-// dye_decay.py:71) and scipy.sparse.linalg.spsolve (py_driver_2d/iage.py:91, forced.py:239).
+// (LAPACK dgbtf2-style right-looking elimination inside the band) and the factor is then applied
+// to every member's right-hand side.  Replaces scipy.linalg.solve_banded((1,1), ...)
+// (test_problem/iage.py:50, dye_decay.py:71) and scipy.sparse.linalg.spsolve
+// (py_driver_2d/iage.py:91, forced.py:239).
+//
+// Parallelism of a solve (banded_solve_win_kernel):
+//   * independent diagonal blocks (rows that no band entry couples: the per-column systems of a
+//     grid without lateral processes, the column blocks of the probe preconditioner) are found at
+//     set-up and solved by different CTAs (grid.y) — they are factored in parallel as well;
+//   * members: MB <= 32 member lanes per CTA (coalesced rows of MB doubles), grid.x = B / MB;
+//   * the band: RW row lanes share the kl (forward) / kl+ku (backward) updates of a step, so that a
+//     single right-hand side (B = 1, the usual Krylov case) still uses a whole CTA.
+//   The part of the right-hand side that a step can touch lives in a circular shared-memory window;
+//   rows ahead of the sweep and the factor columns they need (stored transposed at set-up: the
+//   multipliers of a step are contiguous) arrive through a 4-stage cp.async ring, so no global
+//   load sits on the step-to-step dependency chain.  A^-1 (scale y) - y is fused into the backward
+//   sweep.
 //
 // Band storage (row-major): A(i,j) lives at ab[(kv + i - j)*n + j], kv = kl + ku, rows
 // 0..kl-1 are fill-in space, total 2*kl + ku + 1 rows.
+#include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "nkb_common.cuh"
@@ -17,21 +32,33 @@ struct nkb_banded {
     double *ab = nullptr;  // [(2kl+ku+1)][n]
     int *ipiv = nullptr;   // [n]
     int *info = nullptr;
+    double *lt = nullptr;  // [n][kl]      multipliers of column j: L(j+1..j+kl, j)
+    double *ut = nullptr;  // [n][kv+1]    {1/U(j,j), U(j-1,j), ..., U(j-kv,j)}
+    int nblk = 1;          // independent diagonal blocks
+    int *blk = nullptr;    // [nblk+1] first row of each block (device)
+    // narrow bands factored without row interchanges (the per-column tridiagonal systems): compact
+    // rows {L(j,j-K..j-1), 1/U(j,j), U(j,j+1..j+K)}, K = max(kl, ku) <= 4, for banded_thomas_kernel
+    int nb_k = 0;
+    double *nb = nullptr;  // [n][2K+1]
 };
 
 namespace nkb {
 
+// one CTA per independent diagonal block [blk[b], blk[b+1]); *info (zeroed by the host) receives
+// 1 + the first column with a zero pivot
 __global__ void __launch_bounds__(256) banded_factor_kernel(double *__restrict__ ab, int *__restrict__ ipiv,
-                                                            int n, int kl, int ku, int *info) {
+                                                            int n, int kl, int ku, const int *__restrict__ blk,
+                                                            int *info) {
     __shared__ double s_val[256];
     __shared__ int s_idx[256];
     __shared__ int s_ju;
     const int kv = kl + ku;
     const int tid = threadIdx.x, nt = blockDim.x;
-    if (tid == 0) { s_ju = 0; *info = 0; }
+    const int r0 = blk[blockIdx.x], r1 = blk[blockIdx.x + 1];
+    if (tid == 0) s_ju = r0;
     __syncthreads();
-    for (int j = 0; j < n; ++j) {
-        const int km = min(kl, n - 1 - j);
+    for (int j = r0; j < r1; ++j) {
+        const int km = min(kl, r1 - 1 - j);
         // pivot search over the km+1 candidates of column j
         double best = -1.0;
         int besti = 0;
@@ -54,8 +81,8 @@ __global__ void __launch_bounds__(256) banded_factor_kernel(double *__restrict__
         const double pv = s_val[0];
         if (tid == 0) {
             ipiv[j] = j + jp;
-            if (pv == 0.0 && *info == 0) *info = j + 1;
-            if (pv != 0.0) s_ju = max(s_ju, min(j + ku + jp, n - 1));
+            if (pv == 0.0) atomicCAS(info, 0, j + 1);
+            if (pv != 0.0) s_ju = max(s_ju, min(j + ku + jp, r1 - 1));
         }
         __syncthreads();
         if (pv != 0.0) {
@@ -83,7 +110,281 @@ __global__ void __launch_bounds__(256) banded_factor_kernel(double *__restrict__
     }
 }
 
-// one thread per member; x [n][ldb] in place
+// transposed copies of the factor for the solves: the coefficients of one step are contiguous
+__global__ void banded_transpose_kernel(const double *__restrict__ ab, int n, int kl, int ku,
+                                        double *__restrict__ lt, double *__restrict__ ut) {
+    const int kv = kl + ku;
+    const int j = blockIdx.x;
+    for (int i = threadIdx.x; i < kl; i += blockDim.x) {
+        const int row = j + 1 + i;
+        lt[(size_t)j * kl + i] = (row < n) ? ab[(size_t)(kv + 1 + i) * n + j] : 0.0;
+    }
+    for (int i = threadIdx.x; i <= kv; i += blockDim.x) {
+        double v = 0.0;
+        if (i == 0) v = 1.0 / ab[(size_t)kv * n + j];
+        else if (j - i >= 0) v = ab[(size_t)(kv - i) * n + j];
+        ut[(size_t)j * (kv + 1) + i] = v;
+    }
+}
+
+__device__ __forceinline__ void bs_cp8(void *dst_smem, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)),
+                 "l"(src)
+                 : "memory");
+}
+__device__ __forceinline__ void bs_cp4(void *dst_smem, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)),
+                 "l"(src)
+                 : "memory");
+}
+__device__ __forceinline__ void bs_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bs_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// Batched Thomas / narrow-band substitution, members fastest: one warp per (32 members, diagonal
+// block), a lane owns one member; many small CTAs per SM hide the latency of the recurrences.
+// Forward: y streams from HBM in chunks of UR rows (all loads of a chunk in flight before the first
+// use); z = L^-1 y goes through the output buffer (it comes back from L2: keeping it in shared
+// memory instead costs occupancy and measured 25 % slower).  Backward: x = U^-1 z and the epilogue
+// scale*x - y, where y_j is rebuilt from the z values (y_j = z_j + sum_i L(j,j-i) z_(j-i)) instead of
+// being read again.
+template <int K, int UR>
+__global__ void __launch_bounds__(32) banded_thomas_kernel(const double *__restrict__ nb, const int *__restrict__ blk,
+                                                           const double *__restrict__ y, double *__restrict__ x,
+                                                           int B, size_t ldb, double scale, int subtract) {
+    constexpr int NC = 2 * K + 1;
+    const int b = blockIdx.x * 32 + threadIdx.x;
+    if (b >= B) return;
+    const int r0 = blk[blockIdx.y], r1 = blk[blockIdx.y + 1];
+    double zp[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) zp[i] = 0.0;
+    for (int j0 = r0; j0 < r1; j0 += UR) {
+        double yv[UR], cl[UR][K];
+#pragma unroll
+        for (int q = 0; q < UR; ++q) {
+            const int j = min(j0 + q, r1 - 1);
+            yv[q] = __ldcs(y + (size_t)j * ldb + b);
+#pragma unroll
+            for (int i = 0; i < K; ++i) cl[q][i] = __ldg(nb + (size_t)j * NC + i);
+        }
+#pragma unroll
+        for (int q = 0; q < UR; ++q) {
+            if (j0 + q < r1) {
+                double z = yv[q];
+#pragma unroll
+                for (int i = 1; i <= K; ++i) z = fma(-cl[q][K - i], zp[i - 1], z);
+#pragma unroll
+                for (int i = K - 1; i > 0; --i) zp[i] = zp[i - 1];
+                zp[0] = z;
+                x[(size_t)(j0 + q) * ldb + b] = z;
+            }
+        }
+    }
+    // backward; zc[i] = z_(j-i) (zero above the block), xp[i] = x_(j+1+i)
+    auto zload = [&](int j) -> double { return (j < r0) ? 0.0 : x[(size_t)j * ldb + b]; };
+    double xp[K], zc[K + 1];
+#pragma unroll
+    for (int i = 0; i < K; ++i) xp[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i <= K; ++i) zc[i] = zload(r1 - 1 - i);
+    for (int j0 = r1 - 1; j0 >= r0; j0 -= UR) {
+        double cu[UR][NC], zn[UR];
+#pragma unroll
+        for (int q = 0; q < UR; ++q) {
+            const int j = max(j0 - q, r0);
+#pragma unroll
+            for (int i = 0; i < NC; ++i) cu[q][i] = __ldg(nb + (size_t)j * NC + i);
+            zn[q] = zload(j0 - q - K - 1);  // enters the z window after row j0 - q (read before any store of
+                                            // this chunk can reach it)
+        }
+#pragma unroll
+        for (int q = 0; q < UR; ++q) {
+            const int j = j0 - q;
+            if (j >= r0) {
+                double t = zc[0];
+#pragma unroll
+                for (int i = 1; i <= K; ++i) t = fma(-cu[q][K + i], xp[i - 1], t);
+                const double xj = t * cu[q][K];
+                double o = scale * xj;
+                if (subtract) {
+                    double yj = zc[0];
+#pragma unroll
+                    for (int i = 1; i <= K; ++i) yj = fma(cu[q][K - i], zc[i], yj);
+                    o -= yj;
+                }
+                __stcs(x + (size_t)j * ldb + b, o);
+#pragma unroll
+                for (int i = K - 1; i > 0; --i) xp[i] = xp[i - 1];
+                xp[0] = xj;
+#pragma unroll
+                for (int i = 0; i < K; ++i) zc[i] = zc[i + 1];
+                zc[K] = zn[q];
+            }
+        }
+    }
+}
+
+template <int K>
+static int launch_thomas(const nkb_banded *f, const double *y, double *x, int B, size_t ldb, double scale,
+                         int subtract, cudaStream_t st) {
+    // in place (x == y, no subtraction) is safe: row j of x is written after row j of y has been read, and
+    // every row is visited once per sweep
+    dim3 grid((B + 31) / 32, f->nblk);
+    banded_thomas_kernel<K, 8><<<grid, 32, 0, st>>>(f->nb, f->blk, y, x, B, ldb, scale, subtract);
+    count_launch();
+    NKB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+constexpr int BS_NSTG = 4;  // cp.async stages in flight
+
+struct BandedSolveArgs {
+    const double *lt, *ut;
+    const int *ipiv, *blk;
+    int kl, ku;
+    const double *y;
+    double *x;
+    int B;
+    size_t ldb;
+    double scale;
+    int subtract;
+    int MB, RW, CH, Wn;  // member lanes, row lanes, steps per stage, window rows
+};
+
+// threads = RW row lanes x MB member lanes (member fastest); grid (member groups, diagonal blocks).
+// Shared memory: W[Wn][MB] window | C[NSTG][CH*(kv+1)] factor columns | Y[NSTG][CH][MB] | P[NSTG][CH]
+__global__ void __launch_bounds__(256) banded_solve_win_kernel(const BandedSolveArgs a) {
+    extern __shared__ __align__(16) double bs_smem[];
+    const int MB = a.MB, RW = a.RW, CH = a.CH, Wn = a.Wn, kl = a.kl, kv = a.kl + a.ku;
+    double *W = bs_smem;
+    double *C = W + (size_t)Wn * MB;
+    const int cstride = CH * (kv + 1);
+    double *Y = C + (size_t)BS_NSTG * cstride;
+    int *P = reinterpret_cast<int *>(Y + (size_t)BS_NSTG * CH * MB);
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int m = tid % MB, rl = tid / MB;
+    const int b0 = blockIdx.x * MB;
+    const bool live = (rl == 0) && (b0 + m < a.B);
+    const int nlive = min(MB, a.B - b0);
+    const int r0 = a.blk[blockIdx.y], r1 = a.blk[blockIdx.y + 1];
+    const int len = r1 - r0;
+    for (int i = tid; i < Wn * MB; i += nt) W[i] = 0.0;
+    __syncthreads();
+
+    // rows [ra, rb) of src -> window slots (row - r0) % Wn
+    auto load_rows = [&](const double *src, int ra, int rb) {
+        ra = max(ra, r0);
+        rb = min(rb, r1);
+        const int cnt = (rb - ra) * MB;
+        for (int i = tid; i < cnt; i += nt) {
+            const int r = ra + i / MB, mm = i % MB;
+            if (mm < nlive) bs_cp8(W + (size_t)((r - r0) % Wn) * MB + mm, src + (size_t)r * a.ldb + b0 + mm);
+        }
+    };
+
+    // ---------------- forward: L z = P y (scale is applied at the very end: the solve is linear) ----------------
+    const int nchunk = (len + CH - 1) / CH;
+    auto stage_fwd = [&](int q) {
+        if (q < nchunk) {
+            const int jq = r0 + q * CH, je = min(jq + CH, r1);
+            const double *src = a.lt + (size_t)jq * kl;
+            double *dst = C + (size_t)(q % BS_NSTG) * cstride;
+            for (int i = tid; i < (je - jq) * kl; i += nt) bs_cp8(dst + i, src + i);
+            for (int i = tid; i < je - jq; i += nt) bs_cp4(P + (q % BS_NSTG) * CH + i, a.ipiv + jq + i);
+            load_rows(a.y, q == 0 ? r0 : jq + kl, jq + kl + CH);
+        }
+        bs_commit();
+    };
+    for (int q = 0; q < BS_NSTG - 1; ++q) stage_fwd(q);
+    for (int q = 0; q < nchunk; ++q) {
+        stage_fwd(q + BS_NSTG - 1);
+        bs_wait<BS_NSTG - 1>();
+        __syncthreads();
+        const int jq = r0 + q * CH, je = min(jq + CH, r1);
+        const double *cq = C + (size_t)(q % BS_NSTG) * cstride;
+        const int *pq = P + (q % BS_NSTG) * CH;
+        int sj = (jq - r0) % Wn;
+        for (int j = jq; j < je; ++j) {
+            const int p = pq[j - jq];
+            if (p != j) {  // uniform over the CTA
+                if (rl == 0) {
+                    int sp = sj + (p - j);
+                    if (sp >= Wn) sp -= Wn;
+                    const double t = W[(size_t)sj * MB + m];
+                    W[(size_t)sj * MB + m] = W[(size_t)sp * MB + m];
+                    W[(size_t)sp * MB + m] = t;
+                }
+                __syncthreads();
+            }
+            const double xj = W[(size_t)sj * MB + m];
+            const int lm = min(kl, r1 - 1 - j);
+            const double *cj = cq + (size_t)(j - jq) * kl;
+            for (int i = 1 + rl; i <= lm; i += RW) {
+                int si = sj + i;
+                if (si >= Wn) si -= Wn;
+                W[(size_t)si * MB + m] = fma(-cj[i - 1], xj, W[(size_t)si * MB + m]);
+            }
+            if (live) a.x[(size_t)j * a.ldb + b0 + m] = xj;
+            if (++sj == Wn) sj = 0;
+            __syncthreads();
+        }
+    }
+    bs_wait<0>();
+    __threadfence_block();
+    __syncthreads();
+
+    // ---------------- backward: U x = z, out = scale * x [- y] ----------------
+    auto stage_bwd = [&](int q) {
+        if (q < nchunk) {
+            const int jq = r1 - 1 - q * CH, jl = max(jq - CH + 1, r0);  // steps jq, jq-1, ..., jl
+            const double *src = a.ut + (size_t)jl * (kv + 1);
+            double *dst = C + (size_t)(q % BS_NSTG) * cstride;
+            for (int i = tid; i < (jq - jl + 1) * (kv + 1); i += nt) bs_cp8(dst + i, src + i);
+            if (a.subtract) {
+                double *yd = Y + (size_t)(q % BS_NSTG) * CH * MB;
+                for (int i = tid; i < (jq - jl + 1) * MB; i += nt) {
+                    const int mm = i % MB;
+                    if (mm < nlive) bs_cp8(yd + i, a.y + (size_t)(jl + i / MB) * a.ldb + b0 + mm);
+                }
+            }
+            load_rows(a.x, jq - CH + 1 - kv, q == 0 ? r1 : jq - kv + 1);
+        }
+        bs_commit();
+    };
+    for (int q = 0; q < BS_NSTG - 1; ++q) stage_bwd(q);
+    for (int q = 0; q < nchunk; ++q) {
+        stage_bwd(q + BS_NSTG - 1);
+        bs_wait<BS_NSTG - 1>();
+        __syncthreads();
+        const int jq = r1 - 1 - q * CH, jl = max(jq - CH + 1, r0);
+        const double *cq = C + (size_t)(q % BS_NSTG) * cstride;
+        const double *yq = Y + (size_t)(q % BS_NSTG) * CH * MB;
+        int sj = (jq - r0) % Wn;
+        for (int j = jq; j >= jl; --j) {
+            const double *cj = cq + (size_t)(j - jl) * (kv + 1);
+            const double xj = W[(size_t)sj * MB + m] * cj[0];
+            const int um = min(kv, j - r0);
+            for (int i = 1 + rl; i <= um; i += RW) {
+                int si = sj - i;
+                if (si < 0) si += Wn;
+                W[(size_t)si * MB + m] = fma(-cj[i], xj, W[(size_t)si * MB + m]);
+            }
+            if (live) {
+                double o = a.scale * xj;
+                if (a.subtract) o -= yq[(size_t)(j - jl) * MB + m];
+                a.x[(size_t)j * a.ldb + b0 + m] = o;
+            }
+            if (--sj < 0) sj = Wn - 1;
+            __syncthreads();
+        }
+    }
+    bs_wait<0>();
+}
+
+// fallback for bands too wide for the shared-memory window: one thread per member; x [n][ldb] in place
 __global__ void banded_solve_kernel(const double *__restrict__ ab, const int *__restrict__ ipiv, int n, int kl,
                                     int ku, const double *__restrict__ y, double *__restrict__ x, int B,
                                     size_t ldb, double scale, int subtract_rhs) {
@@ -133,14 +434,40 @@ int nkb_banded_create(nkb_banded **out, int n, int kl, int ku, const double *h_a
     // scipy solve_banded layout in: ab_in[ku + i - j][j]  ->  rows kl.. of the working band
     for (int r = 0; r < kl + ku + 1; ++r)
         for (int j = 0; j < n; ++j) host[(size_t)(kl + r) * n + j] = h_ab[(size_t)r * n + j];
+    // independent diagonal blocks: a boundary in front of row b is "cut" by every non-zero A(i,c) with
+    // min(i,c) < b <= max(i,c); rows between two uncut boundaries form a system of their own
+    std::vector<int> cut(n + 1, 0);
+    for (int r = 0; r < kl + ku + 1; ++r) {
+        const int d = r - ku;  // i - c
+        if (d == 0) continue;
+        for (int c = 0; c < n; ++c) {
+            const int i = c + d;
+            if (i < 0 || i >= n || h_ab[(size_t)r * n + c] == 0.0) continue;
+            cut[std::min(i, c) + 1] += 1;
+            cut[std::max(i, c) + 1] -= 1;
+        }
+    }
+    std::vector<int> blk(1, 0);
+    for (int b = 1, acc = 0; b < n; ++b) {
+        acc += cut[b];
+        if (acc == 0) blk.push_back(b);
+    }
+    blk.push_back(n);
+    f->nblk = (int)blk.size() - 1;
+    const int kv = kl + ku;
     if (cudaMalloc(&f->ab, host.size() * sizeof(double)) != cudaSuccess ||
-        cudaMalloc(&f->ipiv, n * sizeof(int)) != cudaSuccess || cudaMalloc(&f->info, sizeof(int)) != cudaSuccess) {
+        cudaMalloc(&f->ipiv, n * sizeof(int)) != cudaSuccess || cudaMalloc(&f->info, sizeof(int)) != cudaSuccess ||
+        cudaMalloc(&f->lt, std::max<size_t>(1, (size_t)n * kl) * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&f->ut, (size_t)n * (kv + 1) * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&f->blk, blk.size() * sizeof(int)) != cudaSuccess) {
         nkb::set_error("nkb_banded_create: cudaMalloc failed (is a CUDA device present?)");
-        delete f;
+        nkb_banded_destroy(f);
         return 1;
     }
     NKB_CUDA(cudaMemcpy(f->ab, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice));
-    nkb::banded_factor_kernel<<<1, 256>>>(f->ab, f->ipiv, n, kl, ku, f->info);
+    NKB_CUDA(cudaMemcpy(f->blk, blk.data(), blk.size() * sizeof(int), cudaMemcpyHostToDevice));
+    NKB_CUDA(cudaMemset(f->info, 0, sizeof(int)));
+    nkb::banded_factor_kernel<<<f->nblk, 256>>>(f->ab, f->ipiv, n, kl, ku, f->blk, f->info);
     nkb::count_launch();
     int info = 0;
     NKB_CUDA(cudaMemcpy(&info, f->info, sizeof(int), cudaMemcpyDeviceToHost));
@@ -149,13 +476,46 @@ int nkb_banded_create(nkb_banded **out, int n, int kl, int ku, const double *h_a
         nkb_banded_destroy(f);
         return 3;
     }
+    nkb::banded_transpose_kernel<<<n, 128>>>(f->ab, n, kl, ku, f->lt, f->ut);
+    nkb::count_launch();
+    NKB_CUDA(cudaDeviceSynchronize());
+    const int K = std::max(std::max(kl, ku), 1);
+    if (K <= 4) {
+        // narrow band: compact rows for the Thomas kernel if the factorisation did not interchange rows
+        std::vector<int> piv(n);
+        NKB_CUDA(cudaMemcpy(piv.data(), f->ipiv, n * sizeof(int), cudaMemcpyDeviceToHost));
+        bool plain = true;
+        for (int j = 0; j < n && plain; ++j) plain = (piv[j] == j);
+        if (plain) {
+            NKB_CUDA(cudaMemcpy(host.data(), f->ab, host.size() * sizeof(double), cudaMemcpyDeviceToHost));
+            const int NC = 2 * K + 1;
+            std::vector<double> nbh((size_t)n * NC, 0.0);
+            for (int j = 0; j < n; ++j) {
+                for (int i = 1; i <= kl; ++i)
+                    if (j - i >= 0) nbh[(size_t)j * NC + K - i] = host[(size_t)(kv + i) * n + (j - i)];
+                nbh[(size_t)j * NC + K] = 1.0 / host[(size_t)kv * n + j];
+                for (int i = 1; i <= ku; ++i)
+                    if (j + i < n) nbh[(size_t)j * NC + K + i] = host[(size_t)(kv - i) * n + (j + i)];
+            }
+            if (cudaMalloc(&f->nb, nbh.size() * sizeof(double)) != cudaSuccess) {
+                nkb::set_error("nkb_banded_create: cudaMalloc failed");
+                nkb_banded_destroy(f);
+                return 1;
+            }
+            NKB_CUDA(cudaMemcpy(f->nb, nbh.data(), nbh.size() * sizeof(double), cudaMemcpyHostToDevice));
+            f->nb_k = K;
+        }
+    }
     *out = f;
     return 0;
 }
 
+int nkb_banded_blocks(const nkb_banded *f) { return f ? f->nblk : 0; }
+
 void nkb_banded_destroy(nkb_banded *f) {
     if (!f) return;
     cudaFree(f->ab); cudaFree(f->ipiv); cudaFree(f->info);
+    cudaFree(f->lt); cudaFree(f->ut); cudaFree(f->blk); cudaFree(f->nb);
     delete f;
 }
 
@@ -163,6 +523,52 @@ int nkb_banded_solve(nkb_banded *f, const double *d_y, double *d_x, int B, int l
                      void *stream) {
     NKB_REQUIRE(f && d_y && d_x && B >= 1 && ldb >= B, "nkb_banded_solve: bad argument");
     NKB_REQUIRE(!(subtract_rhs && d_y == d_x), "nkb_banded_solve: subtract_rhs needs distinct x and y");
+    {
+        const char *env = getenv("NKB_BANDED_THOMAS");
+        if (f->nb_k > 0 && B >= 16 && !(env && env[0] == '0')) {
+            cudaStream_t st = (cudaStream_t)stream;
+            switch (f->nb_k) {
+                case 1: return nkb::launch_thomas<1>(f, d_y, d_x, B, (size_t)ldb, scale, subtract_rhs, st);
+                case 2: return nkb::launch_thomas<2>(f, d_y, d_x, B, (size_t)ldb, scale, subtract_rhs, st);
+                case 3: return nkb::launch_thomas<3>(f, d_y, d_x, B, (size_t)ldb, scale, subtract_rhs, st);
+                default: return nkb::launch_thomas<4>(f, d_y, d_x, B, (size_t)ldb, scale, subtract_rhs, st);
+            }
+        }
+    }
+    // window kernel: pick the stage depth and the member lanes so that the shared memory fits
+    {
+        const int kv = f->kl + f->ku;
+        const size_t budget = 200 * 1024;
+        int CH = 16, MB = 1;
+        while (MB < B && MB < 32) MB <<= 1;
+        while (CH > 1 && (size_t)nkb::BS_NSTG * CH * (kv + 1) * 8 > budget / 2) CH >>= 1;
+        auto need = [&](int mb) {
+            const size_t wn = (size_t)nkb::BS_NSTG * CH + kv + 1;
+            return (wn * mb + (size_t)nkb::BS_NSTG * CH * (kv + 1) + (size_t)nkb::BS_NSTG * CH * mb) * 8 +
+                   (size_t)nkb::BS_NSTG * CH * 4 + 16;
+        };
+        while (MB > 1 && need(MB) > budget) MB >>= 1;
+        const char *env = getenv("NKB_BANDED_WINDOW");
+        if (need(MB) <= budget && !(env && env[0] == '0')) {
+            int RW = 1;
+            while (RW < kv && RW * MB < 256) RW <<= 1;
+            nkb::BandedSolveArgs a;
+            a.lt = f->lt; a.ut = f->ut; a.ipiv = f->ipiv; a.blk = f->blk; a.kl = f->kl; a.ku = f->ku;
+            a.y = d_y; a.x = d_x; a.B = B; a.ldb = (size_t)ldb; a.scale = scale; a.subtract = subtract_rhs;
+            a.MB = MB; a.RW = RW; a.CH = CH; a.Wn = nkb::BS_NSTG * CH + kv + 1;
+            static bool attr_set = false;
+            if (!attr_set) {
+                NKB_CUDA(cudaFuncSetAttribute(nkb::banded_solve_win_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)budget));
+                attr_set = true;
+            }
+            dim3 grid((B + MB - 1) / MB, f->nblk);
+            nkb::banded_solve_win_kernel<<<grid, RW * MB, need(MB), (cudaStream_t)stream>>>(a);
+            nkb::count_launch();
+            NKB_CUDA(cudaGetLastError());
+            return 0;
+        }
+    }
     const int bs = B >= 128 ? 128 : 32;
     nkb::banded_solve_kernel<<<(B + bs - 1) / bs, bs, 0, (cudaStream_t)stream>>>(
         f->ab, f->ipiv, f->n, f->kl, f->ku, d_y, d_x, B, (size_t)ldb, scale, subtract_rhs);

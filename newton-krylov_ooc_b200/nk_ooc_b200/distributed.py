@@ -39,6 +39,64 @@ def gather_members(local, n_members, group=None):
     return torch.cat(parts, dim=0)
 
 
+def is_sharded(group=None):
+    """True inside an initialised process group with more than one rank"""
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+
+
+def _to_member_major(vals, B):
+    """[..., ldb] member-fastest -> [B, n] (layout conversion for the gather: library kernel on the GPU)"""
+    if vals.is_cuda:
+        from . import engine
+
+        return engine.unpack(vals, B).reshape(B, -1)
+    return vals.movedim(-1, 0)[:B].reshape(B, -1).contiguous()
+
+
+def _from_member_major(major, like):
+    """[B, n] -> member-fastest tensor shaped like `like` ([..., ldb]); padding members are zero"""
+    B = major.shape[0]
+    if like.is_cuda:
+        from . import engine
+
+        fast = engine.pack(major.reshape((B,) + tuple(like.shape[:-1])))
+        if fast.shape[-1] == like.shape[-1]:
+            return fast
+        out = torch.zeros_like(like)
+        out[..., :B] = fast[..., :B]
+        return out
+    out = torch.zeros_like(like)
+    out[..., :B] = major.reshape((B,) + tuple(like.shape[:-1])).movedim(0, -1)
+    return out
+
+
+def sharded_comp_fcn(state, group=None, hist_fname=None):
+    """F(x) of a batched state (coloured probes, Armijo candidates, perturbed iterates) with its
+    members sharded over the ranks: every rank holds the same `state`, evaluates the members of
+    member_range(state.members, rank, world) — a model year each, no collective on the data path —
+    and the result columns are all-gathered so that every rank returns the full batched F.
+    Member results do not depend on which other members share a launch (tested bit for bit), so
+    the sharded result equals the single-GPU one.  Outside a process group this is state.comp_fcn."""
+    if not is_sharded(group):
+        return state.comp_fcn(None, None, hist_fname)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    B = state.members
+    lo, hi = member_range(B, rank, world)
+    res = state._like(clone_vals=False)
+    local_fcn = None
+    if hi > lo:
+        local_fcn = state.member_slice(lo, hi).comp_fcn(None, None, hist_fname if lo == 0 else None)
+    for ind, tms in enumerate(state.tracer_modules):
+        n = tms.vals[..., 0].numel()
+        if local_fcn is not None:
+            local = _to_member_major(local_fcn.tracer_modules[ind].vals, hi - lo)
+        else:
+            local = tms.vals.new_zeros((0, n))
+        full = gather_members(local, B, group)
+        res.tracer_modules[ind].vals = _from_member_major(full, tms.vals)
+    return res
+
+
 def allreduce_sum(partial, group=None):
     """sum of [n_modules, region_cnt(, k)] partial dot products over the ranks (in place)"""
     dist.all_reduce(partial, op=dist.ReduceOp.SUM, group=group)

@@ -296,6 +296,7 @@ class BandedFactor:
         self.n = ab.shape[1]
         self.handle = ctypes.c_void_p()
         check(self.lib.nkb_banded_create(ctypes.byref(self.handle), self.n, kl, ku, dptr(ab)), "nkb_banded_create")
+        self.n_blocks = self.lib.nkb_banded_blocks(self.handle)  # independent diagonal blocks (solved in parallel)
 
     def __del__(self):
         try:

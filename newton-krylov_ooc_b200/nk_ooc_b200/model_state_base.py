@@ -283,6 +283,13 @@ class ModelStateBase:
             tms.vals[..., 0] = self.tracer_modules[i].vals[..., b]
         return res
 
+    def member_slice(self, lo, hi):
+        """batched state holding the members [lo, hi) (the shard of one rank, distributed.py)"""
+        res = type(self)("zeros", members=hi - lo)
+        for i, tms in enumerate(res.tracer_modules):
+            tms.vals[..., : hi - lo] = self.tracer_modules[i].vals[..., lo:hi]
+        return res
+
     # ---- file output --------------------------------------------------------------------
     def _axes(self):
         raise NotImplementedError("Method must be implemented in derived class")

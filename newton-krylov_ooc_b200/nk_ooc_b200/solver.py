@@ -28,7 +28,7 @@ import tempfile
 
 import numpy as np
 
-from . import model_state_base
+from . import distributed, model_state_base
 
 
 def comp_krylov_basis_coeffs(beta, h_mat):
@@ -78,7 +78,9 @@ class ProbePreconditioner:
         batched = type(iterate)("zeros", members=B)
         batched.tracer_modules[0].vals[..., :B] = torch.from_numpy(
             np.ascontiguousarray(np.moveaxis(probes, 0, -1))).cuda()
-        fprobe = np.moveaxis(batched.comp_fcn(None, None).tracer_modules[0].vals[..., :B].cpu().numpy(), -1, 0)
+        # one batched evaluation; inside a process group the probes are sharded over the GPUs and the
+        # result columns gathered over NCCL (distributed.sharded_comp_fcn)
+        fprobe = np.moveaxis(distributed.sharded_comp_fcn(batched).tracer_modules[0].vals[..., :B].cpu().numpy(), -1, 0)
         jac = colouring.decode_probes(f0, fprobe, colour, eps, reach)  # [ny, 2*reach+1, n, n]
         self.members_probed = B
         n = T * nz
@@ -268,7 +270,7 @@ class NewtonSolver:
             k = self._armijo_batch
             factors = [armijo_factor * 0.5 ** i for i in range(k)]
             provs = [self._iterate + f * increment for f in factors]
-            batched_fcn = type(self._iterate).from_members(provs).comp_fcn(None, None)
+            batched_fcn = distributed.sharded_comp_fcn(type(self._iterate).from_members(provs))
             norms = batched_fcn.norm()  # [n_modules, R, k]
             for i in range(k):
                 cond = (factors[i] == 0.0) | (norms[..., i] <= (1.0 - alpha * factors[i]) * fcn_norm)

@@ -70,3 +70,82 @@ def test_member_range_partitions_exactly():
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         member_range(4, 2, 2)
+
+
+# ---- sharded batched evaluation (distributed.sharded_comp_fcn) with a stand-in state ---------------
+class _FakeTms:
+    def __init__(self, vals):
+        self.vals = vals
+
+
+class _FakeState:
+    """the surface sharded_comp_fcn uses: members, tracer_modules[i].vals [..., ldb], member_slice,
+    comp_fcn, _like — F here is a deterministic per-member function so that any mix-up of members
+    between ranks shows"""
+
+    def __init__(self, vals_list, members):
+        self.members = members
+        self.tracer_modules = [_FakeTms(v) for v in vals_list]
+        self.evaluated = 0
+
+    def member_slice(self, lo, hi):
+        out = []
+        for tms in self.tracer_modules:
+            v = torch.zeros(tms.vals.shape[:-1] + (hi - lo + 3,), dtype=torch.float64)  # own padding
+            v[..., : hi - lo] = tms.vals[..., lo:hi]
+            out.append(v)
+        return _FakeState(out, hi - lo)
+
+    def comp_fcn(self, res_fname, solver_state, hist_fname=None):
+        self.evaluated += self.members
+        return _FakeState([t.vals ** 2 + 3.0 * t.vals.sum(dim=tuple(range(t.vals.dim() - 1)), keepdim=True)
+                           for t in self.tracer_modules], self.members)
+
+    def _like(self, clone_vals=True):
+        return _FakeState([t.vals.clone() if clone_vals else t.vals for t in self.tracer_modules], self.members)
+
+
+def _worker_sharded(rank, world, port, n_members, tmpdir):
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "newton-krylov_ooc_b200"))
+    from nk_ooc_b200 import distributed as D
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        gen = torch.Generator().manual_seed(5)
+        ldb = n_members + 2
+        vals = [torch.zeros((2, 4, 3, ldb), dtype=torch.float64), torch.zeros((1, 5, ldb), dtype=torch.float64)]
+        for v in vals:
+            v[..., :n_members] = torch.rand(v.shape[:-1] + (n_members,), generator=gen, dtype=torch.float64)
+        state = _FakeState(vals, n_members)
+        want = _FakeState([v.clone() for v in vals], n_members).comp_fcn(None, None)
+        got = D.sharded_comp_fcn(state)
+        for g, w in zip(got.tracer_modules, want.tracer_modules):
+            assert torch.equal(g.vals[..., :n_members], w.vals[..., :n_members])
+            assert torch.count_nonzero(g.vals[..., n_members:]) == 0
+        open(os.path.join(tmpdir, f"ok_{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_members", [(2, 7), (2, 1), (3, 8)])
+def test_sharded_comp_fcn_gloo(tmp_path, world, n_members):
+    """every rank evaluates only its member block; the gathered result equals the unsharded one bit
+    for bit, also when a rank owns no member (world 2, one member)"""
+    port = _free_port()
+    mp.spawn(_worker_sharded, args=(world, port, n_members, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert (tmp_path / f"ok_{r}").exists()
+
+
+def test_sharded_comp_fcn_without_process_group_is_plain_comp_fcn():
+    from nk_ooc_b200 import distributed as D
+
+    v = torch.rand((1, 3, 4), dtype=torch.float64)
+    state = _FakeState([v], 4)
+    got = D.sharded_comp_fcn(state)
+    assert torch.equal(got.tracer_modules[0].vals, state.comp_fcn(None, None).tracer_modules[0].vals)

@@ -136,3 +136,157 @@ def test_limiter_scalef_matches_oracle(B):
     bad[0, 1, 1, 0] = -1.0
     with pytest.raises(ValueError):
         rw.limiter_scalef(_dev(bad), _dev(inc), 0.0, None, B)
+
+
+# ---- wide batches (two-members-per-lane kernels) and the windowed banded solver -------------------
+@pytest.mark.parametrize("B", [64, 101, 256])
+@pytest.mark.parametrize("regions", ["one", "columns", "masked"])
+def test_wide_batch_wdot_axpby_limiter_match_narrow_path(B, regions):
+    """B >= 64 takes the vectorised kernels: compared with the oracle (dot, mean, axpby, limiter) on
+    ragged member counts (odd B: the second member of the last lane pair does not exist)"""
+    from oracle import nk_oracle as o
+    from nk_ooc_b200 import engine
+
+    rng = np.random.default_rng(B)
+    nz, ny, T = 21, 13, 2  # 273 cells: not a multiple of the cells per warp
+    wgt = np.outer(rng.uniform(1, 5, nz), rng.uniform(1, 2, ny))
+    if regions == "one":
+        mask = np.ones((nz, ny), dtype=np.int32)
+    elif regions == "columns":
+        mask = o.column_region_mask(nz, ny, 0.0, 0.0)
+    else:
+        mask = rng.integers(0, 4, size=(nz, ny)).astype(np.int32)
+    w = o.region_weights(mask, wgt)
+    rw = engine.RegionWeights(mask, wgt)
+    R = rw.region_cnt
+    a = rng.normal(size=(T, nz, ny, B))
+    b = rng.normal(size=(T, nz, ny, B))
+    got = rw.dot(_dev(a), _dev(b), B).cpu().numpy()
+    want = np.stack([o.dot_prod(w, a[..., i], b[..., i]) for i in range(B)], axis=-1)
+    np.testing.assert_allclose(got, want, rtol=1e-13, atol=1e-15)
+    got = rw.dot(_dev(a), None, B).cpu().numpy()
+    want = np.stack([o.mean(w, a[..., i]) for i in range(B)], axis=-1)
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-15)
+    # axpby with per-(region, member) scalars, with x = None and with beta = 0 over NaN
+    alpha, beta = rng.normal(size=(R, B)), rng.normal(size=(R, B))
+    yd = _dev(b)
+    rw.axpby(torch.from_numpy(alpha).cuda(), _dev(a), torch.from_numpy(beta).cuda(), yd, B)
+    want = np.empty_like(b)
+    for i in range(B):
+        al, be = o.broadcast_region_vals(mask, alpha[:, i]), o.broadcast_region_vals(mask, beta[:, i])
+        want[..., i] = al * a[..., i] + be * b[..., i]
+    # (the kernel fuses be*y + (al*x) into one fma: differences of one rounding, amplified where the two
+    # terms cancel)
+    np.testing.assert_allclose(yd.cpu().numpy()[..., :B], want, rtol=1e-12, atol=1e-15)
+    yd = _dev(b)
+    rw.axpby(None, None, torch.from_numpy(beta).cuda(), yd, B)
+    for i in range(B):
+        want[..., i] = o.broadcast_region_vals(mask, beta[:, i]) * b[..., i]
+    np.testing.assert_allclose(yd.cpu().numpy()[..., :B], want, rtol=1e-14, atol=0)
+    yd = torch.full_like(_dev(b), float("nan"))
+    rw.axpby(2.0, _dev(a), 0.0, yd, B)
+    np.testing.assert_array_equal(yd.cpu().numpy()[..., :B], 2.0 * a)
+    # limiter
+    base = rng.random(size=(T, nz, ny, B)) + 0.05
+    inc = rng.normal(size=(T, nz, ny, B))
+    got = rw.limiter_scalef(_dev(base), _dev(inc), 0.0, None, B).cpu().numpy()
+    for i in range(0, B, 7):
+        want = np.minimum.reduce([o.comp_scalef_lob(R, mask, base[t, ..., i], inc[t, ..., i], 0.0) for t in range(T)])
+        np.testing.assert_array_equal(np.minimum(got[:, i], 1.0), want)
+    bad = base.copy()
+    bad[1, 3, 3, B - 1] = -1.0
+    if mask[3, 3] > 0:
+        with pytest.raises(ValueError):
+            rw.limiter_scalef(_dev(bad), _dev(inc), 0.0, None, B)
+
+
+@pytest.mark.parametrize("n,kl,ku,B", [(900, 90, 90, 1), (900, 90, 90, 5), (400, 61, 33, 40), (2000, 1, 1, 130),
+                                       (300, 2, 5, 33), (64, 63, 63, 3)])
+def test_banded_window_solver(n, kl, ku, B):
+    """the shared-memory window kernel: wide bands with one right-hand side (band-parallel), narrow
+    bands with many (member-parallel), pivoting, scale/subtract epilogue, in place"""
+    from scipy import linalg
+    from nk_ooc_b200 import engine
+
+    rng = np.random.default_rng(n + kl)
+    ab = rng.normal(size=(kl + ku + 1, n))
+    ab[ku] += 0.5 * np.sqrt(kl + ku)
+    y = rng.normal(size=(n, B))
+    want = linalg.solve_banded((kl, ku), ab, y)
+    f = engine.BandedFactor(ab, kl, ku)
+    assert f.n_blocks == 1
+    tol = 1e-9 * np.abs(want).max()
+    got = f.solve(_dev(y), B).cpu().numpy()[:, :B]
+    np.testing.assert_allclose(got, want, rtol=0, atol=tol)
+    got = f.solve(_dev(y), B, scale=0.25, subtract_rhs=True).cpu().numpy()[:, :B]
+    np.testing.assert_allclose(got, 0.25 * want - y, rtol=0, atol=tol)
+    yd = _dev(y)
+    ldb = yd.shape[-1]
+    engine.check(f.lib.nkb_banded_solve(f.handle, yd.data_ptr(), yd.data_ptr(), B, ldb, 1.0, 0, None), "in place")
+    np.testing.assert_allclose(yd.cpu().numpy()[:, :B], want, rtol=0, atol=tol)
+
+
+@pytest.mark.parametrize("kl,ku", [(1, 1), (2, 1), (1, 3), (4, 4)])
+@pytest.mark.parametrize("n", [7, 125, 700])
+def test_banded_thomas_kernel_narrow_bands(n, kl, ku):
+    """diagonally dominant narrow bands are factored without row interchanges and take the batched
+    Thomas kernel (B >= 16; z in shared memory up to 256 rows, through the output buffer beyond);
+    compared with scipy and with the window kernel on the same factor"""
+    from scipy import linalg
+    from nk_ooc_b200 import engine
+
+    rng = np.random.default_rng(n * 10 + kl)
+    ab = rng.normal(size=(kl + ku + 1, n))
+    ab[ku] = 6.0 + rng.random(n)
+    B = 45
+    y = rng.normal(size=(n, B))
+    want = linalg.solve_banded((kl, ku), ab, y)
+    f = engine.BandedFactor(ab, kl, ku)
+    tol = 1e-12 * np.abs(want).max()
+    got = f.solve(_dev(y), B).cpu().numpy()[:, :B]
+    np.testing.assert_allclose(got, want, rtol=0, atol=tol)
+    got = f.solve(_dev(y), B, scale=3.0, subtract_rhs=True).cpu().numpy()[:, :B]
+    np.testing.assert_allclose(got, 3.0 * want - y, rtol=0, atol=10 * tol)
+    yd = _dev(y)
+    engine.check(f.lib.nkb_banded_solve(f.handle, yd.data_ptr(), yd.data_ptr(), B, yd.shape[-1], 1.0, 0, None), "in place")
+    np.testing.assert_allclose(yd.cpu().numpy()[:, :B], want, rtol=0, atol=tol)
+    got1 = f.solve(_dev(y[:, :3]), 3, scale=3.0, subtract_rhs=True).cpu().numpy()[:, :3]  # B < 16: window kernel
+    np.testing.assert_allclose(got1, 3.0 * want[:, :3] - y[:, :3], rtol=0, atol=10 * tol)
+
+
+@pytest.mark.parametrize("B", [1, 70])
+def test_banded_block_diagonal_systems_are_found_and_solved(B):
+    """per-column tridiagonal systems stored as ONE band (grid without lateral processes): the blocks
+    are detected, factored and solved in parallel; ragged block sizes; a wider block-diagonal band"""
+    from scipy import linalg
+    from nk_ooc_b200 import engine
+
+    rng = np.random.default_rng(3)
+    sizes = [20, 1, 33, 20, 7]
+    n = sum(sizes)
+    ab = rng.normal(size=(3, n))
+    ab[1] += 3.0
+    edge = np.cumsum(sizes)[:-1]
+    ab[0, edge] = 0.0      # A(edge-1, edge)
+    ab[2, edge - 1] = 0.0  # A(edge, edge-1)
+    f = engine.BandedFactor(ab, 1, 1)
+    assert f.n_blocks == len(sizes)
+    y = rng.normal(size=(n, B))
+    want = linalg.solve_banded((1, 1), ab, y)
+    got = f.solve(_dev(y), B, scale=2.0, subtract_rhs=True).cpu().numpy()[:, :B]
+    np.testing.assert_allclose(got, 2.0 * want - y, rtol=0, atol=1e-11 * np.abs(want).max())
+    # dense diagonal blocks of size 12 inside a band of half-width 11
+    nb, m = 9, 12
+    dense = np.zeros((nb * m, nb * m))
+    for i in range(nb):
+        dense[i * m:(i + 1) * m, i * m:(i + 1) * m] = rng.normal(size=(m, m)) + 4.0 * np.eye(m)
+    kl = ku = m - 1
+    ab = np.zeros((kl + ku + 1, nb * m))
+    r, c = np.nonzero(dense)
+    ab[ku + r - c, c] = dense[r, c]
+    f = engine.BandedFactor(ab, kl, ku)
+    assert f.n_blocks == nb
+    y = rng.normal(size=(nb * m, B))
+    want = np.linalg.solve(dense, y)
+    got = f.solve(_dev(y), B).cpu().numpy()[:, :B]
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-10 * np.abs(want).max())
