@@ -228,7 +228,7 @@ static int ensure_fused_tables(nkb_model *m) {
         if (nkb::launch_step_ctab(v, ns, d_t + 2 * s0, d_hg + 2 * s0, d_te + 2 * s0, m->ctab + (size_t)s0 * per_step, 0))
             return 1;
     }
-    if (nkb::fused_encode_ctab_map(v.nz, v.ny, (size_t)n_steps * v.n_classes * 8, m->ctab, &m->map_ctab)) return 1;
+    if (nkb::fused_encode_ctab_map(v.nz, v.ny, (size_t)n_steps * v.n_classes * 8, m->ctab, &m->map_ctab, v.kind)) return 1;
     NKB_CUDA(cudaDeviceSynchronize());
     cudaFree(d_t); cudaFree(d_hg); cudaFree(d_te);
     return 0;
@@ -357,7 +357,7 @@ int nkb_model_eval(nkb_model *m, const double *d_x0, double *d_f, double *d_work
         if (nkb::fused_encode_state_maps(v, B, ldb, d_f, &fm.in_f, &fm.out_f)) return 1;
         if (nkb::fused_encode_state_maps(v, B, ldb, w_alt, &fm.in_w, &fm.out_w)) return 1;
         // encoded per evaluation: the box shape follows the thread layout in use (NKB_FUSED_MPT)
-        if (nkb::fused_encode_ctab_map(v.nz, v.ny, (size_t)S * v.n_classes * 8, m->ctab, &fm.ctab)) return 1;
+        if (nkb::fused_encode_ctab_map(v.nz, v.ny, (size_t)S * v.n_classes * 8, m->ctab, &fm.ctab, v.kind)) return 1;
         bool persist = nkb::fused_persistent();
         int n = 0;
         while (n < S) {

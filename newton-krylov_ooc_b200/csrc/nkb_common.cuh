@@ -119,7 +119,7 @@ int launch_step_ctab(const ModelDev &m, int n_steps, const double *d_t, const do
 // fused step kernel (nkb_step_fused.cu)
 bool fused_step_usable(const ModelDev &v, int B, int ldb, const double *x0, const double *f, const double *work);
 int fused_encode_state_maps(const ModelDev &v, int B, int ldb, const double *buf, CUtensorMap *in, CUtensorMap *out);
-int fused_encode_ctab_map(int nz, int ny, size_t nplanes, const double *buf, CUtensorMap *map);
+int fused_encode_ctab_map(int nz, int ny, size_t nplanes, const double *buf, CUtensorMap *map, int kind);
 struct FusedMaps {
     CUtensorMap in_x0, in_f, in_w, out_f, out_w, ctab;
 };

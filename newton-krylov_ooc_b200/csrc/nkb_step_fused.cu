@@ -81,6 +81,7 @@ struct StepArgs {
     double src_const[NKB_MAX_TRACERS];
     double sink_thres_r;
     double r, a0r;             // P = r*rhs1 + a0r*u_n (see launch_steps_fused)
+    double p3_hs, p3_sigma, p3_rd, p3_rp;  // phosphorus: half saturation, dop fraction, remineralisation rates
     const double *h;           // [n_steps] step sizes
     const double *aff;         // [2*n_steps][ncls][ny]: gamma*h*(affine surface source) of every stage
     int *done;                 // [ntiles] number of time steps completed for the tile (inter-CTA dependencies)
@@ -766,6 +767,462 @@ __global__ void __launch_bounds__(fs_cfg(MPT).threads, 1) step_fused_kernel(cons
     }
 }
 
+// ---- phosphorus (py_driver_2d/phosphorus.py:58-95): three coupled tracers per tile ------------------
+// The explicit sources couple po4, dop and pop cell by cell, so the three tracers of a (column, member)
+// pair must be resident together and the tensor-memory scratch holds 3 x 125 levels per pair: a tile is
+// 4 members x 14 interior columns x all levels x 3 tracers (rows of 4 members = 32 bytes, 32-byte TMA
+// swizzle), six consumer warps = 3 tracers x 2 member pairs, lane = 2*column + (member & 1) as above.
+// Sweep A reads the other two tracers' centre values from their state boxes of the same ring slot;
+// in sweep B the three warps that share a member pair exchange the stage-1 solution of a chunk through
+// a double-buffered shared-memory block and a named barrier before the stage-2 right-hand side.
+constexpr int P3_MEM = 4, P3_T = 3, P3_KC = 8, P3_NCW = 6, P3_NS = 5, P3_NO = 2, P3_NCLS = 2;
+constexpr int P3_UBOX = P3_KC * FS_UCOLS * P3_MEM * 8;            // 4608
+constexpr int P3_PP = P3_KC * FS_COLS * 16;                       // bytes of one pair plane (2048)
+constexpr int P3_SLOT = P3_T * P3_UBOX + P3_NCLS * 4 * P3_PP;     // 30208
+constexpr int P3_OBOX = P3_KC * FS_JT * P3_MEM * 8;               // 3584
+constexpr int P3_OUT = P3_T * P3_OBOX;
+constexpr int P3_EX = 2 * P3_T * P3_KC * 64 * 8;                  // u1 exchange, two chunks deep
+constexpr int P3_SMEM = 1024 + P3_NS * P3_SLOT + P3_NO * P3_OUT + P3_EX;
+constexpr int P3_THREADS = (P3_NCW + 2) * 32;
+static_assert(P3_UBOX % 256 == 0 && P3_SLOT % 256 == 0 && P3_OBOX % 256 == 0 && P3_OUT % 256 == 0,
+              "32-byte-swizzled boxes need 256-byte aligned bases");
+static_assert(P3_SMEM <= 227 * 1024, "shared memory");
+
+// explicit source of tracer TR times the stage weight: fw = w * max_uptake_rate * light, wrd = w * dop
+// remineralisation rate, wrp = w * pop remineralisation rate (phosphorus.py:75-95)
+__device__ __forceinline__ double p3_source(int tr, double fw, double wrd, double wrp, double hs, double sg, double po4,
+                                            double dop, double pop) {
+    const double u = fw * (po4 / (po4 + hs));
+    const double d = wrd * dop, q = wrp * pop;
+    if (tr == 0) return (d + q) - u;
+    if (tr == 1) return fma(sg, u, -d);
+    return fma(1.0 - sg, u, -q);
+}
+
+__global__ void __launch_bounds__(P3_THREADS, 1) step_fused_p3_kernel(const StepArgs p,
+                                                                      const __grid_constant__ StepMaps maps) {
+    constexpr int KC = P3_KC, NCW = P3_NCW, NS = P3_NS, NO = P3_NO;
+    constexpr int W = KC * 2;  // TMEM columns per chunk and thread
+    extern __shared__ __align__(1024) unsigned char fs_smem[];
+    const uint32_t smem0 = fs_smem_u32(fs_smem);
+    if (smem0 & 1023u) __trap();
+    const uint32_t bar_full = smem0, bar_empty = smem0 + 8 * NS, bar_ofull = smem0 + 16 * NS,
+                   bar_oempty = smem0 + 16 * NS + 8 * NO;
+    uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(fs_smem + 960);
+    unsigned char *ring = fs_smem + 1024;
+    unsigned char *oring = ring + NS * P3_SLOT;
+    double *exch = reinterpret_cast<double *>(oring + NO * P3_OUT);
+    const uint32_t ring_a = smem0 + 1024, oring_a = ring_a + NS * P3_SLOT;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NS; ++s) {
+            fs_mbar_init(bar_full + 8 * s, 1);
+            fs_mbar_init(bar_empty + 8 * s, NCW);
+        }
+        for (int s = 0; s < NO; ++s) {
+            fs_mbar_init(bar_ofull + 8 * s, NCW);
+            fs_mbar_init(bar_oempty + 8 * s, 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(
+                         fs_smem_u32(tmem_holder))
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(tmem_holder);
+
+    const int nz = p.nz, ny = p.ny;
+    const int nchunk = (nz + KC - 1) / KC;
+
+    struct Item {
+        int n, tile;
+    };
+    auto item_first = [&](int n) { return (int)((blockIdx.x + (unsigned)n * (unsigned)p.rot) % gridDim.x); };
+    auto item_valid = [&](const Item &it) { return it.n < p.step1; };
+    auto item_next = [&](const Item &it) {
+        Item nx = {it.n, it.tile + (int)gridDim.x};
+        if (nx.tile >= p.ntiles) {
+            nx.n = it.n + 1;
+            nx.tile = item_first(nx.n);
+        }
+        return nx;
+    };
+    auto item_depends = [&](const Item &nx, const Item &it) {
+        if (nx.n == it.n) return false;
+        if (!p.cross_step_fuse) return true;
+        const int d = nx.tile - it.tile;
+        return d == 0 || d == p.nmb || d == -p.nmb;
+    };
+    Item it0 = {p.step0, item_first(p.step0)};
+    if (it0.tile >= p.ntiles) it0.n = p.step1;
+
+    if (warp == NCW) {
+        // ===== producer =====
+        if (lane == 0) {
+            uint32_t g = 0;
+            struct TileP {
+                const CUtensorMap *uin;
+                int m0, j0, ct, zt;
+            };
+            auto tile_p = [&](const Item &it) {
+                TileP t;
+                const bool to_f = (((p.n_steps - 1 - it.n) & 1) == 0);
+                t.uin = (it.n == 0) ? &maps.in_x0 : (to_f ? &maps.in_w : &maps.in_f);
+                t.ct = it.tile / p.nmb;
+                t.m0 = (it.tile % p.nmb) * P3_MEM;
+                t.j0 = t.ct * p.jt;
+                t.zt = it.n * P3_NCLS * 8;
+                return t;
+            };
+            auto dep_wait = [&](const Item &it, const TileP &t) {
+                if (it.n > 0) {
+                    fs_wait_done(p.done + it.tile, it.n, p.err);
+                    if (t.ct > 0) fs_wait_done(p.done + it.tile - p.nmb, it.n, p.err);
+                    if (t.ct + 1 < p.nct) fs_wait_done(p.done + it.tile + p.nmb, it.n, p.err);
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                }
+            };
+            auto issue = [&](int sweep, const TileP &ta, const TileP &tc) {
+                for (int cc = 0; cc < nchunk; ++cc) {
+                    const int c = (sweep == 1) ? nchunk - 1 - cc : cc;
+                    const int k0 = c * KC;
+                    const uint32_t s = g % NS, ph = (g / NS) & 1;
+                    fs_mbar_wait<2000>(bar_empty + 8 * s, ph ^ 1);
+                    const uint32_t sb = ring_a + s * P3_SLOT;
+                    const uint32_t pl = sb + P3_T * P3_UBOX;
+                    const uint32_t fb = bar_full + 8 * s;
+                    if (sweep == 0 || sweep == 3) {
+                        fs_mbar_expect_tx(fb, P3_T * P3_UBOX + P3_NCLS * (3 + (sweep == 3 ? 1 : 0)) * P3_PP);
+#pragma unroll
+                        for (int t = 0; t < P3_T; ++t)
+                            fs_tma_load_4d(sb + t * P3_UBOX, ta.uin, fb, ta.m0, ta.j0 - 2, k0, t, kEvictNormal);
+#pragma unroll
+                        for (int cl = 0; cl < P3_NCLS; ++cl) {
+#pragma unroll
+                            for (int q = 0; q < 3; ++q)
+                                fs_tma_load_3d(pl + (cl * 4 + q) * P3_PP, &maps.ctab, fb, 2 * ta.j0, k0, ta.zt + cl * 8 + q,
+                                               kEvictLast);
+                            if (sweep == 3)
+                                fs_tma_load_3d(pl + (cl * 4 + 3) * P3_PP, &maps.ctab, fb, 2 * tc.j0, k0, tc.zt + cl * 8 + 7,
+                                               kEvictLast);
+                        }
+                    } else if (sweep == 1) {
+                        fs_mbar_expect_tx(fb, P3_T * P3_UBOX + P3_NCLS * 4 * P3_PP);
+#pragma unroll
+                        for (int t = 0; t < P3_T; ++t)
+                            fs_tma_load_4d(sb + t * P3_UBOX, ta.uin, fb, ta.m0, ta.j0 - 2, k0, t, kEvictFirst);
+#pragma unroll
+                        for (int cl = 0; cl < P3_NCLS; ++cl)
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                fs_tma_load_3d(pl + (cl * 4 + q) * P3_PP, &maps.ctab, fb, 2 * ta.j0, k0,
+                                               ta.zt + cl * 8 + 3 + q, kEvictLast);
+                    } else {
+                        fs_mbar_expect_tx(fb, P3_NCLS * P3_PP);
+#pragma unroll
+                        for (int cl = 0; cl < P3_NCLS; ++cl)
+                            fs_tma_load_3d(pl + (cl * 4 + 3) * P3_PP, &maps.ctab, fb, 2 * tc.j0, k0, tc.zt + cl * 8 + 7,
+                                           kEvictLast);
+                    }
+                    ++g;
+                }
+            };
+            Item it = it0;
+            if (item_valid(it)) {
+                TileP t = tile_p(it);
+                dep_wait(it, t);
+                issue(0, t, t);
+                while (true) {
+                    issue(1, t, t);
+                    const Item nx = item_next(it);
+                    if (!item_valid(nx)) {
+                        issue(2, t, t);
+                        break;
+                    }
+                    const TileP tn = tile_p(nx);
+                    if (!item_depends(nx, it)) {
+                        dep_wait(nx, tn);
+                        issue(3, tn, t);
+                    } else {
+                        issue(2, t, t);
+                        dep_wait(nx, tn);
+                        issue(0, tn, tn);
+                    }
+                    it = nx;
+                    t = tn;
+                }
+            }
+        }
+    } else if (warp == NCW + 1) {
+        // ===== store warp =====
+        if (lane == 0) {
+            uint32_t go = 0;
+            for (Item it = it0; item_valid(it); it = item_next(it)) {
+                const bool to_f = (((p.n_steps - 1 - it.n) & 1) == 0);
+                const CUtensorMap *uout = to_f ? &maps.out_f : &maps.out_w;
+                const int mb = it.tile % p.nmb, ct = it.tile / p.nmb;
+                for (int c = 0; c < nchunk; ++c) {
+                    const uint32_t s = go % NO, ph = (go / NO) & 1;
+                    fs_mbar_wait<2000>(bar_ofull + 8 * s, ph);
+#pragma unroll
+                    for (int t = 0; t < P3_T; ++t)
+                        fs_tma_store_4d(uout, oring_a + s * P3_OUT + t * P3_OBOX, mb * P3_MEM, ct * p.jt, c * KC, t);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    fs_mbar_arrive(bar_oempty + 8 * s);
+                    ++go;
+                }
+                asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                asm volatile("fence.proxy.async;" ::: "memory");
+                __threadfence();
+                asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.done + it.tile), "r"(it.n + 1) : "memory");
+            }
+        }
+    } else {
+        // ===== consumers: warp = (tracer, member pair) =====
+        constexpr int PP = KC * FS_COLS;  // pairs per plane
+        const int tr = warp >> 1, pr = warp & 1;
+        const int t1 = (tr + 1) % 3, t2 = (tr + 2) % 3;
+        const int cls = p.class_of[tr];
+        const int col = lane >> 1;
+        const int sub = 8 * (lane & 1);
+        const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 256);
+        int offU[KC][3], offO[KC];
+#pragma unroll
+        for (int q = 0; q < KC; ++q) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                const int r = q * FS_UCOLS + col + d;
+                offU[q][d] = 32 * r + 16 * (pr ^ ((r >> 2) & 1)) + sub;
+            }
+            const int ro = q * p.jt + col - 1;
+            offO[q] = 32 * ro + 16 * (pr ^ ((ro >> 2) & 1)) + sub;
+        }
+        const bool interior = (col >= 1 && col <= p.jt);
+        const double hs = p.p3_hs, sg = p.p3_sigma;
+        const int exl = pr * 32 + lane;  // this thread's slot in a [tracer][level] row of the exchange block
+        uint32_t g = 0, go = 0, gx = 0;
+        // po4, dop, pop from {own value, value of tracer t1, value of tracer t2}
+        auto po4_of = [&](double own, double o1, double o2) { return tr == 0 ? own : (tr == 1 ? o2 : o1); };
+        auto dop_of = [&](double own, double o1, double o2) { return tr == 1 ? own : (tr == 2 ? o2 : o1); };
+        auto pop_of = [&](double own, double o1, double o2) { return tr == 2 ? own : (tr == 0 ? o2 : o1); };
+
+        struct TileC {
+            double aff1, aff2, wrd1, wrp1, wrd2, wrp2;
+        };
+        auto tile_c = [&](const Item &it) {
+            TileC t;
+            const double hstep = __ldg(p.h + it.n);
+            const double *aff_n = p.aff + (size_t)(2 * it.n) * p.ncls * ny;
+            const int ct = it.tile / p.nmb;
+            const int j = ct * p.jt - 1 + col;
+            t.aff1 = t.aff2 = 0.0;
+            if (j >= 0 && j < ny) {
+                t.aff1 = __ldg(aff_n + (size_t)cls * ny + j);
+                t.aff2 = __ldg(aff_n + (size_t)(p.ncls + cls) * ny + j);
+            }
+            const double w1 = kGamma * hstep, w2 = hstep * (1.0 - kDelta);
+            t.wrd1 = w1 * p.p3_rd; t.wrp1 = w1 * p.p3_rp;
+            t.wrd2 = w2 * p.p3_rd; t.wrp2 = w2 * p.p3_rp;
+            return t;
+        };
+
+        auto chunk_a = [&](const TileC &t, const unsigned char *sb, int c, double &yprev, Raw<W> &raw) {
+            const double2 *pl = reinterpret_cast<const double2 *>(sb + P3_T * P3_UBOX + cls * 4 * P3_PP) + col;
+            const unsigned char *ub = sb + tr * P3_UBOX, *u1b = sb + t1 * P3_UBOX, *u2b = sb + t2 * P3_UBOX;
+            Vd<1> yb[KC];
+#pragma unroll
+            for (int q = 0; q < KC; ++q) {
+                const double cv = *reinterpret_cast<const double *>(ub + offU[q][1]);
+                const double cl = *reinterpret_cast<const double *>(ub + offU[q][0]);
+                const double cr = *reinterpret_cast<const double *>(ub + offU[q][2]);
+                const double o1 = *reinterpret_cast<const double *>(u1b + offU[q][1]);
+                const double o2 = *reinterpret_cast<const double *>(u2b + offU[q][1]);
+                const double2 lc = pl[q * FS_COLS], rm = pl[PP + q * FS_COLS];
+                const double fw = pl[2 * PP + q * FS_COLS].x;
+                const double sv = p3_source(tr, fw, t.wrd1, t.wrp1, hs, sg, po4_of(cv, o1, o2), dop_of(cv, o1, o2),
+                                            pop_of(cv, o1, o2));
+                double rhs = fma(lc.x, cl, fma(rm.x, cr, fma(lc.y, cv, sv)));
+                if (c == 0 && q == 0) rhs += t.aff1;
+                yprev = fma(-rm.y, yprev, rhs);
+                yb[q].v[0] = yprev;
+            }
+            fs_pack<1, KC>(yb, raw);
+        };
+        auto chunk_c = [&](const unsigned char *sb, unsigned char *ob, const Raw<W> &cur, double &u2p) {
+            const double2 *pl = reinterpret_cast<const double2 *>(sb + P3_T * P3_UBOX + cls * 4 * P3_PP) + col;
+            Vd<1> ycur[KC];
+            double u2[KC];
+            fs_unpack<1, KC>(cur, ycur);
+            double2 ig[KC];
+#pragma unroll
+            for (int q = 0; q < KC; ++q) ig[q] = pl[3 * PP + q * FS_COLS];
+#pragma unroll
+            for (int q = 0; q < KC; ++q) {
+                u2p = fma(-ig[q].y, u2p, ig[q].x * ycur[q].v[0]);
+                u2[q] = u2p;
+            }
+            if (interior) {
+#pragma unroll
+                for (int q = 0; q < KC; ++q) *reinterpret_cast<double *>(ob + tr * P3_OBOX + offO[q]) = u2[q];
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        };
+
+        auto sweep_a = [&](const TileC &t) {
+            double yprev = 0.0;
+            for (int c = 0; c < nchunk; ++c) {
+                const uint32_t s = g % NS, ph = (g / NS) & 1;
+                fs_mbar_wait<20>(bar_full + 8 * s, ph);
+                Raw<W> raw;
+                chunk_a(t, ring + s * P3_SLOT, c, yprev, raw);
+                __syncwarp();
+                if (lane == 0) fs_mbar_arrive(bar_empty + 8 * s);
+                fs_tmem_st(taddr + c * W, raw);
+                ++g;
+            }
+            fs_tmem_wait_st();
+        };
+
+        auto sweep_b = [&](const TileC &t) {
+            Raw<W> ra, rb;
+            double u1n = 0.0, y2n = 0.0;
+            auto chunk_b = [&](Raw<W> &cur, Raw<W> &nxt, int c) {
+                if (c > 0) fs_tmem_ld(taddr + (c - 1) * W, nxt);
+                const uint32_t s = g % NS, ph = (g / NS) & 1;
+                fs_mbar_wait<20>(bar_full + 8 * s, ph);
+                Vd<1> ycur[KC];
+                fs_unpack<1, KC>(cur, ycur);
+                const unsigned char *sb = ring + s * P3_SLOT;
+                const double2 *pl = reinterpret_cast<const double2 *>(sb + P3_T * P3_UBOX + cls * 4 * P3_PP) + col;
+                // stage-1 back substitution of the chunk, published to the two other tracers' warps
+                double *ex = exch + (size_t)(gx & 1) * (P3_T * KC * 64);
+                double u1v[KC];
+#pragma unroll
+                for (int q = KC - 1; q >= 0; --q) {
+                    const double2 ri = pl[PP + q * FS_COLS], gm = pl[2 * PP + q * FS_COLS];
+                    u1n = fma(-gm.x, u1n, ri.y * ycur[q].v[0]);
+                    u1v[q] = u1n;
+                    ex[(tr * KC + q) * 64 + exl] = u1n;
+                }
+                double y1top = 0.0;
+                if (c > 0) {
+                    fs_tmem_wait_ld(nxt);
+                    y1top = __hiloint2double((int)nxt.w[(KC - 1) * 2 + 1], (int)nxt.w[(KC - 1) * 2]);
+                }
+                asm volatile("bar.sync %0, 96;" ::"r"(1 + pr) : "memory");
+                Vd<1> yb[KC];
+#pragma unroll
+                for (int q = KC - 1; q >= 0; --q) {
+                    const double y1 = ycur[q].v[0];
+                    const double y1m = (q > 0) ? ycur[q > 0 ? q - 1 : 0].v[0] : y1top;
+                    const double2 lc = pl[q * FS_COLS], ri = pl[PP + q * FS_COLS], gm = pl[2 * PP + q * FS_COLS],
+                                  mf = pl[3 * PP + q * FS_COLS];
+                    const double u1 = u1v[q];
+                    const double o1 = ex[(t1 * KC + q) * 64 + exl], o2 = ex[(t2 * KC + q) * 64 + exl];
+                    double rhs1 = fma(gm.y, y1m, y1);
+                    if (c == 0 && q == 0) rhs1 -= t.aff1;
+                    const double un = *reinterpret_cast<const double *>(sb + tr * P3_UBOX + offU[q][1]);
+                    const double src = p3_source(tr, mf.y, t.wrd2, t.wrp2, hs, sg, po4_of(u1, o1, o2), dop_of(u1, o1, o2),
+                                                 pop_of(u1, o1, o2));
+                    const double pp = fma(p.r, rhs1, p.a0r * un) + src;
+                    const double ul = __shfl_up_sync(0xffffffffu, u1, 2, 32), ur = __shfl_down_sync(0xffffffffu, u1, 2, 32);
+                    double rhs2 = fma(lc.x, ul, fma(ri.x, ur, fma(lc.y, u1, pp)));
+                    if (c == 0 && q == 0) rhs2 += t.aff2;
+                    y2n = fma(-mf.x, y2n, rhs2);
+                    yb[q].v[0] = y2n;
+                }
+                __syncwarp();
+                if (lane == 0) fs_mbar_arrive(bar_empty + 8 * s);
+                Raw<W> raw;
+                fs_pack<1, KC>(yb, raw);
+                fs_tmem_st(taddr + c * W, raw);
+                ++g;
+                ++gx;
+            };
+            fs_tmem_ld(taddr + (nchunk - 1) * W, ra);
+            fs_tmem_wait_ld(ra);
+            int c = nchunk - 1;
+            for (; c >= 1; c -= 2) {
+                chunk_b(ra, rb, c);
+                chunk_b(rb, ra, c - 1);
+            }
+            if (c == 0) chunk_b(ra, rb, 0);
+            fs_tmem_wait_st();
+        };
+
+        auto sweep_c = [&](bool with_a, const TileC &ta) {
+            Raw<W> ra, rb;
+            double u2p = 0.0, yprev = 0.0;
+            auto chunk_ca = [&](Raw<W> &cur, Raw<W> &nxt, int c) {
+                if (c + 1 < nchunk) fs_tmem_ld(taddr + (c + 1) * W, nxt);
+                const uint32_t s = g % NS, ph = (g / NS) & 1;
+                const uint32_t so = go % NO, pho = (go / NO) & 1;
+                fs_mbar_wait<20>(bar_full + 8 * s, ph);
+                fs_mbar_wait<20>(bar_oempty + 8 * so, pho ^ 1);
+                const unsigned char *sb = ring + s * P3_SLOT;
+                chunk_c(sb, oring + so * P3_OUT, cur, u2p);
+                Raw<W> raw;
+                if (with_a) chunk_a(ta, sb, c, yprev, raw);
+                __syncwarp();
+                if (lane == 0) {
+                    fs_mbar_arrive(bar_empty + 8 * s);
+                    fs_mbar_arrive(bar_ofull + 8 * so);
+                }
+                if (with_a) fs_tmem_st(taddr + c * W, raw);
+                if (c + 1 < nchunk) fs_tmem_wait_ld(nxt);
+                ++g;
+                ++go;
+            };
+            fs_tmem_ld(taddr, ra);
+            fs_tmem_wait_ld(ra);
+            int c = 0;
+            for (; c + 1 < nchunk; c += 2) {
+                chunk_ca(ra, rb, c);
+                chunk_ca(rb, ra, c + 1);
+            }
+            if (c < nchunk) chunk_ca(ra, rb, c);
+            if (with_a) fs_tmem_wait_st();
+        };
+
+        Item it = it0;
+        if (item_valid(it)) {
+            TileC t = tile_c(it);
+            sweep_a(t);
+            while (true) {
+                sweep_b(t);
+                const Item nx = item_next(it);
+                if (!item_valid(nx)) {
+                    sweep_c(false, t);
+                    break;
+                }
+                const TileC tn = tile_c(nx);
+                if (!item_depends(nx, it)) {
+                    sweep_c(true, tn);
+                } else {
+                    sweep_c(false, t);
+                    sweep_a(tn);
+                }
+                it = nx;
+                t = tn;
+            }
+        }
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
 // out = out - x0 (the final F = x(T) - x(0), once per model year)
 __global__ void sub_inplace_kernel(double *__restrict__ out, const double *__restrict__ x0, size_t n2) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -836,7 +1293,11 @@ static void fs_col_tiles(int ny, int &nct, int &jt) {
 bool fused_step_usable(const ModelDev &v, int B, int ldb, const double *x0, const double *f, const double *work) {
     if (fs_env_int("NKB_FUSED", 1) == 0) return false;
     if (v.column_model == 1 && v.ny == 1) return false;
-    if (v.kind != NKB_MOD_LINEAR && v.kind != NKB_MOD_FORCED_FILE) return false;
+    if (v.kind == NKB_MOD_PHOSPHORUS) {
+        if (fs_env_int("NKB_FUSED_P3", 1) == 0 || v.T != P3_T || v.n_classes != P3_NCLS) return false;
+    } else if (v.kind != NKB_MOD_LINEAR && v.kind != NKB_MOD_FORCED_FILE) {
+        return false;
+    }
     if (v.nz > 128) return false;  // TMEM: 2 x 32-bit columns per level and member, 256 per thread
     if (B < fs_env_int("NKB_FUSED_MIN_B", 8) || (ldb % 2) != 0) return false;
     if (((uintptr_t)x0 | (uintptr_t)f | (uintptr_t)work) & 15) return false;
@@ -846,18 +1307,21 @@ bool fused_step_usable(const ModelDev &v, int B, int ldb, const double *x0, cons
 int fused_encode_state_maps(const ModelDev &v, int B, int ldb, const double *buf, CUtensorMap *in, CUtensorMap *out) {
     int nct, jt;
     fs_col_tiles(v.ny, nct, jt);
-    const cuuint32_t kc = (cuuint32_t)fs_cfg(fs_mpt()).kc;
+    const bool p3 = (v.kind == NKB_MOD_PHOSPHORUS);
+    const cuuint32_t kc = p3 ? (cuuint32_t)P3_KC : (cuuint32_t)fs_cfg(fs_mpt()).kc;
+    const cuuint32_t mem = p3 ? P3_MEM : FS_MEM;
+    const CUtensorMapSwizzle swz = p3 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B;
     // members beyond B are never read (zero-filled) nor written (clipped)
     const cuuint64_t dims[4] = {(cuuint64_t)B, (cuuint64_t)v.ny, (cuuint64_t)v.nz, (cuuint64_t)v.T};
     const cuuint64_t strides[3] = {(cuuint64_t)ldb * 8, (cuuint64_t)v.ny * ldb * 8, (cuuint64_t)v.nz * v.ny * ldb * 8};
-    const cuuint32_t box_in[4] = {FS_MEM, FS_UCOLS, kc, 1};
-    const cuuint32_t box_out[4] = {FS_MEM, (cuuint32_t)jt, kc, 1};
-    if (in && fs_encode(in, buf, 4, dims, strides, box_in, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
-    if (out && fs_encode(out, buf, 4, dims, strides, box_out, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+    const cuuint32_t box_in[4] = {mem, FS_UCOLS, kc, 1};
+    const cuuint32_t box_out[4] = {mem, (cuuint32_t)jt, kc, 1};
+    if (in && fs_encode(in, buf, 4, dims, strides, box_in, swz)) return 1;
+    if (out && fs_encode(out, buf, 4, dims, strides, box_out, swz)) return 1;
     return 0;
 }
 
-int fused_encode_ctab_map(int nz, int ny, size_t nplanes, const double *buf, CUtensorMap *map) {
+int fused_encode_ctab_map(int nz, int ny, size_t nplanes, const double *buf, CUtensorMap *map, int kind) {
     // rows of (ny + 1) coefficient pairs, one zero pair on the left: the box of a column tile starts at
     // column j0 - 1 = pair index j0, double index 2*j0 — always even.  TMA faults ("illegal
     // instruction") on a box whose innermost start address is not 16-byte aligned (an odd float64
@@ -865,7 +1329,8 @@ int fused_encode_ctab_map(int nz, int ny, size_t nplanes, const double *buf, CUt
     const cuuint64_t np = 2 * ((cuuint64_t)ny + 1);
     const cuuint64_t dims[3] = {np, (cuuint64_t)nz, (cuuint64_t)nplanes};
     const cuuint64_t strides[2] = {np * 8, (cuuint64_t)nz * np * 8};
-    const cuuint32_t box[3] = {2 * FS_COLS, (cuuint32_t)fs_cfg(fs_mpt()).kc, 1};
+    const cuuint32_t kc = (kind == NKB_MOD_PHOSPHORUS) ? (cuuint32_t)P3_KC : (cuuint32_t)fs_cfg(fs_mpt()).kc;
+    const cuuint32_t box[3] = {2 * FS_COLS, kc, 1};
     return fs_encode(map, buf, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
 }
 
@@ -906,8 +1371,10 @@ int launch_steps_fused(const ModelDev &v, int B, int n_steps, int step0, int ste
     std::memset(&a, 0, sizeof(a));
     a.nz = v.nz; a.ny = v.ny; a.B = B; a.T = v.T; a.ncls = v.n_classes; a.n_steps = n_steps;
     fs_col_tiles(v.ny, a.nct, a.jt);
-    a.nmb = (B + FS_MEM - 1) / FS_MEM;
-    a.ntiles = a.nmb * a.nct * v.T;
+    const bool p3 = (v.kind == NKB_MOD_PHOSPHORUS);
+    a.nmb = p3 ? (B + P3_MEM - 1) / P3_MEM : (B + FS_MEM - 1) / FS_MEM;
+    a.ntiles = p3 ? a.nmb * a.nct : a.nmb * a.nct * v.T;
+    a.p3_hs = v.po4_halfsat; a.p3_sigma = v.sigma; a.p3_rd = v.dop_remin_rate; a.p3_rp = v.pop_remin_rate;
     a.step0 = step0; a.step1 = step1;
     for (int t = 0; t < NKB_MAX_TRACERS; ++t) { a.class_of[t] = v.class_of[t]; a.src_const[t] = v.src_const[t]; }
     a.sink_thres_r = v.sink_thres > 0.0 ? 1.0 / v.sink_thres : 0.0;
@@ -934,6 +1401,32 @@ int launch_steps_fused(const ModelDev &v, int B, int n_steps, int step0, int ste
     a.rot = (step1 - step0 > 1) ? a.ntiles % grid : 0;
     a.cross_step_fuse = (a.ntiles > 2 * grid + a.nmb) ? 1 : 0;
     const bool coop = (step1 - step0 > 1);
+    if (p3) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            NKB_CUDA(cudaFuncSetAttribute(step_fused_p3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P3_SMEM));
+            attr_set = true;
+        }
+        cudaLaunchConfig_t cfg;
+        std::memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(P3_THREADS);
+        cfg.dynamicSmemBytes = P3_SMEM;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeCooperative;
+        attr[0].val.cooperative = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = coop ? 1 : 0;
+        const cudaError_t err = cudaLaunchKernelEx(&cfg, step_fused_p3_kernel, a, maps);
+        if (coop && err == cudaErrorCooperativeLaunchTooLarge) {
+            cudaGetLastError();
+            return -1;
+        }
+        NKB_CUDA(err);
+        count_launch();
+        return 0;
+    }
     const int mpt = fs_mpt();
     if (v.kind == NKB_MOD_LINEAR)
         return mpt == 2 ? fs_launch_m<NKB_MOD_LINEAR, 2>(a, maps, grid, coop, st)
@@ -950,6 +1443,7 @@ bool fused_persistent() { return fs_env_int("NKB_FUSED_PERSIST", 1) != 0; }
 int fused_tile_count(const ModelDev &v, int B) {
     int nct, jt;
     fs_col_tiles(v.ny, nct, jt);
+    if (v.kind == NKB_MOD_PHOSPHORUS) return ((B + P3_MEM - 1) / P3_MEM) * nct;
     return ((B + FS_MEM - 1) / FS_MEM) * nct * v.T;
 }
 

@@ -225,7 +225,11 @@ __global__ void step_ctab_kernel(ModelDev m, int n_steps, const double *__restri
                     base[0 * pl + 1] = 1.0 + hg * eC;
                     base[1 * pl + 0] = hg * eR;
                     base[1 * pl + 1] = mk;
-                    base[2 * pl + 0] = (m.kind == NKB_MOD_FORCED_FILE) ? hg * forcing_at(m, t_exp[2 * s], cell) : 0.0;
+                    // explicit source table times the stage weight: forcing record (forced.py:141-151) or
+                    // max_uptake_rate * light (phosphorus.py:75-78)
+                    base[2 * pl + 0] = (m.kind == NKB_MOD_FORCED_FILE) ? hg * forcing_at(m, t_exp[2 * s], cell)
+                                       : (m.kind == NKB_MOD_PHOSPHORUS) ? hg * m.max_uptake_rate * m.light[cell]
+                                                                        : 0.0;
                     base[2 * pl + 1] = 0.0;
                     base[3 * pl + 0] = he1 * eL;
                     base[3 * pl + 1] = a1 + he1 * eC;
@@ -239,8 +243,9 @@ __global__ void step_ctab_kernel(ModelDev m, int n_steps, const double *__restri
                     base[6 * pl + 0] = a;
                     base[7 * pl + 0] = b;
                     base[7 * pl + 1] = cc;
-                    base[6 * pl + 1] =
-                        (m.kind == NKB_MOD_FORCED_FILE) ? he1 * forcing_at(m, t_exp[2 * s + 1], cell) : 0.0;
+                    base[6 * pl + 1] = (m.kind == NKB_MOD_FORCED_FILE) ? he1 * forcing_at(m, t_exp[2 * s + 1], cell)
+                                       : (m.kind == NKB_MOD_PHOSPHORUS) ? he1 * m.max_uptake_rate * m.light[cell]
+                                                                        : 0.0;
                 }
             }
             mc_up = mc_dn;

@@ -28,7 +28,7 @@ import tempfile
 
 import numpy as np
 
-from . import distributed, model_state_base
+from . import distributed, model_state_base, solver_state
 
 
 def comp_krylov_basis_coeffs(beta, h_mat):
@@ -131,6 +131,7 @@ class KrylovSolver:
         self.h_mat = None
         self.precond_resid_norm = []
         os.makedirs(workdir, exist_ok=True)
+        self._state = self._stats = None
         self.precond_fname = self._fname("precond", 0)
         if precond is None:
             iterate.gen_precond_jacobian(hist_fname, self.precond_fname, solver_state=None)
@@ -162,8 +163,18 @@ class KrylovSolver:
         caller = f"{type(self).__name__}.solve"
         fn = self._fname if dump else (lambda *a, **k: None)
         # step 1 of alg. 9.4: r0 = -M^-1 fcn, beta = ||r0||, v0 = r0 / beta
+        if dump:
+            # Krylov_state.json (beta, h_mat as the reference saves them, krylov_solver.py:101,136) and
+            # Krylov_stats.nc in the Krylov work directory
+            cfg = type(self._iterate).model_config_obj
+            mods = [(tms.name, getattr(tms, "units", None)) for tms in self._iterate.tracer_modules]
+            self._state = solver_state.SolverState("Krylov", self._workdir)
+            self._stats = solver_state.StatsFile("Krylov", self._workdir, cfg.region_cnt, mods, solver_state.KRYLOV_VARS)
         precond_fcn = self._apply_precond(fcn, fn("precond_fcn"), caller)
         self.beta = precond_fcn.norm()
+        if self._stats is not None:
+            self._stats.put_invariant(precond_rhs_norm=self.beta)
+            self._state.set_value_saved_state("beta", np.asarray(self.beta))
         self.basis.append((-precond_fcn / self.beta).dump(fn("basis"), caller))
         n_mod, region_cnt = self.beta.shape[0], self.beta.shape[1]
         while True:
@@ -185,6 +196,10 @@ class KrylovSolver:
             precond_resid += precond_fcn
             resid_norm = precond_resid.norm()
             self.precond_resid_norm.append(resid_norm)
+            if self._stats is not None:
+                self._state.set_value_saved_state("h_mat", h_mat)
+                self._stats.put(j_val, precond_resid_norm=resid_norm)
+                self._state.inc_iteration()
             logger.info("Krylov iteration %d: precond_resid_norm/beta = %s", j_val, resid_norm / self.beta)
             self.iteration += 1
             if self.converged(resid_norm).all():
@@ -200,20 +215,48 @@ class NewtonSolver:
     """Newton's method with Armijo damping and post-Newton fixed-point iterations
     (newton_solver.py:22-334) on a device-resident iterate"""
 
-    def __init__(self, iterate, solverinfo, workdir=None, armijo_batch=1, dump=True, precond_factory=None):
+    def __init__(self, iterate, solverinfo, workdir=None, armijo_batch=1, dump=True, precond_factory=None,
+                 resume=False):
         """precond_factory: optional callable (iterate, fcn) -> preconditioner callable, called once per
-        Newton iteration (e.g. ProbePreconditioner)"""
+        Newton iteration (e.g. ProbePreconditioner).
+        With dump=True the work directory also receives the reference's Newton_state.json (iteration
+        counter + step log, solver_state.py) and Newton_stats.nc (stats_file.py); resume=True continues
+        from them: the iterate (and, if its evaluation had completed, fcn) of the logged iteration are
+        read back instead of recomputed (newton_solver.py:30-47,140-172)."""
         self._precond_factory = precond_factory
         self._info = dict(solverinfo)
         self._workdir = workdir or tempfile.mkdtemp(prefix="nkb200_newton_")
         os.makedirs(self._workdir, exist_ok=True)
         self._armijo_batch = int(armijo_batch)
         self._dump = dump
+        if resume and not dump:
+            raise ValueError("resume needs the files of a dumped solve")
         self.iteration = 0
-        self._iterate = iterate
+        self._state = solver_state.SolverState("Newton", self._workdir, resume=resume) if dump else None
+        self._stats = None
+        if dump:
+            cfg = type(iterate).model_config_obj
+            mods = [(tms.name, getattr(tms, "units", None)) for tms in iterate.tracer_modules]
+            self._stats = solver_state.StatsFile("Newton", self._workdir, cfg.region_cnt, mods,
+                                                 solver_state.NEWTON_VARS, resume=resume)
+            self.iteration = self._state.get_iteration()
         caller = f"{type(self).__name__}.__init__"
-        iterate.dump(self._fname("iterate") if dump else None, caller)
-        self._fcn = iterate.comp_fcn(self._fname("fcn") if dump else None, None, self._fname("hist"))
+        step0 = "Newton iterate 0 written"
+        if resume and self._state.step_logged(step0, per_iteration=False):
+            iterate = type(iterate)(self._fname("iterate"))
+        else:
+            iterate.dump(self._fname("iterate") if dump else None, caller)
+            if dump:
+                self._state.log_step(step0, per_iteration=False)
+        self._iterate = iterate
+        fcn_step = f"comp_fcn complete for {self._fname('fcn')}"
+        if resume and self._state.step_logged(fcn_step):
+            self._fcn = type(iterate)(self._fname("fcn"))
+        else:
+            self._fcn = iterate.comp_fcn(self._fname("fcn") if dump else None, None, self._fname("hist"))
+            if dump:
+                self._state.log_step(fcn_step)
+                self._stats.put(self.iteration, iterate=self._iterate, fcn=self._fcn)
         self.history = []  # per iteration: dict(fcn_norm, iterate_norm, krylov_iterations, armijo_factor, ...)
         self._record()
 
@@ -313,6 +356,15 @@ class NewtonSolver:
                 self.iteration += 1
                 prov.dump(self._fname("iterate") if self._dump else None, caller)
                 prov_fcn = prov.comp_fcn(self._fname("fcn") if self._dump else None, None, self._fname("hist"))
+        if self._dump:
+            # statistics of the iteration that ends here, then the new iteration's iterate / fcn
+            # (newton_solver.py:262-329; the iteration counter was advanced above)
+            prev = self.iteration - 1
+            self._stats.put(prev, increment=increment, Krylov_iterations=krylov.iteration,
+                            increment_scalef=scalef, Armijo_factor=armijo_factor)
+            self._state.inc_iteration()
+            self._state.log_step(f"comp_fcn complete for {self._fname('fcn')}")
+            self._stats.put(self.iteration, iterate=prov, fcn=prov_fcn)
         self._iterate, self._fcn = prov, prov_fcn
         self._record(krylov_iterations=krylov.iteration, krylov_precond_resid_norm=krylov.precond_resid_norm,
                      krylov_beta=krylov.beta, increment_scalef=scalef, armijo_factor=armijo_factor,

@@ -1,0 +1,250 @@
+"""Persistence of an iterative solver's progress and its statistics file.
+
+`SolverState` keeps the reference's `<name>_state.json` (nk_ooc/solver_state.py:14-146): the
+iteration counter, the log of completed steps ("NN:step" for per-iteration steps) and saved values
+(numpy arrays tagged `__ndarray__`), rewritten after every change so that an interrupted solve can
+be resumed (`resume=True`) or its last step redone (`rewind=True`).
+
+`StatsFile` writes `<name>_stats.nc` (nk_ooc/stats_file.py:13-139; variables defined by
+solver_base.py:71-125): NETCDF3 64-bit offset, unlimited `iteration` dimension, `region` dimension,
+per tracer module `{iterate,fcn,increment}_{mean,norm}_<module>`, `increment_scalef_<module>`,
+`Armijo_factor_<module>`, `Krylov_iterations` (Newton) and `precond_rhs_norm_<module>`,
+`precond_resid_norm_<module>` (Krylov).  The file is rewritten from an in-memory copy at every put
+(classic netCDF cannot be grown in place by scipy's writer); a resumed solve reloads it first.
+"""
+
+import json
+import os
+from datetime import datetime
+
+import numpy as np
+from scipy.io import netcdf_file
+
+FILL_F8 = 9.969209968386869e36  # netCDF4 default_fillvals["f8"]
+FILL_I4 = -2147483647
+
+
+class _NumpyEncoder(json.JSONEncoder):
+    def default(self, o):  # pylint: disable=method-hidden
+        if isinstance(o, np.ndarray):
+            return {"__ndarray__": o.tolist()}
+        if isinstance(o, (np.floating, np.integer)):
+            return o.item()
+        return json.JSONEncoder.default(self, o)
+
+
+def _decode(dct):
+    if "__ndarray__" in dct:
+        return np.asarray(dct["__ndarray__"])
+    return dct
+
+
+class SolverState:
+    """step log + saved values of one solver (solver_state.py:14-146)"""
+
+    def __init__(self, name, workdir, resume=False, rewind=False):
+        os.makedirs(workdir, exist_ok=True)
+        self._name = name
+        self._workdir = workdir
+        self._state_fname = os.path.join(workdir, f"{name}_state.json")
+        self._rewound_step_string = None
+        if resume:
+            self._read()
+            if rewind:
+                self._rewound_step_string = self._saved_state["step_log"].pop()
+        else:
+            if rewind:
+                raise RuntimeError(f"rewind cannot be True if resume is False, name={name}")
+            self._saved_state = {"iteration": 0, "step_log": []}
+            self.log_step("__init__", per_iteration=False)
+
+    def get_workdir(self):
+        return self._workdir
+
+    def get_iteration(self):
+        return self._saved_state["iteration"]
+
+    def inc_iteration(self):
+        self._saved_state["iteration"] += 1
+        self.log_step("inc_iteration")
+        return self._saved_state["iteration"]
+
+    def _step_log_string(self, stepval, per_iteration):
+        return f"{self.get_iteration():02}:{stepval}" if per_iteration else stepval
+
+    def log_step(self, stepval, per_iteration=True):
+        if not self.step_logged(stepval, per_iteration):
+            self._saved_state["step_log"].append(self._step_log_string(stepval, per_iteration))
+            self._write()
+
+    def step_logged(self, stepval, per_iteration=True):
+        return self._step_log_string(stepval, per_iteration) in self._saved_state["step_log"]
+
+    def step_was_rewound(self, stepval, per_iteration=True):
+        if self._rewound_step_string is None:
+            return False
+        return self._step_log_string(stepval, per_iteration) == self._rewound_step_string
+
+    def set_value_saved_state(self, key, value):
+        """store a value and confirm that it is read back exactly (solver_state.py:107-118)"""
+        self._saved_state[key] = value
+        self._write()
+        self._read()
+        back = self._saved_state[key]
+        same = np.array_equal(back, value) if isinstance(value, np.ndarray) else back == value
+        if not same:
+            raise RuntimeError("saved_state value not recovered on reread")
+
+    def get_value_saved_state(self, key):
+        return self._saved_state[key]
+
+    def has_value(self, key):
+        return key in self._saved_state
+
+    def _write(self):
+        with open(self._state_fname, mode="w") as fptr:
+            json.dump(self._saved_state, fptr, indent=2, cls=_NumpyEncoder)
+
+    def _read(self):
+        with open(self._state_fname, mode="r") as fptr:
+            self._saved_state = json.load(fptr, object_hook=_decode)
+
+
+NEWTON_VARS = {  # newton_solver.py:62-118
+    "iterate": ("model_state", "{method} of {name} Newton iterate", None),
+    "fcn": ("model_state", "{method} of {name} Newton fcn", None),
+    "increment": ("model_state", "{method} of {name} Newton increment", None),
+    "increment_scalef": ("per_tracer_module", "factor applied to {name} Newton increment to satisfy bounds", "1"),
+    "Armijo_factor": ("per_tracer_module", "factor applied to {name} Newton increment to satisfy Armijo condition", "1"),
+    "Krylov_iterations": ("tracer_module_independent", "number of iterations in Krylov solver", "1"),
+}
+KRYLOV_VARS = {  # krylov_solver.py:50-73
+    "precond_rhs_norm": ("per_tracer_module_invariant", "norm of {name} preconditioned rhs", None),
+    "precond_resid_norm": ("per_tracer_module", "norm of {name} preconditioned residual", None),
+}
+
+
+class StatsFile:
+    """`<name>_stats.nc` of a solver (stats_file.py:13-139)"""
+
+    def __init__(self, name, workdir, region_cnt, tracer_modules, var_table, resume=False):
+        """tracer_modules: list of (module name, units or None)"""
+        self._name = name
+        self._fname = os.path.join(workdir, f"{name}_stats.nc")
+        self._region_cnt = region_cnt
+        self._vars = {}  # varname -> dict(dims, dtype, attrs, data)
+        self._n_iter = 0
+        self._history = (f"{datetime.now():%Y-%m-%d %H:%M:%S}: created by StatsFile._create_stats_file "
+                         f"for {name} solver")
+        self._keys = {}  # key -> (category, [varnames] or {"mean": [...], "norm": [...]})
+        for key, (category, long_name, units) in var_table.items():
+            if category == "model_state":
+                names = {"mean": [], "norm": []}
+                for method in ("mean", "norm"):
+                    for mod, mod_units in tracer_modules:
+                        vname = f"{key}_{method}_{mod}"
+                        self._define(vname, ("iteration", "region"), "f8",
+                                     long_name.format(method=method, name=mod), mod_units)
+                        names[method].append(vname)
+                self._keys[key] = (category, names)
+            elif category in ("per_tracer_module", "per_tracer_module_invariant"):
+                names = []
+                for mod, mod_units in tracer_modules:
+                    vname = f"{key}_{mod}"
+                    dims = ("iteration", "region") if category == "per_tracer_module" else ("region",)
+                    self._define(vname, dims, "f8", long_name.format(name=mod), units if units else mod_units)
+                    names.append(vname)
+                self._keys[key] = (category, names)
+            else:
+                self._define(key, ("iteration",), "i4", long_name, units)
+                self._keys[key] = (category, [key])
+        if resume and os.path.exists(self._fname):
+            self._load()
+        else:
+            self._flush()
+
+    def _define(self, vname, dims, dtype, long_name, units):
+        attrs = {"long_name": long_name}
+        if units is not None:
+            attrs["units"] = units
+        if "iteration" in dims:
+            attrs["_FillValue"] = FILL_F8 if dtype == "f8" else FILL_I4
+        shape = tuple(0 if d == "iteration" else self._region_cnt for d in dims)
+        self._vars[vname] = {"dims": dims, "dtype": dtype, "attrs": attrs,
+                             "data": np.zeros(shape, dtype=np.float64 if dtype == "f8" else np.int32)}
+
+    def _grow(self, n_iter):
+        for var in self._vars.values():
+            if "iteration" not in var["dims"]:
+                continue
+            cur = var["data"]
+            if cur.shape[0] >= n_iter:
+                continue
+            pad = np.full((n_iter - cur.shape[0],) + cur.shape[1:], var["attrs"]["_FillValue"], dtype=cur.dtype)
+            var["data"] = np.concatenate([cur, pad], axis=0)
+        self._n_iter = max(self._n_iter, n_iter)
+
+    def put(self, iteration, **kwargs):
+        """values of one iteration: key -> ModelState (model_state category: its mean and norm are
+        written), ndarray [n_modules, region_cnt] (per_tracer_module) or int"""
+        self._grow(iteration + 1)
+        for key, vals in kwargs.items():
+            category, names = self._keys[key]
+            if category == "model_state":
+                for method in ("mean", "norm"):
+                    red = vals.mean() if method == "mean" else vals.norm()
+                    for ind, vname in enumerate(names[method]):
+                        self._vars[vname]["data"][iteration] = np.asarray(red[ind]).reshape(-1)[: self._region_cnt]
+            elif category == "per_tracer_module":
+                for ind, vname in enumerate(names):
+                    self._vars[vname]["data"][iteration] = vals[ind]
+            elif category == "per_tracer_module_invariant":
+                raise ValueError(f"{key} has no iteration dimension: use put_invariant")
+            else:
+                self._vars[names[0]]["data"][iteration] = vals
+        self._flush()
+
+    def put_invariant(self, **kwargs):
+        for key, vals in kwargs.items():
+            category, names = self._keys[key]
+            if category != "per_tracer_module_invariant":
+                raise RuntimeError(f"iteration is a dimension for {key}")
+            for ind, vname in enumerate(names):
+                self._vars[vname]["data"][:] = vals[ind]
+        self._flush()
+
+    def _flush(self):
+        with netcdf_file(self._fname, "w", version=2) as fptr:
+            fptr.history = self._history
+            fptr.createDimension("iteration", None)
+            fptr.createDimension("region", self._region_cnt)
+            it = fptr.createVariable("iteration", "i4", ("iteration",))
+            it.long_name = f"{self._name} solver iteration"
+            reg = fptr.createVariable("region", "i4", ("region",))
+            reg.long_name = "region index (0-based)"
+            reg.comment = "axis attribute is a work-around to enable pyferret to read stats files"
+            reg.axis = "T"
+            reg[:] = np.arange(self._region_cnt, dtype=np.int32)
+            handles = {}
+            for vname, var in self._vars.items():
+                handle = fptr.createVariable(vname, var["dtype"], var["dims"])
+                for att, val in var["attrs"].items():
+                    setattr(handle, att, val)
+                handles[vname] = handle
+            if self._n_iter > 0:
+                it[: self._n_iter] = np.arange(self._n_iter, dtype=np.int32)
+            for vname, var in self._vars.items():
+                if "iteration" in var["dims"]:
+                    if self._n_iter > 0:
+                        handles[vname][: self._n_iter] = var["data"][: self._n_iter]
+                else:
+                    handles[vname][:] = var["data"]
+
+    def _load(self):
+        with netcdf_file(self._fname, "r", mmap=False) as fptr:
+            self._history = fptr.history.decode() if isinstance(fptr.history, bytes) else str(fptr.history)
+            self._n_iter = int(fptr.variables["iteration"].shape[0])
+            for vname, var in self._vars.items():
+                if vname in fptr.variables:
+                    var["data"] = np.array(fptr.variables[vname].data, dtype=var["data"].dtype)
+        self._grow(self._n_iter)

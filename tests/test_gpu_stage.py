@@ -189,6 +189,46 @@ def test_fused_step_kernel_matches_scheme_oracle(kind, nz, ny, B, monkeypatch):
     np.testing.assert_allclose(got, unfused, rtol=0.0, atol=1e-10 * scale)
 
 
+@pytest.mark.parametrize("nz,ny,B", [(21, 33, 20), (37, 15, 50), (125, 16, 9), (10, 7, 70), (40, 50, 13)])
+def test_fused_phosphorus_step_kernel_matches_scheme_oracle(nz, ny, B, monkeypatch):
+    """three coupled tracers per tile (step_fused_p3_kernel: 4-member rows, cross-tracer exchange of
+    the stage-1 solution between warps) against the numpy statement of the scheme and against the
+    stage-per-launch kernels; persistent launch and one launch per step give the same bits.  Member
+    counts that are not multiples of 4, several column tiles, level counts that are not multiples
+    of the chunk, the refined grid's 125 levels."""
+    from oracle import imex_oracle as im
+    from oracle import nk_oracle as o
+    from nk_ooc_b200 import _lib
+    from nk_ooc_b200.py_driver_2d import modules
+
+    rng = np.random.default_rng(31)
+    g, tr = _grid(nz, ny)
+    nsteps = 240  # the explicit uptake term (1/(3 days)) needs h well below 3 days
+    mod, m = im.Module2D("phosphorus", g, phos=o.Phosphorus2D(g)), modules.phosphorus_model(tr)
+    x = np.abs(rng.normal(size=(3, g.nz, g.ny, B))) * 0.5
+    m.set_uniform_schedule(nsteps)
+    lib = _lib.load()
+    xd = _to_dev(x)
+    monkeypatch.setenv("NKB_FUSED_P3", "1")
+    m.eval(xd, B)
+    n0 = lib.nkb_launch_count()
+    got = m.eval(xd, B).cpu().numpy()[..., :B]
+    assert lib.nkb_launch_count() - n0 == 2, "the persistent fused phosphorus kernel did not run"
+    m.check_health()
+    monkeypatch.setenv("NKB_FUSED_PERSIST", "0")
+    per_step = m.eval(xd, B).cpu().numpy()[..., :B]
+    np.testing.assert_array_equal(got, per_step)
+    monkeypatch.delenv("NKB_FUSED_PERSIST")
+    monkeypatch.setenv("NKB_FUSED_P3", "0")
+    n0 = lib.nkb_launch_count()
+    unfused = m.eval(xd, B).cpu().numpy()[..., :B]
+    assert lib.nkb_launch_count() - n0 == 2 * nsteps
+    want = im.model_year_2d(mod, x, nsteps)
+    scale = np.abs(want).max()
+    np.testing.assert_allclose(unfused, want, rtol=0.0, atol=1e-10 * scale)
+    np.testing.assert_allclose(got, want, rtol=0.0, atol=1e-10 * scale)
+
+
 def test_fused_kernel_hist_snapshots_and_two_members_per_thread(monkeypatch):
     """B >= 8: hist snapshots cut the persistent launch into segments (one cooperative launch per
     interval between snapshots); the alternative thread layout (NKB_FUSED_MPT=2: 4 consumer warps x 2

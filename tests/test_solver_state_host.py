@@ -1,0 +1,95 @@
+"""CPU tests of the solver persistence (Newton_state.json / *_stats.nc), no GPU needed"""
+import json
+
+import numpy as np
+import pytest
+from scipy.io import netcdf_file
+
+from nk_ooc_b200 import solver_state as ss
+
+
+def test_step_log_strings_and_resume_rewind(tmp_path):
+    """same strings as the reference's state files (baselines/ci_long_iage/Newton_state.json):
+    per-iteration steps are prefixed NN:, inc_iteration is logged under the new iteration"""
+    st = ss.SolverState("Newton", str(tmp_path))
+    st.log_step("Newton iterate 0 written", per_iteration=False)
+    st.log_step("comp_fcn complete for X/fcn_00.nc")
+    st.log_step("comp_fcn complete for X/fcn_00.nc")  # idempotent
+    assert st.inc_iteration() == 1
+    st.log_step("comp_fcn complete for X/fcn_01.nc")
+    saved = json.load(open(tmp_path / "Newton_state.json"))
+    assert saved == {"iteration": 1, "step_log": ["__init__", "Newton iterate 0 written",
+                                                  "00:comp_fcn complete for X/fcn_00.nc", "01:inc_iteration",
+                                                  "01:comp_fcn complete for X/fcn_01.nc"]}
+    back = ss.SolverState("Newton", str(tmp_path), resume=True)
+    assert back.get_iteration() == 1 and back.step_logged("comp_fcn complete for X/fcn_01.nc")
+    assert not back.step_logged("comp_fcn complete for X/fcn_00.nc")  # other iteration
+    rew = ss.SolverState("Newton", str(tmp_path), resume=True, rewind=True)
+    assert not rew.step_logged("comp_fcn complete for X/fcn_01.nc")
+    assert rew.step_was_rewound("comp_fcn complete for X/fcn_01.nc")
+    with pytest.raises(RuntimeError):
+        ss.SolverState("Newton", str(tmp_path), resume=False, rewind=True)
+
+
+def test_saved_values_roundtrip_exactly(tmp_path):
+    st = ss.SolverState("Krylov", str(tmp_path))
+    h_mat = np.random.default_rng(0).normal(size=(2, 3, 2, 4))
+    st.set_value_saved_state("h_mat", h_mat)
+    st.set_value_saved_state("armijo_ind", 3)
+    back = ss.SolverState("Krylov", str(tmp_path), resume=True)
+    np.testing.assert_array_equal(back.get_value_saved_state("h_mat"), h_mat)
+    assert back.get_value_saved_state("armijo_ind") == 3
+    raw = json.load(open(tmp_path / "Krylov_state.json"))
+    assert set(raw["h_mat"]) == {"__ndarray__"}  # the reference's tagging (solver_state.py:149-166)
+
+
+class _State:
+    def __init__(self, mean, norm):
+        self._m, self._n = np.asarray(mean), np.asarray(norm)
+
+    def mean(self):
+        return self._m
+
+    def norm(self):
+        return self._n
+
+
+def test_stats_file_layout_growth_and_resume(tmp_path):
+    mods = [("iage", "years"), ("phosphorus", None)]
+    sf = ss.StatsFile("Newton", str(tmp_path), 3, mods, ss.NEWTON_VARS)
+    it0 = _State(np.arange(6.0).reshape(2, 3), 10 + np.arange(6.0).reshape(2, 3))
+    sf.put(0, iterate=it0, fcn=it0)
+    sf.put(0, increment=it0, Krylov_iterations=4, increment_scalef=np.ones((2, 3)), Armijo_factor=0.5 * np.ones((2, 3)))
+    sf.put(1, iterate=it0)
+    with netcdf_file(str(tmp_path / "Newton_stats.nc"), "r", mmap=False) as f:
+        assert f.version_byte == 2
+        assert f.dimensions["iteration"] is None and f.dimensions["region"] == 3
+        names = set(f.variables)
+        for key in ("iterate", "fcn", "increment"):
+            for method in ("mean", "norm"):
+                for mod, _ in mods:
+                    assert f"{key}_{method}_{mod}" in names
+        assert {"increment_scalef_iage", "Armijo_factor_phosphorus", "Krylov_iterations", "iteration", "region"} <= names
+        np.testing.assert_array_equal(f.variables["iteration"].data, [0, 1])
+        np.testing.assert_array_equal(f.variables["region"].data, [0, 1, 2])
+        np.testing.assert_array_equal(f.variables["iterate_norm_phosphorus"].data, [[13, 14, 15], [13, 14, 15]])
+        assert f.variables["iterate_mean_iage"].units == b"years"
+        assert f.variables["iterate_mean_iage"].long_name == b"mean of iage Newton iterate"
+        assert not hasattr(f.variables["iterate_mean_phosphorus"], "units")
+        # iteration 1 of the variables not yet written holds the fill value (stats_file.py:129-139)
+        assert (f.variables["fcn_mean_iage"].data[1] == ss.FILL_F8).all()
+        assert f.variables["Krylov_iterations"].data[1] == ss.FILL_I4
+        np.testing.assert_array_equal(f.variables["Krylov_iterations"].data[:1], [4])
+    again = ss.StatsFile("Newton", str(tmp_path), 3, mods, ss.NEWTON_VARS, resume=True)
+    again.put(1, fcn=it0)
+    with netcdf_file(str(tmp_path / "Newton_stats.nc"), "r", mmap=False) as f:
+        np.testing.assert_array_equal(f.variables["fcn_mean_iage"].data, [[0, 1, 2], [0, 1, 2]])
+        np.testing.assert_array_equal(f.variables["Armijo_factor_iage"].data[0], [0.5, 0.5, 0.5])
+    kf = ss.StatsFile("Krylov", str(tmp_path), 3, mods, ss.KRYLOV_VARS)
+    kf.put_invariant(precond_rhs_norm=np.ones((2, 3)))
+    kf.put(0, precond_resid_norm=2 * np.ones((2, 3)))
+    with pytest.raises(RuntimeError):
+        kf.put_invariant(precond_resid_norm=np.ones((2, 3)))
+    with netcdf_file(str(tmp_path / "Krylov_stats.nc"), "r", mmap=False) as f:
+        assert f.variables["precond_rhs_norm_iage"].dimensions == ("region",)
+        assert f.variables["precond_resid_norm_iage"].dimensions == ("iteration", "region")
