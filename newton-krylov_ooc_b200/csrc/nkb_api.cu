@@ -353,9 +353,20 @@ int nkb_model_eval(nkb_model *m, const double *d_x0, double *d_f, double *d_work
         }
         NKB_CUDA(cudaMemsetAsync(m->d_done, 0, ntiles * sizeof(int), st));
         nkb::FusedMaps fm;
-        if (nkb::fused_encode_state_maps(v, B, ldb, d_x0, &fm.in_x0, nullptr)) return 1;
-        if (nkb::fused_encode_state_maps(v, B, ldb, d_f, &fm.in_f, &fm.out_f)) return 1;
-        if (nkb::fused_encode_state_maps(v, B, ldb, w_alt, &fm.in_w, &fm.out_w)) return 1;
+        // buffers the steps alternate between: the last step writes buf_f.  Phosphorus integrates in a
+        // member-block-major copy (nkb_step_fused.cu): x0 is converted into the work buffer that step 0
+        // does not write, the result is converted back (minus x0) at the end.
+        const bool tm = nkb::fused_tile_major(v);
+        double *buf_f = tm ? w_alt : d_f, *buf_w = tm ? w_u1 : w_alt;
+        const double *buf_x0 = d_x0;
+        if (tm) {
+            double *x0_tm = (((S - 1) & 1) == 0) ? buf_w : buf_f;
+            if (nkb::launch_p3_to_tm(v, d_x0, x0_tm, B, ldb, st)) return 1;
+            buf_x0 = x0_tm;
+        }
+        if (nkb::fused_encode_state_maps(v, B, ldb, buf_x0, &fm.in_x0, nullptr)) return 1;
+        if (nkb::fused_encode_state_maps(v, B, ldb, buf_f, &fm.in_f, &fm.out_f)) return 1;
+        if (nkb::fused_encode_state_maps(v, B, ldb, buf_w, &fm.in_w, &fm.out_w)) return 1;
         // encoded per evaluation: the box shape follows the thread layout in use (NKB_FUSED_MPT)
         if (nkb::fused_encode_ctab_map(v.nz, v.ny, (size_t)S * v.n_classes * 8, m->ctab, &fm.ctab, v.kind)) return 1;
         bool persist = nkb::fused_persistent();
@@ -373,11 +384,22 @@ int nkb_model_eval(nkb_model *m, const double *d_x0, double *d_f, double *d_work
             if (rc) return 1;
             n = end;
             if (n_hist > 0 && n < S) {
-                double *dest = (((S - n) & 1) == 0) ? d_f : w_alt;  // buffer written by step n - 1
-                if (emit_hist(n, dest)) return 1;
+                double *dest = (((S - n) & 1) == 0) ? buf_f : buf_w;  // buffer written by step n - 1
+                if (tm) {
+                    while (hist_i < n_hist && h_hist_steps[hist_i] == n) {
+                        if (nkb::launch_p3_gather_member(v, dest, d_hist + (size_t)hist_i * v.T * plane, B, 0, st)) return 1;
+                        ++hist_i;
+                    }
+                } else if (emit_hist(n, dest)) {
+                    return 1;
+                }
             }
         }
-        if (nkb::launch_sub_inplace(d_f, d_x0, nstate, st)) return 1;
+        if (tm) {
+            if (nkb::launch_p3_from_tm_sub(v, buf_f, d_x0, d_f, B, ldb, st)) return 1;
+        } else if (nkb::launch_sub_inplace(d_f, d_x0, nstate, st)) {
+            return 1;
+        }
         NKB_CUDA(cudaGetLastError());
         return 0;
     }

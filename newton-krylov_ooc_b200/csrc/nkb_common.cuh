@@ -128,6 +128,12 @@ int launch_steps_fused(const ModelDev &v, int B, int n_steps, int step0, int ste
 bool fused_persistent();
 int fused_tile_count(const ModelDev &v, int B);
 int launch_sub_inplace(double *out, const double *x0, size_t n, cudaStream_t st);
+// phosphorus step kernel: the year is integrated in a member-block-major copy of the state
+bool fused_tile_major(const ModelDev &v);
+int launch_p3_to_tm(const ModelDev &v, const double *src, double *dst, int B, size_t ldb, cudaStream_t st);
+int launch_p3_from_tm_sub(const ModelDev &v, const double *tm, const double *x0, double *f, int B, size_t ldb,
+                          cudaStream_t st);
+int launch_p3_gather_member(const ModelDev &v, const double *tm, double *dst, int B, int b, cudaStream_t st);
 bool tma_path_usable(const StageArgs &a);
 int launch_stage_tma(int kind, int nin, const StageArgs &a, cudaStream_t st);
 

@@ -77,6 +77,7 @@ struct StepArgs {
     int step0, step1;          // this launch integrates the time steps [step0, step1)
     int rot;                   // tile -> CTA assignment is rotated by rot CTAs per step (load balance)
     int cross_step_fuse;       // sweep C of a step's last tile may share a pass with sweep A of the next step
+    int tgroup;                // phosphorus kernel: member-adjacent tiles taken back to back by one CTA
     int class_of[NKB_MAX_TRACERS];
     double src_const[NKB_MAX_TRACERS];
     double sink_thres_r;
@@ -770,8 +771,14 @@ __global__ void __launch_bounds__(fs_cfg(MPT).threads, 1) step_fused_kernel(cons
 // ---- phosphorus (py_driver_2d/phosphorus.py:58-95): three coupled tracers per tile ------------------
 // The explicit sources couple po4, dop and pop cell by cell, so the three tracers of a (column, member)
 // pair must be resident together and the tensor-memory scratch holds 3 x 125 levels per pair: a tile is
-// 4 members x 14 interior columns x all levels x 3 tracers (rows of 4 members = 32 bytes, 32-byte TMA
-// swizzle), six consumer warps = 3 tracers x 2 member pairs, lane = 2*column + (member & 1) as above.
+// 4 members x 14 interior columns x all levels x 3 tracers, six consumer warps = 3 tracers x 2 member
+// pairs, lane = 2*column + (member & 1) as above.  Rows of 4 members are only 32 bytes, and TMA
+// issues one request per contiguous run of a box: in the member-fastest layout a state box would be
+// 144 runs of 32 bytes, which made the TMA request rate the limit of the kernel.  The model year is
+// therefore integrated in a member-block-major copy of the state,
+//     x_tm[tracer][level][member block][column][4 members]
+// (converted once per evaluation, p3_to_tm_kernel / p3_from_tm_sub_kernel), in which the 18 columns
+// of a tile and level are ONE contiguous run of 576 bytes: 8 requests per box.
 // Sweep A reads the other two tracers' centre values from their state boxes of the same ring slot;
 // in sweep B the three warps that share a member pair exchange the stage-1 solution of a chunk through
 // a double-buffered shared-memory block and a named barrier before the stage-2 right-hand side.
@@ -784,19 +791,31 @@ constexpr int P3_OUT = P3_T * P3_OBOX;
 constexpr int P3_EX = 2 * P3_T * P3_KC * 64 * 8;                  // u1 exchange, two chunks deep
 constexpr int P3_SMEM = 1024 + P3_NS * P3_SLOT + P3_NO * P3_OUT + P3_EX;
 constexpr int P3_THREADS = (P3_NCW + 2) * 32;
-static_assert(P3_UBOX % 256 == 0 && P3_SLOT % 256 == 0 && P3_OBOX % 256 == 0 && P3_OUT % 256 == 0,
-              "32-byte-swizzled boxes need 256-byte aligned bases");
+static_assert(P3_UBOX % 128 == 0 && P3_SLOT % 128 == 0 && P3_OBOX % 128 == 0 && P3_OUT % 128 == 0,
+              "TMA boxes need 128-byte aligned shared-memory bases");
 static_assert(P3_SMEM <= 227 * 1024, "shared memory");
 
-// explicit source of tracer TR times the stage weight: fw = w * max_uptake_rate * light, wrd = w * dop
-// remineralisation rate, wrp = w * pop remineralisation rate (phosphorus.py:75-95)
-__device__ __forceinline__ double p3_source(int tr, double fw, double wrd, double wrp, double hs, double sg, double po4,
+// a / b for b in the normal range (po4 + half saturation): reciprocal seed (MUFU.RCP64H), two Newton
+// steps and one residual correction — 8 dependent-free-of-branches FP64 operations instead of the IEEE
+// division subroutine with its special-case paths (within 1 ulp of the correctly rounded quotient)
+__device__ __forceinline__ double p3_div(double a, double b) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    double e = fma(-b, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-b, r, 1.0);
+    r = fma(r, e, r);
+    const double q = a * r;
+    return fma(fma(-b, q, a), r, q);
+}
+
+// explicit source of one tracer times the stage weight w (phosphorus.py:75-95) in coefficient form:
+//   cu * uptake + kd * dop + kq * pop,  uptake = fw * po4 / (po4 + hs),  fw = w * max_uptake_rate * light
+//   po4: cu = -1, kd = +w rd, kq = +w rp;   dop: cu = sigma, kd = -w rd, kq = 0;   pop: cu = 1 - sigma, kd = 0, kq = -w rp
+__device__ __forceinline__ double p3_source(double fw, double cu, double kd, double kq, double hs, double po4,
                                             double dop, double pop) {
-    const double u = fw * (po4 / (po4 + hs));
-    const double d = wrd * dop, q = wrp * pop;
-    if (tr == 0) return (d + q) - u;
-    if (tr == 1) return fma(sg, u, -d);
-    return fma(1.0 - sg, u, -q);
+    const double u = fw * p3_div(po4, po4 + hs);
+    return fma(kq, pop, fma(kd, dop, cu * u));
 }
 
 __global__ void __launch_bounds__(P3_THREADS, 1) step_fused_p3_kernel(const StepArgs p,
@@ -845,11 +864,16 @@ __global__ void __launch_bounds__(P3_THREADS, 1) step_fused_p3_kernel(const Step
     };
     auto item_first = [&](int n) { return (int)((blockIdx.x + (unsigned)n * (unsigned)p.rot) % gridDim.x); };
     auto item_valid = [&](const Item &it) { return it.n < p.step1; };
+    // a CTA takes groups of p.tgroup member-adjacent tiles back to back: their 32-byte rows share DRAM
+    // bursts and L2 lines, so the second tile of a group finds its rows in L2
     auto item_next = [&](const Item &it) {
-        Item nx = {it.n, it.tile + (int)gridDim.x};
-        if (nx.tile >= p.ntiles) {
-            nx.n = it.n + 1;
-            nx.tile = item_first(nx.n);
+        Item nx = {it.n, it.tile + 1};
+        if (nx.tile % p.tgroup == 0 || nx.tile >= p.ntiles) {
+            nx.tile = (it.tile / p.tgroup + (int)gridDim.x) * p.tgroup;
+            if (nx.tile >= p.ntiles) {
+                nx.n = it.n + 1;
+                nx.tile = item_first(nx.n) * p.tgroup;
+            }
         }
         return nx;
     };
@@ -859,7 +883,7 @@ __global__ void __launch_bounds__(P3_THREADS, 1) step_fused_p3_kernel(const Step
         const int d = nx.tile - it.tile;
         return d == 0 || d == p.nmb || d == -p.nmb;
     };
-    Item it0 = {p.step0, item_first(p.step0)};
+    Item it0 = {p.step0, item_first(p.step0) * p.tgroup};
     if (it0.tile >= p.ntiles) it0.n = p.step1;
 
     if (warp == NCW) {
@@ -868,14 +892,14 @@ __global__ void __launch_bounds__(P3_THREADS, 1) step_fused_p3_kernel(const Step
             uint32_t g = 0;
             struct TileP {
                 const CUtensorMap *uin;
-                int m0, j0, ct, zt;
+                int mb, j0, ct, zt;
             };
             auto tile_p = [&](const Item &it) {
                 TileP t;
                 const bool to_f = (((p.n_steps - 1 - it.n) & 1) == 0);
                 t.uin = (it.n == 0) ? &maps.in_x0 : (to_f ? &maps.in_w : &maps.in_f);
                 t.ct = it.tile / p.nmb;
-                t.m0 = (it.tile % p.nmb) * P3_MEM;
+                t.mb = it.tile % p.nmb;
                 t.j0 = t.ct * p.jt;
                 t.zt = it.n * P3_NCLS * 8;
                 return t;
@@ -901,7 +925,7 @@ __global__ void __launch_bounds__(P3_THREADS, 1) step_fused_p3_kernel(const Step
                         fs_mbar_expect_tx(fb, P3_T * P3_UBOX + P3_NCLS * (3 + (sweep == 3 ? 1 : 0)) * P3_PP);
 #pragma unroll
                         for (int t = 0; t < P3_T; ++t)
-                            fs_tma_load_4d(sb + t * P3_UBOX, ta.uin, fb, ta.m0, ta.j0 - 2, k0, t, kEvictNormal);
+                            fs_tma_load_4d(sb + t * P3_UBOX, ta.uin, fb, 4 * (ta.j0 - 2), ta.mb, k0, t, kEvictNormal);
 #pragma unroll
                         for (int cl = 0; cl < P3_NCLS; ++cl) {
 #pragma unroll
@@ -916,7 +940,7 @@ __global__ void __launch_bounds__(P3_THREADS, 1) step_fused_p3_kernel(const Step
                         fs_mbar_expect_tx(fb, P3_T * P3_UBOX + P3_NCLS * 4 * P3_PP);
 #pragma unroll
                         for (int t = 0; t < P3_T; ++t)
-                            fs_tma_load_4d(sb + t * P3_UBOX, ta.uin, fb, ta.m0, ta.j0 - 2, k0, t, kEvictFirst);
+                            fs_tma_load_4d(sb + t * P3_UBOX, ta.uin, fb, 4 * (ta.j0 - 2), ta.mb, k0, t, kEvictFirst);
 #pragma unroll
                         for (int cl = 0; cl < P3_NCLS; ++cl)
 #pragma unroll
@@ -972,7 +996,7 @@ __global__ void __launch_bounds__(P3_THREADS, 1) step_fused_p3_kernel(const Step
                     fs_mbar_wait<2000>(bar_ofull + 8 * s, ph);
 #pragma unroll
                     for (int t = 0; t < P3_T; ++t)
-                        fs_tma_store_4d(uout, oring_a + s * P3_OUT + t * P3_OBOX, mb * P3_MEM, ct * p.jt, c * KC, t);
+                        fs_tma_store_4d(uout, oring_a + s * P3_OUT + t * P3_OBOX, 4 * ct * p.jt, mb, c * KC, t);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                     fs_mbar_arrive(bar_oempty + 8 * s);
@@ -988,7 +1012,6 @@ __global__ void __launch_bounds__(P3_THREADS, 1) step_fused_p3_kernel(const Step
         // ===== consumers: warp = (tracer, member pair) =====
         constexpr int PP = KC * FS_COLS;  // pairs per plane
         const int tr = warp >> 1, pr = warp & 1;
-        const int t1 = (tr + 1) % 3, t2 = (tr + 2) % 3;
         const int cls = p.class_of[tr];
         const int col = lane >> 1;
         const int sub = 8 * (lane & 1);
@@ -999,22 +1022,21 @@ __global__ void __launch_bounds__(P3_THREADS, 1) step_fused_p3_kernel(const Step
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
                 const int r = q * FS_UCOLS + col + d;
-                offU[q][d] = 32 * r + 16 * (pr ^ ((r >> 2) & 1)) + sub;
+                offU[q][d] = 32 * r + 16 * pr + sub;
             }
             const int ro = q * p.jt + col - 1;
-            offO[q] = 32 * ro + 16 * (pr ^ ((ro >> 2) & 1)) + sub;
+            offO[q] = 32 * ro + 16 * pr + sub;
         }
         const bool interior = (col >= 1 && col <= p.jt);
         const double hs = p.p3_hs, sg = p.p3_sigma;
         const int exl = pr * 32 + lane;  // this thread's slot in a [tracer][level] row of the exchange block
         uint32_t g = 0, go = 0, gx = 0;
-        // po4, dop, pop from {own value, value of tracer t1, value of tracer t2}
-        auto po4_of = [&](double own, double o1, double o2) { return tr == 0 ? own : (tr == 1 ? o2 : o1); };
-        auto dop_of = [&](double own, double o1, double o2) { return tr == 1 ? own : (tr == 2 ? o2 : o1); };
-        auto pop_of = [&](double own, double o1, double o2) { return tr == 2 ? own : (tr == 0 ? o2 : o1); };
+        const double cu = (tr == 0) ? -1.0 : (tr == 1 ? sg : 1.0 - sg);
+        const double sd = (tr == 0) ? p.p3_rd : (tr == 1 ? -p.p3_rd : 0.0);
+        const double sq = (tr == 0) ? p.p3_rp : (tr == 2 ? -p.p3_rp : 0.0);
 
         struct TileC {
-            double aff1, aff2, wrd1, wrp1, wrd2, wrp2;
+            double aff1, aff2, kd1, kq1, kd2, kq2;
         };
         auto tile_c = [&](const Item &it) {
             TileC t;
@@ -1028,27 +1050,32 @@ __global__ void __launch_bounds__(P3_THREADS, 1) step_fused_p3_kernel(const Step
                 t.aff2 = __ldg(aff_n + (size_t)(p.ncls + cls) * ny + j);
             }
             const double w1 = kGamma * hstep, w2 = hstep * (1.0 - kDelta);
-            t.wrd1 = w1 * p.p3_rd; t.wrp1 = w1 * p.p3_rp;
-            t.wrd2 = w2 * p.p3_rd; t.wrp2 = w2 * p.p3_rp;
+            t.kd1 = w1 * sd; t.kq1 = w1 * sq;
+            t.kd2 = w2 * sd; t.kq2 = w2 * sq;
             return t;
         };
 
         auto chunk_a = [&](const TileC &t, const unsigned char *sb, int c, double &yprev, Raw<W> &raw) {
             const double2 *pl = reinterpret_cast<const double2 *>(sb + P3_T * P3_UBOX + cls * 4 * P3_PP) + col;
-            const unsigned char *ub = sb + tr * P3_UBOX, *u1b = sb + t1 * P3_UBOX, *u2b = sb + t2 * P3_UBOX;
+            const unsigned char *ub = sb + tr * P3_UBOX;
             Vd<1> yb[KC];
+            // the sources of the chunk first: eight independent evaluations (instruction-level parallelism
+            // for the reciprocal sequences), then the recurrence
+            double sv[KC];
+#pragma unroll
+            for (int q = 0; q < KC; ++q) {
+                const double po4 = *reinterpret_cast<const double *>(sb + offU[q][1]);
+                const double dop = *reinterpret_cast<const double *>(sb + P3_UBOX + offU[q][1]);
+                const double pop = *reinterpret_cast<const double *>(sb + 2 * P3_UBOX + offU[q][1]);
+                sv[q] = p3_source(pl[2 * PP + q * FS_COLS].x, cu, t.kd1, t.kq1, hs, po4, dop, pop);
+            }
 #pragma unroll
             for (int q = 0; q < KC; ++q) {
                 const double cv = *reinterpret_cast<const double *>(ub + offU[q][1]);
                 const double cl = *reinterpret_cast<const double *>(ub + offU[q][0]);
                 const double cr = *reinterpret_cast<const double *>(ub + offU[q][2]);
-                const double o1 = *reinterpret_cast<const double *>(u1b + offU[q][1]);
-                const double o2 = *reinterpret_cast<const double *>(u2b + offU[q][1]);
                 const double2 lc = pl[q * FS_COLS], rm = pl[PP + q * FS_COLS];
-                const double fw = pl[2 * PP + q * FS_COLS].x;
-                const double sv = p3_source(tr, fw, t.wrd1, t.wrp1, hs, sg, po4_of(cv, o1, o2), dop_of(cv, o1, o2),
-                                            pop_of(cv, o1, o2));
-                double rhs = fma(lc.x, cl, fma(rm.x, cr, fma(lc.y, cv, sv)));
+                double rhs = fma(lc.x, cl, fma(rm.x, cr, fma(lc.y, cv, sv[q])));
                 if (c == 0 && q == 0) rhs += t.aff1;
                 yprev = fma(-rm.y, yprev, rhs);
                 yb[q].v[0] = yprev;
@@ -1117,6 +1144,11 @@ __global__ void __launch_bounds__(P3_THREADS, 1) step_fused_p3_kernel(const Step
                     y1top = __hiloint2double((int)nxt.w[(KC - 1) * 2 + 1], (int)nxt.w[(KC - 1) * 2]);
                 }
                 asm volatile("bar.sync %0, 96;" ::"r"(1 + pr) : "memory");
+                double sv[KC];
+#pragma unroll
+                for (int q = 0; q < KC; ++q)
+                    sv[q] = p3_source(pl[3 * PP + q * FS_COLS].y, cu, t.kd2, t.kq2, hs, ex[q * 64 + exl],
+                                      ex[(KC + q) * 64 + exl], ex[(2 * KC + q) * 64 + exl]);
                 Vd<1> yb[KC];
 #pragma unroll
                 for (int q = KC - 1; q >= 0; --q) {
@@ -1125,13 +1157,10 @@ __global__ void __launch_bounds__(P3_THREADS, 1) step_fused_p3_kernel(const Step
                     const double2 lc = pl[q * FS_COLS], ri = pl[PP + q * FS_COLS], gm = pl[2 * PP + q * FS_COLS],
                                   mf = pl[3 * PP + q * FS_COLS];
                     const double u1 = u1v[q];
-                    const double o1 = ex[(t1 * KC + q) * 64 + exl], o2 = ex[(t2 * KC + q) * 64 + exl];
                     double rhs1 = fma(gm.y, y1m, y1);
                     if (c == 0 && q == 0) rhs1 -= t.aff1;
                     const double un = *reinterpret_cast<const double *>(sb + tr * P3_UBOX + offU[q][1]);
-                    const double src = p3_source(tr, mf.y, t.wrd2, t.wrp2, hs, sg, po4_of(u1, o1, o2), dop_of(u1, o1, o2),
-                                                 pop_of(u1, o1, o2));
-                    const double pp = fma(p.r, rhs1, p.a0r * un) + src;
+                    const double pp = fma(p.r, rhs1, p.a0r * un) + sv[q];
                     const double ul = __shfl_up_sync(0xffffffffu, u1, 2, 32), ur = __shfl_down_sync(0xffffffffu, u1, 2, 32);
                     double rhs2 = fma(lc.x, ul, fma(ri.x, ur, fma(lc.y, u1, pp)));
                     if (c == 0 && q == 0) rhs2 += t.aff2;
@@ -1239,6 +1268,65 @@ static int fs_env_int(const char *name, int dflt) {
     return (v && *v) ? atoi(v) : dflt;
 }
 
+// ---- phosphorus: conversion between the member-fastest layout [row][ldb] (row = (tracer, level, column))
+// and the member-block-major layout of the step kernel.  Members B .. 4*nmb-1 are zero in the copy.
+__global__ void p3_to_tm_kernel(const double *__restrict__ src, double *__restrict__ dst, int ny, int B, size_t ldb,
+                                int nmb) {
+    const int tk = blockIdx.y;
+    const int wm = 4 * nmb;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= ny * wm) return;
+    const int j = idx / wm, m = idx % wm;
+    const double v = (m < B) ? src[((size_t)tk * ny + j) * ldb + m] : 0.0;
+    dst[(((size_t)tk * nmb + (m >> 2)) * ny + j) * 4 + (m & 3)] = v;
+}
+// f = x_tm(T) - x0, back in the member-fastest layout
+__global__ void p3_from_tm_sub_kernel(const double *__restrict__ tm, const double *__restrict__ x0,
+                                      double *__restrict__ f, int ny, int B, size_t ldb, int nmb) {
+    const int tk = blockIdx.y;
+    const int wm = 4 * nmb;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= ny * wm) return;
+    const int j = idx / wm, m = idx % wm;
+    if (m >= B) return;
+    const size_t o = ((size_t)tk * ny + j) * ldb + m;
+    f[o] = tm[(((size_t)tk * nmb + (m >> 2)) * ny + j) * 4 + (m & 3)] - x0[o];
+}
+__global__ void p3_gather_member_kernel(const double *__restrict__ tm, double *__restrict__ dst, int ny, int nmb,
+                                        size_t n, int b) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // (tracer, level, column)
+    if (i >= n) return;
+    const size_t tk = i / ny, j = i % ny;
+    dst[i] = tm[((tk * nmb + (b >> 2)) * ny + j) * 4 + (b & 3)];
+}
+
+int launch_p3_to_tm(const ModelDev &v, const double *src, double *dst, int B, size_t ldb, cudaStream_t st) {
+    const int nmb = (B + P3_MEM - 1) / P3_MEM;
+    dim3 grid((unsigned)((v.ny * 4 * nmb + 255) / 256), (unsigned)(v.T * v.nz));
+    p3_to_tm_kernel<<<grid, 256, 0, st>>>(src, dst, v.ny, B, ldb, nmb);
+    count_launch();
+    NKB_CUDA(cudaGetLastError());
+    return 0;
+}
+int launch_p3_from_tm_sub(const ModelDev &v, const double *tm, const double *x0, double *f, int B, size_t ldb,
+                          cudaStream_t st) {
+    const int nmb = (B + P3_MEM - 1) / P3_MEM;
+    dim3 grid((unsigned)((v.ny * 4 * nmb + 255) / 256), (unsigned)(v.T * v.nz));
+    p3_from_tm_sub_kernel<<<grid, 256, 0, st>>>(tm, x0, f, v.ny, B, ldb, nmb);
+    count_launch();
+    NKB_CUDA(cudaGetLastError());
+    return 0;
+}
+int launch_p3_gather_member(const ModelDev &v, const double *tm, double *dst, int B, int b, cudaStream_t st) {
+    const int nmb = (B + P3_MEM - 1) / P3_MEM;
+    const size_t n = (size_t)v.T * v.nz * v.ny;
+    p3_gather_member_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(tm, dst, v.ny, nmb, n, b);
+    count_launch();
+    NKB_CUDA(cudaGetLastError());
+    return 0;
+}
+bool fused_tile_major(const ModelDev &v) { return v.kind == NKB_MOD_PHOSPHORUS; }
+
 // ---- host side ----------------------------------------------------------------------------------
 typedef CUresult (*FsEncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -1295,6 +1383,7 @@ bool fused_step_usable(const ModelDev &v, int B, int ldb, const double *x0, cons
     if (v.column_model == 1 && v.ny == 1) return false;
     if (v.kind == NKB_MOD_PHOSPHORUS) {
         if (fs_env_int("NKB_FUSED_P3", 1) == 0 || v.T != P3_T || v.n_classes != P3_NCLS) return false;
+        if (((B + P3_MEM - 1) / P3_MEM) * P3_MEM > ldb) return false;  // the member-block-major copy pads B to 4
     } else if (v.kind != NKB_MOD_LINEAR && v.kind != NKB_MOD_FORCED_FILE) {
         return false;
     }
@@ -1307,17 +1396,26 @@ bool fused_step_usable(const ModelDev &v, int B, int ldb, const double *x0, cons
 int fused_encode_state_maps(const ModelDev &v, int B, int ldb, const double *buf, CUtensorMap *in, CUtensorMap *out) {
     int nct, jt;
     fs_col_tiles(v.ny, nct, jt);
-    const bool p3 = (v.kind == NKB_MOD_PHOSPHORUS);
-    const cuuint32_t kc = p3 ? (cuuint32_t)P3_KC : (cuuint32_t)fs_cfg(fs_mpt()).kc;
-    const cuuint32_t mem = p3 ? P3_MEM : FS_MEM;
-    const CUtensorMapSwizzle swz = p3 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B;
+    if (v.kind == NKB_MOD_PHOSPHORUS) {
+        // member-block-major copy: [tracer][level][member block][column * 4 members]
+        const cuuint64_t nmb = (cuuint64_t)((B + P3_MEM - 1) / P3_MEM);
+        const cuuint64_t run = (cuuint64_t)v.ny * P3_MEM;
+        const cuuint64_t dims[4] = {run, nmb, (cuuint64_t)v.nz, (cuuint64_t)v.T};
+        const cuuint64_t strides[3] = {run * 8, nmb * run * 8, (cuuint64_t)v.nz * nmb * run * 8};
+        const cuuint32_t box_in[4] = {FS_UCOLS * P3_MEM, 1, P3_KC, 1};
+        const cuuint32_t box_out[4] = {(cuuint32_t)jt * P3_MEM, 1, P3_KC, 1};
+        if (in && fs_encode(in, buf, 4, dims, strides, box_in, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
+        if (out && fs_encode(out, buf, 4, dims, strides, box_out, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
+        return 0;
+    }
+    const cuuint32_t kc = (cuuint32_t)fs_cfg(fs_mpt()).kc;
     // members beyond B are never read (zero-filled) nor written (clipped)
     const cuuint64_t dims[4] = {(cuuint64_t)B, (cuuint64_t)v.ny, (cuuint64_t)v.nz, (cuuint64_t)v.T};
     const cuuint64_t strides[3] = {(cuuint64_t)ldb * 8, (cuuint64_t)v.ny * ldb * 8, (cuuint64_t)v.nz * v.ny * ldb * 8};
-    const cuuint32_t box_in[4] = {mem, FS_UCOLS, kc, 1};
-    const cuuint32_t box_out[4] = {mem, (cuuint32_t)jt, kc, 1};
-    if (in && fs_encode(in, buf, 4, dims, strides, box_in, swz)) return 1;
-    if (out && fs_encode(out, buf, 4, dims, strides, box_out, swz)) return 1;
+    const cuuint32_t box_in[4] = {FS_MEM, FS_UCOLS, kc, 1};
+    const cuuint32_t box_out[4] = {FS_MEM, (cuuint32_t)jt, kc, 1};
+    if (in && fs_encode(in, buf, 4, dims, strides, box_in, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+    if (out && fs_encode(out, buf, 4, dims, strides, box_out, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
     return 0;
 }
 
@@ -1395,11 +1493,17 @@ int launch_steps_fused(const ModelDev &v, int B, int n_steps, int step0, int ste
     }
     int grid = fs_env_int("NKB_FUSED_GRID", n_sm);
     if (grid > n_sm) grid = n_sm;  // one CTA per SM (shared memory, 512 TMEM columns): all co-resident
-    if (grid > a.ntiles) grid = a.ntiles;
+    a.tgroup = 1;
+    if (p3) {
+        a.tgroup = fs_env_int("NKB_P3_GROUP", 1);
+        if (a.tgroup < 1 || a.tgroup > 8) a.tgroup = 1;
+    }
+    const int ngroups = (a.ntiles + a.tgroup - 1) / a.tgroup;
+    if (grid > ngroups) grid = ngroups;
     // rotate the tile -> CTA assignment by the number of left-over tiles per step so that the CTAs that
     // get one tile more than the others change from step to step
-    a.rot = (step1 - step0 > 1) ? a.ntiles % grid : 0;
-    a.cross_step_fuse = (a.ntiles > 2 * grid + a.nmb) ? 1 : 0;
+    a.rot = (step1 - step0 > 1) ? ngroups % grid : 0;
+    a.cross_step_fuse = (a.ntiles > 2 * a.tgroup * grid + a.nmb) ? 1 : 0;
     const bool coop = (step1 - step0 > 1);
     if (p3) {
         static bool attr_set = false;
