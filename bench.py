@@ -343,7 +343,7 @@ def run_ours(args):
     # stage-per-launch path: 2*S.  The roofline unit of work is one TIME STEP of the fused kernel
     # (one pass of the kernel's tile loop over the whole state batch) or one stage launch.
     launches_per_eval = max(1, int(round(launches / args.steps)))
-    fused = launches_per_eval < 2 * S
+    fused = launches_per_eval < 2 * S  # (the phosphorus path adds two layout-conversion launches per evaluation)
     n_stage_launch = S if fused else 2 * S
     avg_launch_ms = ms_per_step / n_stage_launch
     peak, how = measured_peak_gbs()
@@ -377,7 +377,8 @@ def run_ours(args):
         "roofline": {
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": traffic, "peak_source": how,
-            "kernel": "nkb::step_fused_kernel" if fused else "nkb::stage_tma_kernel",
+            "kernel": ("nkb::step_fused_p3_kernel" if args.module == "phosphorus" else "nkb::step_fused_kernel")
+                      if fused else "nkb::stage_tma_kernel",
             "launches_per_eval": launches_per_eval,
             "unit_of_work": "one time step of the persistent fused step kernel (all members)" if fused
                             else "one stage launch",
@@ -385,8 +386,11 @@ def run_ours(args):
                                "implicit stage); the fused step kernel moves less than that (see traffic)",
             "alg_bytes_per_launch": bytes_alg_eval * B / n_stage_launch, "avg_launch_ms": avg_launch_ms,
             "traffic_unit": "dram bytes per unit of work (ncu, profiles/traffic.json)",
-            "limiter": "shared-memory LSU data pipe at 84 % of peak (ncu l1tex__data_pipe_lsu_wavefronts), DRAM at 46 %: "
-                       "the fused kernel moves 0.57 of the algorithmic bytes (profiles/r01_ncu_full_step_fused_persistent_*.txt)"
+            "limiter": ("instruction latency of the six consumer warps (tensor memory holds 3 x 125 levels for only 64 "
+                        "(column, member) pairs per SM): issue slots 37 %, FP64 pipe 30 %, DRAM 47 % "
+                        "(profiles/r01_ncu_full_step_fused_p3_*.txt)" if args.module == "phosphorus" else
+                        "shared-memory LSU data pipe at 84 % of peak (ncu l1tex__data_pipe_lsu_wavefronts), DRAM at 46 %: "
+                        "the fused kernel moves 0.57 of the algorithmic bytes (profiles/r01_ncu_full_step_fused_persistent_*.txt)")
                        if fused else "L2 round trip of the elimination intermediates",
         },
         "e2e": {

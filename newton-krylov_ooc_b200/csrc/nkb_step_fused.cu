@@ -123,6 +123,23 @@ __device__ __forceinline__ void fs_mbar_wait(uint32_t bar, uint32_t parity) {
             : "memory");
     } while (!ok);
 }
+// plain try_wait + a real sleep between polls (the hinted form above wakes on every barrier event of the CTA:
+// in the phosphorus kernel the producer and store lanes were executing 20 % of all instructions)
+template <int SLEEP_NS>
+__device__ __forceinline__ void fs_mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) break;
+        __nanosleep(SLEEP_NS);
+    }
+}
 // spin until *flag >= want (acquire); gives up after 2e10 cycles (~10 s) and raises *err instead of hanging
 __device__ __forceinline__ void fs_wait_done(const int *flag, int want, int *err) {
     int v;
@@ -776,13 +793,15 @@ __global__ void __launch_bounds__(fs_cfg(MPT).threads, 1) step_fused_kernel(cons
 // issues one request per contiguous run of a box: in the member-fastest layout a state box would be
 // 144 runs of 32 bytes, which made the TMA request rate the limit of the kernel.  The model year is
 // therefore integrated in a member-block-major copy of the state,
-//     x_tm[tracer][level][member block][column][4 members]
+//     x_tm[tracer][level][member block][member pair][column][2 members]
 // (converted once per evaluation, p3_to_tm_kernel / p3_from_tm_sub_kernel), in which the 18 columns
-// of a tile and level are ONE contiguous run of 576 bytes: 8 requests per box.
+// of a tile, level and member pair are ONE contiguous run of 288 bytes (16 requests per box) and the
+// 16 columns x 2 members that a warp reads are 256 contiguous bytes of shared memory (no bank
+// conflicts, no swizzle).
 // Sweep A reads the other two tracers' centre values from their state boxes of the same ring slot;
 // in sweep B the three warps that share a member pair exchange the stage-1 solution of a chunk through
 // a double-buffered shared-memory block and a named barrier before the stage-2 right-hand side.
-constexpr int P3_MEM = 4, P3_T = 3, P3_KC = 8, P3_NCW = 6, P3_NS = 5, P3_NO = 2, P3_NCLS = 2;
+constexpr int P3_MEM = 4, P3_T = 3, P3_KC = 8, P3_NCW = 6, P3_NS = 5, P3_NO = 3, P3_NCLS = 2;
 constexpr int P3_UBOX = P3_KC * FS_UCOLS * P3_MEM * 8;            // 4608
 constexpr int P3_PP = P3_KC * FS_COLS * 16;                       // bytes of one pair plane (2048)
 constexpr int P3_SLOT = P3_T * P3_UBOX + P3_NCLS * 4 * P3_PP;     // 30208
@@ -791,6 +810,7 @@ constexpr int P3_OUT = P3_T * P3_OBOX;
 constexpr int P3_EX = 2 * P3_T * P3_KC * 64 * 8;                  // u1 exchange, two chunks deep
 constexpr int P3_SMEM = 1024 + P3_NS * P3_SLOT + P3_NO * P3_OUT + P3_EX;
 constexpr int P3_THREADS = (P3_NCW + 2) * 32;
+constexpr int P3_PSLEEP = 100;  // ns between barrier polls of the producer and store lanes
 static_assert(P3_UBOX % 128 == 0 && P3_SLOT % 128 == 0 && P3_OBOX % 128 == 0 && P3_OUT % 128 == 0,
               "TMA boxes need 128-byte aligned shared-memory bases");
 static_assert(P3_SMEM <= 227 * 1024, "shared memory");
@@ -917,7 +937,7 @@ __global__ void __launch_bounds__(P3_THREADS, 1) step_fused_p3_kernel(const Step
                     const int c = (sweep == 1) ? nchunk - 1 - cc : cc;
                     const int k0 = c * KC;
                     const uint32_t s = g % NS, ph = (g / NS) & 1;
-                    fs_mbar_wait<2000>(bar_empty + 8 * s, ph ^ 1);
+                    fs_mbar_wait_sleep<P3_PSLEEP>(bar_empty + 8 * s, ph ^ 1);
                     const uint32_t sb = ring_a + s * P3_SLOT;
                     const uint32_t pl = sb + P3_T * P3_UBOX;
                     const uint32_t fb = bar_full + 8 * s;
@@ -925,7 +945,7 @@ __global__ void __launch_bounds__(P3_THREADS, 1) step_fused_p3_kernel(const Step
                         fs_mbar_expect_tx(fb, P3_T * P3_UBOX + P3_NCLS * (3 + (sweep == 3 ? 1 : 0)) * P3_PP);
 #pragma unroll
                         for (int t = 0; t < P3_T; ++t)
-                            fs_tma_load_4d(sb + t * P3_UBOX, ta.uin, fb, 4 * (ta.j0 - 2), ta.mb, k0, t, kEvictNormal);
+                            fs_tma_load_4d(sb + t * P3_UBOX, ta.uin, fb, 2 * (ta.j0 - 2), 2 * ta.mb, k0, t, kEvictNormal);
 #pragma unroll
                         for (int cl = 0; cl < P3_NCLS; ++cl) {
 #pragma unroll
@@ -940,7 +960,7 @@ __global__ void __launch_bounds__(P3_THREADS, 1) step_fused_p3_kernel(const Step
                         fs_mbar_expect_tx(fb, P3_T * P3_UBOX + P3_NCLS * 4 * P3_PP);
 #pragma unroll
                         for (int t = 0; t < P3_T; ++t)
-                            fs_tma_load_4d(sb + t * P3_UBOX, ta.uin, fb, 4 * (ta.j0 - 2), ta.mb, k0, t, kEvictFirst);
+                            fs_tma_load_4d(sb + t * P3_UBOX, ta.uin, fb, 2 * (ta.j0 - 2), 2 * ta.mb, k0, t, kEvictFirst);
 #pragma unroll
                         for (int cl = 0; cl < P3_NCLS; ++cl)
 #pragma unroll
@@ -993,10 +1013,10 @@ __global__ void __launch_bounds__(P3_THREADS, 1) step_fused_p3_kernel(const Step
                 const int mb = it.tile % p.nmb, ct = it.tile / p.nmb;
                 for (int c = 0; c < nchunk; ++c) {
                     const uint32_t s = go % NO, ph = (go / NO) & 1;
-                    fs_mbar_wait<2000>(bar_ofull + 8 * s, ph);
+                    fs_mbar_wait_sleep<P3_PSLEEP>(bar_ofull + 8 * s, ph);
 #pragma unroll
                     for (int t = 0; t < P3_T; ++t)
-                        fs_tma_store_4d(uout, oring_a + s * P3_OUT + t * P3_OBOX, 4 * ct * p.jt, mb, c * KC, t);
+                        fs_tma_store_4d(uout, oring_a + s * P3_OUT + t * P3_OBOX, 2 * ct * p.jt, 2 * mb, c * KC, t);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                     fs_mbar_arrive(bar_oempty + 8 * s);
@@ -1021,11 +1041,9 @@ __global__ void __launch_bounds__(P3_THREADS, 1) step_fused_p3_kernel(const Step
         for (int q = 0; q < KC; ++q) {
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
-                const int r = q * FS_UCOLS + col + d;
-                offU[q][d] = 32 * r + 16 * pr + sub;
+                offU[q][d] = 16 * ((q * 2 + pr) * FS_UCOLS + col + d) + sub;
             }
-            const int ro = q * p.jt + col - 1;
-            offO[q] = 32 * ro + 16 * pr + sub;
+            offO[q] = 16 * ((q * 2 + pr) * p.jt + col - 1) + sub;
         }
         const bool interior = (col >= 1 && col <= p.jt);
         const double hs = p.p3_hs, sg = p.p3_sigma;
@@ -1269,7 +1287,8 @@ static int fs_env_int(const char *name, int dflt) {
 }
 
 // ---- phosphorus: conversion between the member-fastest layout [row][ldb] (row = (tracer, level, column))
-// and the member-block-major layout of the step kernel.  Members B .. 4*nmb-1 are zero in the copy.
+// and the member-block-major layout of the step kernel (member m -> pair m >> 1 of block m >> 2, slot
+// m & 1).  Members B .. 4*nmb-1 are zero in the copy.
 __global__ void p3_to_tm_kernel(const double *__restrict__ src, double *__restrict__ dst, int ny, int B, size_t ldb,
                                 int nmb) {
     const int tk = blockIdx.y;
@@ -1278,7 +1297,7 @@ __global__ void p3_to_tm_kernel(const double *__restrict__ src, double *__restri
     if (idx >= ny * wm) return;
     const int j = idx / wm, m = idx % wm;
     const double v = (m < B) ? src[((size_t)tk * ny + j) * ldb + m] : 0.0;
-    dst[(((size_t)tk * nmb + (m >> 2)) * ny + j) * 4 + (m & 3)] = v;
+    dst[(((size_t)tk * nmb * 2 + (m >> 1)) * ny + j) * 2 + (m & 1)] = v;
 }
 // f = x_tm(T) - x0, back in the member-fastest layout
 __global__ void p3_from_tm_sub_kernel(const double *__restrict__ tm, const double *__restrict__ x0,
@@ -1290,14 +1309,14 @@ __global__ void p3_from_tm_sub_kernel(const double *__restrict__ tm, const doubl
     const int j = idx / wm, m = idx % wm;
     if (m >= B) return;
     const size_t o = ((size_t)tk * ny + j) * ldb + m;
-    f[o] = tm[(((size_t)tk * nmb + (m >> 2)) * ny + j) * 4 + (m & 3)] - x0[o];
+    f[o] = tm[(((size_t)tk * nmb * 2 + (m >> 1)) * ny + j) * 2 + (m & 1)] - x0[o];
 }
 __global__ void p3_gather_member_kernel(const double *__restrict__ tm, double *__restrict__ dst, int ny, int nmb,
                                         size_t n, int b) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // (tracer, level, column)
     if (i >= n) return;
     const size_t tk = i / ny, j = i % ny;
-    dst[i] = tm[((tk * nmb + (b >> 2)) * ny + j) * 4 + (b & 3)];
+    dst[i] = tm[((tk * nmb * 2 + (b >> 1)) * ny + j) * 2 + (b & 1)];
 }
 
 int launch_p3_to_tm(const ModelDev &v, const double *src, double *dst, int B, size_t ldb, cudaStream_t st) {
@@ -1397,13 +1416,13 @@ int fused_encode_state_maps(const ModelDev &v, int B, int ldb, const double *buf
     int nct, jt;
     fs_col_tiles(v.ny, nct, jt);
     if (v.kind == NKB_MOD_PHOSPHORUS) {
-        // member-block-major copy: [tracer][level][member block][column * 4 members]
-        const cuuint64_t nmb = (cuuint64_t)((B + P3_MEM - 1) / P3_MEM);
-        const cuuint64_t run = (cuuint64_t)v.ny * P3_MEM;
-        const cuuint64_t dims[4] = {run, nmb, (cuuint64_t)v.nz, (cuuint64_t)v.T};
-        const cuuint64_t strides[3] = {run * 8, nmb * run * 8, (cuuint64_t)v.nz * nmb * run * 8};
-        const cuuint32_t box_in[4] = {FS_UCOLS * P3_MEM, 1, P3_KC, 1};
-        const cuuint32_t box_out[4] = {(cuuint32_t)jt * P3_MEM, 1, P3_KC, 1};
+        // member-block-major copy: [tracer][level][member pair][column * 2 members]
+        const cuuint64_t npair = 2 * (cuuint64_t)((B + P3_MEM - 1) / P3_MEM);
+        const cuuint64_t run = (cuuint64_t)v.ny * 2;
+        const cuuint64_t dims[4] = {run, npair, (cuuint64_t)v.nz, (cuuint64_t)v.T};
+        const cuuint64_t strides[3] = {run * 8, npair * run * 8, (cuuint64_t)v.nz * npair * run * 8};
+        const cuuint32_t box_in[4] = {FS_UCOLS * 2, 2, P3_KC, 1};
+        const cuuint32_t box_out[4] = {(cuuint32_t)jt * 2, 2, P3_KC, 1};
         if (in && fs_encode(in, buf, 4, dims, strides, box_in, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
         if (out && fs_encode(out, buf, 4, dims, strides, box_out, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
         return 0;

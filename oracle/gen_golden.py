@@ -52,6 +52,11 @@ def baselines():
         out[f"ci_short/hist_00/{var}"] = hist[var]
     np.savez_compressed(os.path.join(OUT, "baselines.npz"), **out)
     print("baselines.npz:", len(out), "arrays")
+    # the step log of the reference's own ci_long_iage run (solver persistence tests)
+    import shutil
+
+    shutil.copyfile(os.path.join(base, "ci_long_iage", "Newton_state.json"),
+                    os.path.join(OUT, "Newton_state_ci_long_iage.json"))
 
 
 def remap_cases():

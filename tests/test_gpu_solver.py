@@ -232,3 +232,57 @@ def test_cli_setup_solver_and_nk_driver_column_regions(base, tmp_path):
     np.testing.assert_allclose(read(os.path.join(work, "fcn_cli.nc")), _want(base, pre + "fcn_0000"), rtol=1e-3,
                                atol=1e-6)
     ModelState.reset()
+
+
+def test_newton_state_stats_files_and_resume(base, tmp_path):
+    """the work directory of a dumped solve carries the reference's Newton_state.json (iteration 3 and
+    the reference's step strings, baselines/ci_long_iage/Newton_state.json) and Newton_stats.nc /
+    Krylov_stats.nc; a resumed solver reads iterate and fcn of the logged iteration back instead of
+    recomputing them, and a solve interrupted after one step continues to the same answer"""
+    import json
+
+    from scipy.io import netcdf_file
+
+    from nk_ooc_b200 import _lib
+    from nk_ooc_b200.solver import NewtonSolver
+
+    ModelState = _configure(str(tmp_path), "iage")
+    work = str(tmp_path / "work")
+    iterate = ModelState({"iage": base["ci_short/init_iterate/iage"]})
+    solver = NewtonSolver(iterate, TP_SOLVERINFO, workdir=work)
+    solver.step()
+    # "interrupted" here: a second solver resumes from the files and finishes
+    lib = _lib.load()
+    n0 = lib.nkb_launch_count()
+    resumed = NewtonSolver(ModelState("zeros"), TP_SOLVERINFO, workdir=work, resume=True)
+    assert lib.nkb_launch_count() - n0 <= 4, "resume re-evaluated the function"  # only the two norms of _record
+    assert resumed.iteration == 1
+    np.testing.assert_array_equal(resumed.iterate.get_tracer_vals("iage"), solver.iterate.get_tracer_vals("iage"))
+    np.testing.assert_array_equal(resumed.fcn.get_tracer_vals("iage"), solver.fcn.get_tracer_vals("iage"))
+    resumed.solve()
+    solver.solve()
+    assert resumed.iteration == solver.iteration == 3
+    np.testing.assert_allclose(resumed.iterate.get_tracer_vals("iage"), solver.iterate.get_tracer_vals("iage"),
+                               rtol=0, atol=1e-12 * np.abs(solver.iterate.get_tracer_vals("iage")).max())
+    state = json.load(open(os.path.join(work, "Newton_state.json")))
+    assert state["iteration"] == 3
+    want_log = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "Newton_state_ci_long_iage.json")))
+    ours = set(s.replace(work, "W") for s in state["step_log"])
+    for step in want_log["step_log"]:
+        step = step.replace("HOME/ci_long_iage_workdir", "W")
+        if step.startswith(("__init__", "Newton iterate 0 written")) or ":inc_iteration" in step or \
+                (":comp_fcn complete for W/fcn_" in step):
+            assert step in ours, step
+    with netcdf_file(os.path.join(work, "Newton_stats.nc"), "r", mmap=False) as f:
+        assert f.variables["iteration"].shape[0] == 4
+        fn = np.array(f.variables["fcn_norm_iage"].data)[:, 0]
+        assert (np.diff(fn) < 0).all() and fn[-1] < 1e-8 * np.array(f.variables["iterate_norm_iage"].data)[-1, 0]
+        assert (np.array(f.variables["Krylov_iterations"].data)[:3] >= 1).all()
+        np.testing.assert_array_equal(np.array(f.variables["Armijo_factor_iage"].data)[:3, 0], 1.0)
+    with netcdf_file(os.path.join(work, "krylov_00", "Krylov_stats.nc"), "r", mmap=False) as f:
+        beta = float(np.array(f.variables["precond_rhs_norm_iage"].data)[0])
+        res = np.array(f.variables["precond_resid_norm_iage"].data)[:, 0]
+        assert res[-1] < 0.01 * beta
+    kstate = json.load(open(os.path.join(work, "krylov_00", "Krylov_state.json")))
+    assert "beta" in kstate and "h_mat" in kstate and kstate["iteration"] == len(res)
+    ModelState.reset()
