@@ -124,7 +124,8 @@ __device__ __forceinline__ void fs_mbar_wait(uint32_t bar, uint32_t parity) {
     } while (!ok);
 }
 // plain try_wait + a real sleep between polls (the hinted form above wakes on every barrier event of the CTA:
-// in the phosphorus kernel the producer and store lanes were executing 20 % of all instructions)
+// in the phosphorus kernel the producer and store lanes were executing 20 % of all instructions; in the
+// single-tracer kernel the two forms measure the same)
 template <int SLEEP_NS>
 __device__ __forceinline__ void fs_mbar_wait_sleep(uint32_t bar, uint32_t parity) {
     uint32_t ok = 0;
