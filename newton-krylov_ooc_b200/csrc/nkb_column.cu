@@ -8,6 +8,8 @@
 // phosphorus.py:28-120 (sources).  Scheme: ARS(2,2,2) IMEX; with no horizontal transport the
 // implicit part is the L-stable SDIRK2, sources of phosphorus are explicit.
 
+#include <cstdlib>
+
 #include "nkb_common.cuh"
 
 namespace nkb {

@@ -267,6 +267,35 @@ def test_fused_kernel_hist_snapshots_and_two_members_per_thread(monkeypatch):
 
 
 
+def test_fused_phosphorus_hist_snapshots_odd_and_even_step_counts():
+    """hist snapshots of the phosphorus step kernel are gathered from the member-block-major work
+    buffers (segmented persistent launches); an odd and an even number of steps put x(0)'s copy and
+    the final state in different work buffers; a member count that is not a multiple of 4"""
+    from oracle import imex_oracle as im
+    from oracle import nk_oracle as o
+    from nk_ooc_b200.py_driver_2d import modules
+
+    rng = np.random.default_rng(41)
+    g, tr = _grid(13, 19)
+    mod = im.Module2D("phosphorus", g, phos=o.Phosphorus2D(g))
+    B = 10
+    x = np.abs(rng.normal(size=(3, g.nz, g.ny, B))) * 0.5
+    for nsteps, marks in ((240, [0, 80, 81, 240]), (241, [0, 7, 240, 241])):
+        m = modules.phosphorus_model(tr)
+        m.set_uniform_schedule(nsteps)
+        snaps = []
+        want = im.model_year_2d(mod, x, nsteps, snapshots=snaps)
+        f, hist = m.eval(_to_dev(x), B, hist_steps=marks)
+        m.check_health()
+        hist = hist.cpu().numpy()
+        scale = np.abs(want).max()
+        np.testing.assert_allclose(f.cpu().numpy()[..., :B], want, rtol=0, atol=1e-10 * scale)
+        np.testing.assert_array_equal(hist[0], x[..., 0])
+        for i, step in enumerate(marks[1:-1], start=1):
+            np.testing.assert_allclose(hist[i], snaps[step - 1][1][..., 0], rtol=0, atol=1e-10 * scale)
+        np.testing.assert_allclose(hist[-1], x[..., 0] + want[..., 0], rtol=0, atol=1e-10 * scale)
+
+
 def test_full_size_properties_refined_grid():
     """BASELINE.json's headline size (refined 125 x 150 grid, 4096 members; 8 steps instead of a year)
     through size-independent properties, since the numpy oracle takes minutes there:
@@ -326,3 +355,58 @@ def test_full_size_properties_refined_grid():
     g = o.Grid2D(ze, ye, 0.1, 1000.0)
     want = im.model_year_2d(im.Module2D("iage", g), x[..., 5:6].cpu().numpy(), schedule=sched)
     np.testing.assert_allclose(f[..., 5:6].cpu().numpy(), want, rtol=0, atol=1e-11 * np.abs(want).max())
+
+
+def test_full_size_properties_refined_grid_phosphorus():
+    """the three-tracer module at BASELINE.json's headline size (refined 125 x 150, 4096 members; the
+    first 8 steps of the production schedule): members are independent bit for bit (a permutation of
+    the members permutes the results — members share 4-member tiles with different neighbours), the
+    persistent launch equals one launch per step, the stage-per-launch kernels agree to rounding, one
+    member against the numpy statement of the scheme, and total phosphorus (po4 + dop + pop, volume
+    weighted) is conserved by the step kernels as it is by the reference's tendencies"""
+    import os
+
+    from oracle import imex_oracle as im
+    from oracle import nk_oracle as o
+    from nk_ooc_b200.engine import graded_schedule
+    from nk_ooc_b200.py_driver_2d import modules
+    from nk_ooc_b200.spatial_axis import SpatialAxis, edges_from_defn
+
+    nz, ny, B, nsteps = 125, 150, 4096, 8
+    ze = edges_from_defn(nz, 0.0, 4000.0, 11.8)
+    ye = edges_from_defn(ny, 0.0, 50.0e5, 1.0)
+    depth, ypos = SpatialAxis("depth", ze), SpatialAxis("ypos", ye)
+    tr = modules.Transport2D(depth, ypos, 0.1, 1000.0)
+    m = modules.phosphorus_model(tr)
+    t_all, h_all = graded_schedule(0.0, 365.0 * 86400.0)
+    sched = (t_all[:nsteps].copy(), h_all[:nsteps].copy())
+    m.set_schedule(*sched)
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    x = torch.rand((3, nz, ny, B), dtype=torch.float64, device="cuda", generator=gen) + 0.1
+    f = m.eval(x, B).clone()
+    m.check_health()
+    perm = torch.randperm(B, device="cuda", generator=gen)
+    fp = m.eval(x[..., perm].contiguous(), B)
+    assert torch.equal(fp, f[..., perm])
+    scale = float(f.abs().max())
+    os.environ["NKB_FUSED_PERSIST"] = "0"
+    try:
+        assert torch.equal(m.eval(x, B), f)
+    finally:
+        del os.environ["NKB_FUSED_PERSIST"]
+    os.environ["NKB_FUSED_P3"] = "0"
+    try:
+        fu = m.eval(x, B)
+    finally:
+        del os.environ["NKB_FUSED_P3"]
+    assert float((fu - f).abs().max()) <= 1e-11 * scale
+    g = o.Grid2D(ze, ye, 0.1, 1000.0)
+    mod = im.Module2D("phosphorus", g, phos=o.Phosphorus2D(g))
+    want = im.model_year_2d(mod, x[..., 7:8].cpu().numpy(), schedule=sched)
+    np.testing.assert_allclose(f[..., 7:8].cpu().numpy(), want, rtol=0, atol=1e-11 * np.abs(want).max())
+    # conservation: sources sum to zero over the tracers, transport and sinking are flux divergences
+    # with closed boundaries -> the volume integral of F summed over the tracers vanishes
+    vol = torch.from_numpy(np.outer(depth.delta, ypos.delta)).cuda()
+    total = (f[..., :64].sum(dim=0) * vol[..., None]).sum(dim=(0, 1))
+    content = (x[..., :64].sum(dim=0) * vol[..., None]).sum(dim=(0, 1))
+    assert float((total / content).abs().max()) <= 1e-12
