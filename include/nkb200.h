@@ -79,6 +79,15 @@ typedef struct nkb_model_desc {
     const double *h_light;               /* [nz][ny] phosphorus light limitation (phosphorus.py:23-26) */
     double po4_halfsat, max_uptake_rate, sigma, dop_remin_rate, pop_remin_rate; /* phosphorus.py:41-47 */
     int32_t po4_s_restoring_opt;         /* test_problem phosphorus.py:58-70 */
+
+    /* optional surface restoring to a time-dependent record (forced_surf_restore_opt = file,
+     * py_driver_2d/forced.py:46-51,124-130): restore_to(t, ypos) linearly interpolated in time (with
+     * extrapolation, utils.py:533-535); srf_rate[c] * restore_to is added to the k=0 tendency of class
+     * c (the matching -rate goes into surf_diag).  n_srf == 0: off */
+    int32_t n_srf;
+    const double *h_srf_time;            /* [n_srf] */
+    const double *h_srf_data;            /* [n_srf][ny], on the model's ypos axis */
+    double srf_rate[NKB_MAX_CLASSES];
 } nkb_model_desc;
 
 typedef struct nkb_model nkb_model; /* opaque */

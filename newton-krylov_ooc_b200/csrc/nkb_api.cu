@@ -34,6 +34,8 @@ int nkb_model_create(nkb_model **out, const nkb_model_desc *d) {
                 "nkb_model_create: test_problem phosphorus needs 6 tracers, ny == 1 and a light table");
     NKB_REQUIRE(d->kind != NKB_MOD_FORCED_FILE || (d->n_frc >= 2 && d->h_frc_time && d->h_frc_data),
                 "nkb_model_create: forced file module needs >= 2 forcing records");
+    NKB_REQUIRE(d->n_srf == 0 || (d->n_srf >= 2 && d->h_srf_time && d->h_srf_data),
+                "nkb_model_create: a surface restoring record needs >= 2 times");
     for (int t = 0; t < d->n_tracers; ++t)
         NKB_REQUIRE(d->class_of[t] >= 0 && d->class_of[t] < d->n_classes, "nkb_model_create: bad class_of");
 
@@ -70,7 +72,7 @@ int nkb_model_create(nkb_model **out, const nkb_model_desc *d) {
         }
     }
     const size_t o_w = push(w.data(), w.size());
-    size_t o_est = 0, o_bld = 0, o_ft = 0, o_fd = 0, o_light = 0;
+    size_t o_est = 0, o_bld = 0, o_ft = 0, o_fd = 0, o_light = 0, o_st = 0, o_sd = 0;
     if (d->h_estencil) {  // [3][nz][ny] -> packed [nz][ny][4] {eL, eC, eR, 0}
         std::vector<double> e4(4 * plane, 0.0);
         for (size_t c = 0; c < plane; ++c)
@@ -83,6 +85,10 @@ int nkb_model_create(nkb_model **out, const nkb_model_desc *d) {
         o_fd = push(d->h_frc_data, (size_t)d->n_frc * plane);
     }
     if (d->h_light) o_light = push(d->h_light, plane);
+    if (d->n_srf > 0) {
+        o_st = push(d->h_srf_time, d->n_srf);
+        o_sd = push(d->h_srf_data, (size_t)d->n_srf * ny);
+    }
 
     nkb_model *m = new nkb_model();
     if (cudaMalloc(&m->arena, host.size() * sizeof(double)) != cudaSuccess) {
@@ -117,6 +123,10 @@ int nkb_model_create(nkb_model **out, const nkb_model_desc *d) {
     v.po4_halfsat = d->po4_halfsat; v.max_uptake_rate = d->max_uptake_rate; v.sigma = d->sigma;
     v.dop_remin_rate = d->dop_remin_rate; v.pop_remin_rate = d->pop_remin_rate;
     v.po4_s_restoring_opt = d->po4_s_restoring_opt;
+    v.n_srf = d->n_srf;
+    v.srf_time = d->n_srf > 0 ? base + o_st : nullptr;
+    v.srf_data = d->n_srf > 0 ? base + o_sd : nullptr;
+    for (int c = 0; c < NKB_MAX_CLASSES; ++c) v.srf_rate[c] = d->srf_rate[c];
 
     NKB_CUDA(cudaMalloc(&m->tri_raw, (size_t)v.n_classes * 4 * plane * sizeof(double)));
     NKB_CUDA(cudaMalloc(&m->aff_raw, (size_t)v.n_classes * ny * sizeof(double)));

@@ -65,6 +65,10 @@ struct ModelDev {
     const double *light;     // [nz][ny]
     double po4_halfsat, max_uptake_rate, sigma, dop_remin_rate, pop_remin_rate;
     int po4_s_restoring_opt;
+    int n_srf;
+    const double *srf_time;  // [n_srf]
+    const double *srf_data;  // [n_srf][ny]
+    double srf_rate[NKB_MAX_CLASSES];
 };
 
 // arguments of one fused stage launch (K1+K2)

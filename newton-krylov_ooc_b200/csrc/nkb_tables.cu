@@ -147,8 +147,17 @@ __global__ void stage_tables_kernel(ModelDev m, int n_stages, const double *__re
         mc_up = mc_dn;
     }
     const double flux = surf_flux(m, time) * m.dz_r[0];
+    // surface restoring to a record (forced.py:124-130): linear in time, extrapolated at the ends
+    double restore_to = 0.0;
+    if (m.n_srf > 0) {
+        int i = 0;
+        while (i < m.n_srf - 2 && time >= m.srf_time[i + 1]) ++i;
+        const double w = (time - m.srf_time[i]) / (m.srf_time[i + 1] - m.srf_time[i]);
+        const double v0 = m.srf_data[(size_t)i * ny + j], v1 = m.srf_data[(size_t)(i + 1) * ny + j];
+        restore_to = v0 + w * (v1 - v0);
+    }
     for (int c = 0; c < nc; ++c) {
-        const double a = m.surf_aff[c] + flux;
+        const double a = m.surf_aff[c] + flux + m.srf_rate[c] * restore_to;
         aff[((size_t)s * nc + c) * ny + j] = (mode == 0) ? a : hg * a;
     }
 }

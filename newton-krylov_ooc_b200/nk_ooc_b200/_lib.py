@@ -61,6 +61,10 @@ class ModelDesc(ctypes.Structure):
         ("dop_remin_rate", c_double),
         ("pop_remin_rate", c_double),
         ("po4_s_restoring_opt", c_int32),
+        ("n_srf", c_int32),
+        ("h_srf_time", POINTER(c_double)),
+        ("h_srf_data", POINTER(c_double)),
+        ("srf_rate", c_double * NKB_MAX_CLASSES),
     ]
 
 

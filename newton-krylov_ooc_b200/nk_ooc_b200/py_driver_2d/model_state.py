@@ -173,8 +173,9 @@ class ModelState(ModelStateBase):
     def _forced_model(cls, info):
         """forced.py:57-112: options from modelinfo (scripts/run_py_driver_2d_forced_*.sh)"""
         kw = {"surf_restore_opt": info["forced_surf_restore_opt"], "sms_opt": info["forced_sms_opt"]}
-        if kw["surf_restore_opt"] == "file":
-            raise NotImplementedError("forced_surf_restore_opt=file is not on the B200 path yet")
+        if kw["surf_restore_opt"] == "file":  # forced.py:46-51
+            kw["surf_restore_times"], kw["surf_restore_data"] = read_forcing(
+                info["forced_surf_restore_fname"], info["forced_surf_restore_varname"], [cls.ypos.mid])
         if "forced_surf_restore_rate_10m" in info:
             kw["surf_restore_rate_10m"] = _eval_expr(info["forced_surf_restore_rate_10m"])
         if kw["surf_restore_opt"] == "const":

@@ -59,11 +59,12 @@ def iage_model(tr):
 
 def forced_model(tr, surf_restore_opt="const", surf_restore_const=0.0, surf_restore_rate_10m=24.0 / 86400.0,
                  sms_opt="none", sms_const=0.0, sms_decay_rate=0.0, sms_times=None, sms_data=None,
-                 sink_thres=None):
+                 sink_thres=None, surf_restore_times=None, surf_restore_data=None):
     """forced_{suff} (py_driver_2d/forced.py:57-154).  sms_data [nt, nz, ny] must already be
-    on the model grid with scalef applied (utils.gen_forcing_fcn does both when reading)."""
-    if surf_restore_opt not in ("none", "const"):
-        raise ValueError(f"unsupported forced_surf_restore_opt={surf_restore_opt}")
+    on the model grid with scalef applied (utils.gen_forcing_fcn does both when reading);
+    surf_restore_data [nt, ny] (forced_surf_restore_opt = file) on the model's ypos axis."""
+    if surf_restore_opt not in ("none", "const", "file"):
+        raise ValueError(f"unknown forced_surf_restore_opt={surf_restore_opt}")
     if sms_opt not in ("none", "const", "decay", "file"):
         raise ValueError(f"unknown forced_sms_opt={sms_opt}")
     if surf_restore_opt == "none" and sms_opt != "decay":
@@ -77,6 +78,17 @@ def forced_model(tr, surf_restore_opt="const", surf_restore_const=0.0, surf_rest
         rate = 10.0 / tr.depth.delta[0] * surf_restore_rate_10m
         d.surf_diag[0] = -rate
         d.surf_aff[0] = rate * surf_restore_const
+    elif surf_restore_opt == "file":
+        rate = 10.0 / tr.depth.delta[0] * surf_restore_rate_10m
+        keep["st"] = np.ascontiguousarray(surf_restore_times, dtype=np.float64)
+        keep["sd"] = np.ascontiguousarray(surf_restore_data, dtype=np.float64)
+        if keep["sd"].shape != (len(keep["st"]), len(tr.ypos)) or len(keep["st"]) < 2:
+            raise ValueError("surf_restore_data must be [nt >= 2, ny] on the model grid")
+        d.surf_diag[0] = -rate
+        d.srf_rate[0] = rate
+        d.n_srf = len(keep["st"])
+        d.h_srf_time = _lib.dptr(keep["st"])
+        d.h_srf_data = _lib.dptr(keep["sd"])
     if sms_opt == "const":
         d.src_const[0] = sms_const
     elif sms_opt == "decay":

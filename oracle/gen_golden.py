@@ -323,6 +323,49 @@ def test_problem_cases():
     print("test_problem.npz:", len(out), "arrays")
 
 
+def forced_restore_file_case():
+    """the reference's forced module with forced_surf_restore_opt = file (forced.py:46-51,124-130): the
+    restoring record [time, ypos] is given on a COARSER ypos axis than the model's, so the reference's
+    gen_forcing_fcn also interpolates it in space (utils.py:518-531); written to its own fixture so that
+    the seeded states of py_driver_2d.npz stay what they are"""
+    from scipy.io import netcdf_file
+
+    rng = np.random.default_rng(410)
+    nz, ny = 12, 9
+    depth, ypos, procs = rh.make_py_driver_2d(nz, ny, 19.0, 0.1, 1000.0)
+    nt, ny_file = 7, 5
+    rtimes = np.linspace(0.0, YEAR, nt)
+    ypos_file = np.linspace(ypos.mid[0], ypos.mid[-1], ny_file)
+    rdata = 1.0 + 0.3 * rng.normal(size=(nt, ny_file))
+    fname = "/tmp/golden_surf_restore.nc"
+    with netcdf_file(fname, "w", version=2) as f:
+        f.createDimension("time", nt)
+        f.createDimension("ypos", ny_file)
+        for name, vals in (("time", rtimes), ("ypos", ypos_file)):
+            v = f.createVariable(name, "f8", (name,))
+            v[:] = vals
+        v = f.createVariable("surf_vals", "f8", ("time", "ypos"))
+        v[:] = rdata
+    modelinfo = {
+        "forced_surf_restore_opt": "file", "forced_surf_restore_fname": fname,
+        "forced_surf_restore_varname": "surf_vals", "forced_surf_restore_rate_10m": "1.0 / 7200.0",
+        "forced_sms_opt": "const", "forced_sms_const": "-1.0e-9",
+    }
+    forced = rh.make_2d_forced(depth, ypos, modelinfo, suff="restore_file")
+    x = np.abs(rng.normal(size=(1, nz, ny)))
+    tt = YEAR * np.array([0.0, 0.21, 0.5, 0.93, 1.0])
+    out = {
+        "params": np.array([nz, ny, 19.0, 0.1, 1000.0]), "depth_edges": depth.edges, "ypos_edges": ypos.edges,
+        "rtimes": rtimes, "ypos_file": ypos_file, "rdata": rdata,
+        "x": x, "times": tt,
+        "restore_to": np.stack([forced.surf_restore_fcn(t) for t in tt]),
+        "tend": np.stack([forced.comp_tend(t, x.reshape(-1), procs).reshape(x.shape) for t in tt]),
+        "jac_dense_t1": forced.comp_jacobian(tt[1], x.reshape(-1), procs).toarray(),
+    }
+    np.savez_compressed(os.path.join(OUT, "forced_restore_file.npz"), **out)
+    print("forced_restore_file.npz:", len(out), "arrays")
+
+
 def main():
     if not rh.available():
         raise SystemExit("reference tree not found: golden vectors can only be generated in the build container")
@@ -332,6 +375,7 @@ def main():
     remap_cases()
     py_driver_2d_cases()
     test_problem_cases()
+    forced_restore_file_case()
 
 
 if __name__ == "__main__":

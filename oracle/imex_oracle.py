@@ -111,9 +111,9 @@ class Module2D:
     def tracer_class(self):
         return {"iage": [0, 1], "forced": [0], "phosphorus": [0, 0, 1]}[self.kind]
 
-    def implicit_extra(self, cls, sub, diag, sup):
+    def implicit_extra(self, cls, sub, diag, sup, time=None):
         """add module terms to the class's tridiagonal (in place); returns affine surface
-        source rate for k=0 (or 0.0)"""
+        source rate for k=0 (0.0, a scalar, or [ny] when the surface is restored to a record)"""
         g = self.g
         aff = 0.0
         if self.kind == "iage":
@@ -124,6 +124,9 @@ class Module2D:
             if f.restore_const is not None:
                 diag[0] -= f.rate
                 aff = f.rate * f.restore_const
+            if f.restore_times is not None:  # forced_surf_restore_opt = file (forced.py:124-130)
+                diag[0] -= f.rate
+                aff = aff + f.rate * f.restore_to(time)
             if f.sms_opt == "decay":
                 diag -= f.sms_decay_rate
         elif self.kind == "phosphorus" and cls == 1:
@@ -172,8 +175,8 @@ def stage_tables_2d(mod, time, hg):
     tabs = []
     for cls in sorted(set(mod.tracer_class())):
         sub, diag, sup = implicit_tridiag_2d(mod.g, time)
-        aff = mod.implicit_extra(cls, sub, diag, sup)
-        tabs.append(thomas_factor(sub, diag, sup, hg) + (aff,))
+        aff = mod.implicit_extra(cls, sub, diag, sup, time)
+        tabs.append(thomas_factor(sub, diag, sup, hg) + (np.asarray(aff, dtype=np.float64)[..., None],))
     return tabs
 
 

@@ -403,9 +403,11 @@ class Forced2D:
 
     def __init__(self, grid, restore_rate_10m=24.0 / 86400.0, restore_const=None,
                  sms_opt="none", sms_const=0.0, sms_decay_rate=0.0, sms_times=None,
-                 sms_data=None, sink_thres=None):
+                 sms_data=None, sink_thres=None, restore_times=None, restore_data=None):
         self.g = grid
         self.restore_const = restore_const
+        self.restore_times = restore_times  # forced_surf_restore_opt = file (forced.py:46-51): [nt], [nt, ny]
+        self.restore_data = restore_data
         self.rate = 10.0 / grid.depth.delta[0] * restore_rate_10m
         self.sms_opt = sms_opt
         self.sms_const = sms_const
@@ -422,12 +424,21 @@ class Forced2D:
         w = (time - t[i]) / (t[i + 1] - t[i])
         return self.sms_data[i] + w * (self.sms_data[i + 1] - self.sms_data[i])
 
+    def restore_to(self, time):
+        """surface restoring value at `time`: interp1d(linear, extrapolate) over the record"""
+        t = self.restore_times
+        i = int(np.clip(np.searchsorted(t, time, side="right") - 1, 0, len(t) - 2))
+        w = (time - t[i]) / (t[i + 1] - t[i])
+        return self.restore_data[i] + w * (self.restore_data[i + 1] - self.restore_data[i])
+
     def comp_tend(self, time, flat):
         g = self.g
         c = flat.reshape(1, g.nz, g.ny)
         tend = g.transport_tend(time, c)
         if self.restore_const is not None:
             tend[0, 0, :] += self.rate * (self.restore_const - c[0, 0, :])
+        if self.restore_times is not None:  # forced.py:124-130
+            tend[0, 0, :] += self.rate * (self.restore_to(time) - c[0, 0, :])
         if self.sms_opt == "const":
             tend[0] += self.sms_const
         elif self.sms_opt == "decay":
@@ -445,7 +456,7 @@ class Forced2D:
         n = g.nz * g.ny
         jac = g.transport_jacobian(time, 1)
         d = np.zeros(n)
-        if self.restore_const is not None:
+        if self.restore_const is not None or self.restore_times is not None:
             d[: g.ny] -= self.rate
         if self.sms_opt == "decay":
             d -= self.sms_decay_rate

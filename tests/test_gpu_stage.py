@@ -410,3 +410,54 @@ def test_full_size_properties_refined_grid_phosphorus():
     total = (f[..., :64].sum(dim=0) * vol[..., None]).sum(dim=(0, 1))
     content = (x[..., :64].sum(dim=0) * vol[..., None]).sum(dim=(0, 1))
     assert float((total / content).abs().max()) <= 1e-12
+
+
+@pytest.mark.parametrize("B", [1, 24])
+def test_forced_surface_restoring_to_a_record(B, golden_dir, tmp_path):
+    """forced_surf_restore_opt = file (py_driver_2d/forced.py:46-51,124-130): the restoring value is a
+    record in time and ypos (K3 interpolates it per implicit stage into the affine surface source).
+    (i) the device tendency against the REFERENCE's own comp_tend (golden vectors, record on a coarser
+    ypos axis read through the host mirror's forcing reader), (ii) the model year — fused step kernel
+    for B >= 8, stage kernels for B = 1 — against the numpy statement of the scheme"""
+    import os
+
+    from scipy.io import netcdf_file
+
+    from oracle import imex_oracle as im
+    from oracle import nk_oracle as o
+    from nk_ooc_b200.py_driver_2d import modules
+    from nk_ooc_b200.py_driver_2d.model_state import read_forcing
+    from nk_ooc_b200.spatial_axis import SpatialAxis
+
+    gv = np.load(os.path.join(golden_dir, "forced_restore_file.npz"))
+    nz, ny, ratio, vvel, kh = gv["params"]
+    depth, ypos = SpatialAxis("depth", gv["depth_edges"]), SpatialAxis("ypos", gv["ypos_edges"])
+    fname = str(tmp_path / "surf_restore.nc")
+    with netcdf_file(fname, "w", version=2) as f:
+        f.createDimension("time", len(gv["rtimes"]))
+        f.createDimension("ypos", len(gv["ypos_file"]))
+        for name, vals in (("time", gv["rtimes"]), ("ypos", gv["ypos_file"])):
+            v = f.createVariable(name, "f8", (name,))
+            v[:] = vals
+        v = f.createVariable("surf_vals", "f8", ("time", "ypos"))
+        v[:] = gv["rdata"]
+    rtimes, rdata = read_forcing(fname, "surf_vals", [ypos.mid])
+    tr = modules.Transport2D(depth, ypos, float(vvel), float(kh))
+    m = modules.forced_model(tr, "file", surf_restore_rate_10m=1.0 / 7200.0, sms_opt="const", sms_const=-1.0e-9,
+                             surf_restore_times=rtimes, surf_restore_data=rdata)
+    x1 = gv["x"]
+    for i, t in enumerate(gv["times"]):
+        got = m.tend(float(t), _to_dev(x1[..., None]), 1).cpu().numpy()[..., 0]
+        np.testing.assert_allclose(got, gv["tend"][i], rtol=0, atol=1e-12 * np.abs(gv["tend"][i]).max())
+    g = o.Grid2D(gv["depth_edges"], gv["ypos_edges"], float(vvel), float(kh))
+    f2 = o.Forced2D(g, restore_rate_10m=1.0 / 7200.0, restore_const=None, sms_opt="const", sms_const=-1.0e-9,
+                    restore_times=rtimes, restore_data=rdata)
+    rng = np.random.default_rng(B)
+    x = np.abs(rng.normal(size=(1, g.nz, g.ny, B)))
+    nsteps = 24
+    m.set_uniform_schedule(nsteps)
+    got = m.eval(_to_dev(x), B).cpu().numpy()[..., :B]
+    want = im.model_year_2d(im.Module2D("forced", g, forced=f2), x, nsteps)
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-10 * np.abs(want).max())
+    with pytest.raises(ValueError):
+        modules.forced_model(tr, "file", surf_restore_times=rtimes[:1], surf_restore_data=rdata[:1])
