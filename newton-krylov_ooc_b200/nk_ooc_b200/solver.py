@@ -257,6 +257,7 @@ class NewtonSolver:
             if dump:
                 self._state.log_step(fcn_step)
                 self._stats.put(self.iteration, iterate=self._iterate, fcn=self._fcn)
+                self._put_hist_stats(self._iterate)
         self.history = []  # per iteration: dict(fcn_norm, iterate_norm, krylov_iterations, armijo_factor, ...)
         self._record()
 
@@ -264,6 +265,20 @@ class NewtonSolver:
     def _fname(self, quantity, iteration=None):
         iteration = self.iteration if iteration is None else iteration
         return os.path.join(self._workdir, f"{quantity}_{iteration:02}.nc")
+
+    def _put_hist_stats(self, state):
+        """the model's own statistics of this iteration's hist file (model_state_base.py:136-180)"""
+        hist_fname = self._fname("hist")
+        if not os.path.exists(hist_fname):
+            return
+        names = []
+        for tms in state.tracer_modules:
+            names += list(tms.tracer_names)  # tracer_module_state_base.py:100-104
+            if ".test_problem." in type(state).__module__ and tms._def.get("py_mod_name", tms.name) == "phosphorus":
+                names.append("po4_uptake")  # test_problem/phosphorus.py:161-167
+        ypos = getattr(type(state), "ypos", None)
+        weights = {ypos.axisname: ypos.delta} if ypos is not None and hasattr(ypos, "axisname") else None
+        self._stats.put_hist_stats(self.iteration, hist_fname, names, weights)
 
     def _record(self, **extra):
         rec = {"iteration": self.iteration, "fcn_norm": self._fcn.norm(), "iterate_norm": self._iterate.norm()}
@@ -365,6 +380,7 @@ class NewtonSolver:
             self._state.inc_iteration()
             self._state.log_step(f"comp_fcn complete for {self._fname('fcn')}")
             self._stats.put(self.iteration, iterate=prov, fcn=prov_fcn)
+            self._put_hist_stats(prov)
         self._iterate, self._fcn = prov, prov_fcn
         self._record(krylov_iterations=krylov.iteration, krylov_precond_resid_norm=krylov.precond_resid_norm,
                      krylov_beta=krylov.beta, increment_scalef=scalef, armijo_factor=armijo_factor,

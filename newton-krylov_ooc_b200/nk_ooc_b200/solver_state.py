@@ -9,7 +9,11 @@ be resumed (`resume=True`) or its last step redone (`rewind=True`).
 solver_base.py:71-125): NETCDF3 64-bit offset, unlimited `iteration` dimension, `region` dimension,
 per tracer module `{iterate,fcn,increment}_{mean,norm}_<module>`, `increment_scalef_<module>`,
 `Armijo_factor_<module>`, `Krylov_iterations` (Newton) and `precond_rhs_norm_<module>`,
-`precond_resid_norm_<module>` (Krylov).  The file is rewritten from an in-memory copy at every put
+`precond_resid_norm_<module>` (Krylov), plus the model's own statistics of every iteration's hist file
+(`ModelStateBase.def_stats_vars / put_stats_vars`, model_state_base.py:136-180): the time mean of each
+tracer-like variable and, on the lat-depth grid, its ypos mean
+(py_driver_2d/tracer_module_state.py:281-345, test_problem/tracer_module_state.py:196-240).
+The file is rewritten from an in-memory copy at every put
 (classic netCDF cannot be grown in place by scipy's writer); a resumed solve reloads it first.
 """
 
@@ -132,6 +136,7 @@ class StatsFile:
         self._name = name
         self._fname = os.path.join(workdir, f"{name}_stats.nc")
         self._region_cnt = region_cnt
+        self._dimlen = {"region": region_cnt}  # fixed dimensions (the unlimited one is "iteration")
         self._vars = {}  # varname -> dict(dims, dtype, attrs, data)
         self._n_iter = 0
         self._history = (f"{datetime.now():%Y-%m-%d %H:%M:%S}: created by StatsFile._create_stats_file "
@@ -169,7 +174,7 @@ class StatsFile:
             attrs["units"] = units
         if "iteration" in dims:
             attrs["_FillValue"] = FILL_F8 if dtype == "f8" else FILL_I4
-        shape = tuple(0 if d == "iteration" else self._region_cnt for d in dims)
+        shape = tuple(0 if d == "iteration" else self._dimlen[d] for d in dims)
         self._vars[vname] = {"dims": dims, "dtype": dtype, "attrs": attrs,
                              "data": np.zeros(shape, dtype=np.float64 if dtype == "f8" else np.int32)}
 
@@ -204,6 +209,50 @@ class StatsFile:
                 self._vars[names[0]]["data"][iteration] = vals
         self._flush()
 
+    def put_hist_stats(self, iteration, hist_fname, names, mean_weights=None):
+        """the model's statistics of one iteration's hist file: time mean of the tracer-like variables
+        `names` (end points of the record down-weighted: the hist file holds t = 0 and t = T,
+        tracer_module_state.py:206-214 / 156-164) and, for each axis in `mean_weights`
+        ({axis name: cell widths}), the weighted mean along it (`<name>_mean_<axis>`).  Dimensions,
+        coordinate variables and metadata are taken from the hist file at the first call."""
+        self._grow(iteration + 1)
+        with netcdf_file(hist_fname, "r", mmap=False) as fptr:
+            timelen = fptr.dimensions["time"] or fptr.variables["time"].shape[0]
+            weights = np.full(timelen, 1.0 / (timelen - 1))
+            weights[0] *= 0.5
+            weights[-1] *= 0.5
+            for name in names:
+                if name not in fptr.variables:
+                    continue
+                var = fptr.variables[name]
+                dims = tuple(var.dimensions[1:])
+                for dim, length in zip(dims, var.shape[1:]):
+                    if dim not in self._dimlen:
+                        self._dimlen[dim] = int(length)
+                        if dim in fptr.variables:  # coordinate variable, iteration invariant
+                            cvar = fptr.variables[dim]
+                            attrs = {k: (v.decode() if isinstance(v, bytes) else v) for k, v in cvar._attributes.items()}
+                            self._vars[dim] = {"dims": (dim,), "dtype": "f8", "attrs": attrs,
+                                               "data": np.array(cvar.data, dtype=np.float64)}
+                attrs = {k: (v.decode() if isinstance(v, bytes) else v) for k, v in var._attributes.items()
+                         if k not in ("cell_methods", "_FillValue")}
+                mean = np.einsum("i,i...", weights, np.array(var.data, dtype=np.float64))
+                targets = [(name, dims, mean)]
+                for axis, widths in (mean_weights or {}).items():
+                    if axis in dims:
+                        w = np.asarray(widths, dtype=np.float64) / np.sum(widths)
+                        pos = dims.index(axis)
+                        targets.append((f"{name}_mean_{axis}", dims[:pos] + dims[pos + 1:],
+                                        np.tensordot(mean, w, axes=([pos], [0]))))
+                for vname, vdims, vals in targets:
+                    if vname not in self._vars:
+                        self._vars[vname] = {"dims": ("iteration",) + vdims, "dtype": "f8",
+                                             "attrs": dict(attrs, _FillValue=FILL_F8),
+                                             "data": np.full((self._n_iter,) + tuple(self._dimlen[d] for d in vdims),
+                                                             FILL_F8)}
+                    self._vars[vname]["data"][iteration] = vals
+        self._flush()
+
     def put_invariant(self, **kwargs):
         for key, vals in kwargs.items():
             category, names = self._keys[key]
@@ -217,7 +266,8 @@ class StatsFile:
         with netcdf_file(self._fname, "w", version=2) as fptr:
             fptr.history = self._history
             fptr.createDimension("iteration", None)
-            fptr.createDimension("region", self._region_cnt)
+            for dim, length in self._dimlen.items():
+                fptr.createDimension(dim, length)
             it = fptr.createVariable("iteration", "i4", ("iteration",))
             it.long_name = f"{self._name} solver iteration"
             reg = fptr.createVariable("region", "i4", ("region",))
@@ -244,7 +294,17 @@ class StatsFile:
         with netcdf_file(self._fname, "r", mmap=False) as fptr:
             self._history = fptr.history.decode() if isinstance(fptr.history, bytes) else str(fptr.history)
             self._n_iter = int(fptr.variables["iteration"].shape[0])
-            for vname, var in self._vars.items():
-                if vname in fptr.variables:
-                    var["data"] = np.array(fptr.variables[vname].data, dtype=var["data"].dtype)
+            for dim, length in fptr.dimensions.items():
+                if dim != "iteration" and dim not in self._dimlen:
+                    self._dimlen[dim] = int(length)
+            for vname, fvar in fptr.variables.items():
+                if vname in ("iteration", "region"):
+                    continue
+                if vname in self._vars:
+                    var = self._vars[vname]
+                    var["data"] = np.array(fvar.data, dtype=var["data"].dtype)
+                else:  # statistics of the hist files, defined on the fly by put_hist_stats
+                    attrs = {k: (v.decode() if isinstance(v, bytes) else v) for k, v in fvar._attributes.items()}
+                    self._vars[vname] = {"dims": tuple(fvar.dimensions), "dtype": "f8", "attrs": attrs,
+                                         "data": np.array(fvar.data, dtype=np.float64)}
         self._grow(self._n_iter)

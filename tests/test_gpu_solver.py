@@ -279,6 +279,15 @@ def test_newton_state_stats_files_and_resume(base, tmp_path):
         assert (np.diff(fn) < 0).all() and fn[-1] < 1e-8 * np.array(f.variables["iterate_norm_iage"].data)[-1, 0]
         assert (np.array(f.variables["Krylov_iterations"].data)[:3] >= 1).all()
         np.testing.assert_array_equal(np.array(f.variables["Armijo_factor_iage"].data)[:3, 0], 1.0)
+        # the model's own statistics: time mean of the tracer over each iteration's hist file
+        assert f.variables["iage"].dimensions[0] == "iteration" and f.variables["iage"].shape[0] == 4
+        stat = np.array(f.variables["iage"].data)
+    with netcdf_file(os.path.join(work, "hist_03.nc"), "r", mmap=False) as f:
+        hv = np.array(f.variables["iage"].data)
+        wts = np.full(hv.shape[0], 1.0 / (hv.shape[0] - 1))
+        wts[0] *= 0.5
+        wts[-1] *= 0.5
+        np.testing.assert_allclose(stat[3], np.einsum("i,i...", wts, hv), rtol=1e-14)
     with netcdf_file(os.path.join(work, "krylov_00", "Krylov_stats.nc"), "r", mmap=False) as f:
         beta = float(np.array(f.variables["precond_rhs_norm_iage"].data)[0])
         res = np.array(f.variables["precond_resid_norm_iage"].data)[:, 0]

@@ -93,3 +93,49 @@ def test_stats_file_layout_growth_and_resume(tmp_path):
     with netcdf_file(str(tmp_path / "Krylov_stats.nc"), "r", mmap=False) as f:
         assert f.variables["precond_rhs_norm_iage"].dimensions == ("region",)
         assert f.variables["precond_resid_norm_iage"].dimensions == ("iteration", "region")
+
+
+def test_hist_statistics_in_the_stats_file(tmp_path):
+    """time mean with down-weighted end points and ypos mean of the tracer-like hist variables
+    (py_driver_2d/tracer_module_state.py:281-345), coordinate variables copied from the hist file,
+    fill values for iterations that have no hist statistics, reload on resume"""
+    rng = np.random.default_rng(1)
+    nt, nz, ny = 5, 4, 3
+    vals = rng.normal(size=(nt, nz, ny))
+    hist = str(tmp_path / "hist_00.nc")
+    with netcdf_file(hist, "w", version=2) as f:
+        f.createDimension("time", None)
+        f.createDimension("depth", nz)
+        f.createDimension("ypos", ny)
+        t = f.createVariable("time", "f8", ("time",))
+        d = f.createVariable("depth", "f8", ("depth",))
+        d.units = "m"
+        y = f.createVariable("ypos", "f8", ("ypos",))
+        v = f.createVariable("iage", "f8", ("time", "depth", "ypos"))
+        v.long_name = "ideal age"
+        v.units = "years"
+        v.cell_methods = "time: point"
+        d[:] = np.arange(nz) + 0.5
+        y[:] = np.arange(ny) * 2.0
+        t[:nt] = np.arange(nt)
+        v[:nt] = vals
+    sf = ss.StatsFile("Newton", str(tmp_path), 1, [("iage", "years")], ss.NEWTON_VARS)
+    widths = np.array([1.0, 2.0, 1.0])
+    sf.put_hist_stats(1, hist, ["iage", "not_in_hist"], {"ypos": widths})
+    w = np.array([0.5, 1, 1, 1, 0.5]) / 4.0
+    want = np.einsum("i,ijk", w, vals)
+    with netcdf_file(str(tmp_path / "Newton_stats.nc"), "r", mmap=False) as f:
+        assert f.variables["iage"].dimensions == ("iteration", "depth", "ypos")
+        assert f.variables["iage_mean_ypos"].dimensions == ("iteration", "depth")
+        np.testing.assert_allclose(f.variables["iage"].data[1], want, rtol=1e-15)
+        np.testing.assert_allclose(f.variables["iage_mean_ypos"].data[1], want @ (widths / 4.0), rtol=1e-15)
+        assert (f.variables["iage"].data[0] == ss.FILL_F8).all()
+        assert f.variables["iage"].units == b"years" and not hasattr(f.variables["iage"], "cell_methods")
+        np.testing.assert_array_equal(f.variables["depth"].data, np.arange(nz) + 0.5)
+        assert f.variables["depth"].units == b"m"
+    again = ss.StatsFile("Newton", str(tmp_path), 1, [("iage", "years")], ss.NEWTON_VARS, resume=True)
+    again.put_hist_stats(2, hist, ["iage"], {"ypos": widths})
+    with netcdf_file(str(tmp_path / "Newton_stats.nc"), "r", mmap=False) as f:
+        np.testing.assert_allclose(f.variables["iage"].data[1], want, rtol=1e-15)
+        np.testing.assert_allclose(f.variables["iage"].data[2], want, rtol=1e-15)
+        assert f.variables["iteration"].shape[0] == 3
