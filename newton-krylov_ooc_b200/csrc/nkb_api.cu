@@ -280,8 +280,10 @@ int nkb_model_tend(nkb_model *m, double time, const double *d_x, double *d_tend,
 }
 
 size_t nkb_model_work_doubles(const nkb_model *m, int B, int ldb) {
-    (void)B;
-    return 2 * (size_t)m->dev.T * m->dev.nz * m->dev.ny * (size_t)ldb;
+    const size_t n1 = (size_t)m->dev.T * m->dev.nz * m->dev.ny;
+    // a single state is staged into a 4-lane batch for the fused step kernels: x, f and two work copies
+    if (B == 1 && ldb == 1) return 16 * n1;
+    return 2 * n1 * (size_t)ldb;
 }
 
 int nkb_model_eval(nkb_model *m, const double *d_x0, double *d_f, double *d_work, int B, int ldb, int n_hist,
@@ -293,6 +295,14 @@ int nkb_model_eval(nkb_model *m, const double *d_x0, double *d_f, double *d_work
     cudaStream_t st = (cudaStream_t)stream;
     const ModelDev &v = m->dev;
     const size_t plane = (size_t)v.nz * v.ny;
+    if (B == 1 && ldb == 1 && nkb::fused_single_state(v)) {
+        // the reference's own layout [tracer, depth, ypos]: stage it as member 0 of a 4-lane batch
+        const size_t n1 = (size_t)v.T * plane, ls = 4;
+        double *xs = d_work, *fs = d_work + n1 * ls, *wk = d_work + 2 * n1 * ls;
+        if (nkb::launch_scatter_member(d_x0, xs, n1, ls, st)) return 1;
+        if (nkb_model_eval(m, xs, fs, wk, 1, (int)ls, n_hist, h_hist_steps, d_hist, stream)) return 1;
+        return nkb::launch_gather_member(fs, d_f, n1, ls, 0, st);
+    }
     const size_t nstate = (size_t)v.T * plane * ldb;
     double *w_u1 = d_work, *w_alt = d_work + nstate;
     const int S = m->n_steps;
@@ -464,7 +474,7 @@ int nkb_model_eval_host(nkb_model *m, const double *h_x0, double *h_f, int B) {
         NKB_CUDA(cudaMalloc(&m->d_stage_major, n * (size_t)B * sizeof(double)));
         NKB_CUDA(cudaMalloc(&m->d_stage_x, need * sizeof(double)));
         NKB_CUDA(cudaMalloc(&m->d_stage_f, need * sizeof(double)));
-        NKB_CUDA(cudaMalloc(&m->d_stage_work, 2 * need * sizeof(double)));
+        NKB_CUDA(cudaMalloc(&m->d_stage_work, nkb_model_work_doubles(m, B, ldb) * sizeof(double)));
         NKB_CUDA(cudaMemset(m->d_stage_x, 0, need * sizeof(double)));
         m->stage_cap = need;
     }

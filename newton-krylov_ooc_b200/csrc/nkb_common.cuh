@@ -114,6 +114,8 @@ int launch_stage_tables(const ModelDev &m, int n_stages, const double *d_t, cons
 int launch_mixing_coeff(const ModelDev &m, double time, double *out, cudaStream_t st);
 int launch_forcing_tables(const ModelDev &m, int n_times, const double *d_t, double *src, cudaStream_t st);
 int launch_gather_member(const double *src, double *dst, size_t n, size_t ldb, int b, cudaStream_t st);
+int launch_scatter_member(const double *src, double *dst, size_t n, size_t ldb, cudaStream_t st);
+bool fused_single_state(const ModelDev &v);
 int launch_pack(const double *src, double *dst, int n, int B, int ldb, cudaStream_t st);
 int launch_unpack(const double *src, double *dst, int n, int B, int ldb, cudaStream_t st);
 int launch_stage(int kind, int nin, const StageArgs &a, cudaStream_t st);

@@ -256,6 +256,20 @@ int launch_tend(int kind, const StageArgs &a, cudaStream_t st) {
     return 0;
 }
 
+// dense [n] vector -> member 0 of a member-fastest batch with row pitch ldb (the other lanes are zeroed)
+__global__ void scatter_member_kernel(const double *__restrict__ src, double *__restrict__ dst, size_t n, size_t ldb) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * ldb) return;
+    dst[i] = (i % ldb == 0) ? src[i / ldb] : 0.0;
+}
+
+int launch_scatter_member(const double *src, double *dst, size_t n, size_t ldb, cudaStream_t st) {
+    scatter_member_kernel<<<(unsigned)((n * ldb + 255) / 256), 256, 0, st>>>(src, dst, n, ldb);
+    count_launch();
+    NKB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int launch_gather_member(const double *src, double *dst, size_t n, size_t ldb, int b, cudaStream_t st) {
     gather_member_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, dst, n, ldb, b);
     count_launch();

@@ -461,3 +461,46 @@ def test_forced_surface_restoring_to_a_record(B, golden_dir, tmp_path):
     np.testing.assert_allclose(got, want, rtol=0, atol=1e-10 * np.abs(want).max())
     with pytest.raises(ValueError):
         modules.forced_model(tr, "file", surf_restore_times=rtimes[:1], surf_restore_data=rdata[:1])
+
+
+@pytest.mark.parametrize("kind", ["iage", "phosphorus"])
+def test_single_state_takes_the_fused_step_kernel(kind, monkeypatch):
+    """a single state in the reference's own layout (B = 1, member pitch 1: the Newton iterate, every
+    Krylov product) is staged into a 4-lane batch and integrated by ONE persistent launch instead of
+    two launches per time step; same result as the stage-per-launch kernels to rounding, hist
+    snapshots included"""
+    from oracle import imex_oracle as im
+    from oracle import nk_oracle as o
+    from nk_ooc_b200 import _lib
+    from nk_ooc_b200.py_driver_2d import modules
+
+    rng = np.random.default_rng(51)
+    g, tr = _grid(21, 33)
+    nsteps = 240
+    if kind == "iage":
+        mod, m = im.Module2D("iage", g), modules.iage_model(tr)
+    else:
+        mod, m = im.Module2D("phosphorus", g, phos=o.Phosphorus2D(g)), modules.phosphorus_model(tr)
+    m.set_uniform_schedule(nsteps)
+    x = np.abs(rng.normal(size=(mod.T, g.nz, g.ny, 1))) * 0.5
+    xd = torch.from_numpy(x).cuda()
+    assert xd.shape[-1] == 1
+    lib = _lib.load()
+    m.eval(xd, 1)
+    n0 = lib.nkb_launch_count()
+    got = m.eval(xd, 1).cpu().numpy()
+    m.check_health()
+    # scatter, [layout conversion,] persistent step launch, final difference, gather
+    assert lib.nkb_launch_count() - n0 == (4 if kind == "iage" else 5)
+    snaps = []
+    want = im.model_year_2d(mod, x, nsteps, snapshots=snaps)
+    scale = np.abs(want).max()
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-10 * scale)
+    f, hist = m.eval(xd, 1, hist_steps=[0, 100, 240])
+    np.testing.assert_allclose(hist[1].cpu().numpy(), snaps[99][1][..., 0], rtol=0, atol=1e-10 * scale)
+    np.testing.assert_allclose(hist[2].cpu().numpy(), x[..., 0] + want[..., 0], rtol=0, atol=1e-10 * scale)
+    monkeypatch.setenv("NKB_FUSED_MIN_B", "8")
+    n0 = lib.nkb_launch_count()
+    unfused = m.eval(xd, 1).cpu().numpy()
+    assert lib.nkb_launch_count() - n0 == 2 * nsteps
+    np.testing.assert_allclose(got, unfused, rtol=0, atol=1e-10 * scale)
