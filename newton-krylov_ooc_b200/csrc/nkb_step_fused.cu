@@ -1565,7 +1565,6 @@ int launch_steps_fused(const ModelDev &v, int B, int n_steps, int step0, int ste
 // a single state in the reference's own layout (B == 1, ldb == 1) is staged into a 4-lane batch so that it
 // can take the fused step kernels too (TMA needs a 16-byte member pitch): one launch per model year
 // instead of two per time step — 3 to 5 times faster for the Newton iterate and the Krylov products
-constexpr int FS_SINGLE_LDB = 4;
 bool fused_single_state(const ModelDev &v) {
     if (fs_env_int("NKB_FUSED", 1) == 0 || fs_env_int("NKB_FUSED_MIN_B", 1) > 1) return false;
     if (v.column_model == 1 && v.ny == 1) return false;
