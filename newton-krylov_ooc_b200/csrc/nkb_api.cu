@@ -140,7 +140,7 @@ void nkb_model_destroy(nkb_model *m) {
     if (!m) return;
     cudaFree(m->arena); cudaFree(m->tri); cudaFree(m->aff); cudaFree(m->src); cudaFree(m->d_h);
     cudaFree(m->tri_raw); cudaFree(m->aff_raw); cudaFree(m->src_raw);
-    cudaFree(m->ctab); cudaFree(m->d_done);
+    cudaFree(m->ctab); cudaFree(m->d_done); cudaFree(m->d_hist_slot);
     if (m->h_err) cudaFreeHost(m->h_err);
     cudaFree(m->d_stage_major); cudaFree(m->d_stage_x); cudaFree(m->d_stage_f); cudaFree(m->d_stage_work);
     if (m->graph) cudaGraphExecDestroy(m->graph);
@@ -317,24 +317,25 @@ int nkb_model_eval(nkb_model *m, const double *d_x0, double *d_f, double *d_work
         c.nz = v.nz; c.B = B; c.ldb = ldb; c.T = v.T; c.n_steps = S; c.ncls = v.n_classes;
         for (int t = 0; t < NKB_MAX_TRACERS; ++t) { c.class_of[t] = v.class_of[t]; c.src_const[t] = v.src_const[t]; }
         c.restoring_opt = v.po4_s_restoring_opt;
-        int *d_slot = nullptr;
         if (n_hist > 0) {
             std::vector<int> slot(S + 1, -1);
             for (int i = 0; i < n_hist; ++i) {
                 NKB_REQUIRE(h_hist_steps[i] >= 0 && h_hist_steps[i] <= S, "nkb_model_eval: hist step out of range");
                 slot[h_hist_steps[i]] = i;
             }
-            NKB_CUDA(cudaMalloc(&d_slot, (S + 1) * sizeof(int)));
-            NKB_CUDA(cudaMemcpy(d_slot, slot.data(), (S + 1) * sizeof(int), cudaMemcpyHostToDevice));
-            c.hist_slot = d_slot;
+            // the slot table lives with the model (no allocation, no host synchronisation per evaluation: the
+            // two legs of a Richardson pair run concurrently on two streams)
+            if ((size_t)(S + 1) > m->hist_slot_cap) {
+                cudaFree(m->d_hist_slot);
+                m->d_hist_slot = nullptr;
+                NKB_CUDA(cudaMalloc(&m->d_hist_slot, (S + 1) * sizeof(int)));
+                m->hist_slot_cap = (size_t)(S + 1);
+            }
+            NKB_CUDA(cudaMemcpyAsync(m->d_hist_slot, slot.data(), (S + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+            c.hist_slot = m->d_hist_slot;
             c.hist = d_hist;
         }
-        const int rc = nkb::launch_column_year(v.kind, c, st);
-        if (d_slot) {
-            NKB_CUDA(cudaStreamSynchronize(st));
-            cudaFree(d_slot);
-        }
-        return rc;
+        return nkb::launch_column_year(v.kind, c, st);
     }
 
     int hist_i = 0;

@@ -163,6 +163,8 @@ struct nkb_model {
     int *d_done = nullptr;      // per-tile step counters of the persistent step kernel
     size_t done_cap = 0;
     int *h_err = nullptr, *d_err = nullptr;  // host-mapped error flag (dependency-wait timeout)
+    int *d_hist_slot = nullptr;              // column model: hist slot of every step (or -1)
+    size_t hist_slot_cap = 0;
     // scratch for tend()/mixing_coeff()
     double *tri_raw = nullptr;  // [n_classes][nz][ny][4]
     double *aff_raw = nullptr;  // [n_classes][ny]

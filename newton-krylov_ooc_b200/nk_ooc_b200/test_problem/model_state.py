@@ -62,6 +62,7 @@ class ModelState(ModelStateBase):
     depth = None
     steps_per_year = None
     richardson = True
+    _side_stream = None  # second CUDA stream for the coarse leg of the Richardson pair
     _models = {}
     _precond_cache = {}
 
@@ -140,16 +141,31 @@ class ModelState(ModelStateBase):
         x = tms.vals.reshape(tms.tracer_cnt, len(self.depth), 1, -1)
         lead = fine if fine is not None else coarse
         snaps = None
+        f_c = snaps_c = None
+        if fine is not None:
+            # the coarse leg runs on a side stream, concurrently with the fine leg (a column-year launch of a
+            # small batch occupies a few SMs only)
+            cur = torch.cuda.current_stream()
+            side = type(self)._side_stream
+            if side is None:
+                side = type(self)._side_stream = torch.cuda.Stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                if hist_times is not None:
+                    f_c, snaps_c = coarse.eval(x, self.members, hist_steps=coarse.step_index_of_times(hist_times))
+                else:
+                    f_c = coarse.eval(x, self.members)
         if hist_times is not None:
             f_lead, snaps = lead.eval(x, self.members, hist_steps=lead.step_index_of_times(hist_times))
         else:
             f_lead = lead.eval(x, self.members)
         if fine is not None:
-            if hist_times is not None:
-                f_c, snaps_c = coarse.eval(x, self.members, hist_steps=coarse.step_index_of_times(hist_times))
+            cur.wait_stream(side)
+            f_c.record_stream(cur)
+            x.record_stream(side)
+            if snaps_c is not None:
+                snaps_c.record_stream(cur)
                 snaps.mul_(4.0 / 3.0).add_(snaps_c, alpha=-1.0 / 3.0)
-            else:
-                f_c = coarse.eval(x, self.members)
             # F <- 4/3 F_fine - 1/3 F_coarse with the library's axpby kernel (K6)
             flat = (tms.tracer_cnt, len(self.depth), f_lead.shape[-1])
             self.model_config_obj.weights.axpby(-1.0 / 3.0, f_c.reshape(flat), 4.0 / 3.0, f_lead.reshape(flat),
