@@ -63,6 +63,7 @@ def parse_args(argv=None):
     parser.add_argument("--workdir", default=None)
     for name in SOLVER_OVERRIDES + MODEL_OVERRIDES:
         parser.add_argument(f"--{name}", default=None, help=f"override {name} from the cfg / defaults")
+    parser.add_argument("--resume", action="store_true", help="nk_driver: resume from the saved solver state")
     parser.add_argument("--persist", action="store_true", help="accepted for compatibility (there is no re-invocation)")
     parser.add_argument("--fp_cnt", type=int, default=2, help="fixed-point iterations applied to the init iterate")
     parser.add_argument("--armijo_batch", type=int, default=1, help="speculative Armijo candidates per evaluation")
@@ -152,15 +153,17 @@ def setup_solver(config, fp_cnt, init_iterate_src="gen_init_iterate"):
     return init_iterate
 
 
-def nk_driver(config, armijo_batch=1):
-    """nk_ooc/nk_driver.py: Newton's method from solverinfo["init_iterate_fname"] to convergence"""
+def nk_driver(config, armijo_batch=1, resume=False):
+    """nk_ooc/nk_driver.py: Newton's method from solverinfo["init_iterate_fname"] to convergence;
+    resume continues an interrupted solve from Newton_state.json / Newton_stats.nc (nk_driver.py --resume)"""
     from .solver import NewtonSolver
 
     cls = _model_state_class(config["modelinfo"]["model_name"])
     if cls.model_config_obj is None:
         cls.configure(config["modelinfo"])
     iterate = cls(config["solverinfo"]["init_iterate_fname"])
-    solver = NewtonSolver(iterate, config["solverinfo"], workdir=config["workdir"], armijo_batch=armijo_batch)
+    solver = NewtonSolver(iterate, config["solverinfo"], workdir=config["workdir"], armijo_batch=armijo_batch,
+                          resume=resume)
     solver.solve()
     return solver
 
@@ -197,7 +200,7 @@ def main(argv=None):
     if args.cmd == "setup_solver":
         setup_solver(config, args.fp_cnt)
     elif args.cmd == "nk_driver":
-        solver = nk_driver(config, args.armijo_batch)
+        solver = nk_driver(config, args.armijo_batch, resume=args.resume)
         logging.getLogger(__name__).info("converged after %d Newton iterations", solver.iteration)
     else:
         run_cmd(config, args)

@@ -226,6 +226,13 @@ def test_cli_setup_solver_and_nk_driver_column_regions(base, tmp_path):
     np.testing.assert_allclose(read(os.path.join(work, "iterate_01.nc")), _want(base, pre + "iterate_01"),
                                rtol=1.9e-2, atol=1e-9)
     assert os.path.exists(os.path.join(work, "krylov_00", "krylov_res_00.nc"))
+    # --resume on the finished solve: reads the last iterate / fcn back, no further Newton step
+    import json
+
+    it_done = json.load(open(os.path.join(work, "Newton_state.json")))["iteration"]
+    ModelState.reset()
+    assert cli.main(["nk_driver", "--newton_max_iter", "5", "--resume"] + common) == 0
+    assert json.load(open(os.path.join(work, "Newton_state.json")))["iteration"] == it_done
     # file-to-file function evaluation
     assert cli.main(["comp_fcn", "--fname_dir", work, "--in_fname", "gen_init_iterate/init_iterate_00.nc",
                      "--res_fname", "fcn_cli.nc"] + common) == 0
