@@ -290,3 +290,65 @@ def test_banded_block_diagonal_systems_are_found_and_solved(B):
     want = np.linalg.solve(dense, y)
     got = f.solve(_dev(y), B).cpu().numpy()[:, :B]
     np.testing.assert_allclose(got, want, rtol=0, atol=1e-10 * np.abs(want).max())
+
+
+def test_production_size_vector_kernels_and_column_solves():
+    """BASELINE.json's headline size (125 x 150 cells, 4096 members) for the Krylov vector kernels and the
+    per-column tridiagonal preconditioner solves, checked on sampled members against numpy / scipy and
+    through size-independent properties (linearity of the solve, dot(a, a) = norm^2, axpby inverse)"""
+    from scipy import linalg
+    from nk_ooc_b200 import engine
+
+    nz, ny, B = 125, 150, 4096
+    n = nz * ny
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    a = torch.randn((1, n, B), dtype=torch.float64, device="cuda", generator=gen)
+    b = torch.randn((1, n, B), dtype=torch.float64, device="cuda", generator=gen)
+    rng = np.random.default_rng(0)
+    wgt = np.outer(rng.uniform(1, 5, nz), rng.uniform(1, 2, ny))
+    mask = np.ones((nz, ny), dtype=np.int32)
+    rw = engine.RegionWeights(mask, wgt)
+    w = (wgt / wgt.sum()).reshape(-1)
+    sample = [0, 1, 777, 4095]
+    dots = rw.dot(a, b, B).cpu().numpy()
+    means = rw.dot(a, None, B).cpu().numpy()
+    for m in sample:
+        am, bm = a[0, :, m].cpu().numpy(), b[0, :, m].cpu().numpy()
+        np.testing.assert_allclose(dots[0, m], np.sum(w * am * bm), rtol=1e-11, atol=1e-14)
+        np.testing.assert_allclose(means[0, m], np.sum(w * am), rtol=0, atol=1e-13)
+    # y <- alpha x + beta y, then its inverse: back to y to rounding
+    alpha = torch.rand((1, B), dtype=torch.float64, device="cuda", generator=gen) + 0.5
+    beta = torch.rand((1, B), dtype=torch.float64, device="cuda", generator=gen) + 0.5
+    y = b.clone()
+    rw.axpby(alpha, a, beta, y, B)
+    np.testing.assert_allclose(y[0, :, 777].cpu().numpy(),
+                               float(alpha[0, 777]) * a[0, :, 777].cpu().numpy() + float(beta[0, 777]) * b[0, :, 777].cpu().numpy(),
+                               rtol=1e-13, atol=1e-15)
+    rw.axpby(-alpha / beta, a, 1.0 / beta, y, B)
+    assert float((y - b).abs().max()) <= 1e-12
+    # limiter: base + scalef * inc stays >= 0 for every member, and is tight for the binding cell
+    base = torch.rand((1, n, B), dtype=torch.float64, device="cuda", generator=gen) + 0.01
+    sc = rw.limiter_scalef(base, a, 0.0, None, B)
+    low = (base + torch.minimum(sc, torch.ones_like(sc)).reshape(1, 1, B) * a).amin(dim=(0, 1))
+    assert float(low.min()) >= -1e-12 and float(low.abs().max()) <= 1.0
+    np.testing.assert_allclose(low[sample].cpu().numpy(), 0.0, atol=1e-12)
+    # 150 per-column tridiagonal systems as one band: blocks found, sampled members against scipy, linearity
+    ab = np.zeros((3, n))
+    ab[1] = 2.0 + rng.random(n)
+    ab[0, 1:] = -rng.random(n - 1)
+    ab[2, :-1] = -rng.random(n - 1)
+    edge = np.arange(nz, n, nz)
+    ab[0, edge] = 0.0
+    ab[2, edge - 1] = 0.0
+    fac = engine.BandedFactor(ab, 1, 1)
+    assert fac.n_blocks == ny
+    ya, yb = a.reshape(n, B), b.reshape(n, B)
+    xa = fac.solve(ya, B)
+    for m in sample:
+        want = linalg.solve_banded((1, 1), ab, ya[:, m].cpu().numpy())
+        np.testing.assert_allclose(xa[:, m].cpu().numpy(), want, rtol=0, atol=1e-12 * np.abs(want).max())
+    xsum = fac.solve((2.0 * ya - 3.0 * yb).contiguous(), B)
+    lin = 2.0 * xa - 3.0 * fac.solve(yb, B)
+    assert float((xsum - lin).abs().max()) <= 1e-11 * float(lin.abs().max())
+    res = fac.solve(ya, B, scale=0.5, subtract_rhs=True)
+    assert float((res - (0.5 * xa - ya)).abs().max()) <= 1e-12 * float(xa.abs().max())
