@@ -21,6 +21,8 @@
 //
 // Band storage (row-major): A(i,j) lives at ab[(kv + i - j)*n + j], kv = kl + ku, rows
 // 0..kl-1 are fill-in space, total 2*kl + ku + 1 rows.
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <cstdlib>
 #include <vector>
@@ -384,6 +386,95 @@ __global__ void __launch_bounds__(256) banded_solve_win_kernel(const BandedSolve
     bs_wait<0>();
 }
 
+// Whole-device factorisation of ONE wide diagonal block (the 2-D preconditioners with lateral processes:
+// n = nz*ny rows, kl = ku = 3*ny): the same unblocked right-looking elimination, but the rank-1 update of a
+// column step (up to kl x (kl+ku) entries) is spread over all CTAs of a cooperative launch, walking the
+// band storage along its rows (coalesced).  Two grid barriers per column: every CTA first copies the
+// pivot row and the multiplier column it needs into shared memory (pivot search redundantly per CTA), then
+// the swap / scale / update writes start.  refined 125 x 150 grid (n = 18 750, kl = ku = 450): seconds with
+// one CTA, ~0.1 s here.
+__global__ void __launch_bounds__(256) banded_factor_coop_kernel(double *__restrict__ ab, int *__restrict__ ipiv,
+                                                                 int n, int kl, int ku, int *info) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ double fc_sh[];  // lcol[kl + 1] | urow[kl + ku + 1] | rowj[kl + ku + 1]
+    __shared__ double s_val[256];
+    __shared__ int s_idx[256];
+    const int kv = kl + ku;
+    double *lcol = fc_sh, *urow = fc_sh + kl + 1, *rowj = urow + kv + 1;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int gwarp = (blockIdx.x * nt + tid) >> 5, nwarp = (gridDim.x * nt) >> 5, lane = tid & 31;
+    int ju = 0;
+    for (int j = 0; j < n; ++j) {
+        const int km = min(kl, n - 1 - j);
+        // ---- read phase: pivot search over column j (every CTA does it: same result) ----
+        double best = -1.0;
+        int besti = 0;
+        for (int i = tid; i <= km; i += nt) {
+            const double v = fabs(ab[(size_t)(kv + i) * n + j]);
+            if (v > best) { best = v; besti = i; }
+        }
+        s_val[tid] = best;
+        s_idx[tid] = besti;
+        __syncthreads();
+        for (int sft = nt / 2; sft > 0; sft >>= 1) {
+            if (tid < sft) {
+                const double o = s_val[tid + sft];
+                const int oi = s_idx[tid + sft];
+                if (o > s_val[tid] || (o == s_val[tid] && oi < s_idx[tid])) { s_val[tid] = o; s_idx[tid] = oi; }
+            }
+            __syncthreads();
+        }
+        const int jp = s_idx[0];
+        const double pv = s_val[0];
+        if (pv != 0.0) ju = max(ju, min(j + ku + jp, n - 1));
+        const int ncol = ju - j;  // columns j+1 .. ju are updated
+        if (pv != 0.0) {
+            // the pivot row (old row j + jp) and old row j over the columns j .. ju, the multiplier column in
+            // its order AFTER the interchange, scaled
+            const double inv = 1.0 / ab[(size_t)(kv + jp) * n + j];
+            for (int e = tid; e <= ncol; e += nt) {
+                const int c = j + e;
+                urow[e] = (jp - e >= -kv) ? ab[(size_t)(kv + jp - e) * n + c] : 0.0;
+                rowj[e] = ab[(size_t)(kv - e) * n + c];
+            }
+            for (int i = 1 + tid; i <= km; i += nt) {
+                const double v = (i == jp) ? ab[(size_t)kv * n + j] : ab[(size_t)(kv + i) * n + j];
+                lcol[i] = v * inv;
+            }
+        }
+        __syncthreads();
+        grid.sync();
+        // ---- write phase ----
+        if (blockIdx.x == 0 && tid == 0) {
+            ipiv[j] = j + jp;
+            if (pv == 0.0) atomicCAS(info, 0, j + 1);
+        }
+        if (pv != 0.0) {
+            if (blockIdx.x == 0) {
+                // column j below the diagonal (the entry of row j + jp is a multiplier too) and row j, which
+                // receives the pivot row; the old row j moves to row j + jp through the update below
+                for (int i = 1 + tid; i <= km; i += nt) ab[(size_t)(kv + i) * n + j] = lcol[i];
+                if (jp != 0)
+                    for (int e = tid; e <= ncol; e += nt) ab[(size_t)(kv - e) * n + j + e] = urow[e];
+            }
+            // A(j+i, j+e) -= l_i * u_e for i = 1..km, e = 1..ncol, one band row (dd = i - e) per warp.  Row j+jp
+            // holds the old row j after the interchange: its new value is formed from rowj (this is the
+            // only write to that row in this step).
+            for (int dd = 1 - ncol + gwarp; dd <= km - 1; dd += nwarp) {
+                const int e_lo = max(1, 1 - dd), e_hi = min(ncol, km - dd);
+                double *row = ab + (size_t)(kv + dd) * n + j;
+                for (int e = e_lo + lane; e <= e_hi; e += 32) {
+                    const int i = dd + e;
+                    const double old = (jp != 0 && i == jp) ? rowj[e] : row[e];
+                    row[e] = fma(-lcol[i], urow[e], old);
+                }
+            }
+        }
+        grid.sync();
+    }
+}
+
 // fallback for bands too wide for the shared-memory window: one thread per member; x [n][ldb] in place
 __global__ void banded_solve_kernel(const double *__restrict__ ab, const int *__restrict__ ipiv, int n, int kl,
                                     int ku, const double *__restrict__ y, double *__restrict__ x, int B,
@@ -467,8 +558,41 @@ int nkb_banded_create(nkb_banded **out, int n, int kl, int ku, const double *h_a
     NKB_CUDA(cudaMemcpy(f->ab, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice));
     NKB_CUDA(cudaMemcpy(f->blk, blk.data(), blk.size() * sizeof(int), cudaMemcpyHostToDevice));
     NKB_CUDA(cudaMemset(f->info, 0, sizeof(int)));
-    nkb::banded_factor_kernel<<<f->nblk, 256>>>(f->ab, f->ipiv, n, kl, ku, f->blk, f->info);
-    nkb::count_launch();
+    // one wide block: all SMs share the column updates (cooperative launch); many blocks: one CTA each
+    bool coop_done = false;
+    {
+        const char *env = getenv("NKB_BANDED_COOP");
+        const bool want = (env && *env) ? (env[0] != '0') : ((double)n * kl * (kv + 1) > 2.0e6);
+        if (f->nblk == 1 && kl >= 1 && want) {
+            int dev = 0, n_sm = 0, coop = 0, per_sm = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+            cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+            const size_t smem = (size_t)(kl + 1 + 2 * (kv + 1)) * sizeof(double);
+            if (coop && smem <= 96 * 1024 &&
+                cudaFuncSetAttribute(nkb::banded_factor_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem) == cudaSuccess &&
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nkb::banded_factor_coop_kernel, 256, smem) ==
+                    cudaSuccess &&
+                per_sm >= 1) {
+                double *ab_d = f->ab;
+                int *ipiv_d = f->ipiv, *info_d = f->info;
+                int nn = n, kll = kl, kuu = ku;
+                void *args[] = {&ab_d, &ipiv_d, &nn, &kll, &kuu, &info_d};
+                if (cudaLaunchCooperativeKernel((void *)nkb::banded_factor_coop_kernel, dim3(n_sm), dim3(256), args,
+                                                smem, 0) == cudaSuccess) {
+                    coop_done = true;
+                    nkb::count_launch();
+                } else {
+                    cudaGetLastError();
+                }
+            }
+        }
+    }
+    if (!coop_done) {
+        nkb::banded_factor_kernel<<<f->nblk, 256>>>(f->ab, f->ipiv, n, kl, ku, f->blk, f->info);
+        nkb::count_launch();
+    }
     int info = 0;
     NKB_CUDA(cudaMemcpy(&info, f->info, sizeof(int), cudaMemcpyDeviceToHost));
     if (info != 0) {

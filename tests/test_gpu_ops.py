@@ -352,3 +352,27 @@ def test_production_size_vector_kernels_and_column_solves():
     assert float((xsum - lin).abs().max()) <= 1e-11 * float(lin.abs().max())
     res = fac.solve(ya, B, scale=0.5, subtract_rhs=True)
     assert float((res - (0.5 * xa - ya)).abs().max()) <= 1e-12 * float(xa.abs().max())
+
+
+@pytest.mark.parametrize("n,kl,ku", [(900, 90, 90), (300, 40, 17), (257, 3, 200), (2000, 151, 151)])
+def test_banded_cooperative_factorisation(n, kl, ku, monkeypatch):
+    """one wide block factored by all SMs (cooperative launch, two grid barriers per column) gives the
+    same pivots and — up to the rounding of the fused update — the same factor as the one-CTA kernel:
+    solutions against scipy with pivoting exercised (not diagonally dominant), 1 and 9 right-hand sides"""
+    from scipy import linalg
+    from nk_ooc_b200 import engine
+
+    rng = np.random.default_rng(n)
+    ab = rng.normal(size=(kl + ku + 1, n))
+    ab[ku] += 0.3
+    y = rng.normal(size=(n, 9))
+    want = linalg.solve_banded((kl, ku), ab, y)
+    tol = 1e-8 * np.abs(want).max()
+    got = {}
+    for coop in ("1", "0"):
+        monkeypatch.setenv("NKB_BANDED_COOP", coop)
+        f = engine.BandedFactor(ab, kl, ku)
+        got[coop] = f.solve(_dev(y), 9).cpu().numpy()[:, :9]
+        np.testing.assert_allclose(got[coop], want, rtol=0, atol=tol)
+        np.testing.assert_allclose(f.solve(_dev(y[:, :1]), 1).cpu().numpy()[:, 0], want[:, 0], rtol=0, atol=tol)
+    np.testing.assert_allclose(got["1"], got["0"], rtol=0, atol=1e-3 * tol)
