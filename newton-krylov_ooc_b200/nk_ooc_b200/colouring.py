@@ -204,14 +204,15 @@ def decode_probes(f0, fprobe, colour_of_column, eps, reach=1):
     d x[t, k, j] and the coupling blocks to the columns j-reach..j+reach:
     returns [ny, 2*reach+1, T*nz, T*nz] (neighbour index reach = the column itself)"""
     T, nz, ny = f0.shape
-    jac = np.zeros((ny, 2 * reach + 1, T * nz, T * nz))
-    for j in range(ny):
-        c = int(colour_of_column[j])
-        for t in range(T):
-            for k in range(nz):
-                resp = (fprobe[(c * T + t) * nz + k] - f0) / eps  # [T, nz, ny]
-                for d in range(-reach, reach + 1):
-                    jj = j + d
-                    if 0 <= jj < ny:
-                        jac[j, d + reach, :, t * nz + k] = resp[:, :, jj].reshape(-1)
+    n = T * nz
+    colour_of_column = np.asarray(colour_of_column)
+    ncol = int(colour_of_column.max()) + 1
+    # responses of all probes at once: [colour, probe (t, k), response (t', k'), column]
+    resp = ((np.asarray(fprobe) - f0[np.newaxis]) / eps).reshape(ncol, n, n, ny)
+    jac = np.zeros((ny, 2 * reach + 1, n, n))
+    cols = np.arange(ny)
+    for d in range(-reach, reach + 1):
+        jv = cols[(cols + d >= 0) & (cols + d < ny)]
+        # jac[j, d + reach, r, p] = resp[colour[j], p, r, j + d]
+        jac[jv, d + reach] = np.transpose(resp[colour_of_column[jv], :, :, jv + d], (0, 2, 1))
     return jac

@@ -20,6 +20,20 @@ ModelState.configure(info)
 it = ModelState("gen_init_iterate")
 pd_info = {"newton_rel_tol": "1.0e-5", "newton_max_iter": "8", "post_newton_fp_iter": "1",
            "krylov_rel_tol": sys.argv[4] if len(sys.argv) > 4 else "0.01"}
+PROBE_ONLY = os.environ.get("NK_PROBE_ONLY") == "1"
+if PROBE_ONLY:
+    import cProfile, pstats, time
+    from nk_ooc_b200.solver import ProbePreconditioner
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    pr = cProfile.Profile(); pr.enable()
+    solver2 = NewtonSolver(ModelState("gen_init_iterate"), pd_info, workdir=os.path.join(tmp, "work2"), dump=False,
+                           precond_factory=lambda itr, fcn: ProbePreconditioner(itr, fcn))
+    solver2.step()
+    torch.cuda.synchronize(); pr.disable()
+    print(f"one probe-preconditioned Newton step: {time.perf_counter()-t0:.2f} s, Krylov iterations "
+          f"{solver2.history[-1].get('krylov_iterations')}")
+    pstats.Stats(pr).sort_stats("cumulative").print_stats(28)
+    sys.exit(0)
 solver = NewtonSolver(it, pd_info, workdir=os.path.join(tmp, "work"), dump=True)
 print("|F| / |x|", solver.fcn.norm() / solver.iterate.norm())
 inc, kr = solver._comp_increment()

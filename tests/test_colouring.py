@@ -125,3 +125,30 @@ def test_column_probes_recover_a_banded_jacobian():
         for d in (-1, 0, 1):
             if 0 <= j + d < ny:  # response of column j+d to a probe in column j = blocks[j+d][-d]
                 np.testing.assert_allclose(jac[j, d + 1], blocks[j + d, 1 - d], rtol=0, atol=1e-12)
+
+
+def test_decode_probes_equals_the_per_probe_loop():
+    """the vectorised decoding of the probe responses against the plain loop over (column, tracer,
+    level) — bit for bit, also for reach 2 and at the domain edges"""
+    from nk_ooc_b200 import colouring as col
+
+    def loop(f0, fprobe, colour, eps, reach):
+        T, nz, ny = f0.shape
+        jac = np.zeros((ny, 2 * reach + 1, T * nz, T * nz))
+        for j in range(ny):
+            c = int(colour[j])
+            for t in range(T):
+                for k in range(nz):
+                    resp = (fprobe[(c * T + t) * nz + k] - f0) / eps
+                    for d in range(-reach, reach + 1):
+                        if 0 <= j + d < ny:
+                            jac[j, d + reach, :, t * nz + k] = resp[:, :, j + d].reshape(-1)
+        return jac
+
+    rng = np.random.default_rng(0)
+    for T, nz, ny, reach in ((2, 5, 7, 1), (1, 4, 9, 2), (3, 3, 3, 1)):
+        colour = col.column_colouring(ny, reach)
+        ncol = int(colour.max()) + 1
+        f0 = rng.normal(size=(T, nz, ny))
+        fprobe = rng.normal(size=(ncol * T * nz, T, nz, ny))
+        np.testing.assert_array_equal(col.decode_probes(f0, fprobe, colour, 1e-2, reach), loop(f0, fprobe, colour, 1e-2, reach))
