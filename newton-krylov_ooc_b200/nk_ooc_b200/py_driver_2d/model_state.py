@@ -273,11 +273,13 @@ class ModelState(ModelStateBase):
             hm[:, 1:-1] = tr.horiz_mix.mixing_coeff * self.ypos.delta_mid
             hm[:, 0], hm[:, -1] = hm[:, 1], hm[:, -2]
             fptr.variables["horiz_mixing_coeff"][:] = hm
+            # all mixing-coefficient fields are computed on the device first: one transfer, one synchronisation
+            mc_all = torch.stack([model.mixing_coeff(t) for t in times]).cpu().numpy()
             for ti, t in enumerate(times):
                 fptr.variables["time"][ti] = t
                 fptr.variables["bldepth"][ti, :] = tr.vert_mix.bldepth(t)
                 vm = np.empty((len(self.depth) + 1, len(self.ypos)))
-                vm[1:-1] = model.mixing_coeff(t).cpu().numpy() * self.depth.delta_mid[:, np.newaxis]
+                vm[1:-1] = mc_all[ti] * self.depth.delta_mid[:, np.newaxis]
                 vm[0], vm[-1] = vm[1], vm[-2]
                 fptr.variables["vert_mixing_coeff"][ti, :] = vm
             for tms in self.tracer_modules:
