@@ -472,11 +472,14 @@ int nkb_model_eval_host(nkb_model *m, const double *h_x0, double *h_f, int B) {
         cudaFree(m->d_stage_major); cudaFree(m->d_stage_x); cudaFree(m->d_stage_f); cudaFree(m->d_stage_work);
         m->d_stage_major = m->d_stage_x = m->d_stage_f = m->d_stage_work = nullptr;
         m->stage_cap = 0;
-        NKB_CUDA(cudaMalloc(&m->d_stage_major, n * (size_t)B * sizeof(double)));
+        // every buffer is sized for the PADDED member count: a later call with another B that rounds to the
+        // same ldb reuses them (the capacity test above is on n * ldb)
+        NKB_CUDA(cudaMalloc(&m->d_stage_major, need * sizeof(double)));
         NKB_CUDA(cudaMalloc(&m->d_stage_x, need * sizeof(double)));
         NKB_CUDA(cudaMalloc(&m->d_stage_f, need * sizeof(double)));
-        NKB_CUDA(cudaMalloc(&m->d_stage_work, nkb_model_work_doubles(m, B, ldb) * sizeof(double)));
-        NKB_CUDA(cudaMemset(m->d_stage_x, 0, need * sizeof(double)));
+        NKB_CUDA(cudaMalloc(&m->d_stage_work, nkb_model_work_doubles(m, ldb, ldb) * sizeof(double)));
+        // ordered before the pack kernel: own_stream is non-blocking, so a legacy-stream memset would not be
+        NKB_CUDA(cudaMemsetAsync(m->d_stage_x, 0, need * sizeof(double), m->own_stream));
         m->stage_cap = need;
     }
     cudaStream_t st = m->own_stream;

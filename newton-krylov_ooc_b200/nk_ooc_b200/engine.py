@@ -141,11 +141,16 @@ class Model:
         n_hist, steps_arr, hist = 0, None, None
         hist_ptr = None
         if hist_steps is not None:
+            # the library fills the slots in the order it meets the steps: the list must be strictly
+            # increasing and within [0, n_steps] or snapshots would land in the wrong slots
+            hs = [int(s) for s in hist_steps]
+            if any(b <= a for a, b in zip(hs[:-1], hs[1:])) or (hs and (hs[0] < 0 or hs[-1] > self.n_steps)):
+                raise ValueError("hist_steps must be strictly increasing and within [0, n_steps]")
             # the final state is x0 + F; the library records steps < n_steps
-            inner = [s for s in hist_steps if s < self.n_steps]
+            inner = [s for s in hs if s < self.n_steps]
             n_hist = len(inner)
             steps_arr = (ctypes.c_int * max(n_hist, 1))(*inner)
-            hist = torch.empty((len(hist_steps), self.T, self.nz, self.ny), dtype=torch.float64, device="cuda")
+            hist = torch.full((len(hist_steps), self.T, self.nz, self.ny), float("nan"), dtype=torch.float64, device="cuda")
             hist_ptr = hist.data_ptr()
         check(
             self.lib.nkb_model_eval(self.handle, x.data_ptr(), out.data_ptr(), self._work.data_ptr(), B, ldb,

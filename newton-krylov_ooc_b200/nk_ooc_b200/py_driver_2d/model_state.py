@@ -211,6 +211,11 @@ class ModelState(ModelStateBase):
                 hist[tms.name] = (times, snaps)
             else:
                 res_tms.vals = model.eval(tms.vals, self.members)
+        # a dependency time-out of the persistent step kernel invalidates F: surface it BEFORE the result
+        # is used (norm, Armijo test, Gram-Schmidt) or written; one stream sync per model year is noise
+        torch.cuda.current_stream().synchronize()
+        for tms in self.tracer_modules:
+            self.model_for(tms).check_health()
         if hist_fname is not None:
             self._write_hist(hist_fname, hist)
         res_ms.comp_fcn_postprocess(res_fname, f"{type(self).__name__}.comp_fcn")

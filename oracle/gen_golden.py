@@ -366,6 +366,75 @@ def forced_restore_file_case():
     print("forced_restore_file.npz:", len(out), "arrays")
 
 
+def precond_2d_cases():
+    """the reference's general 2-D preconditioners WITH lateral processes, run unmodified:
+    iage.apply_precond_jacobian (py_driver_2d/iage.py:66-93) on 14x11 and 30x30, and
+    forced.apply_precond_jacobian (forced.py:204-241) for the o2_like configuration
+    (scripts/run_py_driver_2d_forced_o2_like.sh:14-25; sink record = input/py_driver_2d/po4_sms.nc through the
+    reference's own gen_forcing_fcn) whose Jacobian depends on the precond file's tracer snapshots through
+    the sink_thres term (forced.py:190-202,221-229).  Also the reference's comp_jacobian of both modules at
+    the three interval mid-points, so that the host-side assembly can be compared entry by entry.
+    Own fixture (precond_2d.npz) so that the seeded states of py_driver_2d.npz stay what they are."""
+    rng = np.random.default_rng(500)
+    out = {}
+
+    class _Res:
+        def set_tracer_vals_all(self, vals, reseat_vals=False):
+            self.vals = np.array(vals)
+
+    class _Var:
+        def __init__(self, arr):
+            self._a = arr
+
+        def __getitem__(self, key):
+            return self._a[key]
+
+    class _Precond:
+        def __init__(self, variables):
+            self.variables = {k: _Var(v) for k, v in variables.items()}
+
+    for tag, (nz, ny) in {"g14x11": (14, 11), "g30x30": (30, 30)}.items():
+        depth, ypos, procs = rh.make_py_driver_2d(nz, ny, 19.0, 0.1, 1000.0)
+        out[f"{tag}/params"] = np.array([nz, ny, 19.0, 0.1, 1000.0])
+        out[f"{tag}/depth_edges"], out[f"{tag}/ypos_edges"] = depth.edges, ypos.edges
+        mids = YEAR * (np.arange(3) + 0.5) / 3.0
+        # iage
+        iage = rh.make_2d_iage(depth, ypos)
+        y = rng.normal(size=(2, nz, ny))
+        iage.get_tracer_vals_all = lambda y=y: y
+        res = _Res()
+        iage.apply_precond_jacobian((0.0, YEAR), res, procs)
+        out[f"{tag}/iage/y"], out[f"{tag}/iage/precond"] = y, res.vals
+        if tag == "g14x11":
+            out[f"{tag}/iage/jac_dense_mids"] = np.stack(
+                [iage.comp_jacobian(t, y.reshape(-1), procs).toarray() for t in mids])
+        # forced o2_like
+        from oracle.gen_golden_radau import O2_LIKE
+
+        forced = rh.make_2d_forced(depth, ypos, dict(O2_LIKE))
+        forced._tracer_module_def = {"tracers": {"o2_like": {}}}
+        ftimes = np.linspace(0.0, YEAR, 61)
+        out[f"{tag}/forced/frc_time"] = ftimes
+        out[f"{tag}/forced/frc_data"] = np.stack([forced.sms_fcn(t) for t in ftimes])
+        y = rng.normal(size=(1, nz, ny))
+        # precond file: 61 hist times, tracer snapshots with values below, inside and above (0, sink_thres)
+        ptimes = ftimes
+        snaps = np.abs(rng.normal(size=(61, nz, ny))) * 0.06 - 0.005
+        forced.get_tracer_vals_all = lambda y=y: y
+        res = _Res()
+        forced.apply_precond_jacobian((0.0, YEAR), res, procs, _Precond({"time": ptimes, "o2_like": snaps}))
+        out[f"{tag}/forced/y"], out[f"{tag}/forced/precond"] = y, res.vals
+        out[f"{tag}/forced/precond_times"], out[f"{tag}/forced/precond_snaps"] = ptimes, snaps
+        if tag == "g14x11":
+            jacs = []
+            for i, t in enumerate(mids):
+                tv = snaps[np.argmin(abs(YEAR * (i + 1.0) / 3.0 - ptimes))].reshape(-1)
+                jacs.append(forced.comp_jacobian(t, tv, procs).toarray())
+            out[f"{tag}/forced/jac_dense_mids"] = np.stack(jacs)
+    np.savez_compressed(os.path.join(OUT, "precond_2d.npz"), **out)
+    print("precond_2d.npz:", len(out), "arrays")
+
+
 def main():
     if not rh.available():
         raise SystemExit("reference tree not found: golden vectors can only be generated in the build container")
@@ -376,6 +445,7 @@ def main():
     py_driver_2d_cases()
     test_problem_cases()
     forced_restore_file_case()
+    precond_2d_cases()
 
 
 if __name__ == "__main__":

@@ -466,6 +466,21 @@ class Forced2D:
             d += np.where((s < 0.0) & (q > 0.0) & (q < 1.0), s / self.sink_thres, 0.0).reshape(-1)
         return (jac + sparse.diags(d)).tocsr()
 
+    def apply_precond_jacobian(self, y, precond_times, precond_snaps):
+        """res = M^-1 y - y,  M = I - prod_i (I - dt J_i), dt = T/3, J_i = J((i+1/2) dt) evaluated at the
+        precond file's tracer snapshot nearest (i+1) dt (forced.py:204-241)"""
+        shape = y.shape
+        yv = y.reshape(-1)
+        t0, t1 = self.g.time_range
+        dt = (t1 - t0) / 3
+        ident = sparse.identity(yv.size, format="csr")
+        mat = ident.copy()
+        for i in range(3):
+            snap = precond_snaps[np.argmin(abs(t0 + (i + 1.0) * dt - precond_times))]
+            mat = mat @ (ident - dt * self.comp_jacobian(t0 + (i + 0.5) * dt, snap.reshape(-1)))
+        mat = (ident - mat).tocsc()
+        return (sp_linalg.spsolve(mat, yv) - yv).reshape(shape)
+
 
 def comp_fcn_2d(module, x0, t_eval=None, rtol=1.0e-6, atol=1.0e-6, return_sol=False):
     """F(x) = x(T) - x(0) with the reference's solve_ivp call (py_driver_2d/model_state.py:102-121)"""
