@@ -179,6 +179,34 @@ int nkb_axpby(const int32_t *d_region, int R, int T, int ncell, const double *d_
               const double *d_x, const double *d_beta, double *d_y, double fill_alpha,
               double fill_beta, int B, int ldb, void *stream);
 
+/* modified Gram-Schmidt of w against k basis vectors — replaces ModelStateBase.mod_gram_schmidt
+ * (model_state_base.py:365-377: for i < k: h_i = dot(w, v_i); w -= h_i v_i, each step re-reading a basis
+ * file).  One cooperative launch with w resident in registers and every basis vector read once
+ * (8 N (k + 2) bytes) when w fits on the chip and R*B <= 1024, k <= 64; otherwise one dot and one update
+ * per vector.  Either way the k [R][B] scalars are written to d_h and nothing is synchronised with the
+ * host.  Region weights as for nkb_wdot plus their dense form: d_region int32 [ncell] (1-based, 0 = no
+ * region), d_cellw [ncell] (grid_weight / region sum, 0 outside regions).  h_basis: host array of k device
+ * pointers, each [T][ncell][ldb].  d_scratch: nkb_mgs_scratch_doubles(R, B, ncell_max_row) doubles. */
+size_t nkb_mgs_scratch_doubles(int R, int B, int ncell_max_row);
+int nkb_mgs(const int32_t *d_indptr, const int32_t *d_indices, const double *d_wdata, const int32_t *d_region,
+            const double *d_cellw, int R, int T, int ncell, int ncell_max_row, double *d_w,
+            const double *const *h_basis, int k, int B, int ldb, double *d_scratch, size_t scratch_doubles,
+            double *d_h /* [k][R][B] */, void *stream);
+
+/* out = sum_i coeff[i][r(cell)][b] * basis_i (+ add) in one pass — replaces model_state_base.lin_comb
+ * (model_state_base.py:619-624; krylov_solver.py:141-154).  d_coeff [k][R][B]; cells outside every
+ * region use `fill` (broadcast_region_vals, tracer_module_state_base.py:502-515); d_add may be NULL or
+ * equal to d_out. */
+int nkb_lin_comb(const int32_t *d_region, int R, int T, int ncell, const double *d_coeff,
+                 const double *const *h_basis, int k, const double *d_add, double *d_out, double fill, int B,
+                 int ldb, void *stream);
+
+/* result columns gathered from G ranks ([G][n][W], the output of an all-gather of member-fastest blocks of W
+ * members) -> one member-fastest batch [n][ldo] holding the first B of the G*W members: the gather of
+ * F / JVP columns to the owner of the Krylov basis (krylov_solver.py:127). */
+int nkb_interleave_blocks(const double *d_gathered, double *d_out, size_t n, int G, int W, int ldo, int B,
+                          void *stream);
+
 /* finite-difference JVP pieces (model_state_base.py:492-527):
  *   sigma[r][b] = 1e-4*norm (1 where 0);  perturb = x + sigma*v;  jvp = (fp - f0)/sigma */
 int nkb_fd_sigma(const double *d_norm, double *d_sigma, int n, void *stream);

@@ -358,7 +358,7 @@ constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
 
 // pair planes of a ring slot, [KC][FS_COLS] pairs each (see step_ctab_kernel in nkb_tables.cu):
 //   sweep A: 0 {aL,aC}  1 {aR,m1}  2 {fA,-}          sweep C: 3 {ib2,g2}  (C may share a slot with A)
-//   sweep B: 0 {bL,bC}  1 {bR,ib1} 2 {g1,m1} 3 {m2,fB}
+//   sweep B: 0 {bL,bC}  1 {bR,m1}  2 {g1,ib1} 3 {m2,fB}   (the back substitution needs plane 2 only)
 template <int KIND, int MPT>
 __global__ void __launch_bounds__(fs_cfg(MPT).threads, 1) step_fused_kernel(const StepArgs p,
                                                                              const __grid_constant__ StepMaps maps) {
@@ -682,9 +682,9 @@ __global__ void __launch_bounds__(fs_cfg(MPT).threads, 1) step_fused_kernel(cons
                     const V y1m = (q > 0) ? ycur[q > 0 ? q - 1 : 0] : y1top;
                     const double2 lc = pl[q * FS_COLS], ri = pl[PP + q * FS_COLS], gm = pl[2 * PP + q * FS_COLS],
                                   mf = pl[3 * PP + q * FS_COLS];
-                    const V u1 = fs_fma(-gm.x, u1n, fs_mul(ri.y, y1));
+                    const V u1 = fs_fma(-gm.x, u1n, fs_mul(gm.y, y1));
                     u1n = u1;
-                    V rhs1 = fs_fma(gm.y, y1m, y1);  // = u_n + gamma h E(u_n) (+ aff1 at the surface)
+                    V rhs1 = fs_fma(ri.y, y1m, y1);  // = u_n + gamma h E(u_n) (+ aff1 at the surface)
                     if (c == 0 && q == 0) rhs1 = fs_sub(rhs1, fs_splat<MPT>(t.aff1));
                     const V un = fs_ld(sb + offU[q][1], (V *)nullptr);
                     // a0 u_n + h (delta - 1 + gamma) E(u_n) + he1 * source(u1)
@@ -1152,8 +1152,8 @@ __global__ void __launch_bounds__(P3_THREADS, 1) step_fused_p3_kernel(const Step
                 double u1v[KC];
 #pragma unroll
                 for (int q = KC - 1; q >= 0; --q) {
-                    const double2 ri = pl[PP + q * FS_COLS], gm = pl[2 * PP + q * FS_COLS];
-                    u1n = fma(-gm.x, u1n, ri.y * ycur[q].v[0]);
+                    const double2 gm = pl[2 * PP + q * FS_COLS];
+                    u1n = fma(-gm.x, u1n, gm.y * ycur[q].v[0]);
                     u1v[q] = u1n;
                     ex[(tr * KC + q) * 64 + exl] = u1n;
                 }
@@ -1173,10 +1173,9 @@ __global__ void __launch_bounds__(P3_THREADS, 1) step_fused_p3_kernel(const Step
                 for (int q = KC - 1; q >= 0; --q) {
                     const double y1 = ycur[q].v[0];
                     const double y1m = (q > 0) ? ycur[q > 0 ? q - 1 : 0].v[0] : y1top;
-                    const double2 lc = pl[q * FS_COLS], ri = pl[PP + q * FS_COLS], gm = pl[2 * PP + q * FS_COLS],
-                                  mf = pl[3 * PP + q * FS_COLS];
+                    const double2 lc = pl[q * FS_COLS], ri = pl[PP + q * FS_COLS], mf = pl[3 * PP + q * FS_COLS];
                     const double u1 = u1v[q];
-                    double rhs1 = fma(gm.y, y1m, y1);
+                    double rhs1 = fma(ri.y, y1m, y1);
                     if (c == 0 && q == 0) rhs1 -= t.aff1;
                     const double un = *reinterpret_cast<const double *>(sb + tr * P3_UBOX + offU[q][1]);
                     const double pp = fma(p.r, rhs1, p.a0r * un) + sv[q];
@@ -1403,6 +1402,7 @@ bool fused_step_usable(const ModelDev &v, int B, int ldb, const double *x0, cons
     if (v.column_model == 1 && v.ny == 1) return false;
     if (v.kind == NKB_MOD_PHOSPHORUS) {
         if (fs_env_int("NKB_FUSED_P3", 1) == 0 || v.T != P3_T || v.n_classes != P3_NCLS) return false;
+        if (v.class_of[0] != 0 || v.class_of[1] != 0 || v.class_of[2] != 1) return false;  // po4, dop: class 0; pop: class 1
         if (((B + P3_MEM - 1) / P3_MEM) * P3_MEM > ldb) return false;  // the member-block-major copy pads B to 4
     } else if (v.kind != NKB_MOD_LINEAR && v.kind != NKB_MOD_FORCED_FILE) {
         return false;

@@ -242,10 +242,11 @@ __global__ void step_ctab_kernel(ModelDev m, int n_steps, const double *__restri
                     base[2 * pl + 1] = 0.0;
                     base[3 * pl + 0] = he1 * eL;
                     base[3 * pl + 1] = a1 + he1 * eC;
+                    // plane 5 alone serves the stage-1 back substitution (u1_k = ib y_k - g u1_{k+1})
                     base[4 * pl + 0] = he1 * eR;
-                    base[4 * pl + 1] = ib;
+                    base[4 * pl + 1] = mk;
                     base[5 * pl + 0] = (k < nz - 1) ? cc * ib : 0.0;
-                    base[5 * pl + 1] = mk;
+                    base[5 * pl + 1] = ib;
                     prev_ib[c] = ib;
                     prev_c[c] = cc;
                 } else {  // raw rows first (parked in planes 6 and 7), factored bottom-up below

@@ -102,6 +102,18 @@ SYMBOLS = {
         [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_double, c_int,
          c_int, c_void_p],
     ),
+    "nkb_mgs_scratch_doubles": (c_size_t, [c_int, c_int, c_int]),
+    "nkb_mgs": (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, POINTER(c_void_p),
+         c_int, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p],
+    ),
+    "nkb_lin_comb": (
+        c_int,
+        [c_void_p, c_int, c_int, c_int, c_void_p, POINTER(c_void_p), c_int, c_void_p, c_void_p, c_double, c_int, c_int,
+         c_void_p],
+    ),
+    "nkb_interleave_blocks": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_int, c_void_p]),
     "nkb_fd_sigma": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "nkb_limiter_scalef": (
         c_int,

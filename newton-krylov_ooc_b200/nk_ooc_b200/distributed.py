@@ -44,56 +44,74 @@ def is_sharded(group=None):
     return dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
 
 
-def _to_member_major(vals, B):
-    """[..., ldb] member-fastest -> [B, n] (layout conversion for the gather: library kernel on the GPU)"""
-    if vals.is_cuda:
-        from . import engine
+def member_block_width(n_members, world):
+    """members per rank of the 32-aligned block partition used on the data path: rank g owns the members
+    [g*W, min(B, (g+1)*W)), W a multiple of 32 (256-byte rows of the member-fastest layout), so that the
+    all-gathered blocks line up as ONE member-fastest batch with members in their original order"""
+    per = -(-n_members // world)
+    return ((per + 31) // 32) * 32
 
-        return engine.unpack(vals, B).reshape(B, -1)
-    return vals.movedim(-1, 0)[:B].reshape(B, -1).contiguous()
+
+def member_block_range(n_members, rank, world):
+    width = member_block_width(n_members, world)
+    lo = min(n_members, rank * width)
+    return lo, min(n_members, lo + width)
 
 
-def _from_member_major(major, like):
-    """[B, n] -> member-fastest tensor shaped like `like` ([..., ldb]); padding members are zero"""
-    B = major.shape[0]
-    if like.is_cuda:
-        from . import engine
+def gather_member_blocks(local, n_members, group=None, out=None):
+    """all-gather of member-fastest result blocks: `local` [..., W] on every rank (W =
+    member_block_width; lanes beyond the rank's own members are ignored) -> [..., ldb] with all
+    n_members in order.  One all_gather_into_tensor of the packed blocks and one library kernel
+    (nkb_interleave_blocks) — no member-major staging, no per-rank Python lists."""
+    world = dist.get_world_size(group)
+    width = member_block_width(n_members, world)
+    if local.shape[-1] != width:
+        raise ValueError(f"local block has {local.shape[-1]} member lanes, expected {width}")
+    lead = tuple(local.shape[:-1])
+    n = 1
+    for d in lead:
+        n *= d
+    gathered = torch.empty((world * n, width), dtype=local.dtype, device=local.device)  # [G][n][W], concatenated
+    dist.all_gather_into_tensor(gathered, local.reshape(n, width).contiguous(), group=group)
+    gathered = gathered.view(world, n, width)
+    ldb = 1 if n_members == 1 else ((n_members + 31) // 32) * 32
+    if out is None:
+        out = torch.zeros(lead + (ldb,), dtype=local.dtype, device=local.device)
+    if local.is_cuda:
+        from . import _lib, engine
 
-        fast = engine.pack(major.reshape((B,) + tuple(like.shape[:-1])))
-        if fast.shape[-1] == like.shape[-1]:
-            return fast
-        out = torch.zeros_like(like)
-        out[..., :B] = fast[..., :B]
-        return out
-    out = torch.zeros_like(like)
-    out[..., :B] = major.reshape((B,) + tuple(like.shape[:-1])).movedim(0, -1)
+        _lib.check(_lib.load().nkb_interleave_blocks(gathered.data_ptr(), out.data_ptr(), n, world, width, out.shape[-1],
+                                                     n_members, engine._stream_ptr()), "nkb_interleave_blocks")
+    else:  # gloo tests of the host logic
+        full = gathered.permute(1, 0, 2).reshape(n, world * width)[:, :n_members]
+        out.reshape(n, out.shape[-1])[:, :n_members] = full
     return out
 
 
 def sharded_comp_fcn(state, group=None, hist_fname=None):
     """F(x) of a batched state (coloured probes, Armijo candidates, perturbed iterates) with its
-    members sharded over the ranks: every rank holds the same `state`, evaluates the members of
-    member_range(state.members, rank, world) — a model year each, no collective on the data path —
-    and the result columns are all-gathered so that every rank returns the full batched F.
-    Member results do not depend on which other members share a launch (tested bit for bit), so
-    the sharded result equals the single-GPU one.  Outside a process group this is state.comp_fcn."""
+    members sharded over the ranks: rank g evaluates the member block member_block_range(B, g, G) — a
+    model year each, no collective on the data path — and the result blocks are all-gathered
+    (gather_member_blocks) so that every rank returns the full batched F.  Only the rank's own block of
+    the state is touched (a view of `state`; nothing is replicated or re-packed).  Member results do not
+    depend on which other members share a launch (tested bit for bit), so the sharded result equals the
+    single-GPU one.  Outside a process group this is state.comp_fcn."""
     if not is_sharded(group):
         return state.comp_fcn(None, None, hist_fname)
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     B = state.members
-    lo, hi = member_range(B, rank, world)
+    width = member_block_width(B, world)
+    lo, hi = member_block_range(B, rank, world)
     res = state._like(clone_vals=False)
     local_fcn = None
     if hi > lo:
         local_fcn = state.member_slice(lo, hi).comp_fcn(None, None, hist_fname if lo == 0 else None)
     for ind, tms in enumerate(state.tracer_modules):
-        n = tms.vals[..., 0].numel()
+        block = tms.vals.new_zeros(tuple(tms.vals.shape[:-1]) + (width,))
         if local_fcn is not None:
-            local = _to_member_major(local_fcn.tracer_modules[ind].vals, hi - lo)
-        else:
-            local = tms.vals.new_zeros((0, n))
-        full = gather_members(local, B, group)
-        res.tracer_modules[ind].vals = _from_member_major(full, tms.vals)
+            lv = local_fcn.tracer_modules[ind].vals
+            block[..., : hi - lo] = lv[..., : hi - lo]
+        res.tracer_modules[ind].vals = gather_member_blocks(block, B, group)
     return res
 
 

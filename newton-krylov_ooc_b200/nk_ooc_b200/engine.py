@@ -225,6 +225,11 @@ class RegionWeights:
         self.data = torch.tensor(data, dtype=torch.float64, device="cuda")
         self.region = torch.tensor(flat_m, dtype=torch.int32, device="cuda")
         self.max_row = int(np.diff(indptr).max())
+        # dense form of the same weights (the fused Gram-Schmidt kernel walks the cells in storage order)
+        cellw = np.zeros(self.ncell)
+        cellw[np.asarray(indices, dtype=np.int64)] = data
+        self.cellw = torch.tensor(cellw, dtype=torch.float64, device="cuda")
+        self._mgs_scratch = None
 
     def dot(self, a, b, B):
         """[region_cnt, B] region-weighted dot products of member-fastest a, b [T, cells..., ldb];
@@ -269,6 +274,45 @@ class RegionWeights:
         )
         return y
 
+
+    def mgs(self, w, basis, B):
+        """modified Gram-Schmidt of w (in place) against the list `basis` of member-fastest tensors
+        (model_state_base.py:365-377); returns the device tensor h [k, region_cnt, B].  One launch when w fits on
+        the chip; no host synchronisation either way."""
+        lib = _lib.load()
+        k = len(basis)
+        T, ldb = w.shape[0], w.shape[-1]
+        h = torch.empty((k, self.region_cnt, B), dtype=torch.float64, device="cuda")
+        if k == 0:
+            return h
+        need = lib.nkb_mgs_scratch_doubles(self.region_cnt, B, self.max_row)
+        if self._mgs_scratch is None or self._mgs_scratch.numel() < need:
+            self._mgs_scratch = torch.empty(need, dtype=torch.float64, device="cuda")
+        ptrs = (ctypes.c_void_p * k)(*[v.data_ptr() for v in basis])
+        check(
+            lib.nkb_mgs(self.indptr.data_ptr(), self.indices.data_ptr(), self.data.data_ptr(), self.region.data_ptr(),
+                        self.cellw.data_ptr(), self.region_cnt, T, self.ncell, self.max_row, w.data_ptr(), ptrs, k, B,
+                        ldb, self._mgs_scratch.data_ptr(), self._mgs_scratch.numel(), h.data_ptr(), _stream_ptr()),
+            "nkb_mgs",
+        )
+        return h
+
+    def lin_comb(self, coeff, basis, B, add=None, out=None, fill=1.0):
+        """out = sum_i coeff[i][r, b] * basis[i] (+ add) in one pass (model_state_base.py:619-624);
+        coeff: device tensor [k, region_cnt, B]"""
+        lib = _lib.load()
+        k = len(basis)
+        T, ldb = basis[0].shape[0], basis[0].shape[-1]
+        if out is None:
+            out = torch.empty_like(basis[0])
+        ptrs = (ctypes.c_void_p * k)(*[v.data_ptr() for v in basis])
+        check(
+            lib.nkb_lin_comb(self.region.data_ptr(), self.region_cnt, T, self.ncell, coeff.contiguous().data_ptr(), ptrs,
+                             k, None if add is None else add.data_ptr(), out.data_ptr(), float(fill), B, ldb,
+                             _stream_ptr()),
+            "nkb_lin_comb",
+        )
+        return out
 
     def limiter_scalef(self, base, inc, lob, upb, B):
         """[region_cnt, B] largest scale factors in [0, 1] keeping base + scalef*inc in [lob, upb]

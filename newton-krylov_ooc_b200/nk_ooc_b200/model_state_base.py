@@ -432,15 +432,19 @@ class ModelStateBase:
     # ---- Krylov building blocks -----------------------------------------------------------
     def mod_gram_schmidt(self, basis_cnt, fname_fcn, quantity):
         """in-place modified Gram-Schmidt against basis files (model_state_base.py:365-377).
-        fname_fcn may also return an in-memory ModelState (HBM-resident basis)."""
-        h_val = np.empty(self._scalar_shape()[:1] + (basis_cnt,) + self._scalar_shape()[1:])
+        fname_fcn may also return an in-memory ModelState (HBM-resident basis).  Per tracer module ONE
+        library call (nkb_mgs: w resident on the chip, every basis vector read once) and, at the end, one
+        device-to-host copy of all scalars."""
+        basis = []
         for i_val in range(basis_cnt):
             basis_i = fname_fcn(quantity, i_val)
-            if not isinstance(basis_i, ModelStateBase):
-                basis_i = type(self)(basis_i)
-            h_val[:, i_val] = self.dot_prod(basis_i)
-            self -= h_val[:, i_val] * basis_i
-        return h_val
+            basis.append(basis_i if isinstance(basis_i, ModelStateBase) else type(self)(basis_i))
+        per_module = []
+        for ind, tms in enumerate(self.tracer_modules):
+            vecs = [tms._flat(b.tracer_modules[ind].vals) for b in basis]
+            per_module.append(self.model_config_obj.weights.mgs(tms._flat(tms.vals), vecs, self.members))
+        h_val = torch.stack(per_module).cpu().numpy()  # [n_modules, k, R, B]
+        return h_val[..., 0] if self.members == 1 else h_val
 
     def comp_jacobian_fcn_state_prod(self, fcn, direction, res_fname, solver_state):
         """finite-difference Jacobian-vector product (model_state_base.py:492-527)"""
@@ -515,10 +519,21 @@ class ModelStateBase:
 
 
 def lin_comb(res_type, coeff, fname_fcn, quantity):
-    """linear combination of model states in files (or in HBM) (model_state_base.py:619-624)"""
-    first = fname_fcn(quantity, 0)
-    res = coeff[:, 0] * (first if isinstance(first, ModelStateBase) else res_type(first))
-    for ind in range(1, coeff.shape[1]):
-        nxt = fname_fcn(quantity, ind)
-        res += coeff[:, ind] * (nxt if isinstance(nxt, ModelStateBase) else res_type(nxt))
+    """linear combination of model states in files (or in HBM) (model_state_base.py:619-624): one pass over
+    the k vectors per tracer module (nkb_lin_comb); coeff [n_modules, k, region_cnt(, B)]"""
+    coeff = np.asarray(coeff, dtype=np.float64)
+    states = []
+    for ind in range(coeff.shape[1]):
+        st = fname_fcn(quantity, ind)
+        states.append(st if isinstance(st, ModelStateBase) else res_type(st))
+    res = states[0]._like(clone_vals=False)
+    B, R = res.members, res.model_config_obj.region_cnt
+    for ind, tms in enumerate(res.tracer_modules):
+        c = coeff[ind]
+        if c.ndim == 2:  # [k, R] -> [k, R, B]
+            c = np.repeat(c[:, :, None], B, axis=2)
+        cdev = torch.from_numpy(np.ascontiguousarray(c.reshape(len(states), R, B))).cuda()
+        vecs = [tms._flat(s.tracer_modules[ind].vals) for s in states]
+        out = res.model_config_obj.weights.lin_comb(cdev, vecs, B)
+        tms.vals = out.reshape(states[0].tracer_modules[ind].vals.shape)
     return res

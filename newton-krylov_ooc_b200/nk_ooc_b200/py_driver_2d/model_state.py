@@ -57,6 +57,18 @@ TRACER_MODULE_DEFS = {
 DEFAULT_STEPS_PER_YEAR = None
 
 
+def default_schedule(kind, nz):
+    """keyword arguments of engine.graded_schedule for a tracer module on a grid with nz levels, chosen from
+    the measured error of F against the reference's Radau solution (profiles/r02_error_vs_steps.md) so that
+    the error stays below half of the stated tolerance (rtol 1e-3 |F| + atol 1e-6 max(1, max |x0|), DESIGN.md
+    section 2): 2640 steps per year (20 / 120 / 240 per hist interval) everywhere, except for iage on grids
+    finer than 60 levels, whose sharp age gradient below the moving mixed layer needs 5280 (ratio 0.95 and
+    1.36 of the tolerance with 2640 steps on 80 x 100 and 125 x 150, 0.23 and 0.32 with 5280)."""
+    if kind == "iage" and nz > 60:
+        return {"flat": 40, "ramp": 240, "ramp_first": 480}
+    return {"flat": 20, "ramp": 120, "ramp_first": 240}
+
+
 def _eval_expr(expr):
     """arithmetic strings of the cfg files, e.g. "1.0 / 3600.0" (nk_ooc/utils.py:138-164)"""
     import ast
@@ -163,7 +175,7 @@ class ModelState(ModelStateBase):
         else:
             raise NotImplementedError(f"tracer module {tms.name} is not available in py_driver_2d")
         if cls.steps_per_year is None:
-            model.set_graded_schedule()
+            model.set_graded_schedule(**default_schedule(kind, len(cls.depth)))
         else:
             model.set_uniform_schedule(cls.steps_per_year)
         cls._models[tms.name] = model

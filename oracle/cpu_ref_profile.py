@@ -26,11 +26,10 @@ YEAR = 365.0 * 86400.0
 class Instrumented:
     """scipy Radau stepper with per-operation counters/timers (fun, jac, lu, solve_lu)"""
 
-    def __init__(self, mod, sparsity, y0, t_start, t_end):
+    def __init__(self, mod, sparsity, y0, t_start, t_end, first_step=None):
         from scipy import integrate
 
-        self.counts = {"fun": 0, "jac": 0, "lu": 0, "solve": 0, "step": 0}
-        self.times = {"fun": 0.0, "jac": 0.0, "lu": 0.0, "solve": 0.0}
+        self.reset()
 
         def timed(name, f):
             def wrapper(*a, **k):
@@ -44,10 +43,24 @@ class Instrumented:
 
         self.solver = integrate.Radau(
             timed("fun", mod.comp_tend), t_start, y0, t_end, max_step=YEAR * 0.01, rtol=1.0e-6, atol=1.0e-6,
-            jac=timed("jac", mod.comp_jacobian), jac_sparsity=sparsity,
+            jac=timed("jac", mod.comp_jacobian), jac_sparsity=sparsity, first_step=first_step,
         )
         self.solver.lu = timed("lu", self.solver.lu)
         self.solver.solve_lu = timed("solve", self.solver.solve_lu)
+
+    def reset(self):
+        self.counts = {"fun": 0, "jac": 0, "lu": 0, "solve": 0, "step": 0}
+        self.times = {"fun": 0.0, "jac": 0.0, "lu": 0.0, "solve": 0.0}
+
+    def run_steps(self, n_steps):
+        """exactly n_steps accepted Radau steps (or to the end of the interval); wall seconds"""
+        t0 = time.perf_counter()
+        for _ in range(n_steps):
+            if self.solver.status != "running":
+                break
+            self.solver.step()
+            self.counts["step"] += 1
+        return time.perf_counter() - t0
 
     def run(self, budget_s=None):
         t0 = time.perf_counter()

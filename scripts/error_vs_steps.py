@@ -56,12 +56,10 @@ def ratio(got, want, x0):
 
 
 def model_from_golden(g, module):
-    tr = modules.Transport2D(SpatialAxis("depth", g["depth_edges"]), SpatialAxis("ypos", g["ypos_edges"]),
-                             float(g["params"][3]), float(g["params"][4]))
-    if module == "forced":
-        return modules.forced_model(tr, "const", 1.0, 1.0 / 3600.0, "file", sms_times=g["frc_time"],
-                                    sms_data=g["frc_data"], sink_thres=0.05)
-    return modules.iage_model(tr) if module == "iage" else modules.phosphorus_model(tr)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import radau_cases
+
+    return radau_cases.model(g, module)
 
 
 def table(title, rows, header):

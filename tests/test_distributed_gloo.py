@@ -72,6 +72,24 @@ def test_member_range_partitions_exactly():
         member_range(4, 2, 2)
 
 
+def test_member_block_range_is_32_aligned_and_exact():
+    """the partition of the data path: 32-aligned blocks (256-byte rows) so that the all-gathered blocks form
+    one member-fastest batch; 4096 members over 8 ranks = 512 each"""
+    from nk_ooc_b200.distributed import member_block_range, member_block_width
+
+    assert member_block_width(4096, 8) == 512 and member_block_range(4096, 7, 8) == (3584, 4096)
+    for n in (1, 5, 33, 70, 4096, 4099):
+        for world in (1, 2, 3, 8):
+            width = member_block_width(n, world)
+            assert width % 32 == 0 and width * world >= n
+            seen = []
+            for r in range(world):
+                lo, hi = member_block_range(n, r, world)
+                assert lo == min(n, r * width) and hi - lo <= width
+                seen.extend(range(lo, hi))
+            assert seen == list(range(n))
+
+
 # ---- sharded batched evaluation (distributed.sharded_comp_fcn) with a stand-in state ---------------
 class _FakeTms:
     def __init__(self, vals):
@@ -132,7 +150,7 @@ def _worker_sharded(rank, world, port, n_members, tmpdir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n_members", [(2, 7), (2, 1), (3, 8)])
+@pytest.mark.parametrize("world,n_members", [(2, 7), (2, 1), (3, 8), (2, 40), (3, 70), (2, 64)])
 def test_sharded_comp_fcn_gloo(tmp_path, world, n_members):
     """every rank evaluates only its member block; the gathered result equals the unsharded one bit
     for bit, also when a rank owns no member (world 2, one member)"""

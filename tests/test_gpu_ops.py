@@ -376,3 +376,86 @@ def test_banded_cooperative_factorisation(n, kl, ku, monkeypatch):
         np.testing.assert_allclose(got[coop], want, rtol=0, atol=tol)
         np.testing.assert_allclose(f.solve(_dev(y[:, :1]), 1).cpu().numpy()[:, 0], want[:, 0], rtol=0, atol=tol)
     np.testing.assert_allclose(got["1"], got["0"], rtol=0, atol=1e-3 * tol)
+
+
+@pytest.mark.parametrize("resident", [True, False])
+@pytest.mark.parametrize("B", [1, 5, 40])
+@pytest.mark.parametrize("regions", ["one", "columns", "masked"])
+def test_fused_mgs_and_lin_comb_match_the_vector_loop(B, regions, resident, monkeypatch):
+    """nkb_mgs (one cooperative launch, w resident on the chip; or its general path) and nkb_lin_comb against
+    the loop of the reference (model_state_base.py:365-377: h_i = dot(w, v_i); w -= h_i v_i; :619-624) done with
+    numpy in float64 on the host, and against the k x (nkb_wdot, nkb_axpby) loop they replace"""
+    from oracle import nk_oracle as o
+    from nk_ooc_b200 import engine
+
+    if not resident:
+        monkeypatch.setenv("NKB_MGS_RESIDENT", "0")
+    rng = np.random.default_rng(11)
+    nz, ny, T, k = 20, 13, 2, 6
+    wgt = np.outer(rng.uniform(1, 5, nz), rng.uniform(1, 2, ny))
+    if regions == "one":
+        mask = np.ones((nz, ny), dtype=np.int32)
+    elif regions == "columns":
+        mask = o.column_region_mask(nz, ny, 0.0, 0.0)
+    else:
+        mask = rng.integers(0, 4, size=(nz, ny)).astype(np.int32)
+    w = o.region_weights(mask, wgt)
+    rw = engine.RegionWeights(mask, wgt)
+    R = rw.region_cnt
+    basis = [rng.normal(size=(T, nz, ny, B)) for _ in range(k)]
+    x = rng.normal(size=(T, nz, ny, B))
+    # host loop (the reference's algorithm)
+    want_w = x.copy()
+    want_h = np.zeros((k, R, B))
+    reg = np.where(mask > 0, mask - 1, 0)
+    inside = (mask > 0)[None, :, :, None]
+    for i in range(k):
+        for b in range(B):
+            want_h[i, :, b] = o.dot_prod(w, want_w[..., b], basis[i][..., b])
+        want_w = want_w - np.where(inside, want_h[i][reg][None] * basis[i], 0.0)
+    flat = lambda t: t.reshape(T, nz * ny, t.shape[-1])
+    wd = _dev(x)
+    bd = [_dev(v) for v in basis]
+    n0 = engine._lib.load().nkb_launch_count()
+    h = rw.mgs(flat(wd), [flat(v) for v in bd], B)
+    launches = engine._lib.load().nkb_launch_count() - n0
+    assert launches == (1 if resident else 3 * k)  # (the dot is a two-pass reduction)
+    np.testing.assert_allclose(h.cpu().numpy(), want_h, rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(wd.cpu().numpy()[..., :B], want_w, rtol=1e-12, atol=1e-13)
+    # the loop of library calls it replaces
+    w2 = _dev(x)
+    for i in range(k):
+        hi = rw.dot(flat(w2), flat(bd[i]), B)
+        rw.axpby(-hi, flat(bd[i]), 1.0, flat(w2), B, fill_alpha=0.0)
+        np.testing.assert_allclose(hi.cpu().numpy(), h[i].cpu().numpy(), rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(w2.cpu().numpy(), wd.cpu().numpy(), rtol=1e-12, atol=1e-13)
+    # run-to-run determinism of the fused kernel (fixed summation order)
+    w3 = _dev(x)
+    h3 = rw.mgs(flat(w3), [flat(v) for v in bd], B)
+    assert torch.equal(h3, h) and torch.equal(w3, wd)
+    # lin_comb
+    coeff = rng.normal(size=(k, R, B))
+    got = rw.lin_comb(torch.from_numpy(coeff).cuda(), [flat(v) for v in bd], B).cpu().numpy().reshape(T, nz, ny, -1)
+    want = np.zeros((T, nz, ny, B))
+    for i in range(k):
+        want += np.where(inside, coeff[i][reg][None], 1.0) * basis[i]
+    np.testing.assert_allclose(got[..., :B], want, rtol=1e-12, atol=1e-13)
+
+
+def test_interleave_blocks():
+    """[G][n][W] all-gather output -> member-fastest [n][ldo] with the first B of G*W members"""
+    from nk_ooc_b200 import engine
+
+    lib = engine._lib.load()
+    rng = np.random.default_rng(3)
+    G, n, W, B = 3, 50, 32, 70
+    src = rng.normal(size=(G, n, W))
+    ldo = engine.padded_members(B)
+    out = torch.full((n, ldo), -7.0, dtype=torch.float64, device="cuda")
+    sd = torch.from_numpy(src).cuda()
+    engine.check(lib.nkb_interleave_blocks(sd.data_ptr(), out.data_ptr(), n, G, W, ldo, B, engine._stream_ptr()),
+                 "nkb_interleave_blocks")
+    want = np.moveaxis(src, 0, 1).reshape(n, G * W)[:, :B]
+    got = out.cpu().numpy()
+    np.testing.assert_array_equal(got[:, :B], want)
+    assert (got[:, B:] == -7.0).all()

@@ -30,25 +30,18 @@ YEAR = 365.0 * 86400.0
 
 
 def _load(golden_dir, grid, module):
-    path = os.path.join(golden_dir, f"radau_{grid}_{module}.npz")
-    if not os.path.exists(path):
-        pytest.skip(f"{os.path.basename(path)} not generated")
-    return np.load(path)
+    import radau_cases
+
+    g = radau_cases.load(grid, module)
+    if g is None:
+        pytest.skip(f"radau_{grid}_{module}.npz not generated")
+    return g
 
 
 def _model(g, module):
-    from nk_ooc_b200.py_driver_2d import modules
-    from nk_ooc_b200.spatial_axis import SpatialAxis
+    import radau_cases
 
-    tr = modules.Transport2D(SpatialAxis("depth", g["depth_edges"]), SpatialAxis("ypos", g["ypos_edges"]),
-                             float(g["params"][3]), float(g["params"][4]))
-    if module == "forced":
-        # scripts/run_py_driver_2d_forced_o2_like.sh:14-25 (the record already carries scalef = -1/3)
-        return modules.forced_model(tr, "const", 1.0, 1.0 / 3600.0, "file", sms_times=g["frc_time"],
-                                    sms_data=g["frc_data"], sink_thres=0.05)
-    if module == "iage":
-        return modules.iage_model(tr)
-    return modules.phosphorus_model(tr)
+    return radau_cases.model(g, module)
 
 
 def _eval(model, x0, hist_idx=None):
@@ -77,12 +70,14 @@ def _tol_ratio(got, want, x0):
     return float((np.abs(got - want) / (FCN_RTOL * np.abs(want) + FCN_ATOL * scale)).max())
 
 
-@pytest.mark.parametrize("grid", ["g14x11", "g30x30", "g40x50"])
+@pytest.mark.parametrize("grid", ["g14x11", "g30x30", "g40x50", "g80x100", "g125x150"])
 @pytest.mark.parametrize("module", ["iage", "forced", "phosphorus"])
 def test_fcn_vs_reference_radau(golden_dir, grid, module):
+    from nk_ooc_b200.py_driver_2d.model_state import default_schedule
+
     g = _load(golden_dir, grid, module)
     model = _model(g, module)
-    model.set_graded_schedule()
+    model.set_graded_schedule(**default_schedule(module, int(g["params"][0])))
     x0 = g["x0"]
     truth = g["tol1e-09/fcn"]
     idx = [int(i) for i in g["tol1e-09/snap_idx"]]
