@@ -67,6 +67,24 @@ class ModelConfig:
         self.grid_weight = grid_vars["grid_weight"]
         self.weights = engine.RegionWeights(self.region_mask, self.grid_weight)
         self.region_cnt = self.weights.region_cnt
+        self.precond_matrix_defs = self._precond_matrix_defs()
+
+    def _precond_matrix_defs(self):
+        """{matrix name: {"hist_to_precond_varnames": [...]}} (input/<model>/tracer_module_defs.yaml
+        precond_matrix_defs; model_config.py:197-228: the settings of "base" are propagated to all matrices).
+        The models of this package use: base = time (py_driver_2d) or the two mixing-coefficient reductions
+        (test_problem); one matrix per tracer that names one, fed by that tracer's hist variable."""
+        column = self.modelinfo.get("model_name", "") == "test_problem"
+        base = ["mixing_coeff:mean", "mixing_coeff:log_mean"] if column else ["time"]
+        defs = {"base": {"hist_to_precond_varnames": list(base)}}
+        for mdef in self.tracer_module_defs.values():
+            for tname, meta in mdef["tracers"].items():
+                pm = meta.get("precond_matrix")
+                if pm is None or pm in defs:
+                    continue
+                own = ["po4_s_restore_tau_r:mean"] if (column and pm == "phosphorus") else [tname]
+                defs[pm] = {"hist_to_precond_varnames": list(base) + [v for v in own if v not in base]}
+        return defs
 
 
 def read_grid_vars(fname, region_mask_varname):
@@ -215,6 +233,37 @@ class TracerModuleStateBase:
                 res.append(pm)
         return res
 
+    def append_tracer_names_per_precond_matrix(self, res):
+        """{matrix name: [tracer names]} (tracer_module_state_base.py:86-98)"""
+        for tname, meta in self._def["tracers"].items():
+            pm = meta.get("precond_matrix")
+            if pm is not None:
+                res.setdefault(pm, []).append(tname)
+
+    def log_vals(self, msg, vals):
+        """per-tracer-module values to the log, in the reference's format (tracer_module_state_base.py:178-198)"""
+        logger = logging.getLogger(__name__)
+        vals = np.asarray(vals)
+        if vals.ndim >= 1 and vals.shape[-1] == 1:
+            self.log_vals(msg, vals[..., 0])
+            return
+        if vals.ndim == 0:
+            logger.info("%s[%s]=%e", msg, self.name, vals)
+        elif vals.ndim == 1:
+            for j in range(vals.shape[0]):
+                logger.info("%s[%s,%d]=%e", msg, self.name, j, vals[j])
+        elif vals.ndim == 2:
+            for i in range(vals.shape[0]):
+                for j in range(vals.shape[1]):
+                    logger.info("%s[%s,%d,%d]=%e", msg, self.name, i, j, vals[i, j])
+        else:
+            raise ValueError(f"vals.ndim={vals.ndim} not handled")
+
+    # ---- statistics of a hist file (tracer_module_state.py of the models: stats_vars_*) -------------
+    def stats_vars_tracer_like(self):
+        """tracer-like hist variables that go into the stats file (tracer_module_state_base.py:100-104)"""
+        return list(self.tracer_names)
+
 
 class ModelStateBase:
     """state space of a model (nk_ooc/model_state_base.py:24-577)"""
@@ -319,11 +368,77 @@ class ModelStateBase:
                     fptr.variables[tname][:] = tms.get_tracer_vals(tname).reshape([len(a) for a in axes])
         return self
 
-    def log(self, msg=None):
-        logger = logging.getLogger(__name__)
-        mean_vals, norm_vals = self.mean(), self.norm()
+    def log_vals(self, msg, vals):
+        """write per-tracer module values to the log (model_state_base.py:113-122)"""
         for ind, tms in enumerate(self.tracer_modules):
-            logger.info("%s[%s] mean=%s norm=%s", "" if msg is None else msg + ",", tms.name, mean_vals[ind], norm_vals[ind])
+            if isinstance(msg, list):
+                for msg_ind, submsg in enumerate(msg):
+                    tms.log_vals(submsg, vals[msg_ind, ind, ...])
+            else:
+                tms.log_vals(msg, vals[ind, ...])
+
+    def log(self, msg=None):
+        """mean and norm of the instance to the log (model_state_base.py:124-132)"""
+        msg_full = ["mean", "norm"] if msg is None else [f"{msg},mean", f"{msg},norm"]
+        self.log_vals(msg_full, np.stack((self.mean(), self.norm())))
+
+    # ---- model-specific statistics of an iteration's hist file (model_state_base.py:134-180) ----------
+    def _stats_names_and_weights(self):
+        names = []
+        for tms in self.tracer_modules:
+            names += tms.stats_vars_tracer_like()
+        ypos = getattr(type(self), "ypos", None)
+        weights = {ypos.axisname: ypos.delta} if ypos is not None and hasattr(ypos, "axisname") else None
+        return names, weights
+
+    def def_stats_vars(self, stats_file, hist_fname, solver_state):
+        """define the model specific stats variables: dimensions, coordinate variables and one variable per
+        tracer-like hist variable (+ its ypos mean), with the hist file's metadata"""
+        step = "ModelStateBase.def_stats_vars"
+        if solver_state is not None and solver_state.step_logged(step, per_iteration=False):
+            return
+        names, weights = self._stats_names_and_weights()
+        stats_file.def_hist_stats(hist_fname, names, weights)
+        if solver_state is not None:
+            solver_state.log_step(step, per_iteration=False)
+
+    def put_stats_vars_iteration_invariant(self, stats_file, hist_fname, solver_state):
+        """values of the iteration-invariant stats variables (the coordinate variables of the axes)"""
+        step = "ModelStateBase.put_stats_vars_iteration_invariant"
+        if solver_state is not None and solver_state.step_logged(step, per_iteration=False):
+            return
+        stats_file.put_hist_coordinates(hist_fname)
+        if solver_state is not None:
+            solver_state.log_step(step, per_iteration=False)
+
+    def put_stats_vars(self, stats_file, hist_fname, solver_state):
+        """stats variables of the current iteration: time mean of every tracer-like hist variable with the end
+        points of the record down-weighted, and its ypos mean"""
+        step = "ModelStateBase.put_stats_vars"
+        if solver_state is not None and solver_state.step_logged(step):
+            return
+        names, weights = self._stats_names_and_weights()
+        iteration = solver_state.get_iteration() if solver_state is not None else 0
+        stats_file.put_hist_stats(iteration, hist_fname, names, weights)
+        if solver_state is not None:
+            solver_state.log_step(step)
+
+    def hist_vars_for_precond_list(self):
+        """hist variables needed for the preconditioner (model_state_base.py:379-388)"""
+        res = []
+        defs = self.model_config_obj.precond_matrix_defs
+        for matrix_name in self.precond_matrix_list() + ["base"]:
+            for varname in defs[matrix_name]["hist_to_precond_varnames"]:
+                if varname not in res:
+                    res.append(varname)
+        return res
+
+    def tracer_names_per_precond_matrix(self):
+        """{matrix name: [tracer names]} (model_state_base.py:397-402)"""
+        res = {}
+        for tms in self.tracer_modules:
+            tms.append_tracer_names_per_precond_matrix(res)
+        return res
 
     # ---- scalars ------------------------------------------------------------------------
     def _scalar_shape(self):
@@ -387,6 +502,10 @@ class ModelStateBase:
             return self._like().__iadd__(other)
         return NotImplemented
 
+    def __radd__(self, other):
+        """res = other + self (model_state_base.py:201-206)"""
+        return self + other
+
     def __sub__(self, other):
         if isinstance(other, ModelStateBase):
             return self._like().__isub__(other)
@@ -421,6 +540,16 @@ class ModelStateBase:
         if isinstance(other, ModelStateBase):
             return NotImplemented
         return self._like().__itruediv__(other)
+
+    def __rtruediv__(self, other):
+        """res = other / self, other a float or ndarray [n_modules(, region_cnt)] (model_state_base.py:310-328).
+        Not used by the solvers; the elementwise reciprocal is a torch op (cold path), the scaling the library's."""
+        if not isinstance(other, (int, float, np.ndarray)):
+            return NotImplemented
+        res = self._like()
+        for tms in res.tracer_modules:
+            tms.vals = torch.reciprocal(tms.vals)
+        return res.__imul__(other).apply_region_mask()
 
     def apply_limiter(self, base):
         """scale self so that base + scalef*self is within bounds (model_state_base.py:76-84);
@@ -537,3 +666,46 @@ def lin_comb(res_type, coeff, fname_fcn, quantity):
         out = res.model_config_obj.weights.lin_comb(cdev, vecs, B)
         tms.vals = out.reshape(states[0].tracer_modules[ind].vals.shape)
     return res
+
+
+def get_subclasses(mod_name, base_class):
+    """subclasses of base_class defined in module mod_name, [] when the module does not exist
+    (nk_ooc/utils.py:84-96)"""
+    import importlib
+    import inspect
+
+    try:
+        mod = importlib.import_module(mod_name)
+    except ModuleNotFoundError as err:
+        if err.name and mod_name.startswith(err.name):
+            return []
+        raise
+    return [obj for _, obj in inspect.getmembers(mod, inspect.isclass)
+            if issubclass(obj, base_class) and obj is not base_class and obj.__module__ == mod.__name__]
+
+
+def get_model_state_class(model_name, lvl=logging.DEBUG):
+    """model state class of model_name: the first ModelStateBase subclass of
+    nk_ooc_b200.<model_name>.model_state (model_state_base.py:627-646)"""
+    logger = logging.getLogger(__name__)
+    cls = ModelStateBase
+    subclasses = get_subclasses(".".join([__package__, model_name, "model_state"]), ModelStateBase)
+    if subclasses:
+        cls = subclasses[0]
+    logger.log(lvl, "using class %s from %s for model state", cls.__name__, cls.__module__)
+    return cls
+
+
+def get_tracer_module_state_class(model_name, tracer_module_name, tracer_module_def):
+    """tracer module state class: the model's TracerModuleState (nk_ooc_b200.<model>.tracer_module_state),
+    overridden by the tracer module specific class of nk_ooc_b200.<model>.<py_mod_name or module name>
+    (model_state_base.py:649-667)"""
+    cls = TracerModuleStateBase
+    subclasses = get_subclasses(".".join([__package__, model_name, "tracer_module_state"]), cls)
+    if subclasses:
+        cls = subclasses[0]
+    py_mod_name = tracer_module_def.get("py_mod_name", tracer_module_name)
+    subclasses = get_subclasses(".".join([__package__, model_name, py_mod_name]), cls)
+    if subclasses:
+        cls = subclasses[0]
+    return cls

@@ -13,9 +13,10 @@ from scipy.io import netcdf_file
 
 from .. import engine
 from .. import hist as hist_mod
-from ..model_state_base import ModelConfig, ModelStateBase, TracerModuleStateBase
+from ..model_state_base import ModelConfig, ModelStateBase, get_tracer_module_state_class
 from ..spatial_axis import spatial_axis_from_file
 from . import modules
+from .tracer_module_state import tracer_snapshot_nearest
 from .processes import SEC_PER_YEAR
 
 # input/py_driver_2d/tracer_module_defs.yaml of the reference, restated
@@ -138,8 +139,9 @@ class ModelState(ModelStateBase):
         super().__init__(fname, members)
 
     def _new_tracer_module(self, name, tracer_module_def, members):
-        return TracerModuleStateBase(name, tracer_module_def, (len(self.depth), len(self.ypos)),
-                                     self.model_config_obj, members=members)
+        """the tracer module's own class (iage, forced, phosphorus: model_state_base.py:649-667)"""
+        cls = get_tracer_module_state_class("py_driver_2d", name, tracer_module_def)
+        return cls(name, tracer_module_def, (len(self.depth), len(self.ypos)), self.model_config_obj, members=members)
 
     def _gen_init_iterate(self, tms):
         """py_driver_2d/tracer_module_state.py:41-68"""
@@ -339,21 +341,26 @@ class ModelState(ModelStateBase):
             return ModelState(res_fname)
         res_ms = self._like(clone_vals=False)
         for ind, tms in enumerate(self.tracer_modules):
-            if tms._def.get("py_mod_name", tms.name) == "phosphorus":
-                res_ms.tracer_modules[ind].vals = self._apply_precond_phosphorus(tms, precond_fname)
-                continue
-            factors = self._precond_factors(tms, precond_fname)
-            out = torch.empty_like(tms.vals)
-            ncell = len(self.depth) * len(self.ypos)
-            for t in range(tms.tracer_cnt):
-                y = tms.vals[t].reshape(ncell, -1)
-                out[t] = factors[t].solve(y, self.members, 1.0, subtract_rhs=True).reshape(tms.vals[t].shape)
-            res_ms.tracer_modules[ind].vals = out
+            tms.apply_precond_jacobian(self.time_range, res_ms.tracer_modules[ind], self.transport, precond_fname)
         if solver_state is not None:
             solver_state.log_step(step)
         return res_ms.dump(res_fname, f"{type(self).__name__}.apply_precond_jacobian")
 
-    def _apply_precond_phosphorus(self, tms, precond_fname):
+    @classmethod
+    def apply_precond_module(cls, tms, precond_fname):
+        """M^-1 y - y for the members of one tracer module (the work behind TracerModuleState.apply_precond_jacobian)"""
+        if tms._def.get("py_mod_name", tms.name) == "phosphorus":
+            return cls._apply_precond_phosphorus(tms, precond_fname)
+        factors = cls._precond_factors(tms, precond_fname)
+        out = torch.empty_like(tms.vals)
+        ncell = len(cls.depth) * len(cls.ypos)
+        for t in range(tms.tracer_cnt):
+            y = tms.vals[t].reshape(ncell, -1)
+            out[t] = factors[t].solve(y, tms.members, 1.0, subtract_rhs=True).reshape(tms.vals[t].shape)
+        return out
+
+    @classmethod
+    def _apply_precond_phosphorus(cls, tms, precond_fname):
         """phosphorus preconditioner (py_driver_2d/phosphorus.py:197-274): one interval of length T,
         mat = T*J(T/2) with po4 from the precond snapshot nearest T; null vector and shift
         (half the second smallest eigenvalue) from ARPACK shift-invert on the host — member
@@ -366,39 +373,18 @@ class ModelState(ModelStateBase):
         the reference's own result is reproducible to about 1e-2 only; see tests."""
         from scipy.sparse import linalg as sp_linalg
 
-        nz, ny, B = len(self.depth), len(self.ypos), self.members
+        nz, ny, B = len(cls.depth), len(cls.ypos), tms.members
         ncell = nz * ny
         n = 3 * ncell
-        weights = self.model_config_obj.weights
+        cfg = cls.model_config_obj
+        weights = cfg.weights
         key = (tms.name, precond_fname)
-        if key not in self._precond_cache:
-            model = self.model_for(tms)
-            desc = model.desc
-            t0, t1 = self.time_range
+        if key not in cls._precond_cache:
+            t0, t1 = cls.time_range
             time_delta = t1 - t0
-            with netcdf_file(precond_fname, "r", mmap=False) as fptr:
-                ptimes = np.array(fptr.variables["time"].data)
-                po4 = np.array(fptr.variables["po4"].data)[np.argmin(abs(t1 - ptimes))]
-            time_mid = t0 + 0.5 * time_delta
-            blocks = [[None] * 3 for _ in range(3)]
-            for t in range(3):
-                blocks[t][t] = self._jacobian_single_tracer(tms, model, t, time_mid, precond_fname, t1)
-            light = model._keepalive["light"]
-            du = sparse.diags((desc.max_uptake_rate * light * desc.po4_halfsat / (po4 + desc.po4_halfsat) ** 2).reshape(-1))
-            ident = sparse.identity(ncell, format="csr")
-            sink = desc.sink_vel[desc.class_of[2]]
-            d0 = np.broadcast_to(-sink * self.depth.delta_r[:, np.newaxis], (nz, ny)).copy()
-            d0[-1, :] = 0.0
-            dm1 = np.broadcast_to(sink * self.depth.delta_r[1:, np.newaxis], (nz - 1, ny))
-            sinkb = sparse.diags((d0.reshape(-1), dm1.reshape(-1)), (0, -ny))
-            blocks[0][0] = blocks[0][0] - du
-            blocks[1][0] = desc.sigma * du
-            blocks[2][0] = (1.0 - desc.sigma) * du
-            blocks[0][1] = desc.dop_remin_rate * ident
-            blocks[0][2] = desc.pop_remin_rate * ident
-            blocks[1][1] = blocks[1][1] - desc.dop_remin_rate * ident
-            blocks[2][2] = blocks[2][2] - desc.pop_remin_rate * ident + sinkb
-            mat = (time_delta * sparse.bmat(blocks, format="csr")).tocsc()
+            tracer_vals = np.zeros((3, nz, ny))
+            tracer_vals[0] = tracer_snapshot_nearest(precond_fname, "po4", t1)
+            mat = (time_delta * tms.comp_jacobian(t0 + 0.5 * time_delta, tracer_vals)).tocsc()
             e_vals, e_vects = sp_linalg.eigs(mat, k=5, sigma=0.0)
             null_comp = e_vects[:, 0]
             if max(abs(null_comp.imag)) > 1.0e-10 * max(abs(null_comp.real)):
@@ -416,17 +402,17 @@ class ModelState(ModelStateBase):
                 ab[ku, :] -= sh
                 facs.append(engine.BandedFactor(ab, kl, ku))
             null_vect = null_comp.real.reshape(3, nz, ny)
-            grid_w = np.where(self.model_config_obj.region_mask == 0, 0.0, self.model_config_obj.grid_weight)
-            mean_null = np.zeros(self.model_config_obj.region_cnt)
-            for r in range(self.model_config_obj.region_cnt):
-                sel = self.model_config_obj.region_mask == r + 1
+            grid_w = np.where(cfg.region_mask == 0, 0.0, cfg.grid_weight)
+            mean_null = np.zeros(cfg.region_cnt)
+            for r in range(cfg.region_cnt):
+                sel = cfg.region_mask == r + 1
                 mean_null[r] = (grid_w[sel][np.newaxis] * null_vect[:, sel]).sum() / grid_w[sel].sum()
-            e_vect = null_vect / mean_null[self.model_config_obj.region_mask.clip(min=1) - 1][np.newaxis]
+            e_vect = null_vect / mean_null[cfg.region_mask.clip(min=1) - 1][np.newaxis]
             ldb = tms.vals.shape[-1]
             ev = torch.zeros((3, nz, ny, ldb), dtype=torch.float64, device="cuda")
             ev[..., :] = torch.from_numpy(np.ascontiguousarray(e_vect)).cuda().unsqueeze(-1)
-            self._precond_cache[key] = (facs[0], facs[1], ev, e_vect, shift)
-        fac_a, fac_b, ev, _, _ = self._precond_cache[key]
+            cls._precond_cache[key] = (facs[0], facs[1], ev, e_vect, shift)
+        fac_a, fac_b, ev, _, _ = cls._precond_cache[key]
         ldb = tms.vals.shape[-1]
         if ev.shape[-1] != ldb:
             raise ValueError("member count changed between applications of one preconditioner")
@@ -441,80 +427,46 @@ class ModelState(ModelStateBase):
         weights.axpby(-1.0, tms.vals.reshape(flat), 1.0, sol.reshape(flat), B)
         return sol
 
-    def _precond_factors(self, tms, precond_fname):
+    @classmethod
+    def _precond_factors(cls, tms, precond_fname):
         """banded LU of M = I - prod_i (I - dt J((i+1/2) dt)), dt = T/3, one per tracer
-        (py_driver_2d/iage.py:66-93, forced.py:204-241).  J is assembled on the host from the
-        device's vertical mixing coefficients; the factorisation and the solves run on the device."""
+        (py_driver_2d/iage.py:66-93, forced.py:204-241; J at the precond file's tracer snapshot nearest
+        (i+1) dt where it depends on the state).  J comes from the tracer module's comp_jacobian hook
+        (assembled on the host from the device's vertical mixing coefficients); the factorisation and the
+        solves run on the device."""
         kind = tms._def.get("py_mod_name", tms.name)
         if kind not in ("iage", "forced"):
             raise NotImplementedError(f"preconditioner of {tms.name} is not on the B200 path yet")
         key = (tms.name, precond_fname if kind == "forced" else None)
-        if key in self._precond_cache:
-            return self._precond_cache[key]
-        model = self.model_for(tms)
-        t0, t1 = self.time_range
+        if key in cls._precond_cache:
+            return cls._precond_cache[key]
+        model = cls.model_for(tms)
+        state_dependent = model.desc.kind == engine._lib.MOD_FORCED_FILE and model.desc.sink_thres > 0.0
+        t0, t1 = cls.time_range
         n_t = 3
         dt = (t1 - t0) / n_t
-        ncell = len(self.depth) * len(self.ypos)
+        nz, ny = len(cls.depth), len(cls.ypos)
+        ncell = nz * ny
+        jacs = []
+        for ti in range(n_t):
+            tracer_vals = np.zeros((tms.tracer_cnt, nz, ny))
+            if state_dependent:
+                tracer_vals[0] = tracer_snapshot_nearest(precond_fname, tms.tracer_names[0], t0 + (ti + 1.0) * dt)
+            jacs.append(tms.comp_jacobian(t0 + (ti + 0.5) * dt, tracer_vals).tocsr())
         factors = []
+        ident = sparse.identity(ncell, format="csr")
         for t in range(tms.tracer_cnt):
-            ident = sparse.identity(ncell, format="csr")
             mat = ident.copy()
-            for ti in range(n_t):
-                time_mid = t0 + (ti + 0.5) * dt
-                jac = self._jacobian_single_tracer(tms, model, t, time_mid, precond_fname, t0 + (ti + 1.0) * dt)
-                mat = mat @ (ident - dt * jac)
+            for jac in jacs:
+                mat = mat @ (ident - dt * jac[t * ncell:(t + 1) * ncell, t * ncell:(t + 1) * ncell])
             mat = (ident - mat).tocoo()
             kl = int((mat.row - mat.col).max())
             ku = int((mat.col - mat.row).max())
             ab = np.zeros((kl + ku + 1, ncell))
             ab[ku + mat.row - mat.col, mat.col] = mat.data
             factors.append(engine.BandedFactor(ab, kl, ku))
-        self._precond_cache[key] = factors
+        cls._precond_cache[key] = factors
         return factors
-
-    def _jacobian_single_tracer(self, tms, model, tracer_ind, time, precond_fname, time_end):
-        """CSR Jacobian of one tracer's tendency, cell = j + ny*k (advection.py:111-179,
-        horiz_mix.py:100-149, vert_mix.py:140-188, iage.py:55-64, forced.py:156-202)"""
-        nz, ny = len(self.depth), len(self.ypos)
-        n = nz * ny
-        idx = np.arange(n).reshape(nz, ny)
-        tr = self.transport
-        dzr = self.depth.delta_r[:, np.newaxis]
-        mc = model.mixing_coeff(time).cpu().numpy()
-        w = tr.advection.wvel
-        e_l, e_c, e_r = tr.estencil
-        rows, cols, vals = [], [], []
-
-        def add(r, c, v):
-            rows.append(r.ravel())
-            cols.append(c.ravel())
-            vals.append(np.broadcast_to(v, r.shape).ravel())
-
-        diag = e_c.copy()
-        add(idx[:, 1:], idx[:, :-1], e_l[:, 1:])
-        add(idx[:, :-1], idx[:, 1:], e_r[:, :-1])
-        add(idx[1:], idx[:-1], (-0.5 * w[1:-1] + mc) * dzr[1:])
-        diag[1:] += (-0.5 * w[1:-1] - mc) * dzr[1:]
-        add(idx[:-1], idx[1:], (0.5 * w[1:-1] + mc) * dzr[:-1])
-        diag[:-1] += (0.5 * w[1:-1] - mc) * dzr[:-1]
-        desc = model.desc
-        cls_ind = desc.class_of[tracer_ind]
-        diag[0] += desc.surf_diag[cls_ind]
-        diag += desc.decay[cls_ind]
-        if desc.kind == engine._lib.MOD_FORCED_FILE and desc.sink_thres > 0.0:
-            # d sms / d tracer at the precond file's tracer snapshot nearest time_end (forced.py:190-202,221-229)
-            with netcdf_file(precond_fname, "r", mmap=False) as fptr:
-                ptimes = np.array(fptr.variables["time"].data)
-                snap = np.array(fptr.variables[tms.tracer_names[0]].data)[np.argmin(abs(time_end - ptimes))]
-            keep = model._keepalive
-            ft, fd = keep["ft"], keep["fd"]
-            i = int(np.clip(np.searchsorted(ft, time, side="right") - 1, 0, len(ft) - 2))
-            sms = fd[i] + (time - ft[i]) / (ft[i + 1] - ft[i]) * (fd[i + 1] - fd[i])
-            q = snap / desc.sink_thres
-            diag += np.where((sms < 0.0) & (q > 0.0) & (q < 1.0), sms / desc.sink_thres, 0.0)
-        add(idx, idx, diag)
-        return sparse.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n, n))
 
 
 def read_forcing(fname, varname, dims_out, scalef=1.0):

@@ -267,17 +267,14 @@ class NewtonSolver:
         return os.path.join(self._workdir, f"{quantity}_{iteration:02}.nc")
 
     def _put_hist_stats(self, state):
-        """the model's own statistics of this iteration's hist file (model_state_base.py:136-180)"""
+        """the model's own statistics of this iteration's hist file (newton_solver.py:52-58,330 call the
+        three methods of the operator surface)"""
         hist_fname = self._fname("hist")
         if not os.path.exists(hist_fname):
             return
-        names = []
-        for tms in state.tracer_modules:
-            names += list(tms.tracer_names)  # tracer_module_state_base.py:100-104
-            if ".test_problem." in type(state).__module__ and tms._def.get("py_mod_name", tms.name) == "phosphorus":
-                names.append("po4_uptake")  # test_problem/phosphorus.py:161-167
-        ypos = getattr(type(state), "ypos", None)
-        weights = {ypos.axisname: ypos.delta} if ypos is not None and hasattr(ypos, "axisname") else None
+        state.def_stats_vars(self._stats, hist_fname, None)
+        state.put_stats_vars_iteration_invariant(self._stats, hist_fname, None)
+        names, weights = state._stats_names_and_weights()
         self._stats.put_hist_stats(self.iteration, hist_fname, names, weights)
 
     def _record(self, **extra):

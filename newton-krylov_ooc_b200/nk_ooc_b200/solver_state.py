@@ -253,6 +253,43 @@ class StatsFile:
                     self._vars[vname]["data"][iteration] = vals
         self._flush()
 
+    def def_hist_stats(self, hist_fname, names, mean_weights=None):
+        """define the variables put_hist_stats will fill (model_state_base.py:134-151): dimensions and metadata
+        from the hist file; values are fill values until an iteration puts them"""
+        with netcdf_file(hist_fname, "r", mmap=False) as fptr:
+            for name in names:
+                if name not in fptr.variables:
+                    continue
+                var = fptr.variables[name]
+                dims = tuple(var.dimensions[1:])
+                for dim, length in zip(dims, var.shape[1:]):
+                    self._dimlen.setdefault(dim, int(length))
+                attrs = {k: (v.decode() if isinstance(v, bytes) else v) for k, v in var._attributes.items()
+                         if k not in ("cell_methods", "_FillValue")}
+                targets = [(name, dims)]
+                for axis in (mean_weights or {}):
+                    if axis in dims:
+                        pos = dims.index(axis)
+                        targets.append((f"{name}_mean_{axis}", dims[:pos] + dims[pos + 1:]))
+                for vname, vdims in targets:
+                    if vname not in self._vars:
+                        self._vars[vname] = {"dims": ("iteration",) + vdims, "dtype": "f8",
+                                             "attrs": dict(attrs, _FillValue=FILL_F8),
+                                             "data": np.full((self._n_iter,) + tuple(self._dimlen[d] for d in vdims),
+                                                             FILL_F8)}
+        self._flush()
+
+    def put_hist_coordinates(self, hist_fname):
+        """iteration-invariant coordinate variables of the dimensions in use (model_state_base.py:153-167)"""
+        with netcdf_file(hist_fname, "r", mmap=False) as fptr:
+            for dim in list(self._dimlen):
+                if dim in fptr.variables and dim not in self._vars and dim != "region":
+                    cvar = fptr.variables[dim]
+                    attrs = {k: (v.decode() if isinstance(v, bytes) else v) for k, v in cvar._attributes.items()}
+                    self._vars[dim] = {"dims": (dim,), "dtype": "f8", "attrs": attrs,
+                                       "data": np.array(cvar.data, dtype=np.float64)}
+        self._flush()
+
     def put_invariant(self, **kwargs):
         for key, vals in kwargs.items():
             category, names = self._keys[key]

@@ -13,7 +13,7 @@ from scipy.io import netcdf_file
 
 from .. import engine
 from .. import hist as hist_mod
-from ..model_state_base import ModelConfig, ModelStateBase, TracerModuleStateBase
+from ..model_state_base import ModelConfig, ModelStateBase, get_tracer_module_state_class
 from ..spatial_axis import spatial_axis_from_file
 from . import modules
 from .modules import SEC_PER_YEAR
@@ -89,8 +89,9 @@ class ModelState(ModelStateBase):
         super().__init__(fname, members)
 
     def _new_tracer_module(self, name, tracer_module_def, members):
-        return TracerModuleStateBase(name, tracer_module_def, (len(self.depth),), self.model_config_obj,
-                                     members=members)
+        """the tracer module's own class (iage, dye_decay, phosphorus: model_state_base.py:649-667)"""
+        cls = get_tracer_module_state_class("test_problem", name, tracer_module_def)
+        return cls(name, tracer_module_def, (len(self.depth),), self.model_config_obj, members=members)
 
     def _gen_init_iterate(self, tms):
         """test_problem/tracer_module_state.py:41-68"""

@@ -141,31 +141,28 @@ def test_forced_precond_with_sink_thres_jacobian(gold, tmp_path, tag):
 
 
 def test_jacobian_assembly_entry_by_entry(gold, tmp_path):
-    """_jacobian_single_tracer (host assembly from the DEVICE's vertical mixing coefficients) against the
-    reference's comp_jacobian (advection.py:111-179, horiz_mix.py:100-149, vert_mix.py:140-188,
-    iage.py:55-64, forced.py:156-202) at the three interval mid-points, rtol 1e-12"""
+    """TracerModuleState.comp_jacobian (host assembly from the DEVICE's vertical mixing coefficients, the hook
+    the preconditioners are built from) against the reference's comp_jacobian (advection.py:111-179,
+    horiz_mix.py:100-149, vert_mix.py:140-188, iage.py:55-64, forced.py:156-202) at the three interval
+    mid-points, rtol 1e-12"""
     from nk_ooc_b200.py_driver_2d.model_state import ModelState
     from nk_ooc_b200.py_driver_2d.setup_solver import gen_grid_vars_file
 
     tag = "g14x11"
     nz, ny = 14, 11
-    n = nz * ny
     mids = YEAR * (np.arange(3) + 0.5) / 3.0
     info = _info(str(tmp_path), nz, ny, "iage")
     gen_grid_vars_file(info)
     ModelState.configure(info)
     try:
-        ms = ModelState("zeros")
-        tms = ms.tracer_modules[0]
-        model = ms.model_for(tms)
+        tms = ModelState("zeros").tracer_modules[0]
+        assert type(tms).__name__ == "iage"
         want = gold[f"{tag}/iage/jac_dense_mids"]
         for i, t in enumerate(mids):
-            for tr in range(2):
-                got = ms._jacobian_single_tracer(tms, model, tr, t, None, None).toarray()
-                blk = want[i][tr * n:(tr + 1) * n, tr * n:(tr + 1) * n]
-                np.testing.assert_allclose(got, blk, rtol=1e-12, atol=1e-12 * np.abs(blk).max())
-            # the reference's Jacobian has no coupling between the two tracers
-            assert not want[i][:n, n:].any() and not want[i][n:, :n].any()
+            got = tms.comp_jacobian(t, np.zeros(2 * nz * ny), ModelState.transport).toarray()
+            np.testing.assert_allclose(got, want[i], rtol=1e-12, atol=1e-12 * np.abs(want[i]).max())
+            sp = tms.comp_jacobian_sparsity(t, np.zeros(2 * nz * ny), ModelState.transport)
+            assert ((sp.toarray() != 0) == (want[i] != 0)).all()
     finally:
         ModelState.reset()
     sms = str(tmp_path / "sms.nc")
@@ -173,14 +170,13 @@ def test_jacobian_assembly_entry_by_entry(gold, tmp_path):
     info = _info(str(tmp_path), nz, ny, "forced_{suff}:o2_like", dict(O2_LIKE, forced_sms_fname=sms))
     ModelState.configure(info)
     try:
-        precond = str(tmp_path / "precond_00.nc")
-        _write_precond(precond, gold, tag)
-        ms = ModelState("zeros")
-        tms = ms.tracer_modules[0]
-        model = ms.model_for(tms)
+        tms = ModelState("zeros").tracer_modules[0]
+        assert type(tms).__name__ == "forced"
         want = gold[f"{tag}/forced/jac_dense_mids"]
+        snaps, ptimes = gold[f"{tag}/forced/precond_snaps"], gold[f"{tag}/forced/precond_times"]
         for i, t in enumerate(mids):
-            got = ms._jacobian_single_tracer(tms, model, 0, t, precond, YEAR * (i + 1.0) / 3.0).toarray()
+            snap = snaps[np.argmin(abs(YEAR * (i + 1.0) / 3.0 - ptimes))]
+            got = tms.comp_jacobian(t, snap.reshape(-1), ModelState.transport).toarray()
             np.testing.assert_allclose(got, want[i], rtol=1e-12, atol=1e-12 * np.abs(want[i]).max())
     finally:
         ModelState.reset()
