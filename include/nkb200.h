@@ -216,7 +216,9 @@ int nkb_fd_sigma(const double *d_norm, double *d_sigma, int n, void *stream);
  * largest scale factor in [0, 1] such that base + scalef*inc stays inside [lob, upb] for every
  * tracer and cell of the region.  d_out [R][B] must be pre-filled by the caller with the value
  * for regions that hold no cell (+inf in the reference); it is lowered by an exact atomic min.
- * d_flag[0] is set to 1 when base itself is out of bounds (the reference raises ValueError). */
+ * d_flag [B] (zeroed by the caller) collects per member the bits 1: base < lob somewhere, 2: base + inc < lob
+ * somewhere, 4: base > upb, 8: base + inc > upb.  The reference raises ValueError("base < lob") only when 1 and
+ * 2 are both set (a bound that needs enforcing is already violated by base), likewise 4 and 8 for upb. */
 int nkb_limiter_scalef(const int32_t *d_region, int R, int T, int ncell, const double *d_base,
                        const double *d_inc, double lob, int has_lob, double upb, int has_upb, int B,
                        int ldb, double *d_out /* [R][B] */, int32_t *d_flag, void *stream);

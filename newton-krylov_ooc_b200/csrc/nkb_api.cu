@@ -258,6 +258,7 @@ static void fill_args(const nkb_model *m, StageArgs &a, int B, int ldb) {
     a.sink_thres_r = v.sink_thres > 0.0 ? 1.0 / v.sink_thres : 0.0;
     a.halfsat = v.po4_halfsat; a.umax = v.max_uptake_rate; a.sigma = v.sigma;
     a.rdop = v.dop_remin_rate; a.rpop = v.pop_remin_rate;
+    a.restoring_opt = v.po4_s_restoring_opt;
 }
 
 int nkb_model_tend(nkb_model *m, double time, const double *d_x, double *d_tend, int B, int ldb, void *stream) {

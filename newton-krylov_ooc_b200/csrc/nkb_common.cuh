@@ -90,6 +90,7 @@ struct StageArgs {
     double src_const[NKB_MAX_TRACERS];
     double sink_thres_r;  // 1/sink_thres or 0
     double halfsat, umax, sigma, rdop, rpop;
+    int restoring_opt;    // test_problem phosphorus: po4_s restoring option (tendency kernel only)
 };
 
 // arguments of the persistent column-model year kernel (nkb_column.cu)

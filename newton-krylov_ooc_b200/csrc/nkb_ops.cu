@@ -283,7 +283,9 @@ __global__ void fd_sigma_kernel(const double *__restrict__ nrm, double *__restri
 // keeps base + scalef*inc inside [lob, upb] (utils.py:561-600 comp_scalef_lob/upb +
 // min_by_region :544-558).  Scale factors are non-negative doubles, whose bit patterns order like
 // unsigned integers: atomicMin on the bits is exact and order independent (deterministic).
-// flag[0] is set when base itself violates a bound (the reference raises ValueError).
+// flag[b] collects, per member: 1 base < lob somewhere, 2 base + inc < lob somewhere, 4 base > upb, 8 base +
+// inc > upb.  The reference raises ValueError only when a bound needs enforcing (2 / 8) AND base itself violates
+// it (1 / 4); an iterate a hair outside a bound with a harmless increment passes with scale factor 1.
 __global__ void limiter_scalef_kernel(const int *__restrict__ region, int T, size_t ncell,
                                       const double *__restrict__ base, const double *__restrict__ inc, double lob,
                                       int has_lob, double upb, int has_upb, int B, size_t ldb,
@@ -294,18 +296,26 @@ __global__ void limiter_scalef_kernel(const int *__restrict__ region, int T, siz
     const int r = region[cell];
     if (r <= 0) return;
     double sc = 1.0;
+    int bits = 0;
     for (int t = 0; t < T; ++t) {
         const size_t off = ((size_t)t * ncell + cell) * ldb + b;
         const double x = base[off], d = inc[off];
         if (has_lob) {
-            if (x < lob) flag[0] = 1;
-            if (x + d < lob) sc = fmin(sc, fabs((lob - x) / d));
+            if (x < lob) bits |= 1;
+            if (x + d < lob) {
+                bits |= 2;
+                sc = fmin(sc, fabs((lob - x) / d));
+            }
         }
         if (has_upb) {
-            if (x > upb) flag[0] = 1;
-            if (x + d > upb) sc = fmin(sc, fabs((upb - x) / d));
+            if (x > upb) bits |= 4;
+            if (x + d > upb) {
+                bits |= 8;
+                sc = fmin(sc, fabs((upb - x) / d));
+            }
         }
     }
+    if (bits) atomicOr(flag + b, bits);
     atomicMin(out_bits + (size_t)(r - 1) * B + b, (unsigned long long)__double_as_longlong(sc));
 }
 
@@ -325,14 +335,21 @@ limiter_scalef_vec_kernel(const int *__restrict__ region, int T, size_t ncell, c
         atomicMin(out_bits + (size_t)(r - 1) * B + b, (unsigned long long)__double_as_longlong(sc.x));
         if (two) atomicMin(out_bits + (size_t)(r - 1) * B + b + 1, (unsigned long long)__double_as_longlong(sc.y));
     };
-    auto one = [&](double x, double d, double &sc, bool live) {
+    int bits0 = 0, bits1 = 0;
+    auto one = [&](double x, double d, double &sc, bool live, int &bits) {
         if (has_lob) {
-            if (live && x < lob) flag[0] = 1;
-            if (x + d < lob) sc = fmin(sc, fabs((lob - x) / d));
+            if (live && x < lob) bits |= 1;
+            if (x + d < lob) {
+                if (live) bits |= 2;
+                sc = fmin(sc, fabs((lob - x) / d));
+            }
         }
         if (has_upb) {
-            if (live && x > upb) flag[0] = 1;
-            if (x + d > upb) sc = fmin(sc, fabs((upb - x) / d));
+            if (live && x > upb) bits |= 4;
+            if (x + d > upb) {
+                if (live) bits |= 8;
+                sc = fmin(sc, fabs((upb - x) / d));
+            }
         }
     };
     int rcur = 0;
@@ -358,8 +375,8 @@ limiter_scalef_vec_kernel(const int *__restrict__ region, int T, size_t ncell, c
             for (int u = 0; u < U; ++u) {
                 if (r[u] <= 0) continue;
                 double2 s1 = make_double2(1.0, 1.0);
-                one(xv[u].x, dv[u].x, s1.x, true);
-                one(xv[u].y, dv[u].y, s1.y, two);
+                one(xv[u].x, dv[u].x, s1.x, true, bits0);
+                one(xv[u].y, dv[u].y, s1.y, two, bits1);
                 if (r[u] != rcur) {
                     flush(rcur, sc);
                     rcur = r[u];
@@ -372,6 +389,8 @@ limiter_scalef_vec_kernel(const int *__restrict__ region, int T, size_t ncell, c
         }
     }
     flush(rcur, sc);
+    if (bits0) atomicOr(flag + b, bits0);
+    if (bits1) atomicOr(flag + b + 1, bits1);
 }
 
 }  // namespace nkb

@@ -137,6 +137,51 @@ __global__ void tend_kernel(const StageArgs p) {
     }
 }
 
+// test_problem phosphorus (po4, dop, pop and their shadows; test_problem/phosphorus.py:28-120): tendency of the
+// column model, one thread per member.  Sources as in column_sources (nkb_column.cu), vertical operator
+// from the raw tridiagonal rows {sub, diag, sup, 0} of the tracer's class.
+__global__ void tend_p1d_kernel(const StageArgs p) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.B) return;
+    const int nz = p.nz;
+    const size_t ldb = p.ldb;
+    const double day_r = 1.0 / 86400.0, rem = 0.01 * day_r;
+    for (int k = 0; k < nz; ++k) {
+        double c[6], s[6];
+        for (int t = 0; t < 6; ++t) c[t] = p.u[0][((size_t)t * nz + k) * ldb + b];
+        const double po4 = c[0];
+        const double u = day_r * p.light[k] * (po4 / (po4 + 0.5));
+        for (int o3 = 0; o3 < 6; o3 += 3) {
+            s[o3 + 0] = -u + rem * c[o3 + 1] + rem * c[o3 + 2];
+            s[o3 + 1] = 0.67 * u - rem * c[o3 + 1];
+            s[o3 + 2] = (1.0 - 0.67) * u - rem * c[o3 + 2];
+        }
+        double tau;
+        if (p.restoring_opt == 0) {
+            tau = (k == 0) ? day_r : 0.0;
+        } else {
+            double delta = 1.0e-3 * fabs(po4);
+            if (delta < 1.0e-8) delta = 1.0e-8;
+            const double pd = po4 + delta;
+            tau = (day_r * p.light[k] * (pd / (pd + 0.5)) - u) / delta;
+        }
+        const double rest = tau * (c[0] - c[3]);
+        s[3] += rest;
+        s[4] -= 0.67 * rest;
+        s[5] -= 0.33 * rest;
+        for (int t = 0; t < 6; ++t) {
+            const int cls = p.class_of[t];
+            const double *tri = p.tri + ((size_t)cls * nz + k) * 4;
+            const size_t off = ((size_t)t * nz + k) * ldb + b;
+            double v = s[t] + tri[1] * c[t];
+            if (k > 0) v += tri[0] * p.u[0][off - ldb];
+            if (k < nz - 1) v += tri[2] * p.u[0][off + ldb];
+            if (k == 0) v += p.aff[cls];
+            p.out[off] = v;
+        }
+    }
+}
+
 // copy member `b` of a member-fastest batch into a dense [n] vector
 __global__ void gather_member_kernel(const double *__restrict__ src, double *__restrict__ dst, size_t n,
                                      size_t ldb, int b) {
@@ -248,6 +293,13 @@ int launch_tend(int kind, const StageArgs &a, cudaStream_t st) {
         case NKB_MOD_PHOSPHORUS:
             grid.z = a.T / 3;
             tend_kernel<NKB_MOD_PHOSPHORUS, 3><<<grid, block, 0, st>>>(a);
+            break;
+        case NKB_MOD_PHOSPHORUS_1D:
+            if (a.T != 6 || a.ny != 1) {
+                set_error("launch_tend: the column phosphorus module has six tracers");
+                return 2;
+            }
+            tend_p1d_kernel<<<(a.B + 63) / 64, 64, 0, st>>>(a);
             break;
         default: set_error("launch_tend: unsupported module kind"); return 2;
     }

@@ -321,7 +321,7 @@ class RegionWeights:
         ldb = base.shape[-1]
         T = base.shape[0]
         out = torch.full((self.region_cnt, B), float("inf"), dtype=torch.float64, device="cuda")
-        flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+        flag = torch.zeros(padded_members(B) + 1, dtype=torch.int32, device="cuda")
         check(
             lib.nkb_limiter_scalef(self.region.data_ptr(), self.region_cnt, T, self.ncell, base.data_ptr(),
                                    inc.data_ptr(), 0.0 if lob is None else float(lob), 0 if lob is None else 1,
@@ -329,8 +329,13 @@ class RegionWeights:
                                    out.data_ptr(), flag.data_ptr(), _stream_ptr()),
             "nkb_limiter_scalef",
         )
-        if int(flag.item()) != 0:
-            raise ValueError("base < lob" if lob is not None else "base > upb")
+        bits = flag[:B].cpu().numpy()
+        # comp_scalef_lob / comp_scalef_upb (utils.py:561-600): an error only when a bound has to be enforced
+        # (some base + increment violates it) and base itself violates it already
+        if (((bits & 1) != 0) & ((bits & 2) != 0)).any():
+            raise ValueError("base < lob")
+        if (((bits & 4) != 0) & ((bits & 8) != 0)).any():
+            raise ValueError("base > upb")
         return out
 
 

@@ -356,9 +356,19 @@ class NewtonSolver:
             prov_fcn = prov.comp_fcn(None, None, self._fname("prov_hist_fp"))
         n_fp = int(self._info.get("post_newton_fp_iter", 0))
         if n_fp == 0:
+            # the accepted Armijo candidate IS the new iterate: its function value and its hist file (the input of
+            # the next iteration's preconditioner) exist already — no further model year (newton_solver.py:283-291
+            # renames the Armijo hist file the same way).  Only the speculative batched Armijo step and shadow
+            # tracers leave no hist file of the accepted candidate behind.
+            armijo_hist = self._fname("prov_hist_Armijo")
+            have_hist = self._armijo_batch <= 1 and not prov.shadow_tracers_on() and os.path.exists(armijo_hist)
             self.iteration += 1
             prov.dump(self._fname("iterate") if self._dump else None, caller)
-            prov_fcn = prov.comp_fcn(self._fname("fcn") if self._dump else None, None, self._fname("hist"))
+            if have_hist:
+                os.replace(armijo_hist, self._fname("hist"))
+                prov_fcn.dump(self._fname("fcn") if self._dump else None, caller)
+            else:
+                prov_fcn = prov.comp_fcn(self._fname("fcn") if self._dump else None, None, self._fname("hist"))
         for fp_iter in range(n_fp):
             prov += prov_fcn
             prov.copy_shadow_tracers_to_real_tracers()

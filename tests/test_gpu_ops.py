@@ -134,8 +134,20 @@ def test_limiter_scalef_matches_oracle(B):
         np.testing.assert_array_equal(np.minimum(gotu[:, b], 1.0), want)
     bad = base.copy()
     bad[0, 1, 1, 0] = -1.0
-    with pytest.raises(ValueError):
+    with pytest.raises(ValueError, match="base < lob"):
         rw.limiter_scalef(_dev(bad), _dev(inc), 0.0, None, B)
+    with pytest.raises(ValueError, match="base > upb"):
+        rw.limiter_scalef(_dev(-bad), _dev(-inc), None, 0.0, B)
+    # base a hair below the bound with an increment that never needs limiting: the reference returns 1
+    # everywhere and does NOT raise (utils.py:571-573: the all-clear test comes first)
+    hair = np.ones((1,) + shape + (B,))
+    hair[0, 1, 1, 0] = -1.0e-12
+    up = np.full((1,) + shape + (B,), 0.25)
+    for b in range(B):
+        want = o.comp_scalef_lob(region_cnt, mask, hair[0, ..., b], up[0, ..., b], 0.0)
+        assert (want == 1.0).all()
+    got = rw.limiter_scalef(_dev(hair), _dev(up), 0.0, None, B).cpu().numpy()
+    assert (np.minimum(got, 1.0) == 1.0).all()
 
 
 # ---- wide batches (two-members-per-lane kernels) and the windowed banded solver -------------------

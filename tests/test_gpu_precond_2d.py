@@ -162,7 +162,7 @@ def test_jacobian_assembly_entry_by_entry(gold, tmp_path):
             got = tms.comp_jacobian(t, np.zeros(2 * nz * ny), ModelState.transport).toarray()
             np.testing.assert_allclose(got, want[i], rtol=1e-12, atol=1e-12 * np.abs(want[i]).max())
             sp = tms.comp_jacobian_sparsity(t, np.zeros(2 * nz * ny), ModelState.transport)
-            assert ((sp.toarray() != 0) == (want[i] != 0)).all()
+            assert (sp.toarray() != 0)[want[i] != 0].all()  # the pattern covers every non-zero of the reference's
     finally:
         ModelState.reset()
     sms = str(tmp_path / "sms.nc")
