@@ -811,7 +811,10 @@ constexpr int P3_OUT = P3_T * P3_OBOX;
 constexpr int P3_EX = 2 * P3_T * P3_KC * 64 * 8;                  // u1 exchange, two chunks deep
 constexpr int P3_SMEM = 1024 + P3_NS * P3_SLOT + P3_NO * P3_OUT + P3_EX;
 constexpr int P3_THREADS = (P3_NCW + 2) * 32;
-constexpr int P3_PSLEEP = 100;  // ns between barrier polls of the producer and store lanes
+#ifndef P3_PSLEEP_NS
+#define P3_PSLEEP_NS 100
+#endif
+constexpr int P3_PSLEEP = P3_PSLEEP_NS;  // ns between barrier polls of the producer and store lanes
 static_assert(P3_UBOX % 128 == 0 && P3_SLOT % 128 == 0 && P3_OBOX % 128 == 0 && P3_OUT % 128 == 0,
               "TMA boxes need 128-byte aligned shared-memory bases");
 static_assert(P3_SMEM <= 227 * 1024, "shared memory");
@@ -1162,27 +1165,39 @@ __global__ void __launch_bounds__(P3_THREADS, 1) step_fused_p3_kernel(const Step
                     fs_tmem_wait_ld(nxt);
                     y1top = __hiloint2double((int)nxt.w[(KC - 1) * 2 + 1], (int)nxt.w[(KC - 1) * 2]);
                 }
+                // (an mbarrier arrive here with the wait moved below the own-tracer part measured 4 % slower than
+                // the named barrier, and forcing the pair loads to LDS.128 through inline asm 4 % slower than
+                // leaving their scheduling to the compiler: scripts/ab_variants.sh, profiles/r02_p3_variants.md)
                 asm volatile("bar.sync %0, 96;" ::"r"(1 + pr) : "memory");
-                double sv[KC];
-#pragma unroll
-                for (int q = 0; q < KC; ++q)
-                    sv[q] = p3_source(pl[3 * PP + q * FS_COLS].y, cu, t.kd2, t.kq2, hs, ex[q * 64 + exl],
-                                      ex[(KC + q) * 64 + exl], ex[(2 * KC + q) * 64 + exl]);
-                Vd<1> yb[KC];
+                // everything of the stage-2 right-hand side that uses this warp's own tracer, then the coupled sources;
+                // every pair plane is read once as a whole double2 so that the loads stay LDS.128 (a pair whose .x and
+                // .y are first used far apart is split into two LDS.64 of two wavefronts each: 52 -> 44 per level)
+                double part[KC];
+                double2 mf[KC];
 #pragma unroll
                 for (int q = KC - 1; q >= 0; --q) {
                     const double y1 = ycur[q].v[0];
                     const double y1m = (q > 0) ? ycur[q > 0 ? q - 1 : 0].v[0] : y1top;
-                    const double2 lc = pl[q * FS_COLS], ri = pl[PP + q * FS_COLS], mf = pl[3 * PP + q * FS_COLS];
+                    const double2 lc = pl[q * FS_COLS], ri = pl[PP + q * FS_COLS];
+                    mf[q] = pl[3 * PP + q * FS_COLS];
                     const double u1 = u1v[q];
                     double rhs1 = fma(ri.y, y1m, y1);
                     if (c == 0 && q == 0) rhs1 -= t.aff1;
                     const double un = *reinterpret_cast<const double *>(sb + tr * P3_UBOX + offU[q][1]);
-                    const double pp = fma(p.r, rhs1, p.a0r * un) + sv[q];
+                    const double pp = fma(p.r, rhs1, p.a0r * un);
                     const double ul = __shfl_up_sync(0xffffffffu, u1, 2, 32), ur = __shfl_down_sync(0xffffffffu, u1, 2, 32);
-                    double rhs2 = fma(lc.x, ul, fma(ri.x, ur, fma(lc.y, u1, pp)));
-                    if (c == 0 && q == 0) rhs2 += t.aff2;
-                    y2n = fma(-mf.x, y2n, rhs2);
+                    part[q] = fma(lc.x, ul, fma(ri.x, ur, fma(lc.y, u1, pp)));
+                    if (c == 0 && q == 0) part[q] += t.aff2;
+                }
+                double sv[KC];
+#pragma unroll
+                for (int q = 0; q < KC; ++q)
+                    sv[q] = p3_source(mf[q].y, cu, t.kd2, t.kq2, hs, ex[q * 64 + exl], ex[(KC + q) * 64 + exl],
+                                      ex[(2 * KC + q) * 64 + exl]);
+                Vd<1> yb[KC];
+#pragma unroll
+                for (int q = KC - 1; q >= 0; --q) {
+                    y2n = fma(-mf[q].x, y2n, part[q] + sv[q]);
                     yb[q].v[0] = y2n;
                 }
                 __syncwarp();

@@ -17,7 +17,8 @@ MOD_FORCED_FILE = 1
 MOD_PHOSPHORUS = 2
 MOD_PHOSPHORUS_1D = 3
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libnkb200.so")
+# NKB_LIB_PATH selects another build of the SAME library (kernel experiments: scripts/ab_variants.sh); default in-tree
+LIB_PATH = os.environ.get("NKB_LIB_PATH") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libnkb200.so")
 
 
 class NkbError(RuntimeError):

@@ -64,8 +64,13 @@ def parse_args(argv=None):
     for name in SOLVER_OVERRIDES + MODEL_OVERRIDES:
         parser.add_argument(f"--{name}", default=None, help=f"override {name} from the cfg / defaults")
     parser.add_argument("--resume", action="store_true", help="nk_driver: resume from the saved solver state")
+    parser.add_argument("--rewind", action="store_true", help="nk_driver: with --resume, redo the last logged step")
     parser.add_argument("--persist", action="store_true", help="accepted for compatibility (there is no re-invocation)")
     parser.add_argument("--fp_cnt", type=int, default=2, help="fixed-point iterations applied to the init iterate")
+    parser.add_argument("--init_iterate_opt", default="gen_init_iterate",
+                        help="setup_solver: initial iterate (gen_init_iterate, zeros or a file name)")
+    parser.add_argument("--deprecation_warning_to_error", action="store_true",
+                        help="treat DeprecationWarning warnings as errors")
     parser.add_argument("--armijo_batch", type=int, default=1, help="speculative Armijo candidates per evaluation")
     parser.add_argument("--fname_dir", default=".", help="directory that relative fname arguments are relative to")
     parser.add_argument("--hist_fname", default=None)
@@ -142,20 +147,23 @@ def setup_solver(config, fp_cnt, init_iterate_src="gen_init_iterate"):
     caller = "nk_ooc_b200.cli.setup_solver"
     init_iterate = cls(init_iterate_src)
     init_dir = os.path.join(config["workdir"], "gen_init_iterate")
+    # py_driver_2d/setup_solver.py:116-122 numbers these files with four digits, test_problem/setup_solver.py:146-152 with two
+    width = 4 if config["modelinfo"]["model_name"] == "py_driver_2d" else 2
     for fp_iter in range(fp_cnt):
         logger.info("fp_iter=%d", fp_iter)
-        init_iterate.dump(os.path.join(init_dir, f"init_iterate_{fp_iter:02}.nc"), caller)
-        fcn = init_iterate.comp_fcn(os.path.join(init_dir, f"fcn_{fp_iter:02}.nc"), None,
-                                    os.path.join(init_dir, f"hist_{fp_iter:02}.nc"))
+        init_iterate.dump(os.path.join(init_dir, f"init_iterate_{fp_iter:0{width}}.nc"), caller)
+        fcn = init_iterate.comp_fcn(os.path.join(init_dir, f"fcn_{fp_iter:0{width}}.nc"), None,
+                                    os.path.join(init_dir, f"hist_{fp_iter:0{width}}.nc"))
         init_iterate += fcn
         init_iterate.copy_shadow_tracers_to_real_tracers()
     init_iterate.dump(config["solverinfo"]["init_iterate_fname"], caller)
     return init_iterate
 
 
-def nk_driver(config, armijo_batch=1, resume=False):
+def nk_driver(config, armijo_batch=1, resume=False, rewind=False):
     """nk_ooc/nk_driver.py: Newton's method from solverinfo["init_iterate_fname"] to convergence;
-    resume continues an interrupted solve from Newton_state.json / Newton_stats.nc (nk_driver.py --resume)"""
+    resume continues an interrupted solve at the step where it stopped (Newton_state.json / Krylov_state.json step
+    logs), rewind redoes the last logged step first (nk_driver.py --resume / --rewind)"""
     from .solver import NewtonSolver
 
     cls = _model_state_class(config["modelinfo"]["model_name"])
@@ -163,7 +171,7 @@ def nk_driver(config, armijo_batch=1, resume=False):
         cls.configure(config["modelinfo"])
     iterate = cls(config["solverinfo"]["init_iterate_fname"])
     solver = NewtonSolver(iterate, config["solverinfo"], workdir=config["workdir"], armijo_batch=armijo_batch,
-                          resume=resume)
+                          resume=resume, rewind=rewind)
     solver.solve()
     return solver
 
@@ -197,10 +205,14 @@ def main(argv=None):
     logging.basicConfig(level=logging.INFO, format="%(asctime)s:%(name)s:%(message)s")
     config = read_config(args)
     os.makedirs(config["workdir"], exist_ok=True)
+    if args.deprecation_warning_to_error:
+        import warnings
+
+        warnings.filterwarnings("error", category=DeprecationWarning)
     if args.cmd == "setup_solver":
-        setup_solver(config, args.fp_cnt)
+        setup_solver(config, args.fp_cnt, args.init_iterate_opt)
     elif args.cmd == "nk_driver":
-        solver = nk_driver(config, args.armijo_batch, resume=args.resume)
+        solver = nk_driver(config, args.armijo_batch, resume=args.resume, rewind=args.rewind)
         logging.getLogger(__name__).info("converged after %d Newton iterations", solver.iteration)
     else:
         run_cmd(config, args)

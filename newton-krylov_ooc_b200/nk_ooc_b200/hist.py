@@ -2,10 +2,12 @@
 writes its time mean, time anomaly, time standard deviation, end-minus-start difference and spatial
 integrals / means next to the snapshots (nk_ooc/py_driver_2d/tracer_module_state.py:110-260,
 nk_ooc/test_problem/tracer_module_state.py:96-199).  Host-side numpy on member 0's snapshots: this
-is file output, not the hot path.  Units strings of the integrals are written as plain products
-(the reference canonicalises them with pint, which is not a dependency here)."""
+is file output, not the hot path.  Units strings of the integrals are canonicalised as the reference does
+with pint (utils.units_product: "years m", "mmol / m^2 / s"), so that baseline_cmp's metadata check passes."""
 
 import numpy as np
+
+from .utils import units_product
 
 
 def time_mean_weights(n_time):
@@ -18,25 +20,31 @@ def time_mean_weights(n_time):
 
 
 def derived_specs(name, attrs, depth, ypos=None):
-    """[(varname, dimensions, long_name, units)] of the variables derived from tracer-like `name`"""
+    """[(varname, dimensions, long_name, units)] of the variables derived from tracer-like `name`; the two models
+    word the long names differently (test_problem/tracer_module_state.py:115-141: "mean in time";
+    py_driver_2d/tracer_module_state.py:131-160: "time mean")"""
     dn = depth.axisname
     cell = (dn,) if ypos is None else (dn, ypos.axisname)
     ln, un = attrs["long_name"], attrs["units"]
+    if ypos is None:
+        mean_s, anom_s, std_s = "mean in time", "anomaly in time", "std dev in time"
+    else:
+        mean_s, anom_s, std_s = "time mean", "time anomaly", "time std dev"
     out = [
-        (f"{name}_time_mean", cell, f"{ln}, time mean", un),
-        (f"{name}_time_anom", ("time",) + cell, f"{ln}, time anomaly", un),
-        (f"{name}_time_std", cell, f"{ln}, time std dev", un),
+        (f"{name}_time_mean", cell, f"{ln}, {mean_s}", un),
+        (f"{name}_time_anom", ("time",) + cell, f"{ln}, {anom_s}", un),
+        (f"{name}_time_std", cell, f"{ln}, {std_s}", un),
         (f"{name}_time_delta", cell, f"{ln}, end state minus start state", un),
     ]
     if ypos is None:
-        out.append((f"{name}_{dn}_int", ("time",), f"{ln}, {dn} integral", f"({un}) ({depth.units})"))
+        out.append((f"{name}_{dn}_int", ("time",), f"{ln}, {dn} integral", units_product(un, depth.units)))
     else:
         yn = ypos.axisname
         out += [
-            (f"{name}_depth_int", ("time", yn), f"{ln}, depth integral", f"({un}) ({depth.units})"),
+            (f"{name}_depth_int", ("time", yn), f"{ln}, depth integral", units_product(un, depth.units)),
             (f"{name}_ypos_mean", ("time", dn), f"{ln}, ypos mean", un),
             (f"{name}_depth_ypos_int", ("time",), f"{ln}, depth-ypos integral",
-             f"({un}) ({depth.units}) ({ypos.units})"),
+             units_product(un, depth.units, ypos.units)),
         ]
     return out
 

@@ -114,36 +114,143 @@ class ProbePreconditioner:
         return res
 
 
-class KrylovSolver:
+class _MemState:
+    """SolverState look-alike for a solve that writes no files (dump=False): nothing is ever 'logged', values live
+    in memory.  Lets the solvers below keep ONE control flow — the reference's, with its step log — whether or not
+    the work directory is kept (solver_state.py:14-146)."""
+
+    def __init__(self, workdir):
+        self._workdir, self._iteration, self._vals = workdir, 0, {}
+
+    def get_workdir(self):
+        return self._workdir
+
+    def get_iteration(self):
+        return self._iteration
+
+    def inc_iteration(self):
+        self._iteration += 1
+        return self._iteration
+
+    def log_step(self, stepval, per_iteration=True):  # pylint: disable=unused-argument
+        return None
+
+    def step_logged(self, stepval, per_iteration=True):  # pylint: disable=unused-argument
+        return False
+
+    def step_was_rewound(self, stepval, per_iteration=True):  # pylint: disable=unused-argument
+        return False
+
+    def set_value_saved_state(self, key, value):
+        self._vals[key] = value
+
+    def get_value_saved_state(self, key):
+        return self._vals[key]
+
+
+class _SolverBase:
+    """work directory, step log and stats file of a solver (solver_base.py:11-191)"""
+
+    def __init__(self, name, workdir, iterate, var_table, dump, resume, rewind):
+        self._solver_name = name
+        self._workdir = workdir
+        self._dump = dump
+        os.makedirs(workdir, exist_ok=True)
+        if not dump:
+            if resume or rewind:
+                raise ValueError("resume needs the files of a dumped solve")
+            self._solver_state, self._stats = _MemState(workdir), None
+            return
+        self._solver_state = solver_state.SolverState(name, workdir, resume, rewind)
+        cfg = type(iterate).model_config_obj
+        mods = [(tms.name, getattr(tms, "units", None)) for tms in iterate.tracer_modules]
+        stats_fname = os.path.join(workdir, f"{name}_stats.nc")
+        created = self._solver_state.step_logged(f"_create_stats_file {stats_fname}", per_iteration=False)
+        self._stats = solver_state.StatsFile(name, workdir, cfg.region_cnt, mods, var_table, resume=created)
+        self._solver_state.log_step(f"_create_stats_file {stats_fname}", per_iteration=False)
+
+    def _log_stats_vars_defined(self):
+        """solver_base.py:120-125 (the variables themselves are defined when the stats file is created)"""
+        self._solver_state.log_step(f"define {self._solver_name} solver stats file vars", per_iteration=False)
+
+    def get_iteration(self):
+        return self._solver_state.get_iteration()
+
+    def _fname(self, quantity, iteration=None):
+        """solver_base.py:49-53; None when no files are written"""
+        if not self._dump:
+            return None
+        iteration = self.get_iteration() if iteration is None else iteration
+        return os.path.join(self._workdir, f"{quantity}_{iteration:02}.nc")
+
+    def _put_stats(self, **kwargs):
+        """one 'write <key> vals to stats file' step per key, in the order given (solver_base.py:160-191)"""
+        if self._stats is None:
+            return
+        for key, vals in kwargs.items():
+            step = f"write {key} vals to stats file"
+            if self._solver_state.step_logged(step):
+                continue
+            self._stats.put(self.get_iteration(), **{key: vals})
+            self._solver_state.log_step(step)
+
+    def _put_stats_invariant(self, **kwargs):
+        """solver_base.py:127-158"""
+        if self._stats is None:
+            return
+        for key, vals in kwargs.items():
+            step = f"write {key} vals to stats file"
+            if self._solver_state.step_logged(step, per_iteration=False):
+                continue
+            self._stats.put_invariant(**{key: vals})
+            self._solver_state.log_step(step, per_iteration=False)
+
+
+class KrylovSolver(_SolverBase):
     """left-preconditioned GMRES for  J(iterate) x = -fcn  with the basis resident in HBM.
     `precond`: optional callable ModelState -> ModelState applying M^-1 (e.g. ProbePreconditioner)
-    instead of the model's apply_precond_jacobian."""
+    instead of the model's apply_precond_jacobian.
+    With dump=True the work directory carries the reference's Krylov_state.json (step log, beta, h_mat) and
+    Krylov_stats.nc; resume / rewind continue an interrupted solve at the step where it stopped: the basis and
+    the preconditioned products of the completed iterations are read back from basis_jj.nc / w_jj.nc."""
 
-    def __init__(self, iterate, solverinfo, hist_fname, workdir, max_iter=50, precond=None):
+    def __init__(self, iterate, solverinfo, hist_fname, workdir, max_iter=50, precond=None, dump=True, resume=False,
+                 rewind=False):
+        super().__init__("Krylov", workdir, iterate, solver_state.KRYLOV_VARS, dump, resume, rewind)
+        self._log_stats_vars_defined()
         self._precond = precond
         self._iterate = iterate
         self._info = solverinfo
-        self._workdir = workdir
         self._max_iter = max_iter
-        self.iteration = 0
         self.basis, self.w = [], []
         self.beta = None
         self.h_mat = None
         self.precond_resid_norm = []
-        os.makedirs(workdir, exist_ok=True)
-        self._state = self._stats = None
-        self.precond_fname = self._fname("precond", 0)
+        # the precond file is needed even when nothing else is kept: the model's preconditioner reads it
+        self.precond_fname = os.path.join(workdir, "precond_00.nc")
         if precond is None:
-            iterate.gen_precond_jacobian(hist_fname, self.precond_fname, solver_state=None)
+            step = f"ModelStateBase.gen_precond_jacobian {self.precond_fname}"  # model_state_base.py:404-406
+            if not self._solver_state.step_logged(step, per_iteration=False):
+                iterate.gen_precond_jacobian(hist_fname, self.precond_fname, solver_state=None)
+                self._solver_state.log_step(step, per_iteration=False)
+
+    @property
+    def iteration(self):
+        return self.get_iteration()
+
+    def _state_arg(self):
+        """solver_state handed to the model's methods: they log '<method> complete for <res_fname>' steps"""
+        return self._solver_state if self._dump else None
 
     def _apply_precond(self, state, res_fname, caller):
         if self._precond is None:
-            return state.apply_precond_jacobian(self.precond_fname, res_fname, None)
-        return self._precond(state).dump(res_fname, caller)
-
-    def _fname(self, quantity, iteration=None):
-        iteration = self.iteration if iteration is None else iteration
-        return os.path.join(self._workdir, f"{quantity}_{iteration:02}.nc")
+            return state.apply_precond_jacobian(self.precond_fname, res_fname, self._state_arg())
+        step = f"apply_precond_jacobian complete for {res_fname}"
+        if self._dump and self._solver_state.step_logged(step):
+            return type(self._iterate)(res_fname)
+        res = self._precond(state).dump(res_fname, caller)
+        self._solver_state.log_step(step)
+        return res
 
     def _rel_tol(self):
         return float(self._info["krylov_rel_tol"])
@@ -153,129 +260,140 @@ class KrylovSolver:
 
     def converged(self, precond_resid_norm):
         """krylov_solver.py:76-84"""
-        return (self.iteration >= self._min_iter()) & (precond_resid_norm < self._rel_tol() * self.beta)
+        return (self.get_iteration() >= self._min_iter()) & (precond_resid_norm < self._rel_tol() * self.beta)
 
     def _resident(self, quantity, ind):
         return self.basis[ind] if quantity == "basis" else self.w[ind]
 
-    def solve(self, res_fname, fcn, dump=True):
+    def _solve0(self, fcn):
+        """step 1 of alg. 9.4: r0 = -M^-1 fcn, beta = ||r0||, v0 = r0 / beta (krylov_solver.py:86-103)"""
+        step = "KrylovSolver._solve0"
+        cls = type(self._iterate)
+        if self._solver_state.step_logged(step, per_iteration=False):
+            self.beta = np.asarray(self._solver_state.get_value_saved_state("beta"))
+            return cls(self._fname("precond_fcn", 0))
+        caller = f"{type(self).__name__}._solve0"
+        precond_fcn = self._apply_precond(fcn, self._fname("precond_fcn"), caller)
+        self.beta = precond_fcn.norm()
+        fcn.log_vals("beta", self.beta)
+        self._put_stats_invariant(precond_rhs_norm=self.beta)
+        (-precond_fcn / self.beta).dump(self._fname("basis"), caller)
+        self._solver_state.set_value_saved_state("beta", np.asarray(self.beta))
+        self._solver_state.log_step(step, per_iteration=False)
+        return precond_fcn
+
+    def solve(self, res_fname, fcn, dump=None):  # pylint: disable=unused-argument
+        """krylov_solver.py:105-165.  (`dump` is accepted for compatibility; the constructor decides.)"""
         logger = logging.getLogger(__name__)
         caller = f"{type(self).__name__}.solve"
-        fn = self._fname if dump else (lambda *a, **k: None)
-        # step 1 of alg. 9.4: r0 = -M^-1 fcn, beta = ||r0||, v0 = r0 / beta
-        if dump:
-            # Krylov_state.json (beta, h_mat as the reference saves them, krylov_solver.py:101,136) and
-            # Krylov_stats.nc in the Krylov work directory
-            cfg = type(self._iterate).model_config_obj
-            mods = [(tms.name, getattr(tms, "units", None)) for tms in self._iterate.tracer_modules]
-            self._state = solver_state.SolverState("Krylov", self._workdir)
-            self._stats = solver_state.StatsFile("Krylov", self._workdir, cfg.region_cnt, mods, solver_state.KRYLOV_VARS)
-        precond_fcn = self._apply_precond(fcn, fn("precond_fcn"), caller)
-        self.beta = precond_fcn.norm()
-        if self._stats is not None:
-            self._stats.put_invariant(precond_rhs_norm=self.beta)
-            self._state.set_value_saved_state("beta", np.asarray(self.beta))
-        self.basis.append((-precond_fcn / self.beta).dump(fn("basis"), caller))
+        cls = type(self._iterate)
+        resumed = self._dump and self._solver_state.step_logged("KrylovSolver._solve0", per_iteration=False)
+        precond_fcn = self._solve0(fcn)
+        if resumed:
+            # basis vectors and preconditioned products of the completed iterations, back into HBM
+            j_done = self.get_iteration()
+            self.basis = [cls(self._fname("basis", j)) for j in range(j_done)]
+            self.w = [cls(self._fname("w", j)) for j in range(j_done)]
+            if j_done > 0:
+                self.h_mat = np.asarray(self._solver_state.get_value_saved_state("h_mat"))
+            self.basis.append(cls(self._fname("basis")))
+        else:
+            self.basis.append(-precond_fcn / self.beta)
         n_mod, region_cnt = self.beta.shape[0], self.beta.shape[1]
         while True:
-            j_val = self.iteration
+            j_val = self.get_iteration()
             h_mat = np.zeros((n_mod, j_val + 2, j_val + 1, region_cnt))
             if j_val > 0:
                 h_mat[:, :-1, :-1, :] = self.h_mat
-            w_raw = self._iterate.comp_jacobian_fcn_state_prod(fcn, self.basis[j_val], fn("w_raw"), None)
-            w_j = self._apply_precond(w_raw, fn("w"), caller)
+            w_raw = self._iterate.comp_jacobian_fcn_state_prod(fcn, self.basis[j_val], self._fname("w_raw"),
+                                                               self._state_arg())
+            w_j = self._apply_precond(w_raw, self._fname("w"), caller)
             self.w.append(w_j._like())  # un-orthogonalised M^-1 J v_j: needed for the residual below
             h_mat[:, :-1, -1, :] = w_j.mod_gram_schmidt(j_val + 1, self._resident, "basis")
             h_mat[:, -1, -1, :] = w_j.norm()
             w_j /= h_mat[:, -1, -1, :]
             self.h_mat = h_mat
+            self._solver_state.set_value_saved_state("h_mat", h_mat)
             coeff = comp_krylov_basis_coeffs(self.beta, h_mat)
-            res = model_state_base.lin_comb(type(self._iterate), coeff, self._resident, "basis")
-            res.dump(fn("krylov_res", j_val), caller)
-            precond_resid = model_state_base.lin_comb(type(self._iterate), coeff, self._resident, "w")
+            self._iterate.log_vals("KrylovCoeff", coeff)
+            res = model_state_base.lin_comb(cls, coeff, self._resident, "basis")
+            res.dump(self._fname("krylov_res", j_val), caller)
+            precond_resid = model_state_base.lin_comb(cls, coeff, self._resident, "w")
             precond_resid += precond_fcn
             resid_norm = precond_resid.norm()
+            self._iterate.log_vals("precond_resid", resid_norm)
             self.precond_resid_norm.append(resid_norm)
-            if self._stats is not None:
-                self._state.set_value_saved_state("h_mat", h_mat)
-                self._stats.put(j_val, precond_resid_norm=resid_norm)
-                self._state.inc_iteration()
+            self._put_stats(precond_resid_norm=resid_norm)
             logger.info("Krylov iteration %d: precond_resid_norm/beta = %s", j_val, resid_norm / self.beta)
-            self.iteration += 1
+            self._solver_state.inc_iteration()
             if self.converged(resid_norm).all():
                 logger.info("Krylov convergence criterion satisfied")
                 break
-            if self.iteration >= self._max_iter:
+            if self.get_iteration() >= self._max_iter:
                 raise RuntimeError("number of maximum Krylov iterations exceeded")
-            self.basis.append(w_j.dump(fn("basis"), caller))
+            self.basis.append(w_j.dump(self._fname("basis"), caller))
         return res.dump(res_fname, caller)
 
 
-class NewtonSolver:
-    """Newton's method with Armijo damping and post-Newton fixed-point iterations
-    (newton_solver.py:22-334) on a device-resident iterate"""
+class NewtonSolver(_SolverBase):
+    """Newton's method with Armijo damping and post-Newton fixed-point iterations (newton_solver.py:22-334) on a
+    device-resident iterate.
+
+    With dump=True (the default) the work directory receives the reference's files and its Newton_state.json —
+    the SAME step strings in the same order as nk_ooc/newton_solver.py + solver_base.py + stats_file.py log them
+    (baselines/ci_*/Newton_state.json are reproduced verbatim) — so that `resume=True` continues an interrupted
+    solve at the step where it stopped and `rewind=True` redoes the last logged step (solver_state.py:36-45,
+    91-98): every intermediate the reference reads back (increment, Armijo candidates, fixed-point iterates) is
+    read back here too instead of being recomputed.  With dump=False nothing is written and nothing can be resumed;
+    the control flow is the same."""
 
     def __init__(self, iterate, solverinfo, workdir=None, armijo_batch=1, dump=True, precond_factory=None,
-                 resume=False):
+                 resume=False, rewind=False):
         """precond_factory: optional callable (iterate, fcn) -> preconditioner callable, called once per
-        Newton iteration (e.g. ProbePreconditioner).
-        With dump=True the work directory also receives the reference's Newton_state.json (iteration
-        counter + step log, solver_state.py) and Newton_stats.nc (stats_file.py); resume=True continues
-        from them: the iterate (and, if its evaluation had completed, fcn) of the logged iteration are
-        read back instead of recomputed (newton_solver.py:30-47,140-172)."""
+        Newton iteration (e.g. ProbePreconditioner)."""
         self._precond_factory = precond_factory
         self._info = dict(solverinfo)
-        self._workdir = workdir or tempfile.mkdtemp(prefix="nkb200_newton_")
-        os.makedirs(self._workdir, exist_ok=True)
+        workdir = workdir or tempfile.mkdtemp(prefix="nkb200_newton_")
+        super().__init__("Newton", workdir, iterate, solver_state.NEWTON_VARS, dump, resume, rewind)
         self._armijo_batch = int(armijo_batch)
-        self._dump = dump
-        if resume and not dump:
-            raise ValueError("resume needs the files of a dumped solve")
-        self.iteration = 0
-        self._state = solver_state.SolverState("Newton", self._workdir, resume=resume) if dump else None
-        self._stats = None
-        if dump:
-            cfg = type(iterate).model_config_obj
-            mods = [(tms.name, getattr(tms, "units", None)) for tms in iterate.tracer_modules]
-            self._stats = solver_state.StatsFile("Newton", self._workdir, cfg.region_cnt, mods,
-                                                 solver_state.NEWTON_VARS, resume=resume)
-            self.iteration = self._state.get_iteration()
+        state = self._solver_state
         caller = f"{type(self).__name__}.__init__"
         step0 = "Newton iterate 0 written"
-        if resume and self._state.step_logged(step0, per_iteration=False):
+        if state.step_logged(step0, per_iteration=False):
             iterate = type(iterate)(self._fname("iterate"))
         else:
-            iterate.dump(self._fname("iterate") if dump else None, caller)
-            if dump:
-                self._state.log_step(step0, per_iteration=False)
+            iterate.copy_real_tracers_to_shadow_tracers().dump(self._fname("iterate"), caller)
+            state.log_step(step0, per_iteration=False)
+        self._log_stats_vars_defined()
         self._iterate = iterate
-        fcn_step = f"comp_fcn complete for {self._fname('fcn')}"
-        if resume and self._state.step_logged(fcn_step):
-            self._fcn = type(iterate)(self._fname("fcn"))
-        else:
-            self._fcn = iterate.comp_fcn(self._fname("fcn") if dump else None, None, self._fname("hist"))
-            if dump:
-                self._state.log_step(fcn_step)
-                self._stats.put(self.iteration, iterate=self._iterate, fcn=self._fcn)
-                self._put_hist_stats(self._iterate)
+        self._fcn = iterate.comp_fcn(self._fname("fcn"), self._state_arg(), self._hist_fname("hist"))
+        self._put_stats(iterate=self._iterate, fcn=self._fcn)
+        self._put_hist_stats(self._iterate)
         self.history = []  # per iteration: dict(fcn_norm, iterate_norm, krylov_iterations, armijo_factor, ...)
         self._record()
 
     # ---- bookkeeping --------------------------------------------------------------------
-    def _fname(self, quantity, iteration=None):
-        iteration = self.iteration if iteration is None else iteration
+    @property
+    def iteration(self):
+        return self.get_iteration()
+
+    def _state_arg(self):
+        return self._solver_state if self._dump else None
+
+    def _hist_fname(self, quantity, iteration=None):
+        """hist files are written even by a solve that keeps nothing else: the next preconditioner reads them"""
+        iteration = self.get_iteration() if iteration is None else iteration
         return os.path.join(self._workdir, f"{quantity}_{iteration:02}.nc")
 
     def _put_hist_stats(self, state):
         """the model's own statistics of this iteration's hist file (newton_solver.py:52-58,330 call the
         three methods of the operator surface)"""
-        hist_fname = self._fname("hist")
-        if not os.path.exists(hist_fname):
+        if self._stats is None:
             return
-        state.def_stats_vars(self._stats, hist_fname, None)
-        state.put_stats_vars_iteration_invariant(self._stats, hist_fname, None)
-        names, weights = state._stats_names_and_weights()
-        self._stats.put_hist_stats(self.iteration, hist_fname, names, weights)
+        hist_fname = self._hist_fname("hist")
+        state.def_stats_vars(self._stats, hist_fname, self._solver_state)
+        state.put_stats_vars_iteration_invariant(self._stats, hist_fname, self._solver_state)
+        state.put_stats_vars(self._stats, hist_fname, self._solver_state)
 
     def _record(self, **extra):
         rec = {"iteration": self.iteration, "fcn_norm": self._fcn.norm(), "iterate_norm": self._iterate.norm()}
@@ -303,43 +421,92 @@ class NewtonSolver:
 
     # ---- one Newton step ------------------------------------------------------------------
     def _comp_increment(self):
+        """(d fcn / d iterate) increment = -fcn (newton_solver.py:140-181); returns (increment, krylov solver or
+        None when the increment of an interrupted solve was read back)"""
+        state = self._solver_state
+        done_step = "_comp_increment complete"
+        if state.step_logged(done_step):
+            return type(self._iterate)(self._fname("increment")), None
         krylov_dir = os.path.join(self._workdir, f"krylov_{self.iteration:02}")
+        step = "KrylovSolver instantiated"
+        rewind = state.step_was_rewound(step)
+        resume = rewind or state.step_logged(step)
         precond = None if self._precond_factory is None else self._precond_factory(self._iterate, self._fcn)
-        krylov = KrylovSolver(self._iterate, self._info, self._fname("hist"), krylov_dir, precond=precond)
-        increment = krylov.solve(self._fname("increment") if self._dump else None, self._fcn, dump=self._dump)
+        krylov = KrylovSolver(self._iterate, self._info, self._hist_fname("hist"), krylov_dir, precond=precond,
+                              dump=self._dump, resume=resume, rewind=rewind)
+        state.log_step(step)
+        increment = krylov.solve(self._fname("increment"), self._fcn)
+        self._put_stats(Krylov_iterations=krylov.iteration, increment=increment)
+        state.log_step(done_step)
         return increment, krylov
 
-    def _armijo_candidates(self, increment, armijo_factor):
-        """prov = iterate + factor*increment and F(prov) for one factor array [n_modules, R]"""
-        prov = self._iterate + armijo_factor * increment
-        return prov, prov.comp_fcn(None, None, self._fname("prov_hist_Armijo"))
+    def _armijo_init(self):
+        """newton_solver.py:183-189"""
+        state = self._solver_state
+        step = "NewtonSolver._armijo_init"
+        if not state.step_logged(step):
+            state.set_value_saved_state("armijo_ind", 0)
+            state.set_value_saved_state("armijo_factor", np.where(self.converged(), 0.0, 1.0))
+            state.log_step(step)
 
     def _comp_next_iterate(self, increment):
-        """Armijo damping, Eq. (A.1) of Kelley 2003 (newton_solver.py:183-258)"""
+        """Armijo damping, Eq. (A.1) of Kelley 2003 (newton_solver.py:191-258); returns
+        (prov, prov_fcn, armijo_factor, armijo_ind)"""
+        state = self._solver_state
+        self._armijo_init()
+        armijo_ind = int(state.get_value_saved_state("armijo_ind"))
+        armijo_factor = np.asarray(state.get_value_saved_state("armijo_factor"), dtype=np.float64)
+        done_step = "_comp_next_iterate complete"
+        cls = type(self._iterate)
+        if state.step_logged(done_step):
+            return (cls(self._fname(f"prov_Armijo_{armijo_ind:02}")), cls(self._fname(f"prov_fcn_Armijo_{armijo_ind:02}")),
+                    armijo_factor, armijo_ind)
+        caller = f"{type(self).__name__}._comp_next_iterate"
         alpha = 1.0e-4
-        armijo_factor = np.where(self.converged(), 0.0, 1.0)
         fcn_norm = self._fcn.norm()
-        armijo_ind = 0
-        if self._armijo_batch > 1:
-            # speculative: k candidates as k members of one batched evaluation
+        if self._armijo_batch > 1 and armijo_ind == 0:
+            # speculative: k candidates as k members of ONE batched evaluation
             k = self._armijo_batch
             factors = [armijo_factor * 0.5 ** i for i in range(k)]
             provs = [self._iterate + f * increment for f in factors]
-            batched_fcn = distributed.sharded_comp_fcn(type(self._iterate).from_members(provs))
+            batched_fcn = distributed.sharded_comp_fcn(cls.from_members(provs))
             norms = batched_fcn.norm()  # [n_modules, R, k]
             for i in range(k):
                 cond = (factors[i] == 0.0) | (norms[..., i] <= (1.0 - alpha * factors[i]) * fcn_norm)
                 if cond.all():
-                    return provs[i], batched_fcn.member(i), factors[i], i
+                    state.set_value_saved_state("armijo_ind", i)
+                    state.set_value_saved_state("armijo_factor", factors[i])
+                    prov = provs[i].dump(self._fname(f"prov_Armijo_{i:02}"), caller)
+                    prov_fcn = batched_fcn.member(i).dump(self._fname(f"prov_fcn_Armijo_{i:02}"), caller)
+                    state.log_step(done_step)
+                    self._put_stats(Armijo_factor=factors[i])
+                    self._armijo_hist = None  # a batched evaluation leaves no hist file of the accepted candidate
+                    return prov, prov_fcn, factors[i], i
             armijo_factor, armijo_ind = factors[-1] * 0.5, k
+            state.set_value_saved_state("armijo_ind", armijo_ind)
+            state.set_value_saved_state("armijo_factor", armijo_factor)
         while True:
-            prov, prov_fcn = self._armijo_candidates(increment, armijo_factor)
+            prov = self._iterate + armijo_factor * increment
+            prov.dump(self._fname(f"prov_Armijo_{armijo_ind:02}"), caller)
+            hist = self._hist_fname(f"prov_hist_Armijo_{armijo_ind:02}")
+            prov_fcn = prov.comp_fcn(self._fname(f"prov_fcn_Armijo_{armijo_ind:02}"), self._state_arg(), hist)
+            # only the latest Armijo hist file is kept
+            prev = self._hist_fname(f"prov_hist_Armijo_{(armijo_ind - 1):02}")
+            if armijo_ind > 0 and os.path.exists(prev):
+                os.remove(prev)
+            self._armijo_hist = hist
             prov_fcn_norm = prov_fcn.norm()
+            increment.log_vals(["ArmijoFactor", "fcn_norm", "prov_fcn_norm"],
+                               np.stack((armijo_factor, fcn_norm, prov_fcn_norm)))
             armijo_cond = (armijo_factor == 0.0) | (prov_fcn_norm <= (1.0 - alpha * armijo_factor) * fcn_norm)
             if armijo_cond.all():
+                state.log_step(done_step)
+                self._put_stats(Armijo_factor=armijo_factor)
                 return prov, prov_fcn, armijo_factor, armijo_ind
             armijo_factor = np.where(armijo_cond, armijo_factor, 0.5 * armijo_factor)
             armijo_ind += 1
+            state.set_value_saved_state("armijo_ind", armijo_ind)
+            state.set_value_saved_state("armijo_factor", armijo_factor)
             if armijo_ind > 10:
                 raise RuntimeError("Armijo_ind exceeds limit")
 
@@ -348,50 +515,84 @@ class NewtonSolver:
         if self.iteration >= int(self._info["newton_max_iter"]):
             raise RuntimeError("number of maximum Newton iterations exceeded")
         caller = f"{type(self).__name__}.step"
-        increment, krylov = self._comp_increment()
-        scalef = increment.apply_limiter(self._iterate)
-        prov, prov_fcn, armijo_factor, armijo_ind = self._comp_next_iterate(increment)
-        prov.copy_shadow_tracers_to_real_tracers()
-        if prov.shadow_tracers_on():
-            prov_fcn = prov.comp_fcn(None, None, self._fname("prov_hist_fp"))
+        state = self._solver_state
+        cls = type(self._iterate)
         n_fp = int(self._info.get("post_newton_fp_iter", 0))
-        if n_fp == 0:
-            # the accepted Armijo candidate IS the new iterate: its function value and its hist file (the input of
-            # the next iteration's preconditioner) exist already — no further model year (newton_solver.py:283-291
-            # renames the Armijo hist file the same way).  Only the speculative batched Armijo step and shadow
-            # tracers leave no hist file of the accepted candidate behind.
-            armijo_hist = self._fname("prov_hist_Armijo")
-            have_hist = self._armijo_batch <= 1 and not prov.shadow_tracers_on() and os.path.exists(armijo_hist)
-            self.iteration += 1
-            prov.dump(self._fname("iterate") if self._dump else None, caller)
-            if have_hist:
-                os.replace(armijo_hist, self._fname("hist"))
-                prov_fcn.dump(self._fname("fcn") if self._dump else None, caller)
-            else:
-                prov_fcn = prov.comp_fcn(self._fname("fcn") if self._dump else None, None, self._fname("hist"))
-        for fp_iter in range(n_fp):
-            prov += prov_fcn
+        extra = {}
+        increment = None
+        step = "fp iterations started"
+        if not state.step_logged(step):
+            increment, krylov = self._comp_increment()
+            scalef = increment.apply_limiter(self._iterate)
+            self._put_stats(increment_scalef=scalef)
+            self._armijo_hist = None
+            prov, prov_fcn, armijo_factor, armijo_ind = self._comp_next_iterate(increment)
+            extra = dict(increment_scalef=scalef, armijo_factor=armijo_factor, armijo_ind=armijo_ind)
+            if krylov is not None:
+                extra.update(krylov_iterations=krylov.iteration, krylov_precond_resid_norm=krylov.precond_resid_norm,
+                             krylov_beta=krylov.beta)
+            fp_iter = 0
+            state.set_value_saved_state("fp_iter", fp_iter)
             prov.copy_shadow_tracers_to_real_tracers()
-            if fp_iter + 1 < n_fp:
-                prov_fcn = prov.comp_fcn(None, None, self._fname("prov_hist_fp"))
+            prov.dump(self._fname(f"prov_fp_{fp_iter:02}"), caller)
+            # the function value after the shadow tracers were copied; without shadow tracers it is the accepted
+            # Armijo candidate's, whose hist file becomes the first fixed-point hist file (newton_solver.py:283-303)
+            armijo_hist = self._armijo_hist
+            if armijo_hist is None and self._dump:
+                armijo_hist = self._hist_fname(f"prov_hist_Armijo_{armijo_ind:02}")
+            have_hist = armijo_hist is not None and os.path.exists(armijo_hist)
+            fp_hist = self._hist_fname(f"prov_hist_fp_{fp_iter:02}")
+            if prov.shadow_tracers_on() or (n_fp == 0 and not have_hist):
+                prov_fcn = prov.comp_fcn(self._fname(f"prov_fcn_fp_{fp_iter:02}"), self._state_arg(), fp_hist)
+                if have_hist:
+                    os.remove(armijo_hist)
             else:
-                self.iteration += 1
-                prov.dump(self._fname("iterate") if self._dump else None, caller)
-                prov_fcn = prov.comp_fcn(self._fname("fcn") if self._dump else None, None, self._fname("hist"))
-        if self._dump:
-            # statistics of the iteration that ends here, then the new iteration's iterate / fcn
-            # (newton_solver.py:262-329; the iteration counter was advanced above)
-            prev = self.iteration - 1
-            self._stats.put(prev, increment=increment, Krylov_iterations=krylov.iteration,
-                            increment_scalef=scalef, Armijo_factor=armijo_factor)
-            self._state.inc_iteration()
-            self._state.log_step(f"comp_fcn complete for {self._fname('fcn')}")
-            self._stats.put(self.iteration, iterate=prov, fcn=prov_fcn)
-            self._put_hist_stats(prov)
+                prov_fcn.dump(self._fname(f"prov_fcn_fp_{fp_iter:02}"), caller)
+                if have_hist:
+                    os.replace(armijo_hist, fp_hist)
+            state.log_step(step)
+        else:
+            fp_iter = int(state.get_value_saved_state("fp_iter"))
+            prov = cls(self._fname(f"prov_fp_{fp_iter:02}"))
+            prov_fcn = cls(self._fname(f"prov_fcn_fp_{fp_iter:02}"))
+        if n_fp == 0 and fp_iter == 0:
+            # (the reference only advances the iteration inside its fixed-point loop; without fixed-point
+            # iterations the accepted Armijo candidate IS the new iterate and its function value and hist file
+            # — the input of the next preconditioner — exist already: no further model year)
+            fp_hist = self._hist_fname("prov_hist_fp_00")
+            state.inc_iteration()
+            prov.dump(self._fname("iterate"), caller)
+            prov_fcn.dump(self._fname("fcn"), caller)
+            if os.path.exists(fp_hist):
+                os.replace(fp_hist, self._hist_fname("hist"))
+            state.log_step(f"comp_fcn complete for {self._fname('fcn')}")
+            fp_iter = 1
+            state.set_value_saved_state("fp_iter", fp_iter)
+        while fp_iter < n_fp:
+            step = f"prov updated for fp iteration {fp_iter:02}"
+            if not state.step_logged(step):
+                prov += prov_fcn
+                prov.copy_shadow_tracers_to_real_tracers()
+                prov.dump(self._fname(f"prov_fp_{(fp_iter + 1):02}"), caller)
+                state.log_step(step)
+            else:
+                prov = cls(self._fname(f"prov_fp_{(fp_iter + 1):02}"))
+            if fp_iter + 1 < n_fp:
+                res_fname = self._fname(f"prov_fcn_fp_{(fp_iter + 1):02}")
+                hist_fname = self._hist_fname(f"prov_hist_fp_{(fp_iter + 1):02}")
+            else:
+                state.inc_iteration()
+                prov.dump(self._fname("iterate"), caller)
+                res_fname = self._fname("fcn")
+                hist_fname = self._hist_fname("hist")
+            prov_fcn = prov.comp_fcn(res_fname, self._state_arg(), hist_fname)
+            fp_iter += 1
+            state.set_value_saved_state("fp_iter", fp_iter)
         self._iterate, self._fcn = prov, prov_fcn
-        self._record(krylov_iterations=krylov.iteration, krylov_precond_resid_norm=krylov.precond_resid_norm,
-                     krylov_beta=krylov.beta, increment_scalef=scalef, armijo_factor=armijo_factor,
-                     armijo_ind=armijo_ind)
+        self._put_stats(iterate=self._iterate, fcn=self._fcn)
+        if self._stats is not None:
+            self._iterate.put_stats_vars(self._stats, self._hist_fname("hist"), self._solver_state)
+        self._record(**extra)
         return increment
 
     def solve(self):

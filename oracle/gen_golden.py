@@ -13,6 +13,7 @@ import os
 import sys
 
 import numpy as np
+from scipy.io import netcdf_file
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -57,6 +58,45 @@ def baselines():
 
     shutil.copyfile(os.path.join(base, "ci_long_iage", "Newton_state.json"),
                     os.path.join(OUT, "Newton_state_ci_long_iage.json"))
+
+
+def baseline_files():
+    """every committed CI baseline file in full — variable values in baseline_files.npz, dimensions / variable
+    order / attributes in baseline_files_meta.json — so that tests/baseline_files.py can put the reference's
+    baselines/ directory back together on the GPU box (where /root/reference does not exist) and the ports of
+    scripts/ci_*.sh can run `baseline_cmp` against real files, metadata check included"""
+    import glob
+    import json
+    import shutil
+
+    base = os.path.join(rh.REF_ROOT, "baselines")
+    vals, meta = {}, {}
+    for fname in sorted(glob.glob(os.path.join(base, "ci_*", "*.nc"))):
+        key = os.path.relpath(fname, base)[:-3]
+        nc = netcdf_file(fname, "r", mmap=False)
+        dims = [[name, None if length is None else int(length)] for name, length in nc.dimensions.items()]
+        entry = {"dims": dims, "vars": []}
+        for name, var in nc.variables.items():
+            attrs = {}
+            for akey, aval in var._attributes.items():
+                if isinstance(aval, bytes):
+                    aval = aval.decode()
+                elif isinstance(aval, np.ndarray):
+                    aval = aval.tolist()
+                elif isinstance(aval, np.generic):
+                    aval = aval.item()
+                attrs[akey] = aval
+            entry["vars"].append({"name": name, "dims": list(var.dimensions), "dtype": var.data.dtype.str[1:],
+                                  "attrs": attrs})
+            vals[f"{key}/{name}"] = np.array(var.data, dtype=var.data.dtype.newbyteorder("="))
+        nc.close()
+        meta[key] = entry
+    np.savez_compressed(os.path.join(OUT, "baseline_files.npz"), **vals)
+    with open(os.path.join(OUT, "baseline_files_meta.json"), "w") as fptr:
+        json.dump(meta, fptr, indent=1, sort_keys=True)
+    for cfg in ("ci_long_dye_decay", "ci_long_iage", "ci_py_driver_2d_iage_column_regions"):
+        shutil.copyfile(os.path.join(base, cfg, "Newton_state.json"), os.path.join(OUT, f"Newton_state_{cfg}.json"))
+    print("baseline_files.npz:", len(vals), "arrays of", len(meta), "files")
 
 
 def remap_cases():
@@ -441,6 +481,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     rh.install_stubs()
     baselines()
+    baseline_files()
     remap_cases()
     py_driver_2d_cases()
     test_problem_cases()

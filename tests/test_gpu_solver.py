@@ -217,7 +217,7 @@ def test_cli_setup_solver_and_nk_driver_column_regions(base, tmp_path):
 
     with netcdf_file(os.path.join(work, "grid_vars.nc"), "r", mmap=False) as f:
         np.testing.assert_array_equal(np.array(f.variables["region_mask"].data), base[pre + "grid_vars/region_mask"])
-    np.testing.assert_allclose(read(os.path.join(work, "gen_init_iterate", "init_iterate_00.nc")),
+    np.testing.assert_allclose(read(os.path.join(work, "gen_init_iterate", "init_iterate_0000.nc")),
                                _want(base, pre + "init_iterate_0000"), rtol=1e-7, atol=2e-9)
     np.testing.assert_allclose(read(os.path.join(work, "gen_init_iterate", "init_iterate.nc")),
                                _want(base, pre + "init_iterate"), rtol=1e-3, atol=1e-6)
@@ -234,7 +234,7 @@ def test_cli_setup_solver_and_nk_driver_column_regions(base, tmp_path):
     assert cli.main(["nk_driver", "--newton_max_iter", "5", "--resume"] + common) == 0
     assert json.load(open(os.path.join(work, "Newton_state.json")))["iteration"] == it_done
     # file-to-file function evaluation
-    assert cli.main(["comp_fcn", "--fname_dir", work, "--in_fname", "gen_init_iterate/init_iterate_00.nc",
+    assert cli.main(["comp_fcn", "--fname_dir", work, "--in_fname", "gen_init_iterate/init_iterate_0000.nc",
                      "--res_fname", "fcn_cli.nc"] + common) == 0
     np.testing.assert_allclose(read(os.path.join(work, "fcn_cli.nc")), _want(base, pre + "fcn_0000"), rtol=1e-3,
                                atol=1e-6)
