@@ -22,10 +22,13 @@ def parse_args(args_list_in=None):
     parser.add_argument("--baseline_dir", help="directory with baseline file")
     parser.add_argument("--rtol", help="relative tolerance", type=float, default=1.0e-7)
     parser.add_argument("--atol", help="absolute tolerance", type=float, default=2.0e-9)
+    parser.add_argument("--anom_suffix", default=None,
+                        help="(extension) compare variables <x><suffix>, anomalies of x, with x's tolerance "
+                             "atol + rtol |x| instead of atol + rtol |x - mean(x)|")
     return parser.parse_args(args_list)
 
 
-def compare(fname, expr_dir, baseline_dir, rtol=1.0e-7, atol=2.0e-9):
+def compare(fname, expr_dir, baseline_dir, rtol=1.0e-7, atol=2.0e-9, anom_suffix=None):
     """True when metadata and values agree (both checks always run, as in the reference)"""
     logger = logging.getLogger(__name__)
     baseline_fname = os.path.join(baseline_dir, fname)
@@ -35,14 +38,14 @@ def compare(fname, expr_dir, baseline_dir, rtol=1.0e-7, atol=2.0e-9):
     res = True
     if not metadata_same(expr_fname, baseline_fname):
         res = False
-    if not isclose_all_vars(expr_fname, baseline_fname, rtol=rtol, atol=atol):
+    if not isclose_all_vars(expr_fname, baseline_fname, rtol=rtol, atol=atol, anom_suffix=anom_suffix):
         res = False
     return res
 
 
 def main(args):
     logging.basicConfig(format="%(filename)s:%(funcName)s:%(message)s", level="INFO", stream=sys.stdout)
-    sys.exit(0 if compare(args.fname, args.expr_dir, args.baseline_dir, args.rtol, args.atol) else 1)
+    sys.exit(0 if compare(args.fname, args.expr_dir, args.baseline_dir, args.rtol, args.atol, args.anom_suffix) else 1)
 
 
 if __name__ == "__main__":

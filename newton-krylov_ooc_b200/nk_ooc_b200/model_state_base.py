@@ -51,6 +51,20 @@ def _expand_defs(defs, names):
     return out
 
 
+
+def copy_hist_attrs(src, dst, long_name_suffix=None, drop_time_cell_methods=False):
+    """attributes of a hist-file variable carried over to the precond file (model_state_base.py:449-470): all of
+    them, `cell_methods` dropped when it refers to a time dimension the result does not have, the long name
+    extended by the time reduction"""
+    for key, val in src._attributes.items():  # pylint: disable=protected-access
+        if isinstance(val, bytes):
+            val = val.decode()
+        if key == "cell_methods" and drop_time_cell_methods and "time:" in val:
+            continue
+        if key == "long_name" and long_name_suffix:
+            val = val + long_name_suffix
+        setattr(dst, key, val)
+
 class ModelConfig:
     """modelinfo + tracer module definitions + region weights (nk_ooc/model_config.py:17-78,
     249-315).  tracer_module_defs: dict as in input/<model>/tracer_module_defs.yaml."""

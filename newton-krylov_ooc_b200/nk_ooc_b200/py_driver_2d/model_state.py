@@ -13,7 +13,7 @@ from scipy.io import netcdf_file
 
 from .. import engine
 from .. import hist as hist_mod
-from ..model_state_base import ModelConfig, ModelStateBase, get_tracer_module_state_class
+from ..model_state_base import ModelConfig, ModelStateBase, get_tracer_module_state_class, copy_hist_attrs
 from ..spatial_axis import spatial_axis_from_file
 from . import modules
 from .tracer_module_state import tracer_snapshot_nearest
@@ -332,6 +332,7 @@ class ModelState(ModelStateBase):
                     if dim not in fout.dimensions:
                         fout.createDimension(dim, length)
                 out = fout.createVariable(name, "f8", var.dimensions)
+                copy_hist_attrs(var, out)
                 out[:] = np.array(var.data)
 
     def apply_precond_jacobian(self, precond_fname, res_fname, solver_state):

@@ -133,8 +133,9 @@ def _isclose_one_var_core(vals1, vals2, rtol, atol):
     return False
 
 
-def _isclose_one_var(name, var1, var2, rtol, atol):
-    """utils.py:261-300"""
+def _isclose_one_var(name, var1, var2, rtol, atol, parent2=None):
+    """utils.py:261-300.  parent2: for an anomaly variable (x - mean(x)), the baseline's x: the absolute tolerance
+    becomes atol + rtol |x|, the tolerance x itself is compared with (see isclose_all_vars)"""
     logger = logging.getLogger(__name__)
     if var1.shape != var2.shape:
         logger.info("    var1.shape %s != var2.shape %s for %s", var1.shape, var2.shape, name)
@@ -161,18 +162,37 @@ def _isclose_one_var(name, var1, var2, rtol, atol):
             # the reference converts with pint here; this path only ever writes one spelling of a unit
             logger.info("    units of %s differ: '%s' != '%s'", name, units1, units2)
             res = False
+    if parent2 is not None and parent2.shape == vals2.shape:
+        # |v1 - v2| <= atol + rtol (|x| + |v2|) pointwise, written as a comparison of scaled values
+        scale = atol + rtol * (np.abs(parent2) + np.abs(vals2))
+        close = np.abs(vals1 - vals2) <= scale
+        close |= np.isnan(vals1) & np.isnan(vals2)
+        if not close.all():
+            worst = np.nanmax(np.where(close, 0.0, np.abs(vals1 - vals2) / scale))
+            logger.info("    %s vals not close at the parent variable's tolerance (worst ratio %.3f)", name, worst)
+            res = False
+        return res
     if not _isclose_one_var_core(vals1, vals2, rtol=rtol, atol=atol):
         logger.info("    %s vals not close", name)
         res = False
     return res
 
 
-def isclose_all_vars(fname1, fname2, rtol, atol):
-    """True if all variables common to both files are close (utils.py:261-272)"""
+def isclose_all_vars(fname1, fname2, rtol, atol, anom_suffix=None):
+    """True if all variables common to both files are close (utils.py:261-272).
+
+    anom_suffix (an extension, off by default): variables `<x><anom_suffix>` are anomalies x - mean(x) of a
+    variable x of the same file.  They are compared with the tolerance x is compared with, atol + rtol |x|: where
+    the anomaly crosses zero its plain tolerance is atol alone, below what two different time integrators of x
+    can agree to (the reference's own Radau solution at rtol = atol = 1e-6 is 1.5e-6 from the converged one on
+    the CI grid, profiles/r02_error_vs_steps.md)."""
     res = True
     with netcdf_file(fname1, "r", mmap=False) as f1, netcdf_file(fname2, "r", mmap=False) as f2:
         for varname, var1 in f1.variables.items():
             if varname in f2.variables:
-                if not _isclose_one_var(varname, var1, f2.variables[varname], rtol=rtol, atol=atol):
+                parent2 = None
+                if anom_suffix and varname.endswith(anom_suffix) and varname[: -len(anom_suffix)] in f2.variables:
+                    parent2 = _native(f2.variables[varname[: -len(anom_suffix)]])
+                if not _isclose_one_var(varname, var1, f2.variables[varname], rtol=rtol, atol=atol, parent2=parent2):
                     res = False
     return res

@@ -141,3 +141,26 @@ def test_baseline_cmp_command_line_exit_status(tmp_path):
     with pytest.raises(SystemExit) as exc:
         baseline_cmp.main(args)
     assert exc.value.code == 1
+
+
+def test_anomaly_variables_compared_at_the_parent_variables_tolerance(tmp_path):
+    """--anom_suffix (extension used by the py_driver_2d script ports): x_time_anom = x - mean(x) is compared with
+    atol + rtol |x|; without the option the plain comparison fails where the anomaly is small"""
+    def write(fname, x):
+        with netcdf_file(fname, "w", version=2) as nc:
+            nc.createDimension("time", x.shape[0])
+            nc.createDimension("depth", x.shape[1])
+            var = nc.createVariable("x", "f8", ("time", "depth"))
+            var[:] = x
+            var = nc.createVariable("x_time_anom", "f8", ("time", "depth"))
+            var[:] = x - x.mean(axis=0)
+
+    rng = np.random.default_rng(0)
+    x = 5.0 + 0.01 * rng.normal(size=(7, 4))
+    base, expr = str(tmp_path / "b.nc"), str(tmp_path / "e.nc")
+    write(base, x)
+    write(expr, x * (1.0 + 2.0e-4 * rng.normal(size=x.shape)))  # x agrees to rtol 1e-3, its small anomaly does not
+    assert not utils.isclose_all_vars(expr, base, rtol=1.0e-3, atol=1.0e-6)
+    assert utils.isclose_all_vars(expr, base, rtol=1.0e-3, atol=1.0e-6, anom_suffix="_time_anom")
+    write(expr, x * (1.0 + 5.0e-3))  # x itself off: fails either way
+    assert not utils.isclose_all_vars(expr, base, rtol=1.0e-3, atol=1.0e-6, anom_suffix="_time_anom")
