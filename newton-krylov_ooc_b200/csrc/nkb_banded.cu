@@ -42,6 +42,12 @@ struct nkb_banded {
     // rows {L(j,j-K..j-1), 1/U(j,j), U(j,j+1..j+K)}, K = max(kl, ku) <= 4, for banded_thomas_kernel
     int nb_k = 0;
     double *nb = nullptr;  // [n][2K+1]
+    // one wide block factored without row interchanges: panel (blocked) substitution, banded_solve_panel_kernel
+    int klp = 0, kup = 0;      // row pitches of lp / up (kl, ku rounded up to even: 16-byte cp.async)
+    double *lp = nullptr;      // [n][klp]  L(j+1..j+kl, j)
+    double *up = nullptr;      // [n][kup]  U(j-1..j-ku, j)
+    double *linv = nullptr;    // [ceil(n/PR)][PR][PR] inverse of the unit lower diagonal block of rows p*PR.. (top aligned)
+    double *uinv = nullptr;    // [ceil(n/PR)][PR][PR] inverse of the upper diagonal block of rows ..n-1-q*PR (bottom aligned)
 };
 
 namespace nkb {
@@ -386,6 +392,361 @@ __global__ void __launch_bounds__(256) banded_solve_win_kernel(const BandedSolve
     bs_wait<0>();
 }
 
+// ---- panel (blocked) substitution for ONE wide block factored without row interchanges -------------------
+// The window kernel above advances one row per block barrier (0.43 us per row: 16 ms for the refined grid's 2-D
+// preconditioner, n = 18 750, kl = ku = 450, every Krylov iteration).  Without interchanges L and U keep their
+// bandwidths (kl, ku) and the sweeps can advance PR rows per barrier pair:
+//   (1) the PR unknowns of a panel from the panel's right-hand side with the INVERSE of the PR x PR diagonal
+//       block (formed once at set-up, banded_panel_inverse_kernel: the matrices here are diagonally dominant
+//       I - dt J products, their triangular blocks well conditioned) — a small dense product, no recurrence;
+//   (2) the kl (ku) rows below (above) the panel updated with the panel's PR columns at once, one
+//       (row, member) pair per thread and pass, no reduction.
+// The factor columns of a panel are ONE contiguous run of PR*klp doubles (lp / up are stored column by column)
+// and arrive with the panel's inverse block and the rows entering the window through a cp.async ring.
+constexpr int PR = 16;
+
+struct PanelArgs {
+    const double *lp, *up, *linv, *uinv;
+    int n, kl, ku, klp, kup;
+    const double *y;
+    double *x;
+    int B;
+    size_t ldb;
+    double scale;
+    int subtract;
+    int MB, Wn, NS, cw;  // member lanes, window rows, ring stages, doubles per factor column in the ring
+};
+
+__device__ __forceinline__ void bs_cp16(void *dst_smem, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)),
+                 "l"(src)
+                 : "memory");
+}
+// 1-D bulk copy global -> shared through the TMA engine, completion counted on an mbarrier: the PR factor columns
+// of a panel are one contiguous run (57.6 KB for kl = 450) — as 16-byte cp.async requests of 256 threads a single
+// SM fetched them at only 18 GB/s (3.3 us per panel, measured)
+__device__ __forceinline__ void bs_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void bs_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bs_mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bs_bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void bs_wait_dyn(int pending) {  // pending = NS - 2 in {0, 1}
+    if (pending >= 1) bs_wait<1>(); else bs_wait<0>();
+}
+
+// compact copies of the factor for the panel kernel (column j contiguous, zero padded)
+__global__ void banded_panel_pack_kernel(const double *__restrict__ ab, int n, int kl, int ku, int klp, int kup,
+                                         double *__restrict__ lp, double *__restrict__ up) {
+    const int kv = kl + ku;
+    const int j = blockIdx.x;
+    for (int d = threadIdx.x; d < klp; d += blockDim.x)
+        lp[(size_t)j * klp + d] = (d < kl && j + 1 + d < n) ? ab[(size_t)(kv + 1 + d) * n + j] : 0.0;
+    for (int d = threadIdx.x; d < kup; d += blockDim.x)
+        up[(size_t)j * kup + d] = (d < ku && j - 1 - d >= 0) ? ab[(size_t)(kv - 1 - d) * n + j] : 0.0;
+}
+
+// inverses of the PR x PR diagonal blocks: block p of L covers rows p*PR.. (top aligned), block q of U covers
+// rows ..n-1-q*PR (bottom aligned); thread c solves for column c; short blocks are padded with the identity
+__global__ void __launch_bounds__(2 * PR) banded_panel_inverse_kernel(const double *__restrict__ ab,
+                                                                      const double *__restrict__ lp,
+                                                                      const double *__restrict__ up, int n, int kl,
+                                                                      int ku, int klp, int kup,
+                                                                      double *__restrict__ linv,
+                                                                      double *__restrict__ uinv) {
+    const int blk = blockIdx.x, c = threadIdx.x % PR;
+    const int kv = kl + ku;
+    double x[PR];
+    if (threadIdx.x < PR) {
+        const int j0 = blk * PR, nr = min(PR, n - j0);
+        double *out = linv + (size_t)blk * PR * PR;
+        for (int ii = 0; ii < PR; ++ii) x[ii] = (ii == c) ? 1.0 : 0.0;
+        if (c < nr) {
+            for (int ii = c + 1; ii < nr; ++ii) {
+                double acc = 0.0;
+                for (int jj = c; jj < ii; ++jj) {
+                    const int d = ii - jj - 1;
+                    if (d < kl) acc = fma(lp[(size_t)(j0 + jj) * klp + d], x[jj], acc);
+                }
+                x[ii] = -acc;
+            }
+        }
+        for (int ii = 0; ii < PR; ++ii) out[ii * PR + c] = x[ii];
+    } else {
+        const int j1 = n - 1 - blk * PR, jl = max(j1 - PR + 1, 0), nr = j1 - jl + 1;
+        double *out = uinv + (size_t)blk * PR * PR;
+        for (int ii = 0; ii < PR; ++ii) x[ii] = 0.0;
+        if (c < nr) {
+            x[c] = 1.0 / ab[(size_t)kv * n + jl + c];
+            for (int ii = c - 1; ii >= 0; --ii) {
+                double acc = 0.0;
+                for (int jj = ii + 1; jj <= c; ++jj) {
+                    const int d = jj - ii - 1;
+                    if (d < ku) acc = fma(up[(size_t)(jl + jj) * kup + d], x[jj], acc);
+                }
+                x[ii] = -acc / ab[(size_t)kv * n + jl + ii];
+            }
+        } else {
+            x[c] = 1.0;
+        }
+        for (int ii = 0; ii < PR; ++ii) out[ii * PR + c] = x[ii];
+    }
+}
+
+// threads = 256 = RW row lanes x MB member lanes (member fastest, MB a power of two); grid = member groups.
+// Shared memory: W[Wn][MB] window | X[PR][MB] panel unknowns | C[NS][PR*cw] factor columns | D[NS][PR*PR] inverse
+// blocks | Y[NS][PR][MB] right-hand side rows for the epilogue.
+// Ring discipline: wait for panel q's stage, block barrier (every thread has left panel q-1: its ring stage and
+// the window rows behind the sweep may be overwritten), THEN issue the stage of panel q+NS-1.
+__global__ void __launch_bounds__(256) banded_solve_panel_kernel(const PanelArgs a) {
+    extern __shared__ __align__(16) double bs_smem[];
+    const int MB = a.MB, Wn = a.Wn, NS = a.NS, n = a.n, kl = a.kl, ku = a.ku;
+    double *W = bs_smem;
+    double *X = W + (size_t)Wn * MB;
+    double *C = X + PR * MB;
+    double *D = C + (size_t)NS * PR * a.cw;
+    double *Y = D + (size_t)NS * PR * PR;
+    const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(Y + (size_t)NS * PR * MB);  // NS mbarriers
+    const int tid = threadIdx.x, nt = blockDim.x;
+    if (tid == 0) {
+        for (int sidx = 0; sidx < NS; ++sidx) bs_mbar_init(bar0 + 8 * sidx, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    const int msh = 31 - __clz(MB);
+    const int m = tid & (MB - 1), rl = tid >> msh, RW = nt >> msh;
+    const int b0 = blockIdx.x * MB;
+    const bool live = (b0 + m < a.B);
+    const int nlive = min(MB, a.B - b0);
+    for (int i = tid; i < Wn * MB; i += nt) W[i] = 0.0;
+    __syncthreads();
+
+    auto slot = [&](int r) {  // window slot of row r >= 0 (r - Wn*floor(r/Wn) without the division in the hot loops)
+        return r % Wn;
+    };
+    auto load_rows = [&](const double *src, int ra, int rb) {  // rows [ra, rb) -> window
+        ra = max(ra, 0);
+        rb = min(rb, n);
+        if (rb <= ra) return;
+        int s0 = slot(ra);
+        for (int i = tid; i < ((rb - ra) << msh); i += nt) {
+            const int dr = i >> msh, mm = i & (MB - 1);
+            int sl = s0 + dr;
+            if (sl >= Wn) sl -= Wn;
+            if (mm < nlive) bs_cp8(W + ((size_t)sl << msh) + mm, src + (size_t)(ra + dr) * a.ldb + b0 + mm);
+        }
+    };
+    const int nP = (n + PR - 1) / PR;
+    const int half = (PR * PR) / 2;
+    // phase (1) roles: tid = ii*16 + part*MB + m — P = 16/MB lanes per (panel row, member) pair
+    const int P = PR >> msh;
+    const int p_ii = tid >> 4, p_part = (tid & 15) >> msh;
+    // factor columns of ring use g (forward panels 0..nP-1, backward nP..2nP-1): ring stage g % NS keeps the
+    // forward and the backward sweep on ONE phase sequence per mbarrier (backward panel q uses stage (nP + q) % NS)
+    auto bulk = [&](double *dst, const double *src, uint32_t bytes, int g) {
+        const uint32_t bar = bar0 + 8 * (g % NS);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the stage was read through the generic proxy
+        bs_mbar_expect_tx(bar, bytes);
+        uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+        const char *sp = reinterpret_cast<const char *>(src);
+        while (bytes > 0) {  // pieces of at most 32 KB
+            const uint32_t piece = bytes > 32768u ? 32768u : bytes;
+            bs_bulk_load(d, sp, piece, bar);
+            d += piece; sp += piece; bytes -= piece;
+        }
+    };
+
+    // ---------------- forward: L z = y ----------------
+    auto stage_fwd = [&](int q) {
+        if (q < nP) {
+            const int j0 = q * PR, nr = min(PR, n - j0);
+            const double *src = a.lp + (size_t)j0 * a.klp;
+            double *dst = C + (size_t)(q % NS) * PR * a.cw;
+            if (tid == 0) bulk(dst, src, (uint32_t)nr * a.klp * 8u, q);
+            const double *dsrc = a.linv + (size_t)q * PR * PR;
+            double *ddst = D + (size_t)(q % NS) * PR * PR;
+            if (tid < half) bs_cp16(ddst + 2 * tid, dsrc + 2 * tid);
+            load_rows(a.y, q == 0 ? 0 : j0 + kl, j0 + kl + PR);
+        }
+        bs_commit();
+    };
+    for (int q = 0; q < NS - 1; ++q) stage_fwd(q);
+    for (int q = 0; q < nP; ++q) {
+        bs_wait_dyn(NS - 2);
+        bs_mbar_wait(bar0 + 8 * (q % NS), (q / NS) & 1);
+        __syncthreads();
+        stage_fwd(q + NS - 1);
+        const int j0 = q * PR, nr = min(PR, n - j0);
+        const double *cq = C + (size_t)(q % NS) * PR * a.cw;
+        const double *dq = D + (size_t)(q % NS) * PR * PR;
+        const int s0 = slot(j0);
+        // (1) panel unknowns x = Linv w on all 256 threads: 16/MB lanes share the 16 products of a (row, member)
+        //     pair and combine them by xor shuffles (the inverse block is stored with its zeros, no triangle tests)
+        {
+            double acc = 0.0;
+            if (p_ii < nr) {
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const int jj = p_part + t * P;
+                    if (t < MB && jj < nr) {
+                        int sl = s0 + jj;
+                        if (sl >= Wn) sl -= Wn;
+                        acc = fma(dq[p_ii * PR + jj], W[((size_t)sl << msh) + m], acc);
+                    }
+                }
+            }
+            for (int off = MB; off < PR; off <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+            if (p_part == 0 && p_ii < nr) {
+                X[(p_ii << msh) + m] = acc;
+                if (live) a.x[(size_t)(j0 + p_ii) * a.ldb + b0 + m] = acc;
+            }
+        }
+        __syncthreads();
+        // (2) the kl rows below the panel; the panel's unknowns of this thread's member sit in registers, a row
+        //     whose 16 coefficients all lie inside the band takes the unrolled path (all loads ahead of the FMAs)
+        {
+            double xr[PR];
+#pragma unroll
+            for (int jj = 0; jj < PR; ++jj) xr[jj] = (jj < nr) ? X[(jj << msh) + m] : 0.0;
+            int sbase = s0 + nr;
+            if (sbase >= Wn) sbase -= Wn;
+            const int nrow = min(kl, n - (j0 + nr));
+            for (int ir = rl; ir < nrow; ir += RW) {
+                int sl = sbase + ir;
+                if (sl >= Wn) sl -= Wn;
+                double *w = W + ((size_t)sl << msh) + m;
+                const int dmax = ir + nr - 1;  // d = dmax - jj
+                if (nr == PR && dmax < kl) {
+                    const double *c0 = cq + dmax;
+                    double a0 = *w, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+                    for (int jj = 0; jj < PR; jj += 4) {
+                        a0 = fma(-c0[(size_t)jj * (a.klp - 1)], xr[jj], a0);
+                        a1 = fma(-c0[(size_t)(jj + 1) * (a.klp - 1)], xr[jj + 1], a1);
+                        a2 = fma(-c0[(size_t)(jj + 2) * (a.klp - 1)], xr[jj + 2], a2);
+                        a3 = fma(-c0[(size_t)(jj + 3) * (a.klp - 1)], xr[jj + 3], a3);
+                    }
+                    *w = (a0 + a1) + (a2 + a3);
+                } else {
+                    double acc = *w;
+                    for (int jj = max(0, dmax - kl + 1); jj < nr; ++jj)
+                        acc = fma(-cq[(size_t)jj * a.klp + dmax - jj], X[(jj << msh) + m], acc);
+                    *w = acc;
+                }
+            }
+        }
+    }
+    bs_wait<0>();
+    __threadfence_block();
+    __syncthreads();
+
+    // ---------------- backward: U x = z, out = scale * x [- y] ----------------
+    auto stage_bwd = [&](int q) {
+        if (q < nP) {
+            const int j1 = n - 1 - q * PR, jl = max(j1 - PR + 1, 0), nr = j1 - jl + 1;
+            const double *src = a.up + (size_t)jl * a.kup;
+            double *dst = C + (size_t)((nP + q) % NS) * PR * a.cw;
+            if (tid == 0) bulk(dst, src, (uint32_t)nr * a.kup * 8u, nP + q);
+            const double *dsrc = a.uinv + (size_t)q * PR * PR;
+            double *ddst = D + (size_t)(q % NS) * PR * PR;
+            if (tid < half) bs_cp16(ddst + 2 * tid, dsrc + 2 * tid);
+            if (a.subtract) {
+                double *yd = Y + ((size_t)(q % NS) * PR << msh);
+                for (int i = tid; i < (nr << msh); i += nt) {
+                    const int mm = i & (MB - 1);
+                    if (mm < nlive) bs_cp8(yd + i, a.y + (size_t)(jl + (i >> msh)) * a.ldb + b0 + mm);
+                }
+            }
+            load_rows(a.x, j1 - PR + 1 - ku, q == 0 ? n : j1 + 1 - ku);
+        }
+        bs_commit();
+    };
+    for (int q = 0; q < NS - 1; ++q) stage_bwd(q);
+    for (int q = 0; q < nP; ++q) {
+        bs_wait_dyn(NS - 2);
+        bs_mbar_wait(bar0 + 8 * ((nP + q) % NS), ((nP + q) / NS) & 1);
+        __syncthreads();
+        stage_bwd(q + NS - 1);
+        const int j1 = n - 1 - q * PR, jl = max(j1 - PR + 1, 0), nr = j1 - jl + 1;
+        const double *cq = C + (size_t)((nP + q) % NS) * PR * a.cw;
+        const double *dq = D + (size_t)(q % NS) * PR * PR;
+        const double *yq = Y + ((size_t)(q % NS) * PR << msh);
+        const int s0 = slot(jl);
+        // (1) panel unknowns x = Uinv w (as in the forward sweep), and the output rows of the panel
+        {
+            double acc = 0.0;
+            if (p_ii < nr) {
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const int jj = p_part + t * P;
+                    if (t < MB && jj < nr) {
+                        int sl = s0 + jj;
+                        if (sl >= Wn) sl -= Wn;
+                        acc = fma(dq[p_ii * PR + jj], W[((size_t)sl << msh) + m], acc);
+                    }
+                }
+            }
+            for (int off = MB; off < PR; off <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+            if (p_part == 0 && p_ii < nr) {
+                X[(p_ii << msh) + m] = acc;
+                if (live) {
+                    double o = a.scale * acc;
+                    if (a.subtract) o -= yq[(p_ii << msh) + m];
+                    a.x[(size_t)(jl + p_ii) * a.ldb + b0 + m] = o;
+                }
+            }
+        }
+        __syncthreads();
+        // (2) the ku rows above the panel: U(i, jl + jj) = up[jl + jj][jl + jj - i - 1], i = jl - 1 - ir
+        {
+            double xr[PR];
+#pragma unroll
+            for (int jj = 0; jj < PR; ++jj) xr[jj] = (jj < nr) ? X[(jj << msh) + m] : 0.0;
+            const int nrow = min(ku, jl);
+            for (int ir = rl; ir < nrow; ir += RW) {
+                int sl = s0 - 1 - ir;
+                if (sl < 0) sl += Wn;
+                double *w = W + ((size_t)sl << msh) + m;
+                if (nr == PR && ir + PR <= ku) {  // d = ir + jj < ku for every column of the panel
+                    const double *c0 = cq + ir;
+                    double a0 = *w, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+                    for (int jj = 0; jj < PR; jj += 4) {
+                        a0 = fma(-c0[(size_t)jj * (a.kup + 1)], xr[jj], a0);
+                        a1 = fma(-c0[(size_t)(jj + 1) * (a.kup + 1)], xr[jj + 1], a1);
+                        a2 = fma(-c0[(size_t)(jj + 2) * (a.kup + 1)], xr[jj + 2], a2);
+                        a3 = fma(-c0[(size_t)(jj + 3) * (a.kup + 1)], xr[jj + 3], a3);
+                    }
+                    *w = (a0 + a1) + (a2 + a3);
+                } else {
+                    double acc = *w;
+                    const int jhi = min(nr, ku - ir);
+                    for (int jj = 0; jj < jhi; ++jj)
+                        acc = fma(-cq[(size_t)jj * a.kup + ir + jj], X[(jj << msh) + m], acc);
+                    *w = acc;
+                }
+            }
+        }
+    }
+    bs_wait<0>();
+}
+
 // Whole-device factorisation of ONE wide diagonal block (the 2-D preconditioners with lateral processes:
 // n = nz*ny rows, kl = ku = 3*ny): the same unblocked right-looking elimination, but the rank-1 update of a
 // column step (up to kl x (kl+ku) entries) is spread over all CTAs of a cooperative launch, walking the
@@ -630,6 +991,34 @@ int nkb_banded_create(nkb_banded **out, int n, int kl, int ku, const double *h_a
             f->nb_k = K;
         }
     }
+    if (f->nblk == 1 && K >= 16) {
+        // one wide block: panel substitution if the factorisation did not interchange rows
+        std::vector<int> piv(n);
+        NKB_CUDA(cudaMemcpy(piv.data(), f->ipiv, n * sizeof(int), cudaMemcpyDeviceToHost));
+        bool plain = true;
+        for (int j = 0; j < n && plain; ++j) plain = (piv[j] == j);
+        const char *env = getenv("NKB_BANDED_PANEL");
+        if (plain && !(env && env[0] == '0')) {
+            f->klp = (kl + 1) & ~1;
+            f->kup = std::max(2, (ku + 1) & ~1);
+            if (f->klp < 2) f->klp = 2;
+            const size_t np = (size_t)(n + nkb::PR - 1) / nkb::PR;
+            if (cudaMalloc(&f->lp, (size_t)n * f->klp * sizeof(double)) != cudaSuccess ||
+                cudaMalloc(&f->up, (size_t)n * f->kup * sizeof(double)) != cudaSuccess ||
+                cudaMalloc(&f->linv, np * nkb::PR * nkb::PR * sizeof(double)) != cudaSuccess ||
+                cudaMalloc(&f->uinv, np * nkb::PR * nkb::PR * sizeof(double)) != cudaSuccess) {
+                nkb::set_error("nkb_banded_create: cudaMalloc failed");
+                nkb_banded_destroy(f);
+                return 1;
+            }
+            nkb::banded_panel_pack_kernel<<<n, 128>>>(f->ab, n, kl, ku, f->klp, f->kup, f->lp, f->up);
+            nkb::count_launch();
+            nkb::banded_panel_inverse_kernel<<<(unsigned)np, 2 * nkb::PR>>>(f->ab, f->lp, f->up, n, kl, ku, f->klp,
+                                                                          f->kup, f->linv, f->uinv);
+            nkb::count_launch();
+            NKB_CUDA(cudaDeviceSynchronize());
+        }
+    }
     *out = f;
     return 0;
 }
@@ -640,6 +1029,7 @@ void nkb_banded_destroy(nkb_banded *f) {
     if (!f) return;
     cudaFree(f->ab); cudaFree(f->ipiv); cudaFree(f->info);
     cudaFree(f->lt); cudaFree(f->ut); cudaFree(f->blk); cudaFree(f->nb);
+    cudaFree(f->lp); cudaFree(f->up); cudaFree(f->linv); cudaFree(f->uinv);
     delete f;
 }
 
@@ -657,6 +1047,34 @@ int nkb_banded_solve(nkb_banded *f, const double *d_y, double *d_x, int B, int l
                 case 3: return nkb::launch_thomas<3>(f, d_y, d_x, B, (size_t)ldb, scale, subtract_rhs, st);
                 default: return nkb::launch_thomas<4>(f, d_y, d_x, B, (size_t)ldb, scale, subtract_rhs, st);
             }
+        }
+    }
+    // panel kernel (one wide block, no row interchanges): PR rows per barrier pair
+    if (f->lp != nullptr) {
+        const size_t budget = 220 * 1024;
+        const int cw = std::max(f->klp, f->kup);
+        int MB = 1;
+        while (MB < B && MB < 8) MB <<= 1;
+        auto need = [&](int mb, int ns) {
+            const size_t wn = (((size_t)std::max(f->kl, f->ku) + 1) & ~(size_t)1) + (size_t)(ns + 1) * nkb::PR;
+            return (wn * mb + (size_t)nkb::PR * mb + (size_t)ns * nkb::PR * cw + (size_t)ns * nkb::PR * nkb::PR +
+                    (size_t)ns * nkb::PR * mb) * 8 + 64;
+        };
+        int NS = 3;
+        if (need(MB, NS) > budget) NS = 2;
+        while (MB > 1 && need(MB, NS) > budget) MB >>= 1;
+        if (need(MB, NS) <= budget) {
+            nkb::PanelArgs a;
+            a.lp = f->lp; a.up = f->up; a.linv = f->linv; a.uinv = f->uinv;
+            a.n = f->n; a.kl = f->kl; a.ku = f->ku; a.klp = f->klp; a.kup = f->kup;
+            a.y = d_y; a.x = d_x; a.B = B; a.ldb = (size_t)ldb; a.scale = scale; a.subtract = subtract_rhs;
+            a.MB = MB; a.NS = NS; a.cw = cw; a.Wn = ((std::max(f->kl, f->ku) + 1) & ~1) + (NS + 1) * nkb::PR;  // even: the ring behind it is 16-byte aligned
+            NKB_CUDA(cudaFuncSetAttribute(nkb::banded_solve_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)budget));
+            nkb::banded_solve_panel_kernel<<<(B + MB - 1) / MB, 256, need(MB, NS), (cudaStream_t)stream>>>(a);
+            nkb::count_launch();
+            NKB_CUDA(cudaGetLastError());
+            return 0;
         }
     }
     // window kernel: pick the stage depth and the member lanes so that the shared memory fits

@@ -238,6 +238,50 @@ def test_banded_window_solver(n, kl, ku, B):
     np.testing.assert_allclose(yd.cpu().numpy()[:, :B], want, rtol=0, atol=tol)
 
 
+@pytest.mark.parametrize("n,kl,ku,B", [(2000, 40, 40, 1), (1999, 17, 33, 5), (1003, 90, 21, 32), (48, 16, 16, 3),
+                                       (4500, 450, 450, 1), (700, 130, 130, 70)])
+def test_banded_panel_solver(n, kl, ku, B, monkeypatch):
+    """the panel (blocked) substitution kernel: one wide block factored without row interchanges (diagonally
+    dominant, like the 2-D preconditioners I - dt J): 16 rows per barrier pair with inverted diagonal blocks.
+    Against scipy and bit-for-bit-irrelevant but rounding-level against the row-by-row window kernel; sizes that
+    are not multiples of the panel, kl != ku, several member groups, scale/subtract epilogue, in place"""
+    from scipy import linalg
+    from nk_ooc_b200 import _lib, engine
+
+    rng = np.random.default_rng(n + kl + B)
+    ab = rng.normal(size=(kl + ku + 1, n))
+    ab[ku] = 1.5 * np.abs(ab).sum(axis=0) + 1.0  # strictly diagonally dominant by columns: no interchanges
+    y = rng.normal(size=(n, B))
+    want = linalg.solve_banded((kl, ku), ab, y)
+    lib = _lib.load()
+    f = engine.BandedFactor(ab, kl, ku)
+    assert f.n_blocks == 1
+    tol = 1e-12 * np.abs(want).max()
+    n0 = lib.nkb_launch_count()
+    got = f.solve(_dev(y), B).cpu().numpy()[:, :B]
+    assert lib.nkb_launch_count() - n0 == 1
+    np.testing.assert_allclose(got, want, rtol=0, atol=tol)
+    got = f.solve(_dev(y), B, scale=0.25, subtract_rhs=True).cpu().numpy()[:, :B]
+    np.testing.assert_allclose(got, 0.25 * want - y, rtol=0, atol=tol)
+    yd = _dev(y)
+    ldb = yd.shape[-1]
+    engine.check(f.lib.nkb_banded_solve(f.handle, yd.data_ptr(), yd.data_ptr(), B, ldb, 1.0, 0, None), "in place")
+    np.testing.assert_allclose(yd.cpu().numpy()[:, :B], want, rtol=0, atol=tol)
+    # the same factor through the window kernel (panel data not built)
+    monkeypatch.setenv("NKB_BANDED_PANEL", "0")
+    f2 = engine.BandedFactor(ab, kl, ku)
+    got2 = f2.solve(_dev(y), B).cpu().numpy()[:, :B]
+    np.testing.assert_allclose(got, 0.25 * got2 - y, rtol=0, atol=tol)
+    # a matrix that needs interchanges keeps the pivoting window kernel
+    monkeypatch.delenv("NKB_BANDED_PANEL")
+    ab3 = rng.normal(size=(kl + ku + 1, n))
+    ab3[ku] += 0.5 * np.sqrt(kl + ku)
+    f3 = engine.BandedFactor(ab3, kl, ku)
+    got3 = f3.solve(_dev(y), B).cpu().numpy()[:, :B]
+    want3 = linalg.solve_banded((kl, ku), ab3, y)
+    np.testing.assert_allclose(got3, want3, rtol=0, atol=1e-9 * np.abs(want3).max())
+
+
 @pytest.mark.parametrize("kl,ku", [(1, 1), (2, 1), (1, 3), (4, 4)])
 @pytest.mark.parametrize("n", [7, 125, 700])
 def test_banded_thomas_kernel_narrow_bands(n, kl, ku):
