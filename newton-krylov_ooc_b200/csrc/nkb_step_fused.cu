@@ -55,13 +55,19 @@ constexpr int FS_NPP = 4;     // coefficient pair planes per ring slot
 //   MPT = 1, KC = 8: 8 warps, lane = 2*column + (member & 1)   (two warps per scheduler: default)
 //   MPT = 2, KC = 4: 4 warps, lane = column + 16*pair
 // either way one chunk of one thread is 16 32-bit TMEM columns (one tcgen05 x16 access)
+#ifndef FS_NS1
+#define FS_NS1 5  // input ring slots of the 8-warp layout
+#endif
+#ifndef FS_NO1
+#define FS_NO1 2  // output staging slots
+#endif
 struct FsCfg {
     int kc, ncw, threads, ns, no, ubytes, ppbytes, slot, out, smem;
 };
 __host__ __device__ constexpr FsCfg fs_cfg(int mpt) {
     const int kc = (mpt == 1) ? 8 : 4;
     const int ncw = 8 / mpt;
-    const int ns = (mpt == 1) ? 5 : 8, no = (mpt == 1) ? 2 : 3;
+    const int ns = (mpt == 1) ? FS_NS1 : 8, no = (mpt == 1) ? FS_NO1 : 3;
     const int ubytes = kc * FS_UCOLS * FS_MEM * 8;  // 1024-byte multiple
     const int ppbytes = kc * FS_COLS * 16;
     const int slot = ubytes + FS_NPP * ppbytes;

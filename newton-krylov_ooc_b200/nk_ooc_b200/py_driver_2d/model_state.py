@@ -95,6 +95,7 @@ class ModelState(ModelStateBase):
 
     __array_priority__ = 100
     class_vars_set = False
+    _precond_streams = []
     time_range = (0.0, SEC_PER_YEAR)
     depth = None
     ypos = None
@@ -355,9 +356,25 @@ class ModelState(ModelStateBase):
         factors = cls._precond_factors(tms, precond_fname)
         out = torch.empty_like(tms.vals)
         ncell = len(cls.depth) * len(cls.ypos)
+        # the tracers of a module have their own matrices (different surface restoring): independent solves.  With
+        # few right-hand sides a wide-band solve occupies one SM per 8 members, so the T solves run concurrently
+        # on side streams instead of back to back
+        concurrent = tms.tracer_cnt > 1 and tms.members <= 64
+        cur = torch.cuda.current_stream()
+        if concurrent and len(cls._precond_streams) < tms.tracer_cnt:
+            cls._precond_streams += [torch.cuda.Stream() for _ in range(tms.tracer_cnt - len(cls._precond_streams))]
         for t in range(tms.tracer_cnt):
             y = tms.vals[t].reshape(ncell, -1)
-            out[t] = factors[t].solve(y, tms.members, 1.0, subtract_rhs=True).reshape(tms.vals[t].shape)
+            if concurrent:
+                side = cls._precond_streams[t]
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    out[t] = factors[t].solve(y, tms.members, 1.0, subtract_rhs=True).reshape(tms.vals[t].shape)
+            else:
+                out[t] = factors[t].solve(y, tms.members, 1.0, subtract_rhs=True).reshape(tms.vals[t].shape)
+        if concurrent:
+            for t in range(tms.tracer_cnt):
+                cur.wait_stream(cls._precond_streams[t])
         return out
 
     @classmethod

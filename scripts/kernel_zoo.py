@@ -98,6 +98,26 @@ for grid, module, nsteps, b in (("refined125x150", "forced", 12, B), ("default40
               alg_bytes=8.0 * n1 * (3 * k1 + 2))
         r8 = torch.rand((n1, 32), dtype=torch.float64, device="cuda")
         timed(f"banded_solve n={n1} kl=ku={k1} B=32", lambda: fac.solve(r8, 32), alg_bytes=8.0 * n1 * (3 * k1 + 2))
+        # ---- round 2: fused Gram-Schmidt / lin_comb over k = 8 basis vectors (single states: the Krylov case, and
+        # a 64-member batch), the panel substitution kernel on the refined grid's 2-D preconditioner shape ----
+        for bb in (1, 64):
+            xb = torch.rand(model.state_shape(bb), dtype=torch.float64, device="cuda")
+            basis = [torch.rand_like(xb) for _ in range(8)]
+            wv = torch.rand_like(xb)
+            co = torch.rand((8, 1, bb), dtype=torch.float64, device="cuda")
+            ldbb = xb.shape[-1]
+            timed(f"mgs k=8 B={bb} (w in registers, one cooperative launch)", lambda: rw.mgs(wv, basis, bb),
+                  alg_bytes=8.0 * N * ldbb * 10)
+            timed(f"lin_comb k=8 B={bb}", lambda: rw.lin_comb(co, basis, bb), alg_bytes=8.0 * N * ldbb * 9)
+            del xb, basis, wv
+        n2, k2 = 18750, 450
+        ab = np.random.default_rng(1).normal(size=(2 * k2 + 1, n2)) * 0.01
+        ab[k2] = 1.0 + np.abs(ab).sum(axis=0)
+        fac = engine.BandedFactor(ab, k2, k2)
+        for bb in (1, 32):
+            rb = torch.rand((n2, engine.padded_members(bb)), dtype=torch.float64, device="cuda")
+            timed(f"banded_solve (panel) n={n2} kl=ku={k2} B={bb} (factor columns {16e-6 * n2 * k2:.0f} MB)",
+                  lambda: fac.solve(rb, bb), alg_bytes=16.0 * n2 * k2)
         del fac, rhs, maj, y
     del model, x, f
     torch.cuda.empty_cache()
