@@ -377,10 +377,14 @@ def _roofline(args, model, B, ms_per_step, launches, steps):
         "traffic_unit": "dram bytes per unit of work (ncu, profiles/traffic.json)",
         "limiter": ("fixed-latency FP64 dependency chains of only six consumer warps (tensor memory holds 3 x 125 "
                     "levels for 64 (column, member) pairs per SM): stall_wait 30 % of the warp samples, issue slots "
-                    "39 %, FP64 pipe 31 %, shared-memory pipe 78 %, DRAM 35 % (profiles/r02_ncu_step_fused_p3.txt)" if p3 else
-                    "shared-memory LSU data pipe at 83 % of peak, every LDS at its ideal wavefront count "
-                    "(profiles/r02_ncu_step_fused_lds_table.txt), DRAM at 46 %: the fused kernel moves 0.57 of the "
-                    "algorithmic bytes") if fused else "L2 round trip of the elimination intermediates",
+                    "38 %, FP64 pipe 32 %, shared-memory pipe 72 %, DRAM 36 %; the four schedulers hold the six warps "
+                    "as 2 + 2 + 1 + 1 (profiles/r02_ncu_full_step_fused_p3_refined125x150_B4096.txt, "
+                    "profiles/r02_p3_variants.md)" if p3 else
+                    "the board's 1000 W power cap (throughput follows the SM clock it leaves: ring-depth A/B in "
+                    "profiles/r02_ncu_full_step_fused_persistent_refined125x150_forced_B4096.txt), then the "
+                    "shared-memory LSU data pipe at 84 % of peak with every LDS at its ideal wavefront count; DRAM at "
+                    "46 %: the fused kernel moves 0.57 of the algorithmic bytes") if fused
+                    else "L2 round trip of the elimination intermediates",
     }
 
 

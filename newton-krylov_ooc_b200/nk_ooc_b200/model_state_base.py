@@ -23,6 +23,7 @@ import torch
 from scipy.io import netcdf_file
 
 from . import engine
+from .solver_state import as_hist_stats
 
 
 def _expand_defs(defs, names):
@@ -412,7 +413,7 @@ class ModelStateBase:
         if solver_state is not None and solver_state.step_logged(step, per_iteration=False):
             return
         names, weights = self._stats_names_and_weights()
-        stats_file.def_hist_stats(hist_fname, names, weights)
+        as_hist_stats(stats_file).def_hist_stats(hist_fname, names, weights)
         if solver_state is not None:
             solver_state.log_step(step, per_iteration=False)
 
@@ -421,7 +422,7 @@ class ModelStateBase:
         step = "ModelStateBase.put_stats_vars_iteration_invariant"
         if solver_state is not None and solver_state.step_logged(step, per_iteration=False):
             return
-        stats_file.put_hist_coordinates(hist_fname)
+        as_hist_stats(stats_file).put_hist_coordinates(hist_fname)
         if solver_state is not None:
             solver_state.log_step(step, per_iteration=False)
 
@@ -433,7 +434,7 @@ class ModelStateBase:
             return
         names, weights = self._stats_names_and_weights()
         iteration = solver_state.get_iteration() if solver_state is not None else 0
-        stats_file.put_hist_stats(iteration, hist_fname, names, weights)
+        as_hist_stats(stats_file).put_hist_stats(iteration, hist_fname, names, weights)
         if solver_state is not None:
             solver_state.log_step(step)
 

@@ -345,3 +345,78 @@ class StatsFile:
                     self._vars[vname] = {"dims": tuple(fvar.dimensions), "dtype": "f8", "attrs": attrs,
                                          "data": np.array(fvar.data, dtype=np.float64)}
         self._grow(self._n_iter)
+
+
+class RefStatsFileAdapter:
+    """Lets the model-state stats hooks (ModelStateBase.def_stats_vars / put_stats_vars_iteration_invariant /
+    put_stats_vars) write into the REFERENCE's own StatsFile (nk_ooc/stats_file.py:13-139: def_dimensions, def_vars,
+    put_vars_iteration_invariant, put_vars) when this package's ModelState runs under the reference's NewtonSolver
+    (newton_solver.py:52-58,330 hands its own stats file to those hooks).  Same variables as StatsFile's methods
+    of the same names: per tracer-like hist variable its time mean with down-weighted end points
+    (tracer_module_state.py:325-341) and the weighted mean along the axes in `mean_weights`, plus the
+    coordinate variables of the axes."""
+
+    def __init__(self, ref_stats_file):
+        self._ref = ref_stats_file
+
+    @staticmethod
+    def _attrs(var, drop=()):
+        return {k: (v.decode() if isinstance(v, bytes) else v) for k, v in var._attributes.items() if k not in drop}
+
+    def _targets(self, fptr, names, mean_weights):
+        for name in names:
+            if name not in fptr.variables:
+                continue
+            var = fptr.variables[name]
+            dims = tuple(var.dimensions[1:])
+            yield name, name, dims, None
+            for axis in (mean_weights or {}):
+                if axis in dims:
+                    pos = dims.index(axis)
+                    yield name, f"{name}_mean_{axis}", dims[:pos] + dims[pos + 1:], (axis, pos)
+
+    def def_hist_stats(self, hist_fname, names, mean_weights=None):
+        dimensions, vars_metadata = {}, {}
+        with netcdf_file(hist_fname, "r", mmap=False) as fptr:
+            for name, vname, dims, _ in self._targets(fptr, names, mean_weights):
+                var = fptr.variables[name]
+                for dim, length in zip(var.dimensions[1:], var.shape[1:]):
+                    if dim not in dimensions:
+                        dimensions[dim] = int(length)
+                        if dim in fptr.variables:
+                            vars_metadata[dim] = {"datatype": "f8", "dimensions": (dim,),
+                                                  "attrs": self._attrs(fptr.variables[dim])}
+                vars_metadata[vname] = {"datatype": "f8", "dimensions": ("iteration",) + dims,
+                                        "attrs": self._attrs(var, drop=("cell_methods", "_FillValue"))}
+        self._ref.def_dimensions(dimensions)
+        self._ref.def_vars(vars_metadata)
+
+    def put_hist_coordinates(self, hist_fname):
+        with netcdf_file(hist_fname, "r", mmap=False) as fptr:
+            vals = {dim: np.array(fptr.variables[dim].data, dtype=np.float64) for dim in fptr.dimensions
+                    if dim in fptr.variables and dim != "time"}
+        self._ref.put_vars_iteration_invariant(vals)
+
+    def put_hist_stats(self, iteration, hist_fname, names, mean_weights=None):
+        vals = {}
+        with netcdf_file(hist_fname, "r", mmap=False) as fptr:
+            timelen = fptr.dimensions["time"] or fptr.variables["time"].shape[0]
+            weights = np.full(timelen, 1.0 / (timelen - 1))
+            weights[0] *= 0.5
+            weights[-1] *= 0.5
+            means = {}
+            for name, vname, _, axis in self._targets(fptr, names, mean_weights):
+                if name not in means:
+                    means[name] = np.einsum("i,i...", weights, np.array(fptr.variables[name].data, dtype=np.float64))
+                if axis is None:
+                    vals[vname] = means[name]
+                else:
+                    w = np.asarray(mean_weights[axis[0]], dtype=np.float64)
+                    vals[vname] = np.tensordot(means[name], w / w.sum(), axes=([axis[1]], [0]))
+        self._ref.put_vars(iteration, vals)
+
+
+def as_hist_stats(stats_file):
+    """the object the model-state stats hooks write through: a StatsFile of this package as it is, the
+    reference's StatsFile behind RefStatsFileAdapter"""
+    return stats_file if hasattr(stats_file, "def_hist_stats") else RefStatsFileAdapter(stats_file)

@@ -139,3 +139,64 @@ def test_hist_statistics_in_the_stats_file(tmp_path):
         np.testing.assert_allclose(f.variables["iage"].data[1], want, rtol=1e-15)
         np.testing.assert_allclose(f.variables["iage"].data[2], want, rtol=1e-15)
         assert f.variables["iteration"].shape[0] == 3
+
+
+class _RefStatsFile:
+    """records the calls of the reference's StatsFile API (nk_ooc/stats_file.py:70-125)"""
+
+    def __init__(self):
+        self.dimensions, self.vars_metadata, self.invariant, self.per_iteration = {}, {}, {}, {}
+
+    def def_dimensions(self, dimensions):
+        self.dimensions.update(dimensions)
+
+    def def_vars(self, vars_metadata, caller=None):
+        self.vars_metadata.update(vars_metadata)
+
+    def put_vars_iteration_invariant(self, name_vals_dict):
+        self.invariant.update(name_vals_dict)
+
+    def put_vars(self, iteration, name_vals_dict):
+        self.per_iteration[iteration] = dict(name_vals_dict)
+
+
+def test_stats_hooks_write_through_the_references_stats_file_api(tmp_path):
+    """ModelStateBase.def_stats_vars / put_stats_vars* hand whatever stats file the solver owns to
+    solver_state.as_hist_stats: under the reference's NewtonSolver that is the reference's StatsFile
+    (newton_solver.py:52-58,330), served by RefStatsFileAdapter with the same variables and values as this
+    package's own StatsFile"""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from baseline_files import materialise
+
+    hist = os.path.join(materialise(str(tmp_path / "baselines")), "ci_py_driver_2d_iage", "hist_0000.nc")
+    with netcdf_file(hist, "r", mmap=False) as f:
+        ypos_delta = np.array(f.variables["ypos_delta"].data)
+        iage = np.array(f.variables["iage"].data)
+    names, weights = ["iage", "iage_slow_rest"], {"ypos": ypos_delta}
+    ref = _RefStatsFile()
+    ad = ss.as_hist_stats(ref)
+    assert isinstance(ad, ss.RefStatsFileAdapter)
+    ad.def_hist_stats(hist, names, weights)
+    ad.put_hist_coordinates(hist)
+    ad.put_hist_stats(2, hist, names, weights)
+    assert ref.dimensions == {"depth": 30, "ypos": 30}
+    assert set(ref.vars_metadata) == {"depth", "ypos", "iage", "iage_mean_ypos", "iage_slow_rest",
+                                      "iage_slow_rest_mean_ypos"}
+    meta = ref.vars_metadata["iage_mean_ypos"]
+    assert meta["dimensions"] == ("iteration", "depth") and meta["attrs"] == {"long_name": "ideal age", "units": "years"}
+    assert set(ref.invariant) >= {"depth", "ypos"} and ref.invariant["depth"].shape == (30,)
+    w = np.full(61, 1.0 / 60.0)
+    w[[0, -1]] *= 0.5
+    want = np.einsum("i,i...", w, iage)
+    np.testing.assert_allclose(ref.per_iteration[2]["iage"], want, rtol=1e-14)
+    np.testing.assert_allclose(ref.per_iteration[2]["iage_mean_ypos"], want @ (ypos_delta / ypos_delta.sum()), rtol=1e-13)
+    # the same numbers as this package's own StatsFile
+    own = ss.StatsFile("Newton", str(tmp_path), 1, [("iage", "years")], ss.NEWTON_VARS)
+    assert ss.as_hist_stats(own) is own
+    own.put_hist_stats(0, hist, names, weights)
+    with netcdf_file(str(tmp_path / "Newton_stats.nc"), "r", mmap=False) as f:
+        np.testing.assert_allclose(np.array(f.variables["iage_mean_ypos"].data)[0], ref.per_iteration[2]["iage_mean_ypos"],
+                                   rtol=1e-14)
