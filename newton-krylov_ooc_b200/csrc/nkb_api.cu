@@ -176,9 +176,10 @@ int nkb_model_set_schedule(nkb_model *m, int n_steps, const double *h_t_start, c
         t_exp[2 * n] = t;
         t_exp[2 * n + 1] = t + nkb::kGamma * h;
     }
-    double *d_t = nullptr, *d_hg = nullptr;
-    NKB_CUDA(cudaMalloc(&d_t, n_stages * sizeof(double)));
-    NKB_CUDA(cudaMalloc(&d_hg, n_stages * sizeof(double)));
+    nkb::DevBuf<double> t_buf, hg_buf;  // released on every exit path
+    NKB_CUDA(t_buf.alloc(n_stages));
+    NKB_CUDA(hg_buf.alloc(n_stages));
+    double *d_t = t_buf.p, *d_hg = hg_buf.p;
     NKB_CUDA(cudaMemcpy(d_t, t_imp.data(), n_stages * sizeof(double), cudaMemcpyHostToDevice));
     NKB_CUDA(cudaMemcpy(d_hg, hg.data(), n_stages * sizeof(double), cudaMemcpyHostToDevice));
     NKB_CUDA(cudaMalloc(&m->tri, (size_t)n_stages * v.n_classes * 4 * plane * sizeof(double)));
@@ -204,7 +205,6 @@ int nkb_model_set_schedule(nkb_model *m, int n_steps, const double *h_t_start, c
     NKB_CUDA(cudaMalloc(&m->d_h, n_steps * sizeof(double)));
     NKB_CUDA(cudaMemcpy(m->d_h, h_h, n_steps * sizeof(double), cudaMemcpyHostToDevice));
     NKB_CUDA(cudaDeviceSynchronize());
-    cudaFree(d_t); cudaFree(d_hg);
     return 0;
 }
 
@@ -265,8 +265,9 @@ int nkb_model_tend(nkb_model *m, double time, const double *d_x, double *d_tend,
     NKB_REQUIRE(m && d_x && d_tend && B >= 1 && ldb >= B, "nkb_model_tend: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     const ModelDev &v = m->dev;
-    double *d_t = nullptr;
-    NKB_CUDA(cudaMalloc(&d_t, 2 * sizeof(double)));
+    nkb::DevBuf<double> t_buf;  // released on every exit path
+    NKB_CUDA(t_buf.alloc(2));
+    double *d_t = t_buf.p;
     const double th[2] = {time, time};
     NKB_CUDA(cudaMemcpyAsync(d_t, th, 2 * sizeof(double), cudaMemcpyHostToDevice, st));
     if (nkb::launch_stage_tables(v, 1, d_t, d_t + 1, 0, m->tri_raw, m->aff_raw, st)) return 1;
@@ -276,7 +277,6 @@ int nkb_model_tend(nkb_model *m, double time, const double *d_x, double *d_tend,
     a.u[0] = d_x; a.out = d_tend; a.tri = m->tri_raw; a.aff = m->aff_raw; a.src2 = m->src_raw;
     const int rc = nkb::launch_tend(v.kind, a, st);
     NKB_CUDA(cudaStreamSynchronize(st));
-    cudaFree(d_t);
     return rc;
 }
 

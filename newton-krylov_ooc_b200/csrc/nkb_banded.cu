@@ -880,6 +880,10 @@ extern "C" {
 int nkb_banded_create(nkb_banded **out, int n, int kl, int ku, const double *h_ab) {
     NKB_REQUIRE(out && h_ab && n >= 1 && kl >= 0 && ku >= 0, "nkb_banded_create: bad argument");
     nkb_banded *f = new nkb_banded();
+    struct Guard {  // the handle is released on every early return below
+        nkb_banded *f;
+        ~Guard() { if (f) nkb_banded_destroy(f); }
+    } guard{f};
     f->n = n; f->kl = kl; f->ku = ku;
     const int rows = 2 * kl + ku + 1;
     std::vector<double> host((size_t)rows * n, 0.0);
@@ -913,7 +917,6 @@ int nkb_banded_create(nkb_banded **out, int n, int kl, int ku, const double *h_a
         cudaMalloc(&f->ut, (size_t)n * (kv + 1) * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&f->blk, blk.size() * sizeof(int)) != cudaSuccess) {
         nkb::set_error("nkb_banded_create: cudaMalloc failed (is a CUDA device present?)");
-        nkb_banded_destroy(f);
         return 1;
     }
     NKB_CUDA(cudaMemcpy(f->ab, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice));
@@ -958,7 +961,6 @@ int nkb_banded_create(nkb_banded **out, int n, int kl, int ku, const double *h_a
     NKB_CUDA(cudaMemcpy(&info, f->info, sizeof(int), cudaMemcpyDeviceToHost));
     if (info != 0) {
         nkb::set_error("nkb_banded_create: matrix is singular at column " + std::to_string(info));
-        nkb_banded_destroy(f);
         return 3;
     }
     nkb::banded_transpose_kernel<<<n, 128>>>(f->ab, n, kl, ku, f->lt, f->ut);
@@ -984,8 +986,7 @@ int nkb_banded_create(nkb_banded **out, int n, int kl, int ku, const double *h_a
             }
             if (cudaMalloc(&f->nb, nbh.size() * sizeof(double)) != cudaSuccess) {
                 nkb::set_error("nkb_banded_create: cudaMalloc failed");
-                nkb_banded_destroy(f);
-                return 1;
+                        return 1;
             }
             NKB_CUDA(cudaMemcpy(f->nb, nbh.data(), nbh.size() * sizeof(double), cudaMemcpyHostToDevice));
             f->nb_k = K;
@@ -1008,8 +1009,7 @@ int nkb_banded_create(nkb_banded **out, int n, int kl, int ku, const double *h_a
                 cudaMalloc(&f->linv, np * nkb::PR * nkb::PR * sizeof(double)) != cudaSuccess ||
                 cudaMalloc(&f->uinv, np * nkb::PR * nkb::PR * sizeof(double)) != cudaSuccess) {
                 nkb::set_error("nkb_banded_create: cudaMalloc failed");
-                nkb_banded_destroy(f);
-                return 1;
+                        return 1;
             }
             nkb::banded_panel_pack_kernel<<<n, 128>>>(f->ab, n, kl, ku, f->klp, f->kup, f->lp, f->up);
             nkb::count_launch();
@@ -1019,6 +1019,7 @@ int nkb_banded_create(nkb_banded **out, int n, int kl, int ku, const double *h_a
             NKB_CUDA(cudaDeviceSynchronize());
         }
     }
+    guard.f = nullptr;
     *out = f;
     return 0;
 }
@@ -1098,11 +1099,10 @@ int nkb_banded_solve(nkb_banded *f, const double *d_y, double *d_x, int B, int l
             a.lt = f->lt; a.ut = f->ut; a.ipiv = f->ipiv; a.blk = f->blk; a.kl = f->kl; a.ku = f->ku;
             a.y = d_y; a.x = d_x; a.B = B; a.ldb = (size_t)ldb; a.scale = scale; a.subtract = subtract_rhs;
             a.MB = MB; a.RW = RW; a.CH = CH; a.Wn = nkb::BS_NSTG * CH + kv + 1;
-            static bool attr_set = false;
-            if (!attr_set) {
+            static unsigned long long attr_mask = 0;
+            if (nkb::first_use_on_device(attr_mask)) {
                 NKB_CUDA(cudaFuncSetAttribute(nkb::banded_solve_win_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               (int)budget));
-                attr_set = true;
             }
             dim3 grid((B + MB - 1) / MB, f->nblk);
             nkb::banded_solve_win_kernel<<<grid, RW * MB, need(MB), (cudaStream_t)stream>>>(a);

@@ -144,6 +144,25 @@ int launch_p3_gather_member(const ModelDev &v, const double *tm, double *dst, in
 bool tma_path_usable(const StageArgs &a);
 int launch_stage_tma(int kind, int nin, const StageArgs &a, cudaStream_t st);
 
+
+// cudaFuncSetAttribute is per device (and context): a process that switches devices must repeat it there.
+// `mask` is a function-local static, one bit per device ordinal.
+inline bool first_use_on_device(unsigned long long &mask) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (mask & bit) return false;
+    mask |= bit;
+    return true;
+}
+
+// device temporary released on every exit path (the NKB_CUDA / NKB_REQUIRE macros return early)
+template <class T>
+struct DevBuf {
+    T *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t count) { return cudaMalloc(&p, count * sizeof(T)); }
+};
 }  // namespace nkb
 
 // the opaque handle of the C ABI

@@ -236,10 +236,9 @@ static StageGeom pick_geometry(int nz, int ny, int T, int TG, int B, int ldb) {
 template <int KIND, int TG, int NIN, int MPT, int KC>
 static int launch_stage_k(const StageArgs &a, const StageGeom &g, cudaStream_t st) {
     auto kern = stage_kernel<KIND, TG, NIN, MPT, KC>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_mask = 0;
+    if (nkb::first_use_on_device(attr_mask)) {
         NKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        attr_set = true;
     }
     kern<<<g.grid, g.block, g.smem, st>>>(a);
     count_launch();

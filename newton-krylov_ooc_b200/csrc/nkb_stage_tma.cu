@@ -320,10 +320,9 @@ static int launch_tma_t(const StageArgs &a, cudaStream_t st) {
     const size_t pad = (size_t)env_int_tma("NKB_TMA_MIN_SMEM_KB", 0) * 1024;
     if (smem < pad) smem = pad;
     auto kern = stage_tma_kernel<KIND, TG, NIN, KC, NS>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_mask = 0;
+    if (nkb::first_use_on_device(attr_mask)) {
         NKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
     }
     if (smem > 227 * 1024) {
         set_error("stage_tma_kernel: tile does not fit in shared memory");

@@ -1477,10 +1477,9 @@ template <int KIND, int MPT>
 static int fs_launch_m(const StepArgs &a, const StepMaps &maps, int grid, bool cooperative, cudaStream_t st) {
     auto kern = step_fused_kernel<KIND, MPT>;
     constexpr FsCfg C = fs_cfg(MPT);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_mask = 0;
+    if (nkb::first_use_on_device(attr_mask)) {
         NKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C.smem));
-        attr_set = true;
     }
     cudaLaunchConfig_t cfg;
     std::memset(&cfg, 0, sizeof(cfg));
@@ -1547,10 +1546,9 @@ int launch_steps_fused(const ModelDev &v, int B, int n_steps, int step0, int ste
     a.cross_step_fuse = (a.ntiles > 2 * a.tgroup * grid + a.nmb) ? 1 : 0;
     const bool coop = (step1 - step0 > 1);
     if (p3) {
-        static bool attr_set = false;
-        if (!attr_set) {
+        static unsigned long long attr_mask = 0;
+        if (nkb::first_use_on_device(attr_mask)) {
             NKB_CUDA(cudaFuncSetAttribute(step_fused_p3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P3_SMEM));
-            attr_set = true;
         }
         cudaLaunchConfig_t cfg;
         std::memset(&cfg, 0, sizeof(cfg));
