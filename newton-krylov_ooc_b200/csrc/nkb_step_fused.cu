@@ -1041,6 +1041,8 @@ __global__ void __launch_bounds__(P3_THREADS, 1) step_fused_p3_kernel(const Step
     } else {
         // ===== consumers: warp = (tracer, member pair) =====
         constexpr int PP = KC * FS_COLS;  // pairs per plane
+        // (which tracer / member pair shares a scheduler with which makes no difference: three role maps measured
+        // within 1 %, profiles/r02_p3_variants.md)
         const int tr = warp >> 1, pr = warp & 1;
         const int cls = p.class_of[tr];
         const int col = lane >> 1;
