@@ -63,6 +63,44 @@ def parse_args():
     return ap.parse_args()
 
 
+def default_steps_per_year(args):
+    """time steps per model year of the workload: --nsteps, else the product's graded schedule
+    (nk_ooc_b200/py_driver_2d/model_state.py:default_schedule — 2640, 5280 for iage on grids finer than 60 levels)"""
+    if args.nsteps:
+        return int(args.nsteps)
+    nz = GRIDS[args.grid][0]
+    return 5280 if (args.module == "iage" and nz > 60) else 2640
+
+
+def workload_config(args, world, S=None):
+    """the `config` object of the JSON line — ONE function for both arms, so that the reference arm reports exactly
+    the workload of ours (rank 0's shard under strong scaling)"""
+    nz, ny, _ = GRIDS[args.grid]
+    T = TRACERS[args.module]
+    N = T * nz * ny
+    strong = args.scaling == "strong" and world > 1
+    if strong:
+        B_total = args.members
+        width = ((B_total + world - 1) // world + 31) // 32 * 32  # distributed.member_block_width
+        B = min(B_total, width)
+        per_gpu = f"{B} of {B_total} members per GPU (strong scaling)"
+    else:
+        B_total, B = world * args.members, args.members
+        per_gpu = f"{B} perturbed members per GPU"
+    return {
+        "workload": f"py_driver_2d {args.module}{'_o2_like' if args.module == 'forced' else ''} on {args.grid} "
+                    f"({nz}x{ny}, T={T}), {per_gpu}, one model year per step",
+        "members_per_gpu": B, "members_total": B_total, "grid": args.grid, "module": args.module, "N": N,
+        "time_steps_per_year": int(S if S is not None else default_steps_per_year(args)),
+        "implicit_stages_per_step": 2, "scheme": "IMEX ARS(2,2,2)",
+        "cache": "state batch (%.0f MB) larger than L2; no flush needed" % (8e-6 * N * B),
+        "parallelism": (f"{B_total} members sharded over {world} GPU(s) in 32-aligned blocks; per step one NCCL "
+                        f"all-gather of the result columns and one all-reduce of the residual norms, both inside "
+                        f"the timed region" if strong else
+                        f"members sharded over {world} GPU(s), no data-path collective"),
+    }
+
+
 def axes(grid):
     from nk_ooc_b200.spatial_axis import SpatialAxis, edges_from_defn
 
@@ -538,17 +576,7 @@ def run_ours(args):
         "vs_baseline": None,
         "dtype": "f64",
         "data": "synthetic",
-        "config": {
-            "workload": f"py_driver_2d {args.module}{'_o2_like' if args.module == 'forced' else ''} on {args.grid} "
-                        f"({nz}x{ny}, T={T}), {per_gpu}, one model year per step",
-            "members_per_gpu": B, "members_total": B_total, "grid": args.grid, "module": args.module, "N": N,
-            "time_steps_per_year": S, "implicit_stages_per_step": s, "scheme": "IMEX ARS(2,2,2)",
-            "cache": "state batch (%.0f MB) larger than L2; no flush needed" % (8e-6 * N * B),
-            "parallelism": (f"{B_total} members sharded over {world} GPU(s) in 32-aligned blocks; per step one NCCL "
-                            f"all-gather of the result columns and one all-reduce of the residual norms, both inside "
-                            f"the timed region" if strong and world > 1 else
-                            f"members sharded over {world} GPU(s), no data-path collective"),
-        },
+        "config": dict(workload_config(args, world, S), members_per_gpu=B, members_total=B_total),
         "roofline": _roofline(args, model, B, kernel_ms, launches - (2 * args.steps if coll else 0), args.steps),
         "e2e": {
             "value": B_total / e2e_s, "unit": "model-year evals/s",
@@ -652,11 +680,7 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
         "scaling": "strong" if (args.scaling == "strong" and world > 1) else "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {
-            "workload": f"py_driver_2d {args.module}{'_o2_like' if args.module == 'forced' else ''} on {args.grid} "
-                        f"({nz}x{ny}, T={T}), {args.members} perturbed members per GPU, one model year per step",
-            "members_per_gpu": args.members, "grid": args.grid, "module": args.module, "N": T * nz * ny,
-        },
+        "config": workload_config(args, world),
         "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": "model-year evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
