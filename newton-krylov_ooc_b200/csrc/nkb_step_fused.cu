@@ -1390,7 +1390,8 @@ static FsEncodeTiledFn fs_encode_fn() {
 }
 
 static int fs_encode(CUtensorMap *map, const void *ptr, int rank, const cuuint64_t *dims, const cuuint64_t *strides,
-                     const cuuint32_t *box, CUtensorMapSwizzle swz) {
+                     const cuuint32_t *box, CUtensorMapSwizzle swz,
+                     CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B) {
     FsEncodeTiledFn fn = fs_encode_fn();
     if (!fn) {
         set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -1398,8 +1399,7 @@ static int fs_encode(CUtensorMap *map, const void *ptr, int rank, const cuuint64
     }
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     const CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, rank, const_cast<void *>(ptr), dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
-                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, swz, promo,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)rc));
@@ -1447,8 +1447,18 @@ int fused_encode_state_maps(const ModelDev &v, int B, int ldb, const double *buf
         const cuuint64_t strides[3] = {run * 8, npair * run * 8, (cuuint64_t)v.nz * npair * run * 8};
         const cuuint32_t box_in[4] = {FS_UCOLS * 2, 2, P3_KC, 1};
         const cuuint32_t box_out[4] = {(cuuint32_t)jt * 2, 2, P3_KC, 1};
-        if (in && fs_encode(in, buf, 4, dims, strides, box_in, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
-        if (out && fs_encode(out, buf, 4, dims, strides, box_out, CU_TENSOR_MAP_SWIZZLE_NONE)) return 1;
+        // the 288-byte runs of a tile are not aligned to anything: with the 256-byte L2 promotion every run pulls
+        // two or three 256-byte chunks (ncu: 2.1x the state read per step).  NKB_P3_L2PROMO = 0 none, 1 64 B (default:
+        // +2.5 % against 256 B, measured), 2 128 B, 3 256 B
+        CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+        switch (fs_env_int("NKB_P3_L2PROMO", 1)) {
+            case 0: promo = CU_TENSOR_MAP_L2_PROMOTION_NONE; break;
+            case 1: promo = CU_TENSOR_MAP_L2_PROMOTION_L2_64B; break;
+            case 2: promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B; break;
+            default: break;
+        }
+        if (in && fs_encode(in, buf, 4, dims, strides, box_in, CU_TENSOR_MAP_SWIZZLE_NONE, promo)) return 1;
+        if (out && fs_encode(out, buf, 4, dims, strides, box_out, CU_TENSOR_MAP_SWIZZLE_NONE, promo)) return 1;
         return 0;
     }
     const cuuint32_t kc = (cuuint32_t)fs_cfg(fs_mpt()).kc;
@@ -1457,8 +1467,15 @@ int fused_encode_state_maps(const ModelDev &v, int B, int ldb, const double *buf
     const cuuint64_t strides[3] = {(cuuint64_t)ldb * 8, (cuuint64_t)v.ny * ldb * 8, (cuuint64_t)v.nz * v.ny * ldb * 8};
     const cuuint32_t box_in[4] = {FS_MEM, FS_UCOLS, kc, 1};
     const cuuint32_t box_out[4] = {FS_MEM, (cuuint32_t)jt, kc, 1};
-    if (in && fs_encode(in, buf, 4, dims, strides, box_in, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
-    if (out && fs_encode(out, buf, 4, dims, strides, box_out, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+    CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+    switch (fs_env_int("NKB_FUSED_L2PROMO", 3)) {
+        case 0: promo = CU_TENSOR_MAP_L2_PROMOTION_NONE; break;
+        case 1: promo = CU_TENSOR_MAP_L2_PROMOTION_L2_64B; break;
+        case 2: promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B; break;
+        default: break;
+    }
+    if (in && fs_encode(in, buf, 4, dims, strides, box_in, CU_TENSOR_MAP_SWIZZLE_128B, promo)) return 1;
+    if (out && fs_encode(out, buf, 4, dims, strides, box_out, CU_TENSOR_MAP_SWIZZLE_128B, promo)) return 1;
     return 0;
 }
 
