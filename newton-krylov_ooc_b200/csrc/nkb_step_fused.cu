@@ -808,7 +808,22 @@ __global__ void __launch_bounds__(fs_cfg(MPT).threads, 1) step_fused_kernel(cons
 // Sweep A reads the other two tracers' centre values from their state boxes of the same ring slot;
 // in sweep B the three warps that share a member pair exchange the stage-1 solution of a chunk through
 // a double-buffered shared-memory block and a named barrier before the stage-2 right-hand side.
-constexpr int P3_MEM = 4, P3_T = 3, P3_KC = 8, P3_NCW = 6, P3_NS = 5, P3_NO = 3, P3_NCLS = 2;
+#ifndef P3_NS_DEF
+#define P3_NS_DEF 5
+#endif
+#ifndef P3_NO_DEF
+#define P3_NO_DEF 2  // output staging slots (2 measured +1.6 % against 3, 1 is -19 %)
+#endif
+#ifndef P3_HINT_A
+#define P3_HINT_A kEvictNormal
+#endif
+#ifndef P3_HINT_B
+#define P3_HINT_B kEvictFirst
+#endif
+#ifndef P3_CWAIT
+#define P3_CWAIT 20  // suspend-time hint (ns) of the consumer warps' barrier waits
+#endif
+constexpr int P3_MEM = 4, P3_T = 3, P3_KC = 8, P3_NCW = 6, P3_NS = P3_NS_DEF, P3_NO = P3_NO_DEF, P3_NCLS = 2;
 constexpr int P3_UBOX = P3_KC * FS_UCOLS * P3_MEM * 8;            // 4608
 constexpr int P3_PP = P3_KC * FS_COLS * 16;                       // bytes of one pair plane (2048)
 constexpr int P3_SLOT = P3_T * P3_UBOX + P3_NCLS * 4 * P3_PP;     // 30208
@@ -955,7 +970,7 @@ __global__ void __launch_bounds__(P3_THREADS, 1) step_fused_p3_kernel(const Step
                         fs_mbar_expect_tx(fb, P3_T * P3_UBOX + P3_NCLS * (3 + (sweep == 3 ? 1 : 0)) * P3_PP);
 #pragma unroll
                         for (int t = 0; t < P3_T; ++t)
-                            fs_tma_load_4d(sb + t * P3_UBOX, ta.uin, fb, 2 * (ta.j0 - 2), 2 * ta.mb, k0, t, kEvictNormal);
+                            fs_tma_load_4d(sb + t * P3_UBOX, ta.uin, fb, 2 * (ta.j0 - 2), 2 * ta.mb, k0, t, P3_HINT_A);
 #pragma unroll
                         for (int cl = 0; cl < P3_NCLS; ++cl) {
 #pragma unroll
@@ -970,7 +985,7 @@ __global__ void __launch_bounds__(P3_THREADS, 1) step_fused_p3_kernel(const Step
                         fs_mbar_expect_tx(fb, P3_T * P3_UBOX + P3_NCLS * 4 * P3_PP);
 #pragma unroll
                         for (int t = 0; t < P3_T; ++t)
-                            fs_tma_load_4d(sb + t * P3_UBOX, ta.uin, fb, 2 * (ta.j0 - 2), 2 * ta.mb, k0, t, kEvictFirst);
+                            fs_tma_load_4d(sb + t * P3_UBOX, ta.uin, fb, 2 * (ta.j0 - 2), 2 * ta.mb, k0, t, P3_HINT_B);
 #pragma unroll
                         for (int cl = 0; cl < P3_NCLS; ++cl)
 #pragma unroll
@@ -1136,7 +1151,7 @@ __global__ void __launch_bounds__(P3_THREADS, 1) step_fused_p3_kernel(const Step
             double yprev = 0.0;
             for (int c = 0; c < nchunk; ++c) {
                 const uint32_t s = g % NS, ph = (g / NS) & 1;
-                fs_mbar_wait<20>(bar_full + 8 * s, ph);
+                fs_mbar_wait<P3_CWAIT>(bar_full + 8 * s, ph);
                 Raw<W> raw;
                 chunk_a(t, ring + s * P3_SLOT, c, yprev, raw);
                 __syncwarp();
@@ -1153,7 +1168,7 @@ __global__ void __launch_bounds__(P3_THREADS, 1) step_fused_p3_kernel(const Step
             auto chunk_b = [&](Raw<W> &cur, Raw<W> &nxt, int c) {
                 if (c > 0) fs_tmem_ld(taddr + (c - 1) * W, nxt);
                 const uint32_t s = g % NS, ph = (g / NS) & 1;
-                fs_mbar_wait<20>(bar_full + 8 * s, ph);
+                fs_mbar_wait<P3_CWAIT>(bar_full + 8 * s, ph);
                 Vd<1> ycur[KC];
                 fs_unpack<1, KC>(cur, ycur);
                 const unsigned char *sb = ring + s * P3_SLOT;
@@ -1234,8 +1249,8 @@ __global__ void __launch_bounds__(P3_THREADS, 1) step_fused_p3_kernel(const Step
                 if (c + 1 < nchunk) fs_tmem_ld(taddr + (c + 1) * W, nxt);
                 const uint32_t s = g % NS, ph = (g / NS) & 1;
                 const uint32_t so = go % NO, pho = (go / NO) & 1;
-                fs_mbar_wait<20>(bar_full + 8 * s, ph);
-                fs_mbar_wait<20>(bar_oempty + 8 * so, pho ^ 1);
+                fs_mbar_wait<P3_CWAIT>(bar_full + 8 * s, ph);
+                fs_mbar_wait<P3_CWAIT>(bar_oempty + 8 * so, pho ^ 1);
                 const unsigned char *sb = ring + s * P3_SLOT;
                 chunk_c(sb, oring + so * P3_OUT, cur, u2p);
                 Raw<W> raw;
