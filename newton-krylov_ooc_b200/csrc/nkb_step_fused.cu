@@ -365,6 +365,15 @@ constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
 // pair planes of a ring slot, [KC][FS_COLS] pairs each (see step_ctab_kernel in nkb_tables.cu):
 //   sweep A: 0 {aL,aC}  1 {aR,m1}  2 {fA,-}          sweep C: 3 {ib2,g2}  (C may share a slot with A)
 //   sweep B: 0 {bL,bC}  1 {bR,m1}  2 {g1,ib1} 3 {m2,fB}   (the back substitution needs plane 2 only)
+#ifndef FS_HINT_A
+#define FS_HINT_A kEvictNormal
+#endif
+#ifndef FS_HINT_B
+#define FS_HINT_B kEvictFirst
+#endif
+#ifndef FS_CWAIT
+#define FS_CWAIT 20
+#endif
 template <int KIND, int MPT>
 __global__ void __launch_bounds__(fs_cfg(MPT).threads, 1) step_fused_kernel(const StepArgs p,
                                                                              const __grid_constant__ StepMaps maps) {
@@ -485,7 +494,7 @@ __global__ void __launch_bounds__(fs_cfg(MPT).threads, 1) step_fused_kernel(cons
                     const uint32_t fb = bar_full + 8 * s;
                     if (sweep == 0 || sweep == 3) {
                         fs_mbar_expect_tx(fb, C.ubytes + (NPA + (sweep == 3 ? 1 : 0)) * C.ppbytes);
-                        fs_tma_load_4d(sb, ta.uin, fb, ta.m0, ta.j0 - 2, k0, ta.tr, kEvictNormal);
+                        fs_tma_load_4d(sb, ta.uin, fb, ta.m0, ta.j0 - 2, k0, ta.tr, FS_HINT_A);
 #pragma unroll
                         for (int q = 0; q < NPA; ++q)
                             fs_tma_load_3d(pl + q * C.ppbytes, &maps.ctab, fb, 2 * ta.j0, k0, ta.zt + q, kEvictLast);
@@ -493,7 +502,7 @@ __global__ void __launch_bounds__(fs_cfg(MPT).threads, 1) step_fused_kernel(cons
                             fs_tma_load_3d(pl + 3 * C.ppbytes, &maps.ctab, fb, 2 * tc.j0, k0, tc.zt + 7, kEvictLast);
                     } else if (sweep == 1) {
                         fs_mbar_expect_tx(fb, C.ubytes + 4 * C.ppbytes);
-                        fs_tma_load_4d(sb, ta.uin, fb, ta.m0, ta.j0 - 2, k0, ta.tr, kEvictFirst);
+                        fs_tma_load_4d(sb, ta.uin, fb, ta.m0, ta.j0 - 2, k0, ta.tr, FS_HINT_B);
 #pragma unroll
                         for (int q = 0; q < 4; ++q)
                             fs_tma_load_3d(pl + q * C.ppbytes, &maps.ctab, fb, 2 * ta.j0, k0, ta.zt + 3 + q, kEvictLast);
@@ -649,7 +658,7 @@ __global__ void __launch_bounds__(fs_cfg(MPT).threads, 1) step_fused_kernel(cons
             V yprev = fs_splat<MPT>(0.0);
             for (int c = 0; c < nchunk; ++c) {
                 const uint32_t s = g % NS, ph = (g / NS) & 1;
-                fs_mbar_wait<20>(bar_full + 8 * s, ph);
+                fs_mbar_wait<FS_CWAIT>(bar_full + 8 * s, ph);
                 Raw<W> raw;
                 chunk_a(t, ring + s * C.slot, c, yprev, raw);
                 __syncwarp();
@@ -667,7 +676,7 @@ __global__ void __launch_bounds__(fs_cfg(MPT).threads, 1) step_fused_kernel(cons
             auto chunk_b = [&](Raw<W> &cur, Raw<W> &nxt, int c) {
                 if (c > 0) fs_tmem_ld(taddr + (c - 1) * W, nxt);
                 const uint32_t s = g % NS, ph = (g / NS) & 1;
-                fs_mbar_wait<20>(bar_full + 8 * s, ph);
+                fs_mbar_wait<FS_CWAIT>(bar_full + 8 * s, ph);
                 V ycur[KC], y1top;
                 fs_unpack<MPT, KC>(cur, ycur);
                 if (c > 0) {
@@ -733,8 +742,8 @@ __global__ void __launch_bounds__(fs_cfg(MPT).threads, 1) step_fused_kernel(cons
                 if (c + 1 < nchunk) fs_tmem_ld(taddr + (c + 1) * W, nxt);
                 const uint32_t s = g % NS, ph = (g / NS) & 1;
                 const uint32_t so = go % NO, pho = (go / NO) & 1;
-                fs_mbar_wait<20>(bar_full + 8 * s, ph);
-                fs_mbar_wait<20>(bar_oempty + 8 * so, pho ^ 1);
+                fs_mbar_wait<FS_CWAIT>(bar_full + 8 * s, ph);
+                fs_mbar_wait<FS_CWAIT>(bar_oempty + 8 * so, pho ^ 1);
                 const unsigned char *sb = ring + s * C.slot;
                 chunk_c(sb, oring + so * C.out, cur, u2p);
                 Raw<W> raw;
