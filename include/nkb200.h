@@ -152,6 +152,10 @@ void nkb_banded_destroy(nkb_banded *f);
  * the per-column systems of a grid without lateral processes): they are factored and solved in
  * parallel */
 int nkb_banded_blocks(const nkb_banded *f);
+/* which substitution the factor was prepared for: 3 = panel kernel (one wide block, no row interchanges: 16 rows per
+ * barrier pair), 2 = batched Thomas kernel (bandwidth <= 4, no interchanges, used for B >= 16), 1 = row-by-row window
+ * kernel (everything else, incl. every matrix that needed interchanges) */
+int nkb_banded_path(const nkb_banded *f);
 /* d_y, d_x: [n][ldb]; x = A^-1 y (in place allowed); if subtract_rhs, x = A^-1 (scale*y) - y */
 int nkb_banded_solve(nkb_banded *f, const double *d_y, double *d_x, int B, int ldb, double scale,
                      int subtract_rhs, void *stream);

@@ -1026,6 +1026,11 @@ int nkb_banded_create(nkb_banded **out, int n, int kl, int ku, const double *h_a
 
 int nkb_banded_blocks(const nkb_banded *f) { return f ? f->nblk : 0; }
 
+int nkb_banded_path(const nkb_banded *f) {
+    if (!f) return 0;
+    return f->lp ? 3 : (f->nb_k > 0 ? 2 : 1);
+}
+
 void nkb_banded_destroy(nkb_banded *f) {
     if (!f) return;
     cudaFree(f->ab); cudaFree(f->ipiv); cudaFree(f->info);

@@ -89,6 +89,7 @@ SYMBOLS = {
     "nkb_banded_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, POINTER(c_double)]),
     "nkb_banded_destroy": (None, [c_void_p]),
     "nkb_banded_blocks": (c_int, [c_void_p]),
+    "nkb_banded_path": (c_int, [c_void_p]),
     "nkb_banded_solve": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_int, c_void_p]),
     "nkb_pack_members": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "nkb_unpack_members": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),

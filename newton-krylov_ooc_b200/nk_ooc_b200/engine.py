@@ -356,6 +356,7 @@ class BandedFactor:
         self.handle = ctypes.c_void_p()
         check(self.lib.nkb_banded_create(ctypes.byref(self.handle), self.n, kl, ku, dptr(ab)), "nkb_banded_create")
         self.n_blocks = self.lib.nkb_banded_blocks(self.handle)  # independent diagonal blocks (solved in parallel)
+        self.path = {3: "panel", 2: "thomas", 1: "window"}.get(self.lib.nkb_banded_path(self.handle), "?")
 
     def __del__(self):
         try:

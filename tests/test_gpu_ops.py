@@ -255,7 +255,7 @@ def test_banded_panel_solver(n, kl, ku, B, monkeypatch):
     want = linalg.solve_banded((kl, ku), ab, y)
     lib = _lib.load()
     f = engine.BandedFactor(ab, kl, ku)
-    assert f.n_blocks == 1
+    assert f.n_blocks == 1 and f.path == "panel"
     tol = 1e-12 * np.abs(want).max()
     n0 = lib.nkb_launch_count()
     got = f.solve(_dev(y), B).cpu().numpy()[:, :B]
@@ -270,6 +270,7 @@ def test_banded_panel_solver(n, kl, ku, B, monkeypatch):
     # the same factor through the window kernel (panel data not built)
     monkeypatch.setenv("NKB_BANDED_PANEL", "0")
     f2 = engine.BandedFactor(ab, kl, ku)
+    assert f2.path == "window"
     got2 = f2.solve(_dev(y), B).cpu().numpy()[:, :B]
     np.testing.assert_allclose(got, 0.25 * got2 - y, rtol=0, atol=tol)
     # a matrix that needs interchanges keeps the pivoting window kernel
@@ -277,6 +278,7 @@ def test_banded_panel_solver(n, kl, ku, B, monkeypatch):
     ab3 = rng.normal(size=(kl + ku + 1, n))
     ab3[ku] += 0.5 * np.sqrt(kl + ku)
     f3 = engine.BandedFactor(ab3, kl, ku)
+    assert f3.path == "window"
     got3 = f3.solve(_dev(y), B).cpu().numpy()[:, :B]
     want3 = linalg.solve_banded((kl, ku), ab3, y)
     np.testing.assert_allclose(got3, want3, rtol=0, atol=1e-9 * np.abs(want3).max())
