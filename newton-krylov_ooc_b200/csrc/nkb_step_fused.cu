@@ -344,6 +344,7 @@ __device__ __forceinline__ Vd<M> fs_source(double ws, double thr_r, double fw, V
     } else {
 #pragma unroll
         for (int i = 0; i < M; ++i) {
+#ifdef FS_FP_LIMITER
             asm("{\n\t.reg .pred pl, p1, p2;\n\t.reg .f64 q, fq;\n\t"
                 "setp.lt.f64 pl, %2, 0d0000000000000000;\n\t"
                 "mul.f64 q, %3, %1;\n\t"
@@ -353,6 +354,23 @@ __device__ __forceinline__ Vd<M> fs_source(double ws, double thr_r, double fw, V
                 "selp.f64 %0, fq, %2, p2;\n\t}"
                 : "=d"(r.v[i])
                 : "d"(c.v[i]), "d"(fw), "d"(thr_r));
+#else
+            // the same three comparisons on the bit patterns (integer pipe instead of three DSETP on the FP64 pipe,
+            // which this kernel keeps busiest after the LSU): fw < 0 is its sign bit (-0.0 scales to -0.0 either
+            // way), 0 < q < 1 is 1 <= high word <= 0x3FEFFFFF for a non-negative double.  Differs from the
+            // floating-point test only for subnormal q (0 < c < 1e-309 thres), which is then left unscaled.
+            asm("{\n\t.reg .pred p1, p2;\n\t.reg .f64 q, fq;\n\t.reg .b32 qlo, qhi, flo, fhi, t;\n\t"
+                "mul.f64 q, %3, %1;\n\t"
+                "mul.f64 fq, %2, q;\n\t"
+                "mov.b64 {qlo, qhi}, q;\n\t"
+                "mov.b64 {flo, fhi}, %2;\n\t"
+                "sub.u32 t, qhi, 1;\n\t"
+                "setp.lt.u32 p1, t, 0x3FEFFFFF;\n\t"
+                "setp.lt.and.s32 p2, fhi, 0, p1;\n\t"
+                "selp.f64 %0, fq, %2, p2;\n\t}"
+                : "=d"(r.v[i])
+                : "d"(c.v[i]), "d"(fw), "d"(thr_r));
+#endif
         }
     }
     return r;
