@@ -116,3 +116,84 @@ def test_nk_driver_resumes_and_rewinds_at_step_granularity(ci_env):
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     with open(os.path.join(work, "Newton_state.json")) as fptr:
         assert json.load(fptr)["step_log"] == resumed["step_log"]
+
+
+def test_nk_driver_resumes_inside_a_krylov_solve(ci_env):
+    """an interruption INSIDE a Krylov solve (krylov_solver.py:105-165 over solver_state.py): Krylov_state.json cut back
+    to the end of its first iteration, Newton_state.json to "KrylovSolver instantiated" — the resumed solve reads beta,
+    h_mat, the basis vectors and the preconditioned products of the completed iteration back from the files
+    (basis_jj.nc, w_jj.nc, precond_fcn_00.nc), continues with iteration 1 and ends with the same increment and the same
+    Newton step log"""
+    import json
+    import shutil
+
+    import numpy as np
+    from scipy.io import netcdf_file
+
+    home = ci_env["HOME"]
+    src = os.path.join(home, "ci_long_iage_workdir")
+    if not os.path.isdir(src):
+        _run("ci_short.sh", ci_env)
+        _run("ci_long_iage.sh", ci_env)
+    # a Newton iteration whose Krylov solve took at least two iterations
+    pick = None
+    for it in range(3):
+        with open(os.path.join(src, f"krylov_{it:02}", "Krylov_state.json")) as fptr:
+            if json.load(fptr)["iteration"] >= 2:
+                pick = it
+                break
+    if pick is None:
+        pytest.skip("every Krylov solve of this run converged in one iteration")
+    work = os.path.join(home, "resume_krylov_workdir")
+    shutil.copytree(src, work)
+    kdir = os.path.join(work, f"krylov_{pick:02}")
+    with open(os.path.join(kdir, "Krylov_state.json")) as fptr:
+        ktext = fptr.read().replace(src, work)
+    kfull = json.loads(ktext)
+    kcut = kfull["step_log"].index("01:inc_iteration") + 1
+    h_mat = np.asarray(kfull["h_mat"]["__ndarray__"])
+    kstate = {"iteration": 1, "step_log": kfull["step_log"][:kcut], "beta": kfull["beta"],
+              "h_mat": {"__ndarray__": h_mat[:, :2, :1, :].tolist()}}
+    with open(os.path.join(kdir, "Krylov_state.json"), "w") as fptr:
+        json.dump(kstate, fptr, indent=2)
+    for j in range(1, kfull["iteration"]):  # files of the iterations that "did not happen"
+        for quantity in ("w_raw", "w", "krylov_res", "perturb_fcn_w_raw"):
+            fname = os.path.join(kdir, f"{quantity}_{j:02}.nc")
+            if os.path.exists(fname):
+                os.remove(fname)
+        later = os.path.join(kdir, f"basis_{j + 1:02}.nc")
+        if os.path.exists(later):
+            os.remove(later)
+    with open(os.path.join(work, "Newton_state.json")) as fptr:
+        ntext = fptr.read().replace(src, work)
+    nfull = json.loads(ntext)
+    ncut = nfull["step_log"].index(f"{pick:02}:KrylovSolver instantiated") + 1
+    nstate = {"iteration": pick, "step_log": nfull["step_log"][:ncut]}
+    with open(os.path.join(work, "Newton_state.json"), "w") as fptr:
+        json.dump(nstate, fptr, indent=2)
+    for later in range(pick + 1, 4):
+        for fname in (f"iterate_{later:02}.nc", f"fcn_{later:02}.nc", f"hist_{later:02}.nc"):
+            if os.path.exists(os.path.join(work, fname)):
+                os.remove(os.path.join(work, fname))
+        shutil.rmtree(os.path.join(work, f"krylov_{later:02}"), ignore_errors=True)
+    os.remove(os.path.join(work, f"increment_{pick:02}.nc"))
+    env = dict(ci_env, PYTHONPATH=os.path.join(ROOT, "newton-krylov_ooc_b200"))
+    cmd = ["python", "-m", "nk_ooc_b200.cli", "nk_driver", "--model_name", "test_problem", "--depth_nlevs", "20",
+           "--tracer_module_names", "iage", "--workdir", work, "--resume"]
+    res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    with open(os.path.join(work, "Newton_state.json")) as fptr:
+        resumed = json.load(fptr)
+    assert resumed["iteration"] == nfull["iteration"] and resumed["step_log"] == nfull["step_log"]
+    with open(os.path.join(kdir, "Krylov_state.json")) as fptr:
+        kres = json.load(fptr)
+    assert kres["iteration"] == kfull["iteration"] and kres["step_log"] == kfull["step_log"]
+    np.testing.assert_allclose(np.asarray(kres["h_mat"]["__ndarray__"]), h_mat, rtol=1e-9, atol=1e-12 * np.abs(h_mat).max())
+
+    def iage(fname):
+        with netcdf_file(fname, "r", mmap=False) as fptr:
+            return np.array(fptr.variables["iage"].data)
+
+    for fname in (f"increment_{pick:02}.nc", f"iterate_{nfull['iteration']:02}.nc"):
+        want = iage(os.path.join(src, fname))
+        np.testing.assert_allclose(iage(os.path.join(work, fname)), want, rtol=0, atol=1e-9 * np.abs(want).max())
