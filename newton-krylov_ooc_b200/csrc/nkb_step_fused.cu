@@ -787,6 +787,40 @@ __global__ void __launch_bounds__(fs_cfg(MPT).threads, 1) step_fused_kernel(cons
             if (with_a) fs_tmem_wait_st();
         };
 
+        // A batch of at most 14 members (one member block: a single state staged into 4 lanes, the Newton iterate and
+        // every Krylov product) fills only some of the eight warps.  The others keep the barrier protocol going —
+        // same waits and arrives in the same order — and leave their schedulers to the warps that work.
+        if (p.nmb == 1 && ((MPT == 2) ? 4 * warp : 2 * warp) >= p.B) {
+            auto pass = [&](bool with_out) {
+                for (int c = 0; c < nchunk; ++c) {
+                    const uint32_t s = g % NS, ph = (g / NS) & 1;
+                    fs_mbar_wait<FS_CWAIT>(bar_full + 8 * s, ph);
+                    if (with_out) {
+                        const uint32_t so = go % NO, pho = (go / NO) & 1;
+                        fs_mbar_wait<FS_CWAIT>(bar_oempty + 8 * so, pho ^ 1);
+                        if (lane == 0) fs_mbar_arrive(bar_ofull + 8 * so);
+                        ++go;
+                    }
+                    if (lane == 0) fs_mbar_arrive(bar_empty + 8 * s);
+                    ++g;
+                }
+            };
+            Item it = it0;
+            if (item_valid(it)) {
+                pass(false);  // sweep A
+                while (true) {
+                    pass(false);  // sweep B
+                    const Item nx = item_next(it);
+                    if (!item_valid(nx)) {
+                        pass(true);  // sweep C
+                        break;
+                    }
+                    pass(true);  // sweep C, alone or sharing the pass with sweep A of the next item
+                    if (item_depends(nx, it)) pass(false);  // sweep A on its own
+                    it = nx;
+                }
+            }
+        } else {
         Item it = it0;
         if (item_valid(it)) {
             TileC t = tile_c(it);
@@ -808,6 +842,7 @@ __global__ void __launch_bounds__(fs_cfg(MPT).threads, 1) step_fused_kernel(cons
                 it = nx;
                 t = tn;
             }
+        }
         }
     }
 
@@ -1303,6 +1338,39 @@ __global__ void __launch_bounds__(P3_THREADS, 1) step_fused_p3_kernel(const Step
             if (with_a) fs_tmem_wait_st();
         };
 
+        // one member block with at most two members (a single state): the three warps of the second member pair
+        // only keep the barrier protocol going (see step_fused_kernel)
+        if (p.nmb == 1 && 2 * pr >= p.B) {
+            auto pass = [&](bool with_out) {
+                for (int c = 0; c < nchunk; ++c) {
+                    const uint32_t s = g % NS, ph = (g / NS) & 1;
+                    fs_mbar_wait<P3_CWAIT>(bar_full + 8 * s, ph);
+                    if (with_out) {
+                        const uint32_t so = go % NO, pho = (go / NO) & 1;
+                        fs_mbar_wait<P3_CWAIT>(bar_oempty + 8 * so, pho ^ 1);
+                        if (lane == 0) fs_mbar_arrive(bar_ofull + 8 * so);
+                        ++go;
+                    }
+                    if (lane == 0) fs_mbar_arrive(bar_empty + 8 * s);
+                    ++g;
+                }
+            };
+            Item it = it0;
+            if (item_valid(it)) {
+                pass(false);
+                while (true) {
+                    pass(false);
+                    const Item nx = item_next(it);
+                    if (!item_valid(nx)) {
+                        pass(true);
+                        break;
+                    }
+                    pass(true);
+                    if (item_depends(nx, it)) pass(false);
+                    it = nx;
+                }
+            }
+        } else {
         Item it = it0;
         if (item_valid(it)) {
             TileC t = tile_c(it);
@@ -1324,6 +1392,7 @@ __global__ void __launch_bounds__(P3_THREADS, 1) step_fused_p3_kernel(const Step
                 it = nx;
                 t = tn;
             }
+        }
         }
     }
 

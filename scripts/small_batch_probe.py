@@ -5,7 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "newton-krylov_ooc_b200")]
 import torch, bench
 class A: pass
-for grid, module in (("refined125x150", "forced"), ("ci30x30", "iage"), ("default40x50", "iage")):
+for grid, module in (("refined125x150", "forced"), ("refined125x150", "iage"), ("refined125x150", "phosphorus"), ("ci30x30", "iage"), ("default40x50", "iage")):
     a = A(); a.grid, a.module, a.nsteps = grid, module, 240
     model, depth, ypos = bench.build_model(a)
     for b in (1, 2, 4):
