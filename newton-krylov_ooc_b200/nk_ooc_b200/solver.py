@@ -114,6 +114,26 @@ class ProbePreconditioner:
         return res
 
 
+class LaggedPrecond:
+    """precond_factory wrapper that keeps a preconditioner for `lag` Newton iterations before it builds the next one
+    (lag=None: for ever).  The Jacobian of F does not depend on the iterate for the linear modules (iage, dye_decay:
+    F is affine in x), so ONE set of coloured probes serves the whole solve; for the others a lagged preconditioner
+    only costs Krylov iterations.  On the refined 125 x 150 grid building the probe preconditioner is half of a
+    Newton step (probe batch, band assembly, factorisation: 2.3 of 4.7 s)."""
+
+    def __init__(self, factory, lag=None):
+        self._factory, self._lag = factory, lag
+        self._cached, self._age = None, 0
+        self.built = 0
+
+    def __call__(self, iterate, fcn):
+        if self._cached is None or (self._lag is not None and self._age >= self._lag):
+            self._cached, self._age = self._factory(iterate, fcn), 0
+            self.built += 1
+        self._age += 1
+        return self._cached
+
+
 class _MemState:
     """SolverState look-alike for a solve that writes no files (dump=False): nothing is ever 'logged', values live
     in memory.  Lets the solvers below keep ONE control flow — the reference's, with its step log — whether or not

@@ -49,8 +49,13 @@ print("|J inc + F| / |F|", (jv + solver.fcn).norm() / solver.fcn.norm())
 import time
 from nk_ooc_b200.solver import ProbePreconditioner
 torch.cuda.synchronize(); t0 = time.perf_counter()
+from nk_ooc_b200.solver import LaggedPrecond
+lag = os.environ.get("NK_PRECOND_LAG")  # "inf": one set of probes for the whole solve (exact for the affine iage module)
+fac = lambda itr, fcn: ProbePreconditioner(itr, fcn)
+if lag:
+    fac = LaggedPrecond(fac, None if lag == "inf" else int(lag))
 solver2 = NewtonSolver(ModelState("gen_init_iterate"), pd_info, workdir=os.path.join(tmp, "work2"), dump=False,
-                       precond_factory=lambda itr, fcn: ProbePreconditioner(itr, fcn))
+                       precond_factory=fac)
 n = 0
 while not solver2.converged_flat() and n < 4:
     solver2.step(); n += 1

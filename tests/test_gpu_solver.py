@@ -192,6 +192,18 @@ def test_probe_preconditioner_newton_in_one_step(base, tmp_path):
     # limited by the finite-difference step of the probes and of the Jacobian-vector product
     assert (rec["krylov_precond_resid_norm"][0] < 1e-5 * rec["krylov_beta"]).all()
     assert (rec["fcn_norm"] < 1e-4 * n0).all() and solver.converged_flat()
+    # iage is affine in x: the Jacobian of F does not depend on the iterate, one set of probes serves every Newton
+    # step (solver.LaggedPrecond) — from a different iterate the same preconditioner converges in one iteration again
+    from nk_ooc_b200.solver import LaggedPrecond
+
+    lagged = LaggedPrecond(factory)
+    other = _state(ModelState, base, pre + "init_iterate") * 0.5
+    solver2 = NewtonSolver(other, dict(PD_SOLVERINFO, post_newton_fp_iter="0", newton_rel_tol="1.0e-12"),
+                           workdir=str(tmp_path / "w1"), dump=False, precond_factory=lagged)
+    solver2.step()
+    solver2.step()
+    assert lagged.built == 1 and len(made) == 2
+    assert [r["krylov_iterations"] for r in solver2.history[1:]] == [1, 1]
     ModelState.reset()
 
 
