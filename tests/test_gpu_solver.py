@@ -74,6 +74,31 @@ def test_speculative_armijo_equals_sequential(base, tmp_path):
     np.testing.assert_array_equal(out[0][2], out[1][2])
     np.testing.assert_allclose(out[0][0], out[1][0], rtol=0, atol=1e-13 * np.abs(out[0][0]).max())
     np.testing.assert_allclose(out[0][1], out[1][1], rtol=0, atol=1e-12 * np.abs(out[0][1]).max())
+    # the same with the work directory kept: the halvings are saved step by step (armijo_ind, armijo_factor), the
+    # accepted candidate and its function value are files, and a second call — "_comp_next_iterate complete" is
+    # logged — reads them back instead of evaluating again (newton_solver.py:199-206)
+    import json
+
+    from nk_ooc_b200 import _lib
+
+    work = str(tmp_path / "wd")
+    solver = NewtonSolver(x0._like(), TP_SOLVERINFO, workdir=work)
+    inc = solver.fcn * 40.0
+    prov, prov_fcn, factor, ind = solver._comp_next_iterate(inc)
+    assert ind == out[0][3]
+    np.testing.assert_array_equal(factor, out[0][2])
+    state = json.load(open(os.path.join(work, "Newton_state.json")))
+    assert state["armijo_ind"] == ind
+    assert f"00:comp_fcn complete for {work}/prov_fcn_Armijo_{ind:02}_00.nc" in state["step_log"]
+    assert "00:_comp_next_iterate complete" in state["step_log"]
+    assert os.path.exists(os.path.join(work, f"prov_Armijo_{ind:02}_00.nc"))
+    assert not os.path.exists(os.path.join(work, f"prov_hist_Armijo_{ind - 1:02}_00.nc"))  # only the latest hist file stays
+    lib = _lib.load()
+    n0 = lib.nkb_launch_count()
+    again, again_fcn, factor2, ind2 = solver._comp_next_iterate(inc)
+    assert lib.nkb_launch_count() == n0 and ind2 == ind
+    np.testing.assert_array_equal(again.get_tracer_vals("iage"), prov.get_tracer_vals("iage"))
+    np.testing.assert_array_equal(again_fcn.get_tracer_vals("iage"), prov_fcn.get_tracer_vals("iage"))
     ModelState.reset()
 
 
