@@ -64,7 +64,11 @@ def default_schedule(kind, nz):
     the error stays below half of the stated tolerance (rtol 1e-3 |F| + atol 1e-6 max(1, max |x0|), DESIGN.md
     section 2): 2640 steps per year (20 / 120 / 240 per hist interval) everywhere, except for iage on grids
     finer than 60 levels, whose sharp age gradient below the moving mixed layer needs 5280 (ratio 0.95 and
-    1.36 of the tolerance with 2640 steps on 80 x 100 and 125 x 150, 0.23 and 0.32 with 5280)."""
+    1.36 of the tolerance with 2640 steps on 80 x 100 and 125 x 150, 0.23 and 0.32 with 5280).
+    scripts/schedule_probe.py separates the two needs: the year-end error of F comes from the intervals with a
+    CONSTANT mixed layer (40/120/240 = 3600 steps already gives 0.27 and 0.35), the error of the hist snapshots
+    inside the year from the ramps (with 40/120/240 a snapshot of the 80 x 100 Radau golden fails the tolerance):
+    both refinements are needed as long as one schedule serves F and the hist file."""
     if kind == "iage" and nz > 60:
         return {"flat": 40, "ramp": 240, "ramp_first": 480}
     return {"flat": 20, "ramp": 120, "ramp_first": 240}
