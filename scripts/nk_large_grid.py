@@ -51,7 +51,8 @@ from nk_ooc_b200.solver import ProbePreconditioner
 torch.cuda.synchronize(); t0 = time.perf_counter()
 from nk_ooc_b200.solver import LaggedPrecond
 lag = os.environ.get("NK_PRECOND_LAG")  # "inf": one set of probes for the whole solve (exact for the affine iage module)
-fac = lambda itr, fcn: ProbePreconditioner(itr, fcn)
+reach = int(os.environ.get("NK_PROBE_REACH", "1"))  # columns of coupling kept on each side (2*reach + 1 colours)
+fac = lambda itr, fcn: ProbePreconditioner(itr, fcn, reach=reach)
 if lag:
     fac = LaggedPrecond(fac, None if lag == "inf" else int(lag))
 solver2 = NewtonSolver(ModelState("gen_init_iterate"), pd_info, workdir=os.path.join(tmp, "work2"), dump=False,
