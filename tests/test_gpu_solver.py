@@ -232,6 +232,42 @@ def test_probe_preconditioner_newton_in_one_step(base, tmp_path):
     ModelState.reset()
 
 
+def test_probe_preconditioned_newton_krylov_with_lateral_processes(tmp_path):
+    """Newton-Krylov from gen_init_iterate on the reference's default 40 x 50 grid WITH lateral processes, the
+    preconditioner built once from coloured probes that keep the coupling to two columns on each side (5 colours x 2
+    tracers x 40 levels = 400 members in one batched evaluation, panel substitution of the block band) and reused for
+    every Newton step (the Jacobian of F does not depend on the iterate for iage): converges to newton_rel_tol"""
+    from nk_ooc_b200.py_driver_2d.model_state import ModelState
+    from nk_ooc_b200.py_driver_2d.setup_solver import gen_grid_vars_file
+    from nk_ooc_b200.solver import LaggedPrecond, NewtonSolver, ProbePreconditioner
+
+    info = _modelinfo(str(tmp_path), 40, 50)
+    gen_grid_vars_file(info)
+    ModelState.configure(info)
+    try:
+        made = []
+
+        def factory(it, fcn):
+            made.append(ProbePreconditioner(it, fcn, reach=2))
+            return made[-1]
+
+        lagged = LaggedPrecond(factory)
+        solverinfo = dict(PD_SOLVERINFO, krylov_rel_tol="1.0e-3", newton_max_iter="6")
+        solver = NewtonSolver(ModelState("gen_init_iterate"), solverinfo, workdir=str(tmp_path / "w"), dump=False,
+                              precond_factory=lagged)
+        start = float((solver.fcn.norm() / solver.iterate.norm()).max())
+        steps = 0
+        while not solver.converged_flat() and steps < 4:
+            solver.step()
+            steps += 1
+        rel = float((solver.fcn.norm() / solver.iterate.norm()).max())
+        assert solver.converged_flat() and rel < 1.0e-5 < 1.0e-2 < start, (steps, rel)
+        assert lagged.built == 1 and made[0].members_probed == 5 * 2 * 40 and made[0]._factor.path == "panel"
+        assert all(rec["krylov_iterations"] <= 40 for rec in solver.history[1:])
+    finally:
+        ModelState.reset()
+
+
 def test_cli_setup_solver_and_nk_driver_column_regions(base, tmp_path):
     """scripts/ci_py_driver_2d_iage_column_regions.sh through the command line: setup_solver (grid
     file, gen_init_iterate + 1 fixed-point iteration) and nk_driver write the reference's files;
