@@ -147,6 +147,9 @@ __device__ __forceinline__ void fs_mbar_wait_sleep(uint32_t bar, uint32_t parity
         __nanosleep(SLEEP_NS);
     }
 }
+#ifndef FS_DEP_SLEEP
+#define FS_DEP_SLEEP 200  // ns between polls of a neighbour tile's step counter
+#endif
 // spin until *flag >= want (acquire); gives up after 2e10 cycles (~10 s) and raises *err instead of hanging
 __device__ __forceinline__ void fs_wait_done(const int *flag, int want, int *err) {
     int v;
@@ -154,7 +157,7 @@ __device__ __forceinline__ void fs_wait_done(const int *flag, int want, int *err
     while (true) {
         asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
         if (v >= want) return;
-        __nanosleep(200);
+        __nanosleep(FS_DEP_SLEEP);
         if (clock64() - t0 > 20000000000ll) {
             *reinterpret_cast<volatile int *>(err) = 1;
             return;
