@@ -101,6 +101,30 @@ struct StepMaps {
     CUtensorMap in_x0, in_f, in_w, out_f, out_w, ctab;
 };
 
+// tile id -> (member block, column tile, tracer).  Column tile fastest: the tiles a round of CTAs works on at the
+// same time are column NEIGHBOURS of one member block, so the two halo columns a tile shares with each neighbour come
+// out of L2 instead of being read from HBM twice (member block fastest: neighbours are nmb ids = almost two rounds
+// apart and the halo was re-read: 1.28 x the state per step, ncu) — and the tiles a tile waits for at a step boundary
+// are the ones the neighbouring CTAs have just finished.
+#ifndef FS_CT_FASTEST
+#define FS_CT_FASTEST 1
+#endif
+__device__ __forceinline__ void fs_tile_split(int tile, int nmb, int nct, int &mb, int &ct, int &tr) {
+#if FS_CT_FASTEST
+    ct = tile % nct;
+    const int r = tile / nct;
+    mb = r % nmb;
+    tr = r / nmb;
+#else
+    mb = tile % nmb;
+    const int r = tile / nmb;
+    ct = r % nct;
+    tr = r / nct;
+#endif
+}
+// distance in tile ids between column neighbours
+__host__ __device__ __forceinline__ int fs_nbr(int nmb) { return FS_CT_FASTEST ? 1 : nmb; }
+
 // ---- PTX wrappers ------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t fs_smem_u32(const void *p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -468,7 +492,7 @@ __global__ void __launch_bounds__(fs_cfg(MPT).threads, 1) step_fused_kernel(cons
         if (!p.cross_step_fuse) return true;
         const int d = nx.tile - it.tile;
         // neighbours in the column direction are nmb apart (a tracer boundary only makes this conservative)
-        return d == 0 || d == p.nmb || d == -p.nmb;
+        return d == 0 || d == fs_nbr(p.nmb) || d == -fs_nbr(p.nmb);
     };
     Item it0 = {p.step0, item_first(p.step0)};
     if (it0.tile >= p.ntiles) it0.n = p.step1;  // (grid <= ntiles: does not happen)
@@ -485,9 +509,8 @@ __global__ void __launch_bounds__(fs_cfg(MPT).threads, 1) step_fused_kernel(cons
                 TileP t;
                 const bool to_f = (((p.n_steps - 1 - it.n) & 1) == 0);  // this step writes f (else w)
                 t.uin = (it.n == 0) ? &maps.in_x0 : (to_f ? &maps.in_w : &maps.in_f);
-                const int mb = it.tile % p.nmb;
-                t.ct = (it.tile / p.nmb) % p.nct;
-                t.tr = it.tile / (p.nmb * p.nct);
+                int mb;
+                fs_tile_split(it.tile, p.nmb, p.nct, mb, t.ct, t.tr);
                 t.m0 = mb * FS_MEM;
                 t.j0 = t.ct * p.jt;
                 t.zt = (it.n * p.ncls + p.class_of[t.tr]) * 8;
@@ -498,8 +521,8 @@ __global__ void __launch_bounds__(fs_cfg(MPT).threads, 1) step_fused_kernel(cons
             auto dep_wait = [&](const Item &it, const TileP &t) {
                 if (it.n > 0) {
                     fs_wait_done(p.done + it.tile, it.n, p.err);
-                    if (t.ct > 0) fs_wait_done(p.done + it.tile - p.nmb, it.n, p.err);
-                    if (t.ct + 1 < p.nct) fs_wait_done(p.done + it.tile + p.nmb, it.n, p.err);
+                    if (t.ct > 0) fs_wait_done(p.done + it.tile - fs_nbr(p.nmb), it.n, p.err);
+                    if (t.ct + 1 < p.nct) fs_wait_done(p.done + it.tile + fs_nbr(p.nmb), it.n, p.err);
                     asm volatile("fence.proxy.async;" ::: "memory");
                 }
             };
@@ -567,9 +590,8 @@ __global__ void __launch_bounds__(fs_cfg(MPT).threads, 1) step_fused_kernel(cons
             for (Item it = it0; item_valid(it); it = item_next(it)) {
                 const bool to_f = (((p.n_steps - 1 - it.n) & 1) == 0);
                 const CUtensorMap *uout = to_f ? &maps.out_f : &maps.out_w;
-                const int mb = it.tile % p.nmb;
-                const int ct = (it.tile / p.nmb) % p.nct;
-                const int tr = it.tile / (p.nmb * p.nct);
+                int mb, ct, tr;
+                fs_tile_split(it.tile, p.nmb, p.nct, mb, ct, tr);
                 for (int c = 0; c < nchunk; ++c) {
                     const uint32_t s = go % NO, ph = (go / NO) & 1;
                     fs_mbar_wait<2000>(bar_ofull + 8 * s, ph);
@@ -618,8 +640,8 @@ __global__ void __launch_bounds__(fs_cfg(MPT).threads, 1) step_fused_kernel(cons
             TileC t;
             const double hstep = __ldg(p.h + it.n);
             const double *aff_n = p.aff + (size_t)(2 * it.n) * p.ncls * ny;
-            const int ct = (it.tile / p.nmb) % p.nct;
-            const int tr = it.tile / (p.nmb * p.nct);
+            int mbu, ct, tr;
+            fs_tile_split(it.tile, p.nmb, p.nct, mbu, ct, tr);
             const int j = ct * p.jt - 1 + col;
             const int cls = p.class_of[tr];
             t.aff1 = t.aff2 = 0.0;
@@ -991,7 +1013,7 @@ __global__ void __launch_bounds__(P3_THREADS, 1) step_fused_p3_kernel(const Step
         if (nx.n == it.n) return false;
         if (!p.cross_step_fuse) return true;
         const int d = nx.tile - it.tile;
-        return d == 0 || d == p.nmb || d == -p.nmb;
+        return d == 0 || d == fs_nbr(p.nmb) || d == -fs_nbr(p.nmb);
     };
     Item it0 = {p.step0, item_first(p.step0) * p.tgroup};
     if (it0.tile >= p.ntiles) it0.n = p.step1;
@@ -1008,8 +1030,8 @@ __global__ void __launch_bounds__(P3_THREADS, 1) step_fused_p3_kernel(const Step
                 TileP t;
                 const bool to_f = (((p.n_steps - 1 - it.n) & 1) == 0);
                 t.uin = (it.n == 0) ? &maps.in_x0 : (to_f ? &maps.in_w : &maps.in_f);
-                t.ct = it.tile / p.nmb;
-                t.mb = it.tile % p.nmb;
+                int tru;
+                fs_tile_split(it.tile, p.nmb, p.nct, t.mb, t.ct, tru);  // (one tile = all three tracers: tru == 0)
                 t.j0 = t.ct * p.jt;
                 t.zt = it.n * P3_NCLS * 8;
                 return t;
@@ -1017,8 +1039,8 @@ __global__ void __launch_bounds__(P3_THREADS, 1) step_fused_p3_kernel(const Step
             auto dep_wait = [&](const Item &it, const TileP &t) {
                 if (it.n > 0) {
                     fs_wait_done(p.done + it.tile, it.n, p.err);
-                    if (t.ct > 0) fs_wait_done(p.done + it.tile - p.nmb, it.n, p.err);
-                    if (t.ct + 1 < p.nct) fs_wait_done(p.done + it.tile + p.nmb, it.n, p.err);
+                    if (t.ct > 0) fs_wait_done(p.done + it.tile - fs_nbr(p.nmb), it.n, p.err);
+                    if (t.ct + 1 < p.nct) fs_wait_done(p.done + it.tile + fs_nbr(p.nmb), it.n, p.err);
                     asm volatile("fence.proxy.async;" ::: "memory");
                 }
             };
@@ -1100,7 +1122,8 @@ __global__ void __launch_bounds__(P3_THREADS, 1) step_fused_p3_kernel(const Step
             for (Item it = it0; item_valid(it); it = item_next(it)) {
                 const bool to_f = (((p.n_steps - 1 - it.n) & 1) == 0);
                 const CUtensorMap *uout = to_f ? &maps.out_f : &maps.out_w;
-                const int mb = it.tile % p.nmb, ct = it.tile / p.nmb;
+                int mb, ct, tru;
+                fs_tile_split(it.tile, p.nmb, p.nct, mb, ct, tru);
                 for (int c = 0; c < nchunk; ++c) {
                     const uint32_t s = go % NO, ph = (go / NO) & 1;
                     fs_mbar_wait_sleep<P3_PSLEEP>(bar_ofull + 8 * s, ph);
@@ -1152,7 +1175,8 @@ __global__ void __launch_bounds__(P3_THREADS, 1) step_fused_p3_kernel(const Step
             TileC t;
             const double hstep = __ldg(p.h + it.n);
             const double *aff_n = p.aff + (size_t)(2 * it.n) * p.ncls * ny;
-            const int ct = it.tile / p.nmb;
+            int mbu, ct, tru;
+            fs_tile_split(it.tile, p.nmb, p.nct, mbu, ct, tru);
             const int j = ct * p.jt - 1 + col;
             t.aff1 = t.aff2 = 0.0;
             if (j >= 0 && j < ny) {
@@ -1676,7 +1700,7 @@ int launch_steps_fused(const ModelDev &v, int B, int n_steps, int step0, int ste
     // rotate the tile -> CTA assignment by the number of left-over tiles per step so that the CTAs that
     // get one tile more than the others change from step to step
     a.rot = (step1 - step0 > 1) ? ngroups % grid : 0;
-    a.cross_step_fuse = (a.ntiles > 2 * a.tgroup * grid + a.nmb) ? 1 : 0;
+    a.cross_step_fuse = (a.ntiles > 2 * a.tgroup * grid + fs_nbr(a.nmb)) ? 1 : 0;
     const bool coop = (step1 - step0 > 1);
     if (p3) {
         static unsigned long long attr_mask = 0;
