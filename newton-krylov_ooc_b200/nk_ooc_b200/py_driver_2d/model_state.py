@@ -71,6 +71,10 @@ def default_schedule(kind, nz):
     both refinements are needed as long as one schedule serves F and the hist file.  The extra refinement of the
     first ramp interval changes neither (scripts/schedule_snapshots_probe.py: 40/240/240 = 4800 steps gives the same
     0.16 for F and 0.67 for the worst snapshot of the 80 x 100 golden as 40/240/480 = 5280), so 4800 it is."""
+    override = os.environ.get("NKB_SCHEDULE")  # "flat,ramp,ramp_first": schedule experiments (scripts/schedule_*probe.py)
+    if override:
+        flat, ramp, first = (int(v) for v in override.split(","))
+        return {"flat": flat, "ramp": ramp, "ramp_first": first}
     if kind == "iage" and nz > 60:
         return {"flat": 40, "ramp": 240, "ramp_first": 240}
     return {"flat": 20, "ramp": 120, "ramp_first": 240}

@@ -10,7 +10,10 @@ grid, module = (sys.argv[1], sys.argv[2]) if len(sys.argv) > 2 else ("g80x100", 
 g = t._load(os.path.join(ROOT, "tests", "golden"), grid, module)
 x0, truth = g["x0"], g["tol1e-09/fcn"]
 idx = [int(i) for i in g["tol1e-09/snap_idx"]]
-for flat, ramp, first in ((20, 120, 240), (40, 120, 240), (40, 180, 360), (40, 240, 240), (40, 240, 480), (30, 240, 480), (40, 200, 400)):
+SETS = ((20, 120, 240), (40, 120, 240), (40, 180, 360), (40, 240, 240), (40, 240, 480), (30, 240, 480), (40, 200, 400))
+if os.environ.get('SCHED_SETS') == 'first':
+    SETS = ((20, 120, 240), (20, 120, 120), (20, 120, 480), (20, 100, 100), (24, 120, 120))
+for flat, ramp, first in SETS:
     model = t._model(g, module)
     model.set_graded_schedule(flat=flat, ramp=ramp, ramp_first=first)
     got, snaps = t._eval(model, x0, idx)
