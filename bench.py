@@ -65,11 +65,11 @@ def parse_args():
 
 def default_steps_per_year(args):
     """time steps per model year of the workload: --nsteps, else the product's graded schedule
-    (nk_ooc_b200/py_driver_2d/model_state.py:default_schedule — 2640, 4800 for iage on grids finer than 60 levels)"""
+    (nk_ooc_b200/py_driver_2d/model_state.py:default_schedule — 2640, 5280 for iage on grids finer than 60 levels)"""
     if args.nsteps:
         return int(args.nsteps)
     nz = GRIDS[args.grid][0]
-    return 4800 if (args.module == "iage" and nz > 60) else 2640
+    return 5280 if (args.module == "iage" and nz > 60) else 2640
 
 
 def workload_config(args, world, S=None):
