@@ -186,6 +186,7 @@ def oracle_module(args):
 CPU_SAMPLE_STEPS = 6     # accepted Radau steps per sample
 CPU_SAMPLE_REPEATS = 3   # samples per worker; the median is used
 CPU_RESTART_FRAC = 0.5   # the samples restart the integration at mid-year
+CPU_LEG_TIMEOUT_S = float(os.environ.get("NKB_CPU_LEG_TIMEOUT_S", "900"))  # a CPU leg that has not delivered its samples by then is reported as unavailable
 CPU_MAX_SPREAD = 1.2     # largest / smallest estimate among the samples of a worker before it is called unstable
 
 
@@ -286,11 +287,20 @@ def cpu_baseline(args, cpus):
 
     args_d = {k: getattr(args, k) for k in ("grid", "module", "members", "nsteps")}
     procs = len(cpus)
-    if procs == 1:
-        res = [_cpu_sample_worker((args_d, 1, cpus[0]))]
-    else:
-        with mp.get_context("spawn").Pool(procs) as pool:
-            res = pool.map(_cpu_sample_worker, [(args_d, 1, cpu) for cpu in cpus])
+    # always in worker processes: a Radau step cannot be interrupted from inside, and one step of the coupled
+    # phosphorus system on refined125x150 (56 250 unknowns, dense column blocks) takes more than 15 minutes on
+    # one core — such a workload is reported as unavailable instead of holding the bench for hours
+    with mp.get_context("spawn").Pool(procs) as pool:
+        pending = pool.map_async(_cpu_sample_worker, [(args_d, 1, cpu) for cpu in cpus])
+        try:
+            res = pending.get(timeout=CPU_LEG_TIMEOUT_S)
+        except mp.TimeoutError:
+            pool.terminate()
+            why = (f"{CPU_SAMPLE_REPEATS} x {CPU_SAMPLE_STEPS} Radau steps of {args.grid}/{args.module} did not finish "
+                   f"within {CPU_LEG_TIMEOUT_S:.0f} s on this host")
+            sys.stderr.write(f"bench.py: CPU reference leg unavailable: {why}\n")
+            return {"value": None, "unit": "model-year evals/s", "cores": procs, "kind": "port", "sample": why,
+                    "unavailable": why, "cpu_model": cpu_model_name()}
     key = f"{args.grid}/{args.module}"
     cpath = os.path.join(ROOT, "profiles", "cpu_ref_counts.json")
     counts = None
@@ -657,9 +667,13 @@ def run_reference(args):
     if rank != 0:
         return
     cpus = usable_cpus()
-    for _ in range(min(args.warmup, 1)):
-        cpu_baseline(args, cpus)
-    vals = [cpu_baseline(args, cpus) for _ in range(max(1, min(args.steps, 5)))]
+    first = None
+    for _ in range(min(args.warmup, 1) + 1):  # (the untimed pass, then the first of the timed ones)
+        first = cpu_baseline(args, cpus)
+        if first["value"] is None:
+            print(json.dumps({"impl": "reference", "unavailable": first["unavailable"]}), flush=True)
+            return
+    vals = [first] + [cpu_baseline(args, cpus) for _ in range(max(1, min(args.steps, 5)) - 1)]
     vals.sort(key=lambda v: v["value"])
     cb = vals[len(vals) // 2]
     cb["passes"] = [v["value"] for v in vals]
