@@ -53,6 +53,22 @@ def _expand_defs(defs, names):
 
 
 
+def _expand_matrix_defs(defs, names):
+    """precond matrix definitions with `{suff}` templating, expanded with the suffixes of the tracer modules in use
+    (input/py_driver_2d/tracer_module_defs.yaml:60-62: `forced_{suff}` -> `forced_o2_like`)"""
+    suffs = [suff for full in names for suff in full.split(":")[1:]]
+    out = {}
+    for name, mdef in defs.items():
+        if "{suff}" not in name:
+            out[name] = copy.deepcopy(mdef)
+            continue
+        for suff in suffs:
+            text = lambda obj: obj.replace("{suff}", suff) if isinstance(obj, str) else obj  # noqa: E731
+            out[text(name)] = {key: [text(v) for v in val] if isinstance(val, list) else copy.deepcopy(val)
+                               for key, val in mdef.items()}
+    return out
+
+
 def copy_hist_attrs(src, dst, long_name_suffix=None, drop_time_cell_methods=False):
     """attributes of a hist-file variable carried over to the precond file (model_state_base.py:449-470): all of
     them, `cell_methods` dropped when it refers to a time dimension the result does not have, the long name
@@ -66,11 +82,45 @@ def copy_hist_attrs(src, dst, long_name_suffix=None, drop_time_cell_methods=Fals
             val = val + long_name_suffix
         setattr(dst, key, val)
 
+def propagate_base_matrix_defs_to_all(matrix_defs):
+    """the settings of the matrix definition "base" become defaults of every other one, in place
+    (model_config.py:197-228, tests/test_model_config.py:25-57): a key the matrix lacks is taken over as a deep copy;
+    list settings are merged by OPTION NAME (the first word of an entry), so an option the matrix sets itself keeps its
+    own sub-option and nothing is added twice; dict settings gain the base's missing keys"""
+    base = matrix_defs.get("base")
+    if base is None:
+        return
+    for name, mdef in matrix_defs.items():
+        if name == "base":
+            continue
+        for key, dflt in base.items():
+            if key not in mdef:
+                mdef[key] = copy.deepcopy(dflt)
+            elif isinstance(dflt, list):
+                have = {entry.split()[0] for entry in mdef[key]}
+                mdef[key].extend(entry for entry in dflt if entry.split()[0] not in have)
+            elif isinstance(dflt, dict):
+                for sub, val in dflt.items():
+                    mdef[key].setdefault(sub, val)
+            else:
+                raise TypeError(f"base defn type {type(dflt)} not supported")
+
+
+def check_precond_matrix_defs(matrix_defs):
+    """hist_to_precond_varnames entries are `name`, `name:mean` or `name:log_mean` (model_config.py:231-246)"""
+    for name, mdef in matrix_defs.items():
+        for hist_var in mdef.get("hist_to_precond_varnames", []):
+            time_op = hist_var.partition(":")[2]
+            if time_op not in ("", "mean", "log_mean"):
+                raise ValueError(f"unknown time_op={time_op} in {hist_var} from {name}")
+
+
 class ModelConfig:
     """modelinfo + tracer module definitions + region weights (nk_ooc/model_config.py:17-78,
-    249-315).  tracer_module_defs: dict as in input/<model>/tracer_module_defs.yaml."""
+    249-315).  tracer_module_defs: dict as in input/<model>/tracer_module_defs.yaml; precond_matrix_defs: the
+    section of that name of the same file (None: the definitions of the modules this package ships)."""
 
-    def __init__(self, modelinfo, tracer_module_defs, grid_vars=None):
+    def __init__(self, modelinfo, tracer_module_defs, grid_vars=None, precond_matrix_defs=None):
         self.modelinfo = modelinfo
         names = modelinfo["tracer_module_names"].split(",")
         self.tracer_module_defs = _expand_defs(tracer_module_defs, names)
@@ -82,7 +132,12 @@ class ModelConfig:
         self.grid_weight = grid_vars["grid_weight"]
         self.weights = engine.RegionWeights(self.region_mask, self.grid_weight)
         self.region_cnt = self.weights.region_cnt
-        self.precond_matrix_defs = self._precond_matrix_defs()
+        if precond_matrix_defs is None:
+            self.precond_matrix_defs = self._precond_matrix_defs()
+        else:
+            self.precond_matrix_defs = _expand_matrix_defs(precond_matrix_defs, names)
+        propagate_base_matrix_defs_to_all(self.precond_matrix_defs)
+        check_precond_matrix_defs(self.precond_matrix_defs)
 
     def _precond_matrix_defs(self):
         """{matrix name: {"hist_to_precond_varnames": [...]}} (input/<model>/tracer_module_defs.yaml
@@ -98,7 +153,7 @@ class ModelConfig:
                 if pm is None or pm in defs:
                     continue
                 own = ["po4_s_restore_tau_r:mean"] if (column and pm == "phosphorus") else [tname]
-                defs[pm] = {"hist_to_precond_varnames": list(base) + [v for v in own if v not in base]}
+                defs[pm] = {"hist_to_precond_varnames": list(own)}
         return defs
 
 
@@ -437,6 +492,58 @@ class ModelStateBase:
         as_hist_stats(stats_file).put_hist_stats(iteration, hist_fname, names, weights)
         if solver_state is not None:
             solver_state.log_step(step)
+
+    def gen_precond_jacobian(self, hist_fname, precond_fname, solver_state=None):
+        """hist file -> precond file (model_state_base.py:404-481, 583-615): for every entry `name[:mean|:log_mean]` of
+        hist_vars_for_precond_list(), in that order, the hist variable reduced over time as the entry says; first all
+        dimensions the results have with their coordinate variables, then the results.  Layout (order of dimensions
+        and variables, names, attributes) as the reference writes it — the CI flows compare these files with the
+        baselines' metadata"""
+        os.makedirs(os.path.dirname(os.path.abspath(precond_fname)), exist_ok=True)
+        entries = [entry.partition(":")[::2] for entry in self.hist_vars_for_precond_list()]
+        with netcdf_file(hist_fname, "r", mmap=False) as fin, netcdf_file(precond_fname, "w", version=2) as fout:
+            stamp = datetime.now().strftime("%Y-%m-%d %H:%M:%S")
+            msg = f"{stamp}: created by {type(self).__name__}.gen_precond_jacobian"
+            prior = getattr(fin, "history", None)
+            fout.history = msg if prior is None else msg + "\n" + (prior.decode() if isinstance(prior, bytes) else prior)
+
+            def result_dims(name, time_op):
+                var = fin.variables[name]
+                dims = list(zip(var.dimensions, var.shape))
+                if time_op in ("mean", "log_mean"):
+                    dims = [d for d in dims if d[0] != "time"]
+                return [d for d in dims if not (d[0] == "time" and d[1] == 1)]
+
+            coords = []
+            for name, time_op in entries:
+                for dim, length in result_dims(name, time_op):
+                    if dim not in fout.dimensions:
+                        fout.createDimension(dim, length)
+                    elif fout.dimensions[dim] != length:
+                        raise ValueError(f"dimension {dim} of {name} has length {length}, not {fout.dimensions[dim]}")
+                    if dim in fin.variables and dim not in coords:
+                        coords.append(dim)
+            for dim in coords:
+                src = fin.variables[dim]
+                dst = fout.createVariable(dim, src.data.dtype.newbyteorder("="), (dim,))
+                copy_hist_attrs(src, dst)
+                dst[:] = np.array(src.data)
+            for name, time_op in entries:
+                if name in fout.dimensions:
+                    continue  # a coordinate variable: written above
+                src = fin.variables[name]
+                dims = tuple(d[0] for d in result_dims(name, time_op))
+                vals = np.array(src.data, dtype=np.float64)
+                if time_op == "mean":
+                    out_name, suffix, vals = f"{name}_mean", ", mean over time dim", vals.mean(axis=0)
+                elif time_op == "log_mean":
+                    out_name, suffix, vals = f"{name}_log_mean", ", log mean over time dim", np.exp(np.log(vals).mean(axis=0))
+                else:
+                    out_name, suffix = name, None
+                    vals = vals.reshape([fout.dimensions[d] for d in dims])
+                dst = fout.createVariable(out_name, "f8", dims)
+                copy_hist_attrs(src, dst, suffix, drop_time_cell_methods="time" not in dims)
+                dst[:] = vals
 
     def hist_vars_for_precond_list(self):
         """hist variables needed for the preconditioner (model_state_base.py:379-388)"""

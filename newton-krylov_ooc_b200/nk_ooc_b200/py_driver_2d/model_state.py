@@ -13,7 +13,7 @@ from scipy.io import netcdf_file
 
 from .. import engine
 from .. import hist as hist_mod
-from ..model_state_base import ModelConfig, ModelStateBase, get_tracer_module_state_class, copy_hist_attrs
+from ..model_state_base import ModelConfig, ModelStateBase, get_tracer_module_state_class
 from ..spatial_axis import spatial_axis_from_file
 from . import modules
 from .tracer_module_state import tracer_snapshot_nearest
@@ -326,27 +326,6 @@ class ModelState(ModelStateBase):
                 for tname, vals in like.items():
                     fptr.variables[tname][:] = vals
                     hist_mod.write_derived(fptr, tname, vals, self.depth, self.ypos)
-
-    def gen_precond_jacobian(self, hist_fname, precond_fname, solver_state=None):
-        """hist -> precond file: time reductions of the hist variables listed in the precond
-        matrix definitions (model_state_base.py:404-481); py_driver_2d iage needs only `time`"""
-        os.makedirs(os.path.dirname(os.path.abspath(precond_fname)), exist_ok=True)
-        wanted = ["time"]
-        for tms in self.tracer_modules:
-            for tname, meta in tms._def["tracers"].items():
-                if "precond_matrix" in meta and tname not in wanted:
-                    wanted.append(tname)
-        with netcdf_file(hist_fname, "r", mmap=False) as fin, netcdf_file(precond_fname, "w", version=2) as fout:
-            stamp = datetime.now().strftime("%Y-%m-%d %H:%M:%S")
-            fout.history = f"{stamp}: created by {type(self).__name__}.gen_precond_jacobian"
-            for name in wanted:
-                var = fin.variables[name]
-                for dim, length in zip(var.dimensions, var.shape):
-                    if dim not in fout.dimensions:
-                        fout.createDimension(dim, length)
-                out = fout.createVariable(name, "f8", var.dimensions)
-                copy_hist_attrs(var, out)
-                out[:] = np.array(var.data)
 
     def apply_precond_jacobian(self, precond_fname, res_fname, solver_state):
         """res = M^-1 self - self per tracer module (py_driver_2d/model_state.py:235-270)"""

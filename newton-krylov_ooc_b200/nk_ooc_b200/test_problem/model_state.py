@@ -13,7 +13,7 @@ from scipy.io import netcdf_file
 
 from .. import engine
 from .. import hist as hist_mod
-from ..model_state_base import ModelConfig, ModelStateBase, get_tracer_module_state_class, copy_hist_attrs
+from ..model_state_base import ModelConfig, ModelStateBase, get_tracer_module_state_class
 from ..spatial_axis import spatial_axis_from_file
 from . import modules
 from .modules import SEC_PER_YEAR
@@ -252,40 +252,6 @@ class ModelState(ModelStateBase):
                 for tname, vals in like.items():
                     fptr.variables[tname][:] = vals
                     hist_mod.write_derived(fptr, tname, vals, self.depth)
-
-    def gen_precond_jacobian(self, hist_fname, precond_fname, solver_state=None):
-        """mixing_coeff:mean and mixing_coeff:log_mean over the hist times
-        (model_state_base.py:404-481; input/test_problem/tracer_module_defs.yaml:57-62)"""
-        os.makedirs(os.path.dirname(os.path.abspath(precond_fname)), exist_ok=True)
-        de = self.depth.dump_names["edges"]
-        with netcdf_file(hist_fname, "r", mmap=False) as fin, netcdf_file(precond_fname, "w", version=2) as fout:
-            stamp = datetime.now().strftime("%Y-%m-%d %H:%M:%S")
-            fout.history = f"{stamp}: created by {type(self).__name__}.gen_precond_jacobian"
-            mc_var = fin.variables["mixing_coeff"]
-            mc = np.array(mc_var.data)
-            fout.createDimension(de, mc.shape[1])
-            var = fout.createVariable(de, "f8", (de,))
-            copy_hist_attrs(fin.variables[de], var)
-            var[:] = self.depth.edges
-            var = fout.createVariable("mixing_coeff_mean", "f8", (de,))
-            copy_hist_attrs(mc_var, var, ", mean over time dim", drop_time_cell_methods=True)
-            var[:] = mc.mean(axis=0)
-            var = fout.createVariable("mixing_coeff_log_mean", "f8", (de,))
-            copy_hist_attrs(mc_var, var, ", log mean over time dim", drop_time_cell_methods=True)
-            var[:] = np.exp(np.log(mc).mean(axis=0))
-            if "phosphorus" in self.precond_matrix_list():
-                # precond_matrix_defs.phosphorus: 'po4_s_restore_tau_r:mean'
-                # (input/test_problem/tracer_module_defs.yaml:62-64)
-                dn = self.depth.axisname
-                tau_var = fin.variables["po4_s_restore_tau_r"]
-                tau = np.array(tau_var.data)
-                fout.createDimension(dn, tau.shape[1])
-                var = fout.createVariable(dn, "f8", (dn,))
-                copy_hist_attrs(fin.variables[dn], var)
-                var[:] = np.array(fin.variables[dn].data)
-                var = fout.createVariable("po4_s_restore_tau_r_mean", "f8", (dn,))
-                copy_hist_attrs(tau_var, var, ", mean over time dim", drop_time_cell_methods=True)
-                var[:] = tau.mean(axis=0)
 
     def apply_precond_jacobian(self, precond_fname, res_fname, solver_state):
         """res = A^-1 (self / T) - self, A the tridiagonal Jacobian with the log-mean mixing

@@ -56,7 +56,7 @@ def test_py_driver_2d_tracer_module_hooks_match_reference(golden_dir, tmp_path):
             np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-12 * np.abs(want).max())
         # bookkeeping of the preconditioner matrices (model_state_base.py:379-402)
         assert ms.precond_matrix_list() == ["phosphorus"]
-        assert ms.hist_vars_for_precond_list() == ["time", "po4"]
+        assert ms.hist_vars_for_precond_list() == ["po4", "time"]  # own entries, then those of "base"
         assert ms.tracer_names_per_precond_matrix() == {"phosphorus": ["po4"]}
     finally:
         ModelState.reset()
