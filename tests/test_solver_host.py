@@ -54,6 +54,14 @@ class _FakeState:
     calls = 0
     fail_at = None
     members = 1
+    steep = False
+
+    @classmethod
+    def fcn_of(cls, x):
+        if cls.steep:
+            # Newton's full step overshoots from x = 1 (the arctangent flattens): the Armijo loop has to damp it
+            return np.arctan(3.0 * (cls.A @ x - cls.b)) + 0.1 * (cls.A @ x - cls.b)
+        return cls.A @ x - cls.b + 0.02 * x ** 3
 
     def __init__(self, vals):
         if isinstance(vals, str):
@@ -82,7 +90,7 @@ class _FakeState:
         cls.calls += 1
         if cls.fail_at is not None and cls.calls == cls.fail_at:
             raise _Interrupted(step)
-        res = _FakeState(self.A @ self.vals - self.b + 0.02 * self.vals ** 3)
+        res = _FakeState(type(self).fcn_of(self.vals))
         if hist_fname is not None:
             os.makedirs(os.path.dirname(hist_fname), exist_ok=True)
             with open(hist_fname, "w") as fptr:
@@ -214,14 +222,18 @@ def fake(monkeypatch):
         return res
 
     monkeypatch.setattr(model_state_base, "lin_comb", lin_comb)
-    _FakeState.calls, _FakeState.fail_at = 0, None
-    return _FakeState
+    _FakeState.calls, _FakeState.fail_at, _FakeState.steep = 0, None, False
+    yield _FakeState
+    _FakeState.steep = False
 
 
 def _solve(cls, workdir, **kw):
     from nk_ooc_b200.solver import NewtonSolver
 
-    solver = NewtonSolver(cls(np.ones(6)), SOLVERINFO, workdir=workdir, **kw)
+    # the damped problem runs without the fixed-point iterations (x + F(x) is no contraction there): this is also the
+    # path on which an accepted Armijo candidate's F becomes the next iteration's F without another evaluation
+    info = dict(SOLVERINFO, post_newton_fp_iter="0") if cls.steep else SOLVERINFO
+    solver = NewtonSolver(cls(np.ones(6)), info, workdir=workdir, **kw)
     solver.solve()
     return solver
 
@@ -250,12 +262,22 @@ def test_newton_krylov_control_flow_and_reference_step_log(fake, tmp_path):
     assert state["fp_iter"] == 1 and state["armijo_ind"] == 0
 
 
-def test_resume_after_an_interruption_at_every_function_evaluation(fake, tmp_path):
+@pytest.mark.parametrize("steep", [False, True])
+def test_resume_after_an_interruption_at_every_function_evaluation(fake, tmp_path, steep):
     """solver_state.py:36-45 / newton_solver.py:140-334 / krylov_solver.py:86-165: a solve interrupted at ANY of its
     function evaluations and resumed from the files ends with the iterate and the step log of the uninterrupted solve,
     and only the interrupted evaluation is done twice"""
+    fake.steep = steep
     ref = _solve(fake, str(tmp_path / "ref"))
     total = fake.calls
+    assert ref.converged_flat()
+    if steep:
+        # (the damped steps of this run: Armijo candidates 01.. were evaluated and logged)
+        from scipy.io import netcdf_file
+
+        with netcdf_file(str(tmp_path / "ref" / "Newton_stats.nc"), "r", mmap=False) as nc:
+            factors = np.array(nc.variables["Armijo_factor_iage"].data)[: ref.iteration, 0]
+        assert factors.min() < 1.0 and any("prov_fcn_Armijo_01_" in f for f in os.listdir(str(tmp_path / "ref")))
     with open(str(tmp_path / "ref" / "Newton_state.json")) as fptr:
         ref_log = [s.replace(str(tmp_path / "ref"), "W") for s in json.load(fptr)["step_log"]]
     assert total >= 12
