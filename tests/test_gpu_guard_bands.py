@@ -117,3 +117,39 @@ def test_banded_solve_writes_only_its_buffers(n, kl, ku, B):
 
     want = solve_banded((kl, ku), ab, y.view(n, ldb)[:, :B].cpu().numpy())
     np.testing.assert_allclose(x.view(n, ldb)[:, :B].cpu().numpy(), want, rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("B", [1, 5, 37])
+def test_krylov_vector_kernels_write_only_their_buffers(B):
+    """nkb_mgs (w in place + scratch), nkb_lin_comb (out), nkb_axpby (y in place) with regions and excluded cells"""
+    from nk_ooc_b200.engine import RegionWeights, padded_members
+
+    T, nz, ny, k = 2, 13, 19, 3
+    rng = np.random.default_rng(17)
+    mask = np.tile(np.arange(ny) % 3 + 1, (nz, 1)).astype(np.int32)
+    mask[rng.random(size=mask.shape) < 0.1] = 0
+    rw = RegionWeights(mask, np.abs(rng.normal(size=(nz, ny))) + 0.1)
+    ldb = padded_members(B)
+    n = T * nz * ny * ldb
+    from nk_ooc_b200 import _lib
+
+    need = _lib.load().nkb_mgs_scratch_doubles(rw.region_cnt, B, rw.max_row)
+    arena = Arena([n] * (k + 3) + [need])
+    bufs = [arena.buf(i) for i in range(k + 3)]
+    for b in bufs:
+        b.copy_(torch.from_numpy(rng.normal(size=n)).cuda())
+    shape = (T, nz, ny, ldb)
+    basis = [b.view(shape) for b in bufs[:k]]
+    w, out, y = (b.view(shape) for b in bufs[k:])
+    rw._mgs_scratch = arena.buf(k + 3)  # pylint: disable=protected-access
+    before = [b.clone() for b in bufs[:k]]
+    h = rw.mgs(w, basis, B)
+    arena.assert_guards_intact("nkb_mgs")
+    rw.lin_comb(h, basis, B, add=w, out=out)
+    arena.assert_guards_intact("nkb_lin_comb")
+    alpha = torch.from_numpy(rng.normal(size=(rw.region_cnt, B))).cuda()
+    rw.axpby(alpha, w, 0.5, y, B)
+    arena.assert_guards_intact("nkb_axpby")
+    for b, b0 in zip(bufs[:k], before):
+        assert torch.equal(b.view(torch.int64), b0.view(torch.int64)), "a basis vector was modified"
+    assert torch.isfinite(h).all() and torch.isfinite(out[..., :B]).all() and torch.isfinite(y[..., :B]).all()
