@@ -73,15 +73,21 @@ def _tol_ratio(got, want, x0):
 @pytest.mark.parametrize("grid", ["g14x11", "g30x30", "g40x50", "g80x100", "g125x150"])
 @pytest.mark.parametrize("module", ["iage", "forced", "phosphorus"])
 def test_fcn_vs_reference_radau(golden_dir, grid, module):
-    from nk_ooc_b200.py_driver_2d.model_state import default_schedule
+    from nk_ooc_b200.py_driver_2d.model_state import default_schedule, hist_schedule
 
     g = _load(golden_dir, grid, module)
     model = _model(g, module)
-    model.set_graded_schedule(**default_schedule(module, int(g["params"][0])))
+    nz = int(g["params"][0])
+    model.set_graded_schedule(**default_schedule(module, nz))
     x0 = g["x0"]
     truth = g["tol1e-09/fcn"]
     idx = [int(i) for i in g["tol1e-09/snap_idx"]]
     got, snaps = _eval(model, x0, idx)
+    if hist_schedule(module, nz) != default_schedule(module, nz):
+        # (phosphorus on fine grids: the evaluations that write a hist file take the snapshots from a second integration
+        # with the mixed-layer ramps resolved more finely, F from the schedule of every other evaluation)
+        model.set_graded_schedule(**hist_schedule(module, nz))
+        _, snaps = _eval(model, x0, idx)
     ratio = _tol_ratio(got, truth, x0)
     ref_ratio = _tol_ratio(g["tol1e-06/fcn"], truth, x0) if "tol1e-06/fcn" in g.files else float("nan")
     print(f"{grid}/{module}: max|F| {np.abs(truth).max():.3e}  max|dF| gpu {np.abs(got - truth).max():.3e} "
@@ -138,6 +144,51 @@ def test_forced_model_state_comp_fcn_vs_reference_radau(golden_dir, tmp_path):
         fcn = x.comp_fcn(None, None)
         got = fcn.get_tracer_vals("o2_like")[None]
         assert _tol_ratio(got, g["tol1e-09/fcn"], g["x0"]) <= 1.0
+    finally:
+        ModelState.reset()
+
+
+def test_phosphorus_fine_grid_hist_file_vs_reference_radau(golden_dir, tmp_path):
+    """ModelState.comp_fcn WITH a hist file on 80 x 100: F is the F of every other evaluation (bit-identical with the
+    evaluation without a hist file: the finite-difference products difference the two), the snapshots in the hist file
+    come from the second, finer integration (model_state.py:hist_schedule) and meet the tolerance against the
+    reference's Radau solution, which the 2640-step snapshots do not in the middle of the first mixed-layer ramp"""
+    from scipy.io import netcdf_file
+
+    from nk_ooc_b200.py_driver_2d.model_state import ModelState, default_schedule, hist_schedule
+    from nk_ooc_b200.py_driver_2d.setup_solver import gen_grid_vars_file
+
+    g = _load(golden_dir, "g80x100", "phosphorus")
+    nz, ny, ratio = int(g["params"][0]), int(g["params"][1]), float(g["params"][2])
+    assert hist_schedule("phosphorus", nz) != default_schedule("phosphorus", nz)
+    info = {
+        "model_name": "py_driver_2d", "tracer_module_names": "phosphorus",
+        "grid_vars_fname": str(tmp_path / "grid_vars.nc"),
+        "depth_axisname": "depth", "depth_units": "m", "depth_edge_start": "0.0", "depth_edge_end": "4000.0",
+        "depth_nlevs": str(nz), "depth_delta_ratio_max": repr(ratio),
+        "ypos_axisname": "ypos", "ypos_units": "m", "ypos_edge_start": "0.0", "ypos_edge_end": "50.0e5",
+        "ypos_nlevs": str(ny), "ypos_delta_ratio_max": "1.0", "max_abs_vvel": repr(float(g["params"][3])),
+        "horiz_mix_coeff": repr(float(g["params"][4])), "reinvoke": "False",
+    }
+    gen_grid_vars_file(info)
+    ModelState.configure(info)
+    try:
+        np.testing.assert_allclose(ModelState.depth.edges, g["depth_edges"], rtol=1e-14)
+        names = ("po4", "dop", "pop")
+        x = ModelState({name: g["x0"][i] for i, name in enumerate(names)})
+        plain = x.comp_fcn(None, None)
+        hist_fname = str(tmp_path / "hist.nc")
+        with_hist = x.comp_fcn(None, None, hist_fname)
+        for name in names:
+            assert np.array_equal(plain.get_tracer_vals(name), with_hist.get_tracer_vals(name)), name
+        got = np.stack([plain.get_tracer_vals(name) for name in names])
+        assert _tol_ratio(got, g["tol1e-09/fcn"], g["x0"]) <= 1.0
+        idx = [int(i) for i in g["tol1e-09/snap_idx"]]
+        with netcdf_file(hist_fname, "r", mmap=False) as nc:
+            snaps = np.stack([np.array(nc.variables[name].data)[idx] for name in names], axis=1)
+        worst = max(_tol_ratio(snaps[i], g["tol1e-09/snaps"][i], g["x0"]) for i in range(len(idx)))
+        print(f"hist snapshots {idx}: worst ratio to the tolerance {worst:.3f}")
+        assert worst <= 1.0
     finally:
         ModelState.reset()
 
