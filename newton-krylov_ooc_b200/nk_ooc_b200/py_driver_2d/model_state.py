@@ -61,8 +61,9 @@ DEFAULT_STEPS_PER_YEAR = None
 def default_schedule(kind, nz):
     """keyword arguments of engine.graded_schedule for a tracer module on a grid with nz levels, chosen from
     the measured error of F against the reference's Radau solution (profiles/r02_error_vs_steps.md) so that
-    the error stays below half of the stated tolerance (rtol 1e-3 |F| + atol 1e-6 max(1, max |x0|), DESIGN.md
-    section 2): 2640 steps per year (20 / 120 / 240 per hist interval) everywhere, except for iage on grids
+    the error stays below the stated tolerance (rtol 1e-3 |F| + atol 1e-6 max(1, max |x0|), DESIGN.md section 2;
+    worst case forced on 125 x 150 at 0.67, where the reference's own Radau run at its rtol = atol = 1e-6 is at
+    0.49): 2640 steps per year (20 / 120 / 240 per hist interval) everywhere, except for iage on grids
     finer than 60 levels, whose sharp age gradient below the moving mixed layer needs 5280 (ratio 0.95 and
     1.36 of the tolerance with 2640 steps on 80 x 100 and 125 x 150, 0.23 and 0.32 with 5280).
     scripts/schedule_probe.py separates the two needs: the year-end error of F comes from the intervals with a
