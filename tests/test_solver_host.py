@@ -37,175 +37,7 @@ from types import SimpleNamespace
 import pytest
 
 
-class _Interrupted(Exception):
-    pass
-
-
-class _FakeState:
-    """the operator surface solver.py uses, on a 6-vector: F(x) = A x - b + 0.02 x^3, preconditioner diag(A)^-1,
-    files are .npy arrays under the reference's file names, steps are logged exactly where the model states of
-    this package (and the reference's) log them"""
-
-    __array_priority__ = 100
-    model_config_obj = SimpleNamespace(region_cnt=1)
-    rng = np.random.default_rng(7)
-    A = np.diag(np.linspace(2.0, 5.0, 6)) + 0.3 * rng.normal(size=(6, 6))
-    b = rng.normal(size=6)
-    calls = 0
-    fail_at = None
-    members = 1
-    steep = False
-
-    @classmethod
-    def fcn_of(cls, x):
-        if cls.steep:
-            # Newton's full step overshoots from x = 1 (the arctangent flattens): the Armijo loop has to damp it
-            return np.arctan(3.0 * (cls.A @ x - cls.b)) + 0.1 * (cls.A @ x - cls.b)
-        return cls.A @ x - cls.b + 0.02 * x ** 3
-
-    def __init__(self, vals):
-        if isinstance(vals, str):
-            with open(vals, "rb") as fptr:
-                vals = np.load(fptr)
-        self.vals = np.array(vals, dtype=float)
-        self.tracer_modules = [SimpleNamespace(name="iage", units="years")]
-
-    # files
-    def dump(self, fname, caller=None):
-        if fname is not None:
-            os.makedirs(os.path.dirname(fname), exist_ok=True)
-            with open(fname, "wb") as fptr:
-                np.save(fptr, self.vals)
-        return self
-
-    def _like(self, clone_vals=True):
-        return _FakeState(self.vals.copy() if clone_vals else np.zeros_like(self.vals))
-
-    # the model
-    def comp_fcn(self, res_fname, solver_state, hist_fname=None):
-        step = f"comp_fcn complete for {res_fname}"
-        if solver_state is not None and solver_state.step_logged(step):
-            return _FakeState(res_fname)
-        cls = type(self)
-        cls.calls += 1
-        if cls.fail_at is not None and cls.calls == cls.fail_at:
-            raise _Interrupted(step)
-        res = _FakeState(type(self).fcn_of(self.vals))
-        if hist_fname is not None:
-            os.makedirs(os.path.dirname(hist_fname), exist_ok=True)
-            with open(hist_fname, "w") as fptr:
-                fptr.write("hist")
-        res.dump(res_fname, "comp_fcn")
-        if solver_state is not None:
-            solver_state.log_step(step)
-        return res
-
-    def comp_jacobian_fcn_state_prod(self, fcn, direction, res_fname, solver_state):
-        step = f"comp_jacobian_fcn_state_prod complete for {res_fname}"
-        if solver_state is not None and solver_state.step_logged(step):
-            return _FakeState(res_fname)
-        sigma = 1.0e-4 * self.norm()
-        sigma = np.where(sigma == 0.0, 1.0, sigma)
-        perturb = self + sigma * direction
-        pname = None
-        if res_fname is not None:
-            pname = os.path.join(os.path.dirname(res_fname), f"perturb_fcn_{os.path.basename(res_fname)}")
-        res = ((perturb.comp_fcn(pname, solver_state) - fcn) / sigma).dump(res_fname, "jvp")
-        if solver_state is not None:
-            solver_state.log_step(step)
-        return res
-
-    def gen_precond_jacobian(self, hist_fname, precond_fname, solver_state=None):
-        assert os.path.exists(hist_fname)
-        os.makedirs(os.path.dirname(precond_fname), exist_ok=True)
-        with open(precond_fname, "w") as fptr:
-            fptr.write("precond")
-
-    def apply_precond_jacobian(self, precond_fname, res_fname, solver_state):
-        step = f"apply_precond_jacobian complete for {res_fname}"
-        if solver_state is not None and solver_state.step_logged(step):
-            return _FakeState(res_fname)
-        res = _FakeState(self.vals / np.diag(self.A)).dump(res_fname, "precond")
-        if solver_state is not None:
-            solver_state.log_step(step)
-        return res
-
-    # reductions
-    def dot_prod(self, other):
-        return np.array([[np.mean(self.vals * other.vals)]])
-
-    def norm(self):
-        return np.sqrt(self.dot_prod(self))
-
-    def mean(self):
-        return np.array([[np.mean(self.vals)]])
-
-    def mod_gram_schmidt(self, basis_cnt, fname_fcn, quantity):
-        h = np.zeros((1, basis_cnt, 1))
-        for i in range(basis_cnt):
-            v = fname_fcn(quantity, i)
-            h[:, i, :] = self.dot_prod(v)
-            self.vals -= h[0, i, 0] * v.vals
-        return h
-
-    # operators with [n_modules, region_cnt] scalars
-    @staticmethod
-    def _s(other):
-        return float(np.asarray(other).reshape(-1)[0]) if not isinstance(other, _FakeState) else other.vals
-
-    def __neg__(self):
-        return _FakeState(-self.vals)
-
-    def __add__(self, other):
-        return _FakeState(self.vals + self._s(other))
-
-    def __sub__(self, other):
-        return _FakeState(self.vals - self._s(other))
-
-    def __mul__(self, other):
-        return _FakeState(self.vals * self._s(other))
-
-    __rmul__ = __mul__
-
-    def __truediv__(self, other):
-        return _FakeState(self.vals / self._s(other))
-
-    def __iadd__(self, other):
-        self.vals = self.vals + self._s(other)
-        return self
-
-    def __itruediv__(self, other):
-        self.vals = self.vals / self._s(other)
-        return self
-
-    # the rest of the surface
-    def apply_limiter(self, base):
-        return np.ones((1, 1))
-
-    def log_vals(self, msg, vals):
-        pass
-
-    def copy_real_tracers_to_shadow_tracers(self):
-        return self
-
-    def copy_shadow_tracers_to_real_tracers(self):
-        return self
-
-    def shadow_tracers_on(self):
-        return False
-
-    def _log_only(self, step, solver_state, per_iteration):
-        if solver_state is not None:
-            solver_state.log_step(step, per_iteration)
-
-    def def_stats_vars(self, stats_file, hist_fname, solver_state):
-        self._log_only("ModelStateBase.def_stats_vars", solver_state, False)
-
-    def put_stats_vars_iteration_invariant(self, stats_file, hist_fname, solver_state):
-        self._log_only("ModelStateBase.put_stats_vars_iteration_invariant", solver_state, False)
-
-    def put_stats_vars(self, stats_file, hist_fname, solver_state):
-        self._log_only("ModelStateBase.put_stats_vars", solver_state, True)
+from fake_state import FakeState as _FakeState, Interrupted as _Interrupted  # noqa: E402
 
 
 SOLVERINFO = {"newton_rel_tol": "1.0e-8", "newton_max_iter": "12", "post_newton_fp_iter": "1", "krylov_rel_tol": "0.01"}
@@ -310,3 +142,58 @@ def test_rewind_redoes_the_last_logged_step(fake, tmp_path):
         assert json.load(fptr)["step_log"] == log
     with pytest.raises(RuntimeError):
         NewtonSolver(fake(np.ones(6)), SOLVERINFO, workdir=str(tmp_path / "x"), resume=False, rewind=True)
+
+
+@pytest.mark.parametrize("problem", ["mild", "damped"])
+def test_same_solve_as_the_references_own_solvers(fake, tmp_path, problem):
+    """tests/golden/ref_solver_<problem>.json records what the REFERENCE's NewtonSolver / KrylovSolver (imported
+    unmodified, oracle/gen_golden_solver.py) did over this very state class: this package's solvers take the same
+    Newton iterates, function values and increments, evaluate F as often, and leave the same Newton and Krylov step
+    logs, saved Hessenberg matrices and files behind"""
+    with open(os.path.join(os.path.dirname(__file__), "golden", f"ref_solver_{problem}.json")) as fptr:
+        ref = json.load(fptr)
+    from nk_ooc_b200.solver import NewtonSolver
+
+    fake.steep = problem == "damped"
+    work = str(tmp_path / "w")
+    solver = NewtonSolver(fake(np.ones(6)), dict(ref["solverinfo"]), workdir=work)
+    solver.solve()
+    assert solver.iteration == ref["iterations"] and fake.calls == ref["evaluations"]
+
+    def arr(name):
+        return fake(os.path.join(work, name)).vals
+
+    for i in range(ref["iterations"] + 1):
+        np.testing.assert_allclose(arr(f"iterate_{i:02}.nc"), ref["iterate"][i], rtol=1e-11, atol=1e-13, err_msg=f"iterate {i}")
+        np.testing.assert_allclose(arr(f"fcn_{i:02}.nc"), ref["fcn"][i], rtol=1e-9, atol=1e-13, err_msg=f"fcn {i}")
+    for i in range(ref["iterations"]):
+        np.testing.assert_allclose(arr(f"increment_{i:02}.nc"), ref["increment"][i], rtol=1e-9, atol=1e-13)
+
+    def state(path):
+        with open(path) as fptr:
+            rec = json.load(fptr)
+        rec["step_log"] = [s.replace(work, "W") for s in rec["step_log"]]
+        return rec
+
+    def vals(rec, key):
+        val = rec[key]
+        return np.array(val["__ndarray__"] if isinstance(val, dict) else val, dtype=float)
+
+    ours = state(os.path.join(work, "Newton_state.json"))
+    assert ours["step_log"] == ref["Newton_state"]["step_log"]
+    assert ours["iteration"] == ref["Newton_state"]["iteration"]
+    for key in ("armijo_ind", "armijo_factor", "fp_iter"):
+        np.testing.assert_array_equal(vals(ours, key), vals(ref["Newton_state"], key), err_msg=key)
+    for i, want in enumerate(ref["Krylov_state"]):
+        got = state(os.path.join(work, f"krylov_{i:02}", "Krylov_state.json"))
+        assert got["step_log"] == want["step_log"], f"Krylov solve {i}"
+        assert got["iteration"] == want["iteration"]
+        np.testing.assert_allclose(vals(got, "beta"), vals(want, "beta"), rtol=1e-10)
+        np.testing.assert_allclose(vals(got, "h_mat"), vals(want, "h_mat"), rtol=1e-8, atol=1e-12)
+    # the files left in the work directory (the reference's stats files were kept in memory by the generator)
+    files = sorted(os.path.relpath(os.path.join(d, f), work) for d, _, fs in os.walk(work) for f in fs)
+    stats = {f for f in files if f.endswith("_stats.nc")}
+    assert stats == {"Newton_stats.nc"} | {os.path.join(f"krylov_{i:02}", "Krylov_stats.nc") for i in range(ref["iterations"])}
+    assert [f for f in files if f not in stats] == [f for f in ref["files"] if f != "init_iterate.nc"]
+    if problem == "damped":
+        assert min(ref["Armijo_factor"]) == 0.25
