@@ -76,6 +76,19 @@ class _MemDim:
         return max(lens, default=0)
 
 
+class _LooseVars(dict):
+    """variables of a stats file that was NOT written through this stand-in (a solve of this package's solvers that the
+    reference resumes, tests/test_solver_host.py): whatever the reference writes to is created on first use"""
+
+    def __init__(self, fptr):
+        super().__init__()
+        self._fptr = fptr
+
+    def __missing__(self, name):
+        self[name] = _MemVar(name, ("iteration", "region"), self._fptr, 9.969209968386869e36)
+        return self[name]
+
+
 class _MemDataset:
     """netCDF4.Dataset stand-in: files written by the solvers live in memory, everything else is read from disk"""
 
@@ -87,10 +100,17 @@ class _MemDataset:
     def __init__(self, fname, mode="r", **kwargs):
         if mode == "w":
             _FILES[fname] = {"dimensions": {}, "variables": {}, "attrs": {}}
+        loose = fname not in _FILES
+        if loose:
+            _FILES[fname] = {"dimensions": {}, "variables": _LooseVars(self), "attrs": {"history": ""}}
         store = _FILES[fname]
         self.__dict__["_store"] = store
         self.__dict__["dimensions"] = store["dimensions"]
         self.__dict__["variables"] = store["variables"]
+        if loose:
+            store["dimensions"].update(iteration=_MemDim(None, self, "iteration"), region=_MemDim(1, self, "region"))
+        if isinstance(store["variables"], _LooseVars):
+            store["variables"]._fptr = self  # pylint: disable=protected-access
 
     def __setattr__(self, key, val):
         self._store["attrs"][key] = val
@@ -120,15 +140,27 @@ class _MemDataset:
         return False
 
 
-def run_reference(problem):
-    """the reference's driver loop (nk_driver.py:58-66) over FakeState; returns the record for the golden file"""
+def reference_newton_solver():
+    """the reference's NewtonSolver class, its stats files redirected to the in-memory stand-in"""
+    ref_harness.install_stubs()
     import netCDF4  # the stub installed by ref_harness
 
     netCDF4.Dataset = _MemDataset
     for name in list(sys.modules):
-        if name.startswith("nk_ooc") and hasattr(sys.modules[name], "Dataset"):
+        if name.startswith("nk_ooc.") and hasattr(sys.modules[name], "Dataset"):
             sys.modules[name].Dataset = _MemDataset
     from nk_ooc.newton_solver import NewtonSolver
+
+    return NewtonSolver
+
+
+def solverinfo(workdir, init_iterate_fname=None, **kw):
+    return _Section(dict(SOLVERINFO, workdir=workdir, init_iterate_fname=init_iterate_fname, **kw))
+
+
+def run_reference(problem):
+    """the reference's driver loop (nk_driver.py:58-66) over FakeState; returns the record for the golden file"""
+    NewtonSolver = reference_newton_solver()  # noqa: N806
 
     from fake_state import FakeState
 
@@ -136,7 +168,7 @@ def run_reference(problem):
     with tempfile.TemporaryDirectory() as work:
         init = os.path.join(work, "init_iterate.nc")
         FakeState(np.ones(6)).dump(init)
-        info = _Section(dict(SOLVERINFO, workdir=work, init_iterate_fname=init))
+        info = solverinfo(work, init)
         solver = NewtonSolver(FakeState, info, resume=False, rewind=False)
         while not solver.converged().all():
             solver.step()

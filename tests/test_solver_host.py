@@ -179,13 +179,24 @@ def test_same_solve_as_the_references_own_solvers(fake, tmp_path, problem):
         val = rec[key]
         return np.array(val["__ndarray__"] if isinstance(val, dict) else val, dtype=float)
 
+    def same_schema(got, want, what):
+        """the same keys, and arrays stored with the same `__ndarray__` tagging (solver_state.py:14-33,137-166)"""
+        assert list(got) == list(want), what
+        for key, val in want.items():
+            assert isinstance(got[key], type(val)), (what, key)
+            if isinstance(val, dict):
+                assert list(got[key]) == list(val) == ["__ndarray__"], (what, key)
+                assert np.shape(got[key]["__ndarray__"]) == np.shape(val["__ndarray__"]), (what, key)
+
     ours = state(os.path.join(work, "Newton_state.json"))
+    same_schema(ours, ref["Newton_state"], "Newton_state.json")
     assert ours["step_log"] == ref["Newton_state"]["step_log"]
     assert ours["iteration"] == ref["Newton_state"]["iteration"]
     for key in ("armijo_ind", "armijo_factor", "fp_iter"):
         np.testing.assert_array_equal(vals(ours, key), vals(ref["Newton_state"], key), err_msg=key)
     for i, want in enumerate(ref["Krylov_state"]):
         got = state(os.path.join(work, f"krylov_{i:02}", "Krylov_state.json"))
+        same_schema(got, want, f"krylov_{i:02}/Krylov_state.json")
         assert got["step_log"] == want["step_log"], f"Krylov solve {i}"
         assert got["iteration"] == want["iteration"]
         np.testing.assert_allclose(vals(got, "beta"), vals(want, "beta"), rtol=1e-10)
@@ -197,3 +208,38 @@ def test_same_solve_as_the_references_own_solvers(fake, tmp_path, problem):
     assert [f for f in files if f not in stats] == [f for f in ref["files"] if f != "init_iterate.nc"]
     if problem == "damped":
         assert min(ref["Armijo_factor"]) == 0.25
+
+
+@pytest.mark.parametrize("problem", ["mild", "damped"])
+def test_the_reference_resumes_a_solve_this_package_interrupted(fake, tmp_path, problem):
+    """state-file compatibility in the direction a user switching back would need: a solve of THIS package's solvers,
+    interrupted at a function evaluation, is picked up by the REFERENCE's `NewtonSolver(resume=True)` (build container
+    only: skipped where /root/reference is absent) — Newton_state.json, the Krylov_state.json of a solve in progress and
+    the iterate / basis / w files are read by the reference's own code, which finishes with the iterate and the Newton
+    step log of its own uninterrupted solve, evaluating only what was not logged"""
+    from oracle import gen_golden_solver as gen
+    from oracle import ref_harness
+
+    if not ref_harness.available():
+        pytest.skip("the reference is not mounted here")
+    with open(os.path.join(os.path.dirname(__file__), "golden", f"ref_solver_{problem}.json")) as fptr:
+        ref = json.load(fptr)
+    from nk_ooc_b200.solver import NewtonSolver
+
+    ref_solver_class = gen.reference_newton_solver()
+    for k in (2, 5, 9, 14, ref["evaluations"] - 1):
+        fake.steep = problem == "damped"
+        work = str(tmp_path / f"w{k}")
+        fake.calls, fake.fail_at = 0, k
+        with pytest.raises(_Interrupted):
+            NewtonSolver(fake(np.ones(6)), dict(ref["solverinfo"]), workdir=work).solve()
+        fake.fail_at = None
+        theirs = ref_solver_class(fake, gen.solverinfo(work), resume=True, rewind=False)
+        while not theirs.converged().all():
+            theirs.step()
+        assert fake.calls == ref["evaluations"] + 1, k
+        final = fake(os.path.join(work, f"iterate_{ref['iterations']:02}.nc")).vals
+        np.testing.assert_allclose(final, ref["iterate"][-1], rtol=1e-11, atol=1e-13, err_msg=str(k))
+        with open(os.path.join(work, "Newton_state.json")) as fptr:
+            log = [s.replace(work, "W") for s in json.load(fptr)["step_log"]]
+        assert log == ref["Newton_state"]["step_log"], k
