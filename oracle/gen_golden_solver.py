@@ -183,6 +183,20 @@ def run_reference(problem):
             rec["step_log"] = [s.replace(work, "W") for s in rec["step_log"]]
             return rec
 
+        def stats(path):
+            """what the reference wrote into a stats file, call by call (dimensions, variables in definition order,
+            attributes, values)"""
+            store = _FILES[path]
+            return {
+                "attrs": sorted(store["attrs"]),
+                "dimensions": [[name, dim.size, len(dim)] for name, dim in store["dimensions"].items()],
+                "variables": [
+                    {"name": var.name, "dimensions": list(var.dimensions),
+                     "attrs": {k: v for k, v in vars(var).items() if k not in ("name", "dimensions", "data", "_fptr")},
+                     "data": np.asarray(var.data).tolist()}
+                    for var in store["variables"].values()],
+            }
+
         rec = {
             "problem": problem, "solverinfo": SOLVERINFO, "iterations": n_iter, "evaluations": FakeState.calls,
             "iterate": [arr(f"iterate_{i:02}.nc") for i in range(n_iter + 1)],
@@ -191,6 +205,8 @@ def run_reference(problem):
             "Newton_state": state(os.path.join(work, "Newton_state.json")),
             "Krylov_state": [state(os.path.join(work, f"krylov_{i:02}", "Krylov_state.json")) for i in range(n_iter)],
             "files": sorted(os.path.relpath(os.path.join(d, f), work) for d, _, fs in os.walk(work) for f in fs),
+            "Newton_stats": stats(os.path.join(work, "Newton_stats.nc")),
+            "Krylov_stats": [stats(os.path.join(work, f"krylov_{i:02}", "Krylov_stats.nc")) for i in range(n_iter)],
             "Armijo_factor": np.asarray(_FILES[os.path.join(work, "Newton_stats.nc")]["variables"]["Armijo_factor_iage"].data)
             [:n_iter, 0].tolist(),
         }

@@ -201,6 +201,34 @@ def test_same_solve_as_the_references_own_solvers(fake, tmp_path, problem):
         assert got["iteration"] == want["iteration"]
         np.testing.assert_allclose(vals(got, "beta"), vals(want, "beta"), rtol=1e-10)
         np.testing.assert_allclose(vals(got, "h_mat"), vals(want, "h_mat"), rtol=1e-8, atol=1e-12)
+    # the stats files: every dimension, variable, attribute and value the reference wrote (stats_file.py,
+    # solver_base.py:68-193, newton_solver.py:62-118, krylov_solver.py:50-73), fill values of the grown iteration
+    # dimension included
+    from scipy.io import netcdf_file
+
+    def same_stats(path, want):
+        with netcdf_file(path, "r", mmap=False) as nc:
+            assert hasattr(nc, "history")
+            for name, size, length in want["dimensions"]:
+                assert name in nc.dimensions and nc.dimensions[name] == size, (path, name)
+            assert sorted(nc.variables) == sorted(v["name"] for v in want["variables"]), path
+            for var in want["variables"]:
+                got = nc.variables[var["name"]]
+                assert list(got.dimensions) == var["dimensions"], var["name"]
+                attrs = {k: (v.decode() if isinstance(v, bytes) else v) for k, v in got._attributes.items()}  # noqa: SLF001
+                assert sorted(attrs) == sorted(var["attrs"]), var["name"]
+                for key, val in var["attrs"].items():
+                    if isinstance(val, str):
+                        assert attrs[key] == val, (var["name"], key)
+                    else:
+                        assert float(np.asarray(attrs[key]).reshape(-1)[0]) == float(val), (var["name"], key)
+                data = np.array(got.data, dtype=float)
+                assert data.shape == np.shape(var["data"]), var["name"]
+                np.testing.assert_allclose(data, var["data"], rtol=1e-9, atol=1e-14, err_msg=var["name"])
+
+    same_stats(os.path.join(work, "Newton_stats.nc"), ref["Newton_stats"])
+    for i, want in enumerate(ref["Krylov_stats"]):
+        same_stats(os.path.join(work, f"krylov_{i:02}", "Krylov_stats.nc"), want)
     # the files left in the work directory (the reference's stats files were kept in memory by the generator)
     files = sorted(os.path.relpath(os.path.join(d, f), work) for d, _, fs in os.walk(work) for f in fs)
     stats = {f for f in files if f.endswith("_stats.nc")}
