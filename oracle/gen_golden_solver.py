@@ -58,6 +58,8 @@ class _MemVar:
     def __setitem__(self, key, val):
         first = key[0] if isinstance(key, tuple) else key
         if isinstance(first, (int, np.integer)):
+            if getattr(self, "_loose", False) and np.shape(val) != self.data.shape[1:]:
+                self.data = np.zeros((self.data.shape[0],) + np.shape(val))  # (first write: takes the value's shape)
             self._grow(int(first) + 1)
         self.data[key] = val
 
@@ -86,6 +88,7 @@ class _LooseVars(dict):
 
     def __missing__(self, name):
         self[name] = _MemVar(name, ("iteration", "region"), self._fptr, 9.969209968386869e36)
+        self[name]._loose = True  # pylint: disable=protected-access
         return self[name]
 
 
@@ -164,7 +167,7 @@ def run_reference(problem):
 
     from fake_state import FakeState
 
-    FakeState.steep, FakeState.calls, FakeState.fail_at = problem == "damped", 0, None
+    FakeState.configure(problem)
     with tempfile.TemporaryDirectory() as work:
         init = os.path.join(work, "init_iterate.nc")
         FakeState(np.ones(6)).dump(init)
@@ -192,7 +195,7 @@ def run_reference(problem):
                 "dimensions": [[name, dim.size, len(dim)] for name, dim in store["dimensions"].items()],
                 "variables": [
                     {"name": var.name, "dimensions": list(var.dimensions),
-                     "attrs": {k: v for k, v in vars(var).items() if k not in ("name", "dimensions", "data", "_fptr")},
+                     "attrs": {k: v for k, v in vars(var).items() if k not in ("name", "dimensions", "data", "_fptr", "_loose")},
                      "data": np.asarray(var.data).tolist()}
                     for var in store["variables"].values()],
             }
@@ -207,10 +210,10 @@ def run_reference(problem):
             "files": sorted(os.path.relpath(os.path.join(d, f), work) for d, _, fs in os.walk(work) for f in fs),
             "Newton_stats": stats(os.path.join(work, "Newton_stats.nc")),
             "Krylov_stats": [stats(os.path.join(work, f"krylov_{i:02}", "Krylov_stats.nc")) for i in range(n_iter)],
-            "Armijo_factor": np.asarray(_FILES[os.path.join(work, "Newton_stats.nc")]["variables"]["Armijo_factor_iage"].data)
-            [:n_iter, 0].tolist(),
+            "Armijo_factor": [np.asarray(_FILES[os.path.join(work, "Newton_stats.nc")]["variables"]
+                                         [f"Armijo_factor_{tm.name}"].data)[:n_iter].tolist() for tm in solver._iterate.tracer_modules],
         }
-    FakeState.steep = False
+    FakeState.configure("mild")
     return rec
 
 
@@ -218,7 +221,7 @@ def main():
     ref_harness.install_stubs()
     if ref_harness.REF_ROOT not in sys.path:
         sys.path.insert(0, ref_harness.REF_ROOT)
-    for problem in ("mild", "damped"):
+    for problem in ("mild", "damped", "regions"):
         rec = run_reference(problem)
         path = os.path.join(ROOT, "tests", "golden", f"ref_solver_{problem}.json")
         with open(path, "w") as fptr:

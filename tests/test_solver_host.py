@@ -50,13 +50,13 @@ def fake(monkeypatch):
     def lin_comb(cls, coeff, fname_fcn, quantity):
         res = cls(np.zeros(6))
         for i in range(coeff.shape[1]):
-            res.vals += coeff[0, i, 0] * fname_fcn(quantity, i).vals
+            res.vals += coeff[:, i, :, None] * fname_fcn(quantity, i).vals
         return res
 
     monkeypatch.setattr(model_state_base, "lin_comb", lin_comb)
-    _FakeState.calls, _FakeState.fail_at, _FakeState.steep = 0, None, False
+    _FakeState.configure("mild")
     yield _FakeState
-    _FakeState.steep = False
+    _FakeState.configure("mild")
 
 
 def _solve(cls, workdir, **kw):
@@ -64,7 +64,7 @@ def _solve(cls, workdir, **kw):
 
     # the damped problem runs without the fixed-point iterations (x + F(x) is no contraction there): this is also the
     # path on which an accepted Armijo candidate's F becomes the next iteration's F without another evaluation
-    info = dict(SOLVERINFO, post_newton_fp_iter="0") if cls.steep else SOLVERINFO
+    info = dict(SOLVERINFO, post_newton_fp_iter="0") if cls.problem == "damped" else SOLVERINFO
     solver = NewtonSolver(cls(np.ones(6)), info, workdir=workdir, **kw)
     solver.solve()
     return solver
@@ -78,7 +78,7 @@ def test_newton_krylov_control_flow_and_reference_step_log(fake, tmp_path):
     solver = _solve(fake, work)
     assert solver.converged_flat() and 3 <= solver.iteration <= 10
     x = solver.iterate.vals
-    np.testing.assert_allclose(fake.A @ x - fake.b + 0.02 * x ** 3, 0.0, atol=1e-6)
+    np.testing.assert_allclose(fake.A @ x[0, 0] - fake.b + 0.02 * x[0, 0] ** 3, 0.0, atol=1e-6)
     nofiles = _solve(fake, str(tmp_path / "n"), dump=False)
     np.testing.assert_allclose(nofiles.iterate.vals, x, rtol=0, atol=1e-12)
     assert not os.path.exists(str(tmp_path / "n" / "Newton_state.json"))
@@ -94,12 +94,13 @@ def test_newton_krylov_control_flow_and_reference_step_log(fake, tmp_path):
     assert state["fp_iter"] == 1 and state["armijo_ind"] == 0
 
 
-@pytest.mark.parametrize("steep", [False, True])
-def test_resume_after_an_interruption_at_every_function_evaluation(fake, tmp_path, steep):
+@pytest.mark.parametrize("problem", ["mild", "damped", "regions"])
+def test_resume_after_an_interruption_at_every_function_evaluation(fake, tmp_path, problem):
     """solver_state.py:36-45 / newton_solver.py:140-334 / krylov_solver.py:86-165: a solve interrupted at ANY of its
     function evaluations and resumed from the files ends with the iterate and the step log of the uninterrupted solve,
     and only the interrupted evaluation is done twice"""
-    fake.steep = steep
+    steep = problem != "mild"
+    fake.configure(problem)
     ref = _solve(fake, str(tmp_path / "ref"))
     total = fake.calls
     assert ref.converged_flat()
@@ -108,7 +109,7 @@ def test_resume_after_an_interruption_at_every_function_evaluation(fake, tmp_pat
         from scipy.io import netcdf_file
 
         with netcdf_file(str(tmp_path / "ref" / "Newton_stats.nc"), "r", mmap=False) as nc:
-            factors = np.array(nc.variables["Armijo_factor_iage"].data)[: ref.iteration, 0]
+            factors = np.array(nc.variables["Armijo_factor_iage"].data)[: ref.iteration]
         assert factors.min() < 1.0 and any("prov_fcn_Armijo_01_" in f for f in os.listdir(str(tmp_path / "ref")))
     with open(str(tmp_path / "ref" / "Newton_state.json")) as fptr:
         ref_log = [s.replace(str(tmp_path / "ref"), "W") for s in json.load(fptr)["step_log"]]
@@ -144,7 +145,7 @@ def test_rewind_redoes_the_last_logged_step(fake, tmp_path):
         NewtonSolver(fake(np.ones(6)), SOLVERINFO, workdir=str(tmp_path / "x"), resume=False, rewind=True)
 
 
-@pytest.mark.parametrize("problem", ["mild", "damped"])
+@pytest.mark.parametrize("problem", ["mild", "damped", "regions"])
 def test_same_solve_as_the_references_own_solvers(fake, tmp_path, problem):
     """tests/golden/ref_solver_<problem>.json records what the REFERENCE's NewtonSolver / KrylovSolver (imported
     unmodified, oracle/gen_golden_solver.py) did over this very state class: this package's solvers take the same
@@ -154,7 +155,7 @@ def test_same_solve_as_the_references_own_solvers(fake, tmp_path, problem):
         ref = json.load(fptr)
     from nk_ooc_b200.solver import NewtonSolver
 
-    fake.steep = problem == "damped"
+    fake.configure(problem)
     work = str(tmp_path / "w")
     solver = NewtonSolver(fake(np.ones(6)), dict(ref["solverinfo"]), workdir=work)
     solver.solve()
@@ -234,11 +235,13 @@ def test_same_solve_as_the_references_own_solvers(fake, tmp_path, problem):
     stats = {f for f in files if f.endswith("_stats.nc")}
     assert stats == {"Newton_stats.nc"} | {os.path.join(f"krylov_{i:02}", "Krylov_stats.nc") for i in range(ref["iterations"])}
     assert [f for f in files if f not in stats] == [f for f in ref["files"] if f != "init_iterate.nc"]
-    if problem == "damped":
-        assert min(ref["Armijo_factor"]) == 0.25
+    if problem != "mild":
+        assert 0.25 in np.ravel(ref["Armijo_factor"])  # a damped step ...
+    if problem == "regions":
+        assert 0.0 in np.ravel(ref["Armijo_factor"])  # ... and blocks that had converged while others had not
 
 
-@pytest.mark.parametrize("problem", ["mild", "damped"])
+@pytest.mark.parametrize("problem", ["mild", "damped", "regions"])
 def test_the_reference_resumes_a_solve_this_package_interrupted(fake, tmp_path, problem):
     """state-file compatibility in the direction a user switching back would need: a solve of THIS package's solvers,
     interrupted at a function evaluation, is picked up by the REFERENCE's `NewtonSolver(resume=True)` (build container
@@ -256,7 +259,7 @@ def test_the_reference_resumes_a_solve_this_package_interrupted(fake, tmp_path, 
 
     ref_solver_class = gen.reference_newton_solver()
     for k in (2, 5, 9, 14, ref["evaluations"] - 1):
-        fake.steep = problem == "damped"
+        fake.configure(problem)
         work = str(tmp_path / f"w{k}")
         fake.calls, fake.fail_at = 0, k
         with pytest.raises(_Interrupted):
