@@ -22,6 +22,8 @@ from oracle import ref_harness  # noqa: E402
 
 SOLVERINFO = {"newton_rel_tol": "1.0e-8", "newton_max_iter": "12", "post_newton_fp_iter": "1", "krylov_rel_tol": "0.01"}
 _FILES = {}
+PERSIST = False  # also write the stats files to disk (tests that hand a reference solve over to this package's solvers)
+_NOT_ATTRS = ("name", "dimensions", "data", "_fptr", "_loose", "_datatype")
 
 
 class _Section(dict):
@@ -38,8 +40,8 @@ class _Section(dict):
 
 
 class _MemVar:
-    def __init__(self, name, dims, fptr, fill):
-        self.name, self.dimensions, self._fptr = name, tuple(dims), fptr
+    def __init__(self, name, dims, fptr, fill, datatype="f8"):
+        self.name, self.dimensions, self._fptr, self._datatype = name, tuple(dims), fptr, datatype
         if fill is not None:
             self._FillValue = fill
         self.data = np.zeros([fptr.dimensions[d].size or 0 for d in dims])
@@ -130,8 +132,30 @@ class _MemDataset:
         self.dimensions[name] = _MemDim(size, self, name)
 
     def createVariable(self, name, datatype, dims, fill_value=None):  # noqa: N802
-        self.variables[name] = _MemVar(name, dims, self, fill_value)
+        self.variables[name] = _MemVar(name, dims, self, fill_value, datatype)
         return self.variables[name]
+
+    def _persist(self, fname):
+        """the same content as a real NETCDF3_64BIT_OFFSET file (scipy's writer), so that a solve the reference was
+        interrupted in can be resumed by this package's solvers, whose StatsFile reads the file back"""
+        from scipy.io import netcdf_file
+
+        with netcdf_file(fname, "w", version=2) as nc:
+            for key, val in self._store["attrs"].items():
+                setattr(nc, key, val)
+            for name, dim in self.dimensions.items():
+                nc.createDimension(name, dim.size)
+            for var in self.variables.values():
+                out = nc.createVariable(var.name, "i4" if var._datatype == "i4" else "f8", var.dimensions)
+                for key, val in vars(var).items():
+                    if key not in _NOT_ATTRS:
+                        setattr(out, key, val)
+                data = np.asarray(var.data)
+                if var.dimensions and self.dimensions[var.dimensions[0]].size is None:
+                    if data.shape[0] > 0:
+                        out[: data.shape[0]] = data
+                else:
+                    out[:] = data
 
     def sync(self):
         pass
@@ -140,6 +164,9 @@ class _MemDataset:
         return self
 
     def __exit__(self, *exc):
+        fname = next(name for name, store in _FILES.items() if store is self._store)
+        if PERSIST and not isinstance(self.variables, _LooseVars):
+            self._persist(fname)
         return False
 
 
@@ -195,7 +222,7 @@ def run_reference(problem):
                 "dimensions": [[name, dim.size, len(dim)] for name, dim in store["dimensions"].items()],
                 "variables": [
                     {"name": var.name, "dimensions": list(var.dimensions),
-                     "attrs": {k: v for k, v in vars(var).items() if k not in ("name", "dimensions", "data", "_fptr", "_loose")},
+                     "attrs": {k: v for k, v in vars(var).items() if k not in _NOT_ATTRS},
                      "data": np.asarray(var.data).tolist()}
                     for var in store["variables"].values()],
             }

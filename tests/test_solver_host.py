@@ -145,6 +145,29 @@ def test_rewind_redoes_the_last_logged_step(fake, tmp_path):
         NewtonSolver(fake(np.ones(6)), SOLVERINFO, workdir=str(tmp_path / "x"), resume=False, rewind=True)
 
 
+def _same_stats(path, want):
+    from scipy.io import netcdf_file
+
+    with netcdf_file(path, "r", mmap=False) as nc:
+        assert hasattr(nc, "history")
+        for name, size, length in want["dimensions"]:
+            assert name in nc.dimensions and nc.dimensions[name] == size, (path, name)
+        assert sorted(nc.variables) == sorted(v["name"] for v in want["variables"]), path
+        for var in want["variables"]:
+            got = nc.variables[var["name"]]
+            assert list(got.dimensions) == var["dimensions"], var["name"]
+            attrs = {k: (v.decode() if isinstance(v, bytes) else v) for k, v in got._attributes.items()}  # noqa: SLF001
+            assert sorted(attrs) == sorted(var["attrs"]), var["name"]
+            for key, val in var["attrs"].items():
+                if isinstance(val, str):
+                    assert attrs[key] == val, (var["name"], key)
+                else:
+                    assert float(np.asarray(attrs[key]).reshape(-1)[0]) == float(val), (var["name"], key)
+            data = np.array(got.data, dtype=float)
+            assert data.shape == np.shape(var["data"]), var["name"]
+            np.testing.assert_allclose(data, var["data"], rtol=1e-9, atol=1e-14, err_msg=var["name"])
+
+
 @pytest.mark.parametrize("problem", ["mild", "damped", "regions"])
 def test_same_solve_as_the_references_own_solvers(fake, tmp_path, problem):
     """tests/golden/ref_solver_<problem>.json records what the REFERENCE's NewtonSolver / KrylovSolver (imported
@@ -205,28 +228,7 @@ def test_same_solve_as_the_references_own_solvers(fake, tmp_path, problem):
     # the stats files: every dimension, variable, attribute and value the reference wrote (stats_file.py,
     # solver_base.py:68-193, newton_solver.py:62-118, krylov_solver.py:50-73), fill values of the grown iteration
     # dimension included
-    from scipy.io import netcdf_file
-
-    def same_stats(path, want):
-        with netcdf_file(path, "r", mmap=False) as nc:
-            assert hasattr(nc, "history")
-            for name, size, length in want["dimensions"]:
-                assert name in nc.dimensions and nc.dimensions[name] == size, (path, name)
-            assert sorted(nc.variables) == sorted(v["name"] for v in want["variables"]), path
-            for var in want["variables"]:
-                got = nc.variables[var["name"]]
-                assert list(got.dimensions) == var["dimensions"], var["name"]
-                attrs = {k: (v.decode() if isinstance(v, bytes) else v) for k, v in got._attributes.items()}  # noqa: SLF001
-                assert sorted(attrs) == sorted(var["attrs"]), var["name"]
-                for key, val in var["attrs"].items():
-                    if isinstance(val, str):
-                        assert attrs[key] == val, (var["name"], key)
-                    else:
-                        assert float(np.asarray(attrs[key]).reshape(-1)[0]) == float(val), (var["name"], key)
-                data = np.array(got.data, dtype=float)
-                assert data.shape == np.shape(var["data"]), var["name"]
-                np.testing.assert_allclose(data, var["data"], rtol=1e-9, atol=1e-14, err_msg=var["name"])
-
+    same_stats = _same_stats
     same_stats(os.path.join(work, "Newton_stats.nc"), ref["Newton_stats"])
     for i, want in enumerate(ref["Krylov_stats"]):
         same_stats(os.path.join(work, f"krylov_{i:02}", "Krylov_stats.nc"), want)
@@ -274,3 +276,44 @@ def test_the_reference_resumes_a_solve_this_package_interrupted(fake, tmp_path, 
         with open(os.path.join(work, "Newton_state.json")) as fptr:
             log = [s.replace(work, "W") for s in json.load(fptr)["step_log"]]
         assert log == ref["Newton_state"]["step_log"], k
+
+
+@pytest.mark.parametrize("problem", ["mild", "damped", "regions"])
+def test_this_package_resumes_a_solve_the_reference_was_interrupted_in(fake, tmp_path, problem, monkeypatch):
+    """the direction a user switching over needs (build container only): the REFERENCE's NewtonSolver is interrupted at
+    a function evaluation; `NewtonSolver(resume=True)` of this package reads the reference's Newton_state.json,
+    Krylov_state.json, stats files, iterate / basis / w files and finishes with the iterate, the step log and the stats
+    files of the reference's own uninterrupted solve, evaluating only what was not logged"""
+    from oracle import gen_golden_solver as gen
+    from oracle import ref_harness
+
+    if not ref_harness.available():
+        pytest.skip("the reference is not mounted here")
+    with open(os.path.join(os.path.dirname(__file__), "golden", f"ref_solver_{problem}.json")) as fptr:
+        ref = json.load(fptr)
+    from nk_ooc_b200.solver import NewtonSolver
+
+    monkeypatch.setattr(gen, "PERSIST", True)  # the reference's stats files as real files
+    ref_solver_class = gen.reference_newton_solver()
+    for k in (2, 5, 9, 14, ref["evaluations"] - 1):
+        fake.configure(problem)
+        work = str(tmp_path / f"w{k}")
+        init = os.path.join(work, "init_iterate.nc")
+        fake(np.ones(6)).dump(init)
+        fake.fail_at = k
+        with pytest.raises(_Interrupted):
+            theirs = ref_solver_class(fake, gen.solverinfo(work, init), resume=False, rewind=False)
+            while not theirs.converged().all():
+                theirs.step()
+        fake.fail_at = None
+        ours = NewtonSolver(fake(np.ones(6)), dict(ref["solverinfo"]), workdir=work, resume=True)
+        ours.solve()
+        assert fake.calls == ref["evaluations"] + 1, k
+        assert ours.iteration == ref["iterations"]
+        np.testing.assert_allclose(ours.iterate.vals, ref["iterate"][-1], rtol=1e-11, atol=1e-13, err_msg=str(k))
+        with open(os.path.join(work, "Newton_state.json")) as fptr:
+            log = [s.replace(work, "W") for s in json.load(fptr)["step_log"]]
+        assert log == ref["Newton_state"]["step_log"], k
+        _same_stats(os.path.join(work, "Newton_stats.nc"), ref["Newton_stats"])
+        for i, want in enumerate(ref["Krylov_stats"]):
+            _same_stats(os.path.join(work, f"krylov_{i:02}", "Krylov_stats.nc"), want)
