@@ -927,23 +927,45 @@ static_assert(P3_UBOX % 128 == 0 && P3_SLOT % 128 == 0 && P3_OBOX % 128 == 0 && 
               "TMA boxes need 128-byte aligned shared-memory bases");
 static_assert(P3_SMEM <= 227 * 1024, "shared memory");
 
-// a / b for b in the normal range (po4 + half saturation): reciprocal seed (MUFU.RCP64H), two Newton
-// steps and one residual correction — 8 dependent-free-of-branches FP64 operations instead of the IEEE
-// division subroutine with its special-case paths (within 1 ulp of the correctly rounded quotient)
+// a / b for b in the normal range (po4 + half saturation) without the IEEE division subroutine and its special-case
+// paths.  The FP64 instruction count of the coupled sources is what the two schedulers that carry two consumer warps
+// run out of (round 2, scripts/ab_variants.sh on one box: every DFMA less per source evaluation is worth 1.5 - 2 %), so
+// the quotient is as short as its use allows:
+//   P3_DIV = 3 (default): reciprocal seed r (MUFU.RCP64H, 2^-23 or better; 2^-20 if only the upper mantissa word is
+//       exact), e = 1 - b r and q0 = a r side by side, q = q0 (1 + e): three FP64 operations, relative error e^2 <= 2^-40
+//       (1e-12) — seven orders below the time integration error of the uptake term it feeds; exactly 0 for a = 0
+//   P3_DIV = 2: the same plus the residual correction with the SEED, q + (a - b q) r: error 2^-40 x 2^-20, within
+//       0.51 ulp of the IEEE quotient (checked with exact rational arithmetic), five operations; 3.5 % slower
+//   P3_DIV = 0: round 1's two Newton steps on r and the correction (eight operations); 7 % slower
+#ifndef P3_DIV
+#define P3_DIV 3
+#endif
 __device__ __forceinline__ double p3_div(double a, double b) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+#if P3_DIV >= 2
+    const double e = fma(-b, r, 1.0);
+    const double q0 = a * r;
+    const double q = fma(q0, e, q0);
+#if P3_DIV >= 3
+    return q;
+#else
+    return fma(fma(-b, q, a), r, q);
+#endif
+#else
     double e = fma(-b, r, 1.0);
     r = fma(r, e, r);
     e = fma(-b, r, 1.0);
     r = fma(r, e, r);
     const double q = a * r;
     return fma(fma(-b, q, a), r, q);
+#endif
 }
 
 // explicit source of one tracer times the stage weight w (phosphorus.py:75-95) in coefficient form:
 //   cu * uptake + kd * dop + kq * pop,  uptake = fw * po4 / (po4 + hs),  fw = w * max_uptake_rate * light
 //   po4: cu = -1, kd = +w rd, kq = +w rp;   dop: cu = sigma, kd = -w rd, kq = 0;   pop: cu = 1 - sigma, kd = 0, kq = -w rp
+// (the terms that do not need the quotient first, fma(cu fw, quotient, kd dop + kq pop), measured 1 % slower)
 __device__ __forceinline__ double p3_source(double fw, double cu, double kd, double kq, double hs, double po4,
                                             double dop, double pop) {
     const double u = fw * p3_div(po4, po4 + hs);
