@@ -423,10 +423,10 @@ def _roofline(args, model, B, ms_per_step, launches, steps):
                            "implicit stage); the fused step kernel moves less than that (see traffic)",
         "alg_bytes_per_launch": bytes_alg_eval * B / n_stage_launch, "avg_launch_ms": avg_launch_ms,
         "traffic_unit": "dram bytes per unit of work (ncu, profiles/traffic.json)",
-        "limiter": ("fixed-latency FP64 dependency chains of only six consumer warps (tensor memory holds 3 x 125 "
-                    "levels for 64 (column, member) pairs per SM): stall_wait 30 % of the warp samples, issue slots "
-                    "38 %, FP64 pipe 32 %, shared-memory pipe 72 %, DRAM 36 %; the four schedulers hold the six warps "
-                    "as 2 + 2 + 1 + 1 (profiles/r02_ncu_full_step_fused_p3_refined125x150_B4096.txt, "
+        "limiter": ("only six consumer warps (tensor memory holds 3 x 125 levels for 64 (column, member) pairs per "
+                    "SM), held by the four schedulers as 2 + 2 + 1 + 1: the FP64 issue slots of the two-warp schedulers "
+                    "in the coupled source evaluations, then the shared-memory pipe at 80 % (issue slots 37 %, FP64 "
+                    "pipe 28 %, DRAM 28 %; profiles/r02_ncu_full_step_fused_p3_refined125x150_B4096.txt, "
                     "profiles/r02_p3_variants.md)" if p3 else
                     "the board's 1000 W power cap (throughput follows the SM clock it leaves: ring-depth A/B in "
                     "profiles/r02_ncu_full_step_fused_persistent_refined125x150_forced_B4096.txt), then the "
