@@ -21,6 +21,14 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 from oracle import ref_harness  # noqa: E402
 
 SOLVERINFO = {"newton_rel_tol": "1.0e-8", "newton_max_iter": "12", "post_newton_fp_iter": "1", "krylov_rel_tol": "0.01"}
+# golden name -> (problem of tests/fake_state.py, solverinfo overrides)
+CASES = {
+    "mild": ("mild", {}),
+    "damped": ("damped", {}),
+    "regions": ("regions", {}),
+    # the iteration floors of solver_base.py:61-68 (input/cime_pop/newton_krylov.cfg:46 runs with krylov_min_iter = 4)
+    "min_iter": ("regions", {"krylov_min_iter": "4", "newton_min_iter": "3"}),
+}
 _FILES = {}
 PERSIST = False  # also write the stats files to disk (tests that hand a reference solve over to this package's solvers)
 _NOT_ATTRS = ("name", "dimensions", "data", "_fptr", "_loose", "_datatype")
@@ -188,17 +196,18 @@ def solverinfo(workdir, init_iterate_fname=None, **kw):
     return _Section(dict(SOLVERINFO, workdir=workdir, init_iterate_fname=init_iterate_fname, **kw))
 
 
-def run_reference(problem):
+def run_reference(case):
     """the reference's driver loop (nk_driver.py:58-66) over FakeState; returns the record for the golden file"""
     NewtonSolver = reference_newton_solver()  # noqa: N806
 
     from fake_state import FakeState
 
+    problem, overrides = CASES[case]
     FakeState.configure(problem)
     with tempfile.TemporaryDirectory() as work:
         init = os.path.join(work, "init_iterate.nc")
         FakeState(np.ones(6)).dump(init)
-        info = solverinfo(work, init)
+        info = solverinfo(work, init, **overrides)
         solver = NewtonSolver(FakeState, info, resume=False, rewind=False)
         while not solver.converged().all():
             solver.step()
@@ -228,7 +237,7 @@ def run_reference(problem):
             }
 
         rec = {
-            "problem": problem, "solverinfo": SOLVERINFO, "iterations": n_iter, "evaluations": FakeState.calls,
+            "problem": problem, "solverinfo": dict(SOLVERINFO, **overrides), "iterations": n_iter, "evaluations": FakeState.calls,
             "iterate": [arr(f"iterate_{i:02}.nc") for i in range(n_iter + 1)],
             "fcn": [arr(f"fcn_{i:02}.nc") for i in range(n_iter + 1)],
             "increment": [arr(f"increment_{i:02}.nc") for i in range(n_iter)],
@@ -248,7 +257,7 @@ def main():
     ref_harness.install_stubs()
     if ref_harness.REF_ROOT not in sys.path:
         sys.path.insert(0, ref_harness.REF_ROOT)
-    for problem in ("mild", "damped", "regions"):
+    for problem in CASES:
         rec = run_reference(problem)
         path = os.path.join(ROOT, "tests", "golden", f"ref_solver_{problem}.json")
         with open(path, "w") as fptr:

@@ -168,7 +168,7 @@ def _same_stats(path, want):
             np.testing.assert_allclose(data, var["data"], rtol=1e-9, atol=1e-14, err_msg=var["name"])
 
 
-@pytest.mark.parametrize("problem", ["mild", "damped", "regions"])
+@pytest.mark.parametrize("problem", ["mild", "damped", "regions", "min_iter"])
 def test_same_solve_as_the_references_own_solvers(fake, tmp_path, problem):
     """tests/golden/ref_solver_<problem>.json records what the REFERENCE's NewtonSolver / KrylovSolver (imported
     unmodified, oracle/gen_golden_solver.py) did over this very state class: this package's solvers take the same
@@ -178,7 +178,7 @@ def test_same_solve_as_the_references_own_solvers(fake, tmp_path, problem):
         ref = json.load(fptr)
     from nk_ooc_b200.solver import NewtonSolver
 
-    fake.configure(problem)
+    fake.configure(ref["problem"])
     work = str(tmp_path / "w")
     solver = NewtonSolver(fake(np.ones(6)), dict(ref["solverinfo"]), workdir=work)
     solver.solve()
@@ -237,13 +237,13 @@ def test_same_solve_as_the_references_own_solvers(fake, tmp_path, problem):
     stats = {f for f in files if f.endswith("_stats.nc")}
     assert stats == {"Newton_stats.nc"} | {os.path.join(f"krylov_{i:02}", "Krylov_stats.nc") for i in range(ref["iterations"])}
     assert [f for f in files if f not in stats] == [f for f in ref["files"] if f != "init_iterate.nc"]
-    if problem != "mild":
+    if ref["problem"] != "mild":
         assert 0.25 in np.ravel(ref["Armijo_factor"])  # a damped step ...
-    if problem == "regions":
+    if ref["problem"] == "regions":
         assert 0.0 in np.ravel(ref["Armijo_factor"])  # ... and blocks that had converged while others had not
 
 
-@pytest.mark.parametrize("problem", ["mild", "damped", "regions"])
+@pytest.mark.parametrize("problem", ["mild", "damped", "regions", "min_iter"])
 def test_the_reference_resumes_a_solve_this_package_interrupted(fake, tmp_path, problem):
     """state-file compatibility in the direction a user switching back would need: a solve of THIS package's solvers,
     interrupted at a function evaluation, is picked up by the REFERENCE's `NewtonSolver(resume=True)` (build container
@@ -261,13 +261,13 @@ def test_the_reference_resumes_a_solve_this_package_interrupted(fake, tmp_path, 
 
     ref_solver_class = gen.reference_newton_solver()
     for k in (2, 5, 9, 14, ref["evaluations"] - 1):
-        fake.configure(problem)
+        fake.configure(ref["problem"])
         work = str(tmp_path / f"w{k}")
         fake.calls, fake.fail_at = 0, k
         with pytest.raises(_Interrupted):
             NewtonSolver(fake(np.ones(6)), dict(ref["solverinfo"]), workdir=work).solve()
         fake.fail_at = None
-        theirs = ref_solver_class(fake, gen.solverinfo(work), resume=True, rewind=False)
+        theirs = ref_solver_class(fake, gen.solverinfo(work, **gen.CASES[problem][1]), resume=True, rewind=False)
         while not theirs.converged().all():
             theirs.step()
         assert fake.calls == ref["evaluations"] + 1, k
@@ -278,7 +278,7 @@ def test_the_reference_resumes_a_solve_this_package_interrupted(fake, tmp_path, 
         assert log == ref["Newton_state"]["step_log"], k
 
 
-@pytest.mark.parametrize("problem", ["mild", "damped", "regions"])
+@pytest.mark.parametrize("problem", ["mild", "damped", "regions", "min_iter"])
 def test_this_package_resumes_a_solve_the_reference_was_interrupted_in(fake, tmp_path, problem, monkeypatch):
     """the direction a user switching over needs (build container only): the REFERENCE's NewtonSolver is interrupted at
     a function evaluation; `NewtonSolver(resume=True)` of this package reads the reference's Newton_state.json,
@@ -296,13 +296,13 @@ def test_this_package_resumes_a_solve_the_reference_was_interrupted_in(fake, tmp
     monkeypatch.setattr(gen, "PERSIST", True)  # the reference's stats files as real files
     ref_solver_class = gen.reference_newton_solver()
     for k in (2, 5, 9, 14, ref["evaluations"] - 1):
-        fake.configure(problem)
+        fake.configure(ref["problem"])
         work = str(tmp_path / f"w{k}")
         init = os.path.join(work, "init_iterate.nc")
         fake(np.ones(6)).dump(init)
         fake.fail_at = k
         with pytest.raises(_Interrupted):
-            theirs = ref_solver_class(fake, gen.solverinfo(work, init), resume=False, rewind=False)
+            theirs = ref_solver_class(fake, gen.solverinfo(work, init, **gen.CASES[problem][1]), resume=False, rewind=False)
             while not theirs.converged().all():
                 theirs.step()
         fake.fail_at = None
