@@ -317,3 +317,66 @@ def test_this_package_resumes_a_solve_the_reference_was_interrupted_in(fake, tmp
         _same_stats(os.path.join(work, "Newton_stats.nc"), ref["Newton_stats"])
         for i, want in enumerate(ref["Krylov_stats"]):
             _same_stats(os.path.join(work, f"krylov_{i:02}", "Krylov_stats.nc"), want)
+
+
+@pytest.mark.parametrize("problem", ["damped", "regions"])
+def test_rewind_after_an_interruption_in_both_implementations(fake, tmp_path, problem, monkeypatch):
+    """`--resume --rewind` (solver_state.py:36-45,91-98; newton_solver.py:158-166: a rewound "KrylovSolver instantiated"
+    step rewinds the Krylov solver too): the last logged step of an interrupted solve is taken back and redone.  This
+    package's solver ends with the iterate of the uninterrupted solve; in the build container the SAME interrupted
+    work directory (written by either implementation) is also handed to the reference's solver, and both leave the
+    same Newton step log behind (a popped "inc_iteration" is not logged again by either: the counter was saved)."""
+    import shutil
+
+    from oracle import gen_golden_solver as gen
+    from oracle import ref_harness
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", f"ref_solver_{problem}.json")) as fptr:
+        ref = json.load(fptr)
+    from nk_ooc_b200.solver import NewtonSolver
+
+    have_ref = ref_harness.available()
+    if have_ref:
+        monkeypatch.setattr(gen, "PERSIST", True)
+        ref_solver_class = gen.reference_newton_solver()
+
+    def ours(work, **kw):
+        NewtonSolver(fake(np.ones(6)), dict(ref["solverinfo"]), workdir=work, **kw).solve()
+
+    def theirs(work, init, **kw):
+        solver = ref_solver_class(fake, gen.solverinfo(work, init), **kw)
+        while not solver.converged().all():
+            solver.step()
+
+    def outcome(work, what):
+        final = fake(os.path.join(work, f"iterate_{ref['iterations']:02}.nc")).vals
+        np.testing.assert_allclose(final, ref["iterate"][-1], rtol=1e-11, atol=1e-13, err_msg=what)
+        with open(os.path.join(work, "Newton_state.json")) as fptr:
+            return [s.replace(work, "W") for s in json.load(fptr)["step_log"]]
+
+    for k in range(2, ref["evaluations"], 3):
+        for first in ["ours"] + (["theirs"] if have_ref else []):
+            fake.configure(ref["problem"])
+            work = str(tmp_path / f"{first}_{k}")
+            init = os.path.join(work, "init_iterate.nc")
+            fake(np.ones(6)).dump(init)
+            fake.fail_at = k
+            with pytest.raises(_Interrupted):
+                if first == "ours":
+                    ours(work)
+                else:
+                    theirs(work, init, resume=False, rewind=False)
+            fake.fail_at = None
+            what = f"{first} interrupted at evaluation {k}"
+            if have_ref:
+                # the reference first, in place (the step strings hold the directory's path), then the directory is put
+                # back as the interruption left it
+                shutil.copytree(work, work + "_bak")
+                theirs(work, None, resume=True, rewind=True)
+                want = outcome(work, what + ", the reference resumed with rewind")
+                shutil.rmtree(work)
+                shutil.copytree(work + "_bak", work)
+            ours(work, resume=True, rewind=True)
+            got = outcome(work, what + ", this package resumed with rewind")
+            if have_ref:
+                assert got == want, what
