@@ -63,6 +63,45 @@ def units_product(*units_strs):
     return _format_units({k: v for k, v in total.items() if v != 0})
 
 
+# named units of the files on this path: name -> (dimension, size in the dimension's reference unit).  The year is
+# pint's Julian year (365.25 d), as the reference's `ureg` has it.
+_UNIT_TABLE = {
+    "m": ("length", 1.0), "cm": ("length", 1.0e-2), "mm": ("length", 1.0e-3), "km": ("length", 1.0e3),
+    "s": ("time", 1.0), "min": ("time", 60.0), "h": ("time", 3600.0), "hr": ("time", 3600.0), "hour": ("time", 3600.0),
+    "d": ("time", 86400.0), "day": ("time", 86400.0), "days": ("time", 86400.0),
+    "a": ("time", 365.25 * 86400.0), "yr": ("time", 365.25 * 86400.0), "year": ("time", 365.25 * 86400.0),
+    "years": ("time", 365.25 * 86400.0),
+    "mol": ("amount", 1.0), "mmol": ("amount", 1.0e-3), "umol": ("amount", 1.0e-6), "nmol": ("amount", 1.0e-9),
+    "kg": ("mass", 1.0), "g": ("mass", 1.0e-3), "mg": ("mass", 1.0e-6),
+    "L": ("length3", 1.0e-3), "l": ("length3", 1.0e-3),
+}
+
+
+def units_conversion_factor(units_from, units_to):
+    """factor f with (value in units_from) * f = (value in units_to), for products and quotients of the named units
+    of _UNIT_TABLE with integer powers — what `ureg.Quantity(vals, u1).to(u2)` does for the reference
+    (utils.py:306-310).  ValueError when the units are not commensurable or hold a name the table does not know."""
+    def reduce(units_str):
+        dims, size = {}, 1.0
+        for name, power in _parse_units(units_str).items():
+            if name not in _UNIT_TABLE:
+                raise ValueError(f"unknown unit '{name}' in '{units_str}'")
+            dim, unit_size = _UNIT_TABLE[name]
+            if dim == "length3":
+                dim, power_dim = "length", 3 * power
+            else:
+                power_dim = power
+            dims[dim] = dims.get(dim, 0) + power_dim
+            size *= unit_size ** power
+        return {k: v for k, v in dims.items() if v != 0}, size
+
+    dims1, size1 = reduce(units_from)
+    dims2, size2 = reduce(units_to)
+    if dims1 != dims2:
+        raise ValueError(f"cannot convert from '{units_from}' to '{units_to}'")
+    return size1 / size2
+
+
 # ---- netCDF comparison ----------------------------------------------------------------------------
 def _attrs(var):
     out = {}
@@ -159,9 +198,12 @@ def _isclose_one_var(name, var1, var2, rtol, atol, parent2=None):
         if "since" in units1 or "since" in units2:
             raise ValueError(f"time-like units disagree '{units1}'!='{units2}'")
         if _parse_units(units1) != _parse_units(units2):
-            # the reference converts with pint here; this path only ever writes one spelling of a unit
-            logger.info("    units of %s differ: '%s' != '%s'", name, units1, units2)
-            res = False
+            # utils.py:306-310: the values of the first file are converted to the units of the second
+            try:
+                vals1 = vals1 * units_conversion_factor(units1, units2)
+            except ValueError as err:
+                logger.info("    units of %s differ and cannot be converted: %s", name, err)
+                res = False
     if parent2 is not None and parent2.shape == vals2.shape:
         # |v1 - v2| <= atol + rtol (|x| + |v2|) pointwise, written as a comparison of scaled values
         scale = atol + rtol * (np.abs(parent2) + np.abs(vals2))
